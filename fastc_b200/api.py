@@ -1,0 +1,233 @@
+"""ctypes mirror of the reference's Core API over libfastc_gpu.so.
+
+Names, argument meaning and error behaviour follow the reference:
+  * ECompressionFormat      reference/Base/include/FasTC/CompressionFormat.h
+  * SCompressionSettings    reference/Core/include/FasTC/TexComp.h:30-76
+  * CompressImageData       reference/Core/include/FasTC/TexComp.h:82-89,
+                            reference/Core/src/TexComp.cpp:427-525
+  * CompressedImage.GetCompressedSize  reference/Core/src/CompressedImage.cpp:136-149
+The heavy lifting is the C ABI declared in include/fastc_gpu.h.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+import sys
+from dataclasses import dataclass
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libfastc_gpu.so"
+
+
+class FastcGpuError(RuntimeError):
+    pass
+
+
+class ECompressionFormat(enum.IntEnum):
+    """Subset of FasTC::ECompressionFormat that has a GPU encoder; values are the
+    C ABI's `fastc_gpu_format`."""
+    DXT1 = 0
+    DXT5 = 1
+    ETC1 = 2
+    BPTC = 3
+
+
+BLOCK_BYTES = {ECompressionFormat.DXT1: 8, ECompressionFormat.DXT5: 16,
+               ECompressionFormat.ETC1: 8, ECompressionFormat.BPTC: 16}
+
+
+@dataclass
+class SCompressionSettings:
+    """Field-for-field mirror of the reference struct (TexComp.h:30-76); every
+    field is initialised (the reference's ctor leaves five of them unset, D5)."""
+    format: ECompressionFormat = ECompressionFormat.BPTC
+    bUseSIMD: bool = False
+    iNumThreads: int = 1
+    iQuality: int = 50
+    iNumCompressions: int = 1
+    iJobSize: int = 0
+    bUseAtomics: bool = False
+    bUsePVRTexLib: bool = False
+    bUseNVTT: bool = False
+    logStream: object = None
+    # extensions (not in the reference): GPU count and RNG seed
+    iNumGPUs: int = 1
+    seed: int = 0
+
+
+class _Timing(C.Structure):
+    _fields_ = [("kernel_ms", C.c_double), ("total_ms", C.c_double),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("kernel_launches", C.c_uint32)]
+
+
+class _Job(C.Structure):
+    _fields_ = [("rgba_host", C.c_void_p), ("out_host", C.c_void_p),
+                ("width", C.c_uint32), ("height", C.c_uint32)]
+
+
+class GpuLibrary:
+    """Loads libfastc_gpu.so and types every symbol include/fastc_gpu.h declares."""
+
+    SYMBOLS = [
+        "fastc_gpu_device_count", "fastc_gpu_init", "fastc_gpu_shutdown", "fastc_gpu_block_bytes",
+        "fastc_gpu_compressed_size", "fastc_gpu_compress", "fastc_gpu_compress_batch",
+        "fastc_gpu_compress_device", "fastc_gpu_count_solid_device", "fastc_gpu_bc7_counters",
+        "fastc_gpu_last_error",
+    ]
+
+    def __init__(self, path: Path = LIB_PATH):
+        if not path.exists():
+            raise FastcGpuError(
+                f"{path} is missing: build it with `make gpu` (or __graft_entry__.build()). "
+                "There is no CPU fallback.")
+        L = self.cdll = C.CDLL(str(path))
+        vp, u32, u64, i = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
+        L.fastc_gpu_device_count.restype = i
+        L.fastc_gpu_init.argtypes = [i]
+        L.fastc_gpu_shutdown.restype = None
+        L.fastc_gpu_block_bytes.argtypes = [i]
+        L.fastc_gpu_block_bytes.restype = u32
+        L.fastc_gpu_compressed_size.argtypes = [i, u32, u32]
+        L.fastc_gpu_compressed_size.restype = u64
+        L.fastc_gpu_compress.argtypes = [i, vp, u32, u32, u32, u32, vp, i, u64, u32, i, C.POINTER(_Timing)]
+        L.fastc_gpu_compress_batch.argtypes = [i, C.POINTER(_Job), u32, i, u64, i, C.POINTER(_Timing)]
+        L.fastc_gpu_compress_device.argtypes = [i, vp, u32, u32, u32, u32, vp, i, u64, u32, u32, vp,
+                                                C.POINTER(u32)]
+        L.fastc_gpu_count_solid_device.argtypes = [vp, u32, u32, u32, u32, vp, C.POINTER(u32)]
+        L.fastc_gpu_bc7_counters.argtypes = [C.POINTER(u64), C.POINTER(u64)]
+        L.fastc_gpu_last_error.restype = C.c_char_p
+
+    def error(self) -> str:
+        return (self.cdll.fastc_gpu_last_error() or b"").decode()
+
+    def check(self, rc: int):
+        if rc != 0:
+            raise FastcGpuError(self.error())
+
+    # ---- host -> host -------------------------------------------------------
+    def compress(self, fmt: int, rgba: np.ndarray, out: np.ndarray | None = None, *, quality: int = 50,
+                 seed: int = 0, first_block: int = 0, num_blocks: int = 0, chunk_blocks: int = 0,
+                 num_gpus: int = 1):
+        """rgba: (H, W, 4) uint8, C-contiguous (pinned or pageable host memory).
+        Returns (out bytes, timing dict)."""
+        if rgba.dtype != np.uint8 or rgba.ndim != 3 or rgba.shape[2] != 4 or not rgba.flags.c_contiguous:
+            raise FastcGpuError("rgba must be a C-contiguous (H, W, 4) uint8 array")
+        h, w = rgba.shape[:2]
+        size = int(self.cdll.fastc_gpu_compressed_size(int(fmt), w, h))
+        if out is None:
+            out = np.zeros(size, dtype=np.uint8)
+        elif out.nbytes < size:
+            # reference: "Not enough space for compressed data!" (TexComp.cpp:493-496)
+            raise FastcGpuError("Not enough space for compressed data!")
+        tm = _Timing()
+        self.check(self.cdll.fastc_gpu_compress(int(fmt), rgba.ctypes.data, w, h, first_block, num_blocks,
+                                                out.ctypes.data, quality, seed, chunk_blocks, num_gpus,
+                                                C.byref(tm)))
+        return out, {"kernel_ms": tm.kernel_ms, "total_ms": tm.total_ms, "h2d_bytes": tm.h2d_bytes,
+                     "d2h_bytes": tm.d2h_bytes, "kernel_launches": tm.kernel_launches}
+
+    def compress_batch(self, fmt: int, images: list[np.ndarray], *, quality: int = 50, seed: int = 0,
+                       num_gpus: int = 1):
+        jobs = (_Job * len(images))()
+        outs = []
+        for k, im in enumerate(images):
+            h, w = im.shape[:2]
+            o = np.zeros(int(self.cdll.fastc_gpu_compressed_size(int(fmt), w, h)), dtype=np.uint8)
+            outs.append(o)
+            jobs[k] = _Job(im.ctypes.data, o.ctypes.data, w, h)
+        tm = _Timing()
+        self.check(self.cdll.fastc_gpu_compress_batch(int(fmt), jobs, len(images), quality, seed, num_gpus,
+                                                      C.byref(tm)))
+        return outs, {"kernel_ms": tm.kernel_ms, "total_ms": tm.total_ms, "h2d_bytes": tm.h2d_bytes,
+                      "d2h_bytes": tm.d2h_bytes, "kernel_launches": tm.kernel_launches}
+
+    # ---- device -> device (torch tensors are only the memory/stream plumbing) --
+    def compress_device(self, fmt: int, rgba_dev, out_dev, *, width: int, height: int, quality: int = 50,
+                        seed: int = 0, first_block: int = 0, num_blocks: int = 0, wm_base: int = 0,
+                        block_index_base: int = 0, stream: int | None = None) -> int:
+        """rgba_dev / out_dev: CUDA torch uint8 tensors on the current device.
+        Asynchronous on `stream` (raw cudaStream_t; default torch's current)."""
+        import torch
+        if stream is None:
+            stream = torch.cuda.current_stream().cuda_stream
+        n = C.c_uint32(0)
+        self.check(self.cdll.fastc_gpu_compress_device(int(fmt), rgba_dev.data_ptr(), width, height, first_block,
+                                                       num_blocks, out_dev.data_ptr(), quality, seed, wm_base,
+                                                       block_index_base, stream, C.byref(n)))
+        return n.value
+
+    def count_solid_device(self, rgba_dev, *, width: int, height: int, first_block: int = 0,
+                           num_blocks: int = 0, stream: int | None = None) -> int:
+        import torch
+        if stream is None:
+            stream = torch.cuda.current_stream().cuda_stream
+        if num_blocks == 0:
+            num_blocks = (width // 4) * (height // 4) - first_block
+        n = C.c_uint32(0)
+        self.check(self.cdll.fastc_gpu_count_solid_device(rgba_dev.data_ptr(), width, height, first_block,
+                                                          num_blocks, stream, C.byref(n)))
+        return n.value
+
+
+_lib: GpuLibrary | None = None
+
+
+def lib() -> GpuLibrary:
+    global _lib
+    if _lib is None:
+        _lib = GpuLibrary()
+    return _lib
+
+
+class CompressedImage:
+    """Owns compressed bytes (reference/Core/include/FasTC/CompressedImage.h)."""
+
+    def __init__(self, width: int, height: int, fmt: ECompressionFormat, data: np.ndarray):
+        self.width, self.height, self.format, self.data = width, height, fmt, data
+
+    @staticmethod
+    def GetCompressedSize(width: int, height: int, fmt: ECompressionFormat) -> int:
+        return ((width + 3) // 4) * ((height + 3) // 4) * BLOCK_BYTES[ECompressionFormat(fmt)]
+
+
+def _report_error(msg: str):
+    # reference: fprintf(stderr, "TexComp -- %s\n", msg) (TexComp.cpp:157-159)
+    print(f"TexComp -- {msg}", file=sys.stderr)
+
+
+def CompressImageData(data: np.ndarray, width: int, height: int, cmpData: np.ndarray, cmpDataSz: int,
+                      settings: SCompressionSettings) -> bool:
+    """Same contract as the reference: returns False (after printing
+    `TexComp -- <msg>` to stderr) on failure, prints `Compression time: %0.3f ms`
+    to stdout on success.  `data`: width*height*4 RGBA bytes; `cmpData`: output."""
+    if settings.bUseSIMD:
+        _report_error("Platform does not support SIMD!")  # TexComp.cpp:440-445 (D7)
+        return False
+    try:
+        fmt = ECompressionFormat(settings.format)
+    except ValueError:
+        _report_error("Unknown compression format")
+        return False
+    if width % 4 or height % 4 or width == 0 or height == 0:
+        _report_error("Image dimensions must be multiples of the block size")  # TexComp.cpp:472-476
+        return False
+    if cmpDataSz < CompressedImage.GetCompressedSize(width, height, fmt):
+        _report_error("Not enough space for compressed data!")  # TexComp.cpp:493-496
+        return False
+    img = np.ascontiguousarray(data, dtype=np.uint8).reshape(height, width, 4)
+    n = max(1, settings.iNumCompressions)
+    total = 0.0
+    try:
+        for _ in range(n):
+            _, tm = lib().compress(fmt, img, cmpData, quality=max(0, settings.iQuality), seed=settings.seed,
+                                   chunk_blocks=max(0, settings.iJobSize), num_gpus=max(1, settings.iNumGPUs))
+            total += tm["total_ms"]
+    except FastcGpuError as e:
+        _report_error(str(e))
+        return False
+    print("Compression time: %0.3f ms" % (total / n))  # TexComp.cpp:517
+    return True

@@ -1,0 +1,486 @@
+// C ABI (include/fastc_gpu.h) over the sm_100a kernels: per-device contexts,
+// workspaces, the host->host sharded path and the device->device path.
+//
+// Replaces, on the reference side: CompressImageData's dispatch + the Serial /
+// ThreadGroup / WorkerQueue schedulers (reference/Core/src/TexComp.cpp:161-365,
+// 427-525; Core/src/ThreadGroup.cpp:133-192; Core/src/WorkerQueue.cpp:196-241).
+// Where the reference splits the raster block range over <=256 pthreads, this
+// splits it over GPUs (contiguous block-row slabs, one host thread + streams
+// per GPU) and, inside a GPU, over pipeline chunks of `chunk_blocks` blocks so
+// that H2D, kernels and D2H of neighbouring chunks overlap.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/fastc_gpu.h"
+#include "kernels.h"
+
+namespace fastc {
+namespace {
+
+thread_local char tl_error[512] = "";
+
+int fail(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(tl_error, sizeof(tl_error), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+
+#define CU_TRY(expr)                                                                         \
+  do {                                                                                       \
+    cudaError_t e_ = (expr);                                                                 \
+    if (e_ != cudaSuccess) return fail("%s failed: %s", #expr, cudaGetErrorString(e_));      \
+  } while (0)
+
+constexpr int kMaxDevices = 16;
+constexpr int kPipeDepth = 3;  // staging slots per device for the host path
+
+struct DeviceCtx {
+  bool tables_ready = false;
+  bool ready = false;
+  cudaStream_t streams[kPipeDepth] = {};
+  cudaEvent_t ev_start[kPipeDepth] = {}, ev_stop[kPipeDepth] = {};
+  void *in_buf[kPipeDepth] = {};
+  void *out_buf[kPipeDepth] = {};
+  size_t in_cap[kPipeDepth] = {}, out_cap[kPipeDepth] = {};
+  // slot i for pipeline slot i of the host path, slot kPipeDepth for the device API;
+  // grown on demand, reused across calls
+  Bc7Workspace bc7ws[kPipeDepth + 1];
+  std::mutex mu;
+};
+
+DeviceCtx g_ctx[kMaxDevices];
+std::mutex g_init_mu;
+int g_num_init = 0;
+
+int device_count() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return -1;
+  return std::min(n, kMaxDevices);
+}
+
+// Uploads constant tables for the current device once (any entry point).
+int ensure_tables(int dev) {
+  DeviceCtx &c = g_ctx[dev];
+  std::lock_guard<std::mutex> lk(c.mu);
+  if (c.tables_ready) return 0;
+  CU_TRY(dxt_upload_tables());
+  CU_TRY(etc1_upload_tables());
+  CU_TRY(bc7_upload_tables());
+  c.tables_ready = true;
+  return 0;
+}
+
+int ensure_ctx(int dev) {
+  CU_TRY(cudaSetDevice(dev));
+  if (ensure_tables(dev)) return 1;
+  DeviceCtx &c = g_ctx[dev];
+  std::lock_guard<std::mutex> lk(c.mu);
+  if (c.ready) return 0;
+  for (int i = 0; i < kPipeDepth; i++) {
+    CU_TRY(cudaStreamCreateWithFlags(&c.streams[i], cudaStreamNonBlocking));
+    CU_TRY(cudaEventCreate(&c.ev_start[i]));
+    CU_TRY(cudaEventCreate(&c.ev_stop[i]));
+  }
+  c.ready = true;
+  return 0;
+}
+
+int grow(void **buf, size_t *cap, size_t need) {
+  if (*cap >= need) return 0;
+  if (*buf) CU_TRY(cudaFree(*buf));
+  *buf = nullptr;
+  *cap = 0;
+  CU_TRY(cudaMalloc(buf, need));
+  *cap = need;
+  return 0;
+}
+
+bool valid_format(int f) { return f >= FASTC_GPU_DXT1 && f <= FASTC_GPU_BPTC; }
+
+int check_dims(int format, uint32_t width, uint32_t height) {
+  if (!valid_format(format)) return fail("unknown compression format %d", format);
+  // reference: "Image dimensions must be multiples of the block size" (TexComp.cpp:472-476)
+  if (width == 0 || height == 0 || (width & 3) || (height & 3))
+    return fail("image dimensions %ux%u are not non-zero multiples of the 4x4 block", width, height);
+  return 0;
+}
+
+// Enqueue every kernel needed to encode [first_block, first_block+num_blocks)
+// on `stream` of the current device.
+int enqueue(int dev, int ws_slot, int format, const void *rgba_dev, uint32_t width, uint32_t height,
+            uint32_t first_block, uint32_t num_blocks, void *out_dev, int quality, uint64_t seed,
+            uint32_t wm_base, uint32_t block_index_base, cudaStream_t stream, uint32_t *launches) {
+  uint32_t n = 0;
+  switch (format) {
+    case FASTC_GPU_DXT1:
+    case FASTC_GPU_DXT5:
+      CU_TRY(launch_dxt(format == FASTC_GPU_DXT5, rgba_dev, width, first_block, num_blocks, out_dev, stream));
+      n = num_blocks ? 1 : 0;
+      break;
+    case FASTC_GPU_ETC1:
+      CU_TRY(launch_etc1(rgba_dev, width, first_block, num_blocks, out_dev, stream));
+      n = num_blocks ? 1 : 0;
+      break;
+    case FASTC_GPU_BPTC: {
+      DeviceCtx &c = g_ctx[dev];
+      std::lock_guard<std::mutex> lk(c.mu);
+      CU_TRY(launch_bc7(c.bc7ws[ws_slot], rgba_dev, width, height, first_block, num_blocks, out_dev, quality, seed,
+                        wm_base, block_index_base, stream, &n));
+      break;
+    }
+  }
+  if (launches) *launches += n;
+  return 0;
+}
+
+struct Shard {
+  int dev;
+  uint32_t first_block, num_blocks;  // within the image
+  uint32_t wm_base = 0;
+  double kernel_ms = 0;
+  uint32_t launches = 0;
+  uint64_t h2d = 0, d2h = 0;
+  int rc = 0;
+  char err[512] = "";
+};
+
+// Host->host for one GPU's slab.  The slab is cut into chunks of whole block
+// rows; chunk k uses staging slot k % kPipeDepth, so its H2D overlaps the
+// kernels of chunk k-1 and the D2H of chunk k-2 (three copy/compute engines).
+int run_shard(Shard &s, int format, const uint8_t *rgba_host, uint32_t width, uint32_t height,
+              uint8_t *out_host, int quality, uint64_t seed, uint32_t chunk_blocks) {
+  if (ensure_ctx(s.dev)) return 1;
+  DeviceCtx &c = g_ctx[s.dev];
+  const uint32_t bx = width / 4;
+  const uint32_t bsz = fastc_gpu_block_bytes(format);
+  // Work in whole block rows: rows [row0, row1) cover the shard's block range.
+  const uint32_t row0 = s.first_block / bx;
+  const uint32_t row1 = (s.first_block + s.num_blocks + bx - 1) / bx;
+  uint32_t rows_per_chunk;
+  if (chunk_blocks == 0) {
+    // auto: ~4 Mi pixels per chunk keeps the copy engines busy without making the
+    // pipeline too coarse; BC7 is compute-bound so larger chunks are fine too.
+    rows_per_chunk = std::max<uint32_t>(1, (1u << 18) / bx);
+  } else {
+    rows_per_chunk = std::max<uint32_t>(1, chunk_blocks / bx);
+  }
+  const uint32_t total_rows = row1 - row0;
+  const uint32_t nchunks = (total_rows + rows_per_chunk - 1) / rows_per_chunk;
+  // BC7's watermark chain needs the solid-block count of every earlier chunk;
+  // bc7 tracks that itself when the whole shard is submitted as one range, so
+  // BPTC shards are uploaded chunk-wise but encoded per chunk with a running base.
+  uint32_t wm_base = s.wm_base;
+
+  std::vector<float> chunk_ms;
+  for (uint32_t k = 0; k < nchunks; k++) {
+    const int slot = k % kPipeDepth;
+    cudaStream_t st = c.streams[slot];
+    const uint32_t r0 = row0 + k * rows_per_chunk;
+    const uint32_t r1 = std::min(row1, r0 + rows_per_chunk);
+    const size_t in_bytes = (size_t)(r1 - r0) * 4 * width * 4;
+    const size_t out_bytes = (size_t)(r1 - r0) * bx * bsz;
+    // slot reuse: wait for the previous occupant (stream order guarantees it,
+    // but the host must not overwrite/free buffers while growing them)
+    if (c.in_cap[slot] < in_bytes || c.out_cap[slot] < out_bytes) {
+      CU_TRY(cudaStreamSynchronize(st));
+      if (grow(&c.in_buf[slot], &c.in_cap[slot], in_bytes)) return 1;
+      if (grow(&c.out_buf[slot], &c.out_cap[slot], out_bytes)) return 1;
+    }
+    if (k >= (uint32_t)kPipeDepth) {
+      // collect the timing of the chunk that used this slot before we re-record
+      CU_TRY(cudaEventSynchronize(c.ev_stop[slot]));
+      float ms = 0;
+      CU_TRY(cudaEventElapsedTime(&ms, c.ev_start[slot], c.ev_stop[slot]));
+      s.kernel_ms += ms;
+    }
+    CU_TRY(cudaMemcpyAsync(c.in_buf[slot], rgba_host + (size_t)r0 * 4 * width * 4, in_bytes,
+                           cudaMemcpyHostToDevice, st));
+    s.h2d += in_bytes;
+    // block range of this chunk in chunk-local coordinates (the staged slab is an
+    // image of (r1-r0)*4 rows)
+    uint32_t lo = (k == 0) ? s.first_block - row0 * bx : 0;
+    uint32_t hi = (r1 - r0) * bx;
+    if (r1 == row1) hi = s.first_block + s.num_blocks - r0 * bx;
+    uint32_t solid = 0;
+    if (format == FASTC_GPU_BPTC && nchunks > 1) {
+      // need this chunk's solid count before the next chunk can be packed
+      if (fastc_gpu_count_solid_device(c.in_buf[slot], width, (r1 - r0) * 4, lo, hi - lo, st, &solid)) return 1;
+      s.launches += 1;
+    }
+    CU_TRY(cudaEventRecord(c.ev_start[slot], st));
+    if (enqueue(s.dev, slot, format, c.in_buf[slot], width, (r1 - r0) * 4, lo, hi - lo, c.out_buf[slot], quality,
+                seed, wm_base, r0 * bx, st, &s.launches))
+      return 1;
+    CU_TRY(cudaEventRecord(c.ev_stop[slot], st));
+    wm_base += solid;
+    CU_TRY(cudaMemcpyAsync(out_host + ((size_t)r0 * bx + lo) * bsz, (uint8_t *)c.out_buf[slot] + (size_t)lo * bsz,
+                           (size_t)(hi - lo) * bsz, cudaMemcpyDeviceToHost, st));
+    s.d2h += (size_t)(hi - lo) * bsz;
+  }
+  for (uint32_t k = (nchunks > (uint32_t)kPipeDepth ? nchunks - kPipeDepth : 0); k < nchunks; k++) {
+    const int slot = k % kPipeDepth;
+    CU_TRY(cudaStreamSynchronize(c.streams[slot]));
+    float ms = 0;
+    CU_TRY(cudaEventElapsedTime(&ms, c.ev_start[slot], c.ev_stop[slot]));
+    s.kernel_ms += ms;
+  }
+  return 0;
+}
+
+}  // namespace
+}  // namespace fastc
+
+using namespace fastc;
+
+extern "C" {
+
+int fastc_gpu_device_count(void) { return device_count(); }
+
+int fastc_gpu_init(int num_gpus) {
+  std::lock_guard<std::mutex> lk(g_init_mu);
+  int n = device_count();
+  if (n <= 0) return fail("no CUDA device available (there is no CPU fallback)");
+  if (num_gpus <= 0 || num_gpus > n) num_gpus = n;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  for (int d = 0; d < num_gpus; d++)
+    if (ensure_ctx(d)) return 1;
+  cudaSetDevice(prev);
+  g_num_init = std::max(g_num_init, num_gpus);
+  return 0;
+}
+
+void fastc_gpu_shutdown(void) {
+  std::lock_guard<std::mutex> lk(g_init_mu);
+  int n = device_count();
+  for (int d = 0; d < n && d < kMaxDevices; d++) {
+    DeviceCtx &c = g_ctx[d];
+    if (!c.ready && !c.tables_ready) continue;
+    cudaSetDevice(d);
+    for (int i = 0; i < kPipeDepth; i++) {
+      if (c.streams[i]) cudaStreamDestroy(c.streams[i]);
+      if (c.ev_start[i]) cudaEventDestroy(c.ev_start[i]);
+      if (c.ev_stop[i]) cudaEventDestroy(c.ev_stop[i]);
+      if (c.in_buf[i]) cudaFree(c.in_buf[i]);
+      if (c.out_buf[i]) cudaFree(c.out_buf[i]);
+      c.streams[i] = nullptr; c.ev_start[i] = c.ev_stop[i] = nullptr;
+      c.in_buf[i] = c.out_buf[i] = nullptr; c.in_cap[i] = c.out_cap[i] = 0;
+    }
+    for (int i = 0; i <= kPipeDepth; i++) bc7_free_workspace(c.bc7ws[i]);
+    c.ready = false;
+  }
+  g_num_init = 0;
+}
+
+uint32_t fastc_gpu_block_bytes(int format) {
+  return (format == FASTC_GPU_DXT1 || format == FASTC_GPU_ETC1) ? 8u : 16u;
+}
+
+uint64_t fastc_gpu_compressed_size(int format, uint32_t width, uint32_t height) {
+  return (uint64_t)((width + 3) / 4) * ((height + 3) / 4) * fastc_gpu_block_bytes(format);
+}
+
+int fastc_gpu_compress_device(int format, const void *rgba_dev, uint32_t width, uint32_t height,
+                              uint32_t first_block, uint32_t num_blocks, void *out_dev, int quality,
+                              uint64_t seed, uint32_t wm_base, uint32_t block_index_base, void *cuda_stream,
+                              uint32_t *launches_out) {
+  if (check_dims(format, width, height)) return 1;
+  const uint32_t total = (width / 4) * (height / 4);
+  if (first_block > total) return fail("first_block %u beyond the image's %u blocks", first_block, total);
+  if (num_blocks == 0) num_blocks = total - first_block;
+  if (first_block + num_blocks > total) return fail("block range exceeds the image");
+  if (!rgba_dev || !out_dev) return fail("null device pointer");
+  if (quality < 0) return fail("quality must be >= 0");
+  int dev = 0;
+  CU_TRY(cudaGetDevice(&dev));
+  if (dev >= kMaxDevices) return fail("device index %d not supported", dev);
+  if (ensure_tables(dev)) return 1;
+  uint32_t n = 0;
+  if (enqueue(dev, kPipeDepth, format, rgba_dev, width, height, first_block, num_blocks, out_dev, quality, seed, wm_base,
+              block_index_base, static_cast<cudaStream_t>(cuda_stream), &n))
+    return 1;
+  if (launches_out) *launches_out = n;
+  return 0;
+}
+
+int fastc_gpu_count_solid_device(const void *rgba_dev, uint32_t width, uint32_t height, uint32_t first_block,
+                                 uint32_t num_blocks, void *cuda_stream, uint32_t *count_out) {
+  if (check_dims(FASTC_GPU_BPTC, width, height)) return 1;
+  int dev = 0;
+  CU_TRY(cudaGetDevice(&dev));
+  if (ensure_tables(dev)) return 1;
+  DeviceCtx &c = g_ctx[dev];
+  std::lock_guard<std::mutex> lk(c.mu);
+  CU_TRY(bc7_count_solid(c.bc7ws[kPipeDepth], rgba_dev, width, first_block, num_blocks, static_cast<cudaStream_t>(cuda_stream),
+                         count_out));
+  return 0;
+}
+
+int fastc_gpu_compress(int format, const uint8_t *rgba_host, uint32_t width, uint32_t height,
+                       uint32_t first_block, uint32_t num_blocks, uint8_t *out_host, int quality, uint64_t seed,
+                       uint32_t chunk_blocks, int num_gpus, fastc_gpu_timing *timing) {
+  auto t0 = std::chrono::steady_clock::now();
+  if (check_dims(format, width, height)) return 1;
+  if (!rgba_host || !out_host) return fail("null host pointer");
+  if (quality < 0) return fail("quality must be >= 0");
+  const uint32_t bx = width / 4, total = bx * (height / 4);
+  if (first_block > total) return fail("first_block %u beyond the image's %u blocks", first_block, total);
+  if (num_blocks == 0) num_blocks = total - first_block;
+  if (first_block + num_blocks > total) return fail("block range exceeds the image");
+  int ndev = device_count();
+  if (ndev <= 0) return fail("no CUDA device available (there is no CPU fallback)");
+  if (num_gpus <= 0) num_gpus = g_num_init > 0 ? g_num_init : 1;
+  num_gpus = std::min(num_gpus, ndev);
+  int prev = 0;
+  cudaGetDevice(&prev);
+
+  // Contiguous block-row slabs, one per GPU.
+  const uint32_t row0 = first_block / bx, row1 = (first_block + num_blocks + bx - 1) / bx;
+  const uint32_t rows = row1 - row0;
+  num_gpus = std::max(1, std::min<int>(num_gpus, rows));
+  std::vector<Shard> shards(num_gpus);
+  for (int g = 0; g < num_gpus; g++) {
+    uint32_t a = row0 + (uint32_t)((uint64_t)rows * g / num_gpus);
+    uint32_t b = row0 + (uint32_t)((uint64_t)rows * (g + 1) / num_gpus);
+    uint32_t lo = std::max(first_block, a * bx), hi = std::min(first_block + num_blocks, b * bx);
+    shards[g].dev = g;
+    shards[g].first_block = lo;
+    shards[g].num_blocks = hi > lo ? hi - lo : 0;
+  }
+  // BC7 watermark chain across shards: the word index of a solid block is the
+  // number of solid blocks before it in raster order (reference: process-global
+  // counter, Compressor.cpp:135-140,1457).  Solid-ness only depends on the
+  // input, so count on the host side of each later shard's predecessor cheaply:
+  // a 64 B compare per block, done by the shard threads below before encoding.
+  if (format == FASTC_GPU_BPTC && num_gpus > 1) {
+    std::vector<uint32_t> counts(num_gpus, 0);
+    std::vector<std::thread> th;
+    for (int g = 0; g + 1 < num_gpus; g++)
+      th.emplace_back([&, g] {
+        uint32_t cnt = 0;
+        const uint32_t *img = reinterpret_cast<const uint32_t *>(rgba_host);
+        for (uint32_t bi = shards[g].first_block; bi < shards[g].first_block + shards[g].num_blocks; bi++) {
+          const uint32_t *p = img + (size_t)(bi / bx) * 4 * width + (size_t)(bi % bx) * 4;
+          const uint32_t v = p[0];
+          bool same = true;
+          for (int j = 0; j < 4 && same; j++)
+            for (int i = 0; i < 4; i++)
+              if (p[(size_t)j * width + i] != v) { same = false; break; }
+          cnt += same;
+        }
+        counts[g] = cnt;
+      });
+    for (auto &t : th) t.join();
+    uint32_t run = 0;
+    for (int g = 0; g < num_gpus; g++) { shards[g].wm_base = run; run += counts[g]; }
+  }
+
+  if (num_gpus == 1) {
+    shards[0].rc = run_shard(shards[0], format, rgba_host, width, height, out_host, quality, seed, chunk_blocks);
+    if (shards[0].rc) snprintf(shards[0].err, sizeof(shards[0].err), "%s", tl_error);
+  } else {
+    std::vector<std::thread> th;
+    for (int g = 0; g < num_gpus; g++)
+      th.emplace_back([&, g] {
+        if (shards[g].num_blocks == 0) return;
+        shards[g].rc = run_shard(shards[g], format, rgba_host, width, height, out_host, quality, seed, chunk_blocks);
+        if (shards[g].rc) snprintf(shards[g].err, sizeof(shards[g].err), "%s", tl_error);
+      });
+    for (auto &t : th) t.join();
+  }
+  cudaSetDevice(prev);
+  fastc_gpu_timing tm = {};
+  for (auto &s : shards) {
+    if (s.rc) return fail("GPU %d: %s", s.dev, s.err);
+    tm.kernel_ms = std::max(tm.kernel_ms, s.kernel_ms);
+    tm.kernel_launches += s.launches;
+    tm.h2d_bytes += s.h2d;
+    tm.d2h_bytes += s.d2h;
+  }
+  tm.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  if (timing) *timing = tm;
+  return 0;
+}
+
+int fastc_gpu_compress_batch(int format, const fastc_gpu_job *jobs, uint32_t num_jobs, int quality, uint64_t seed,
+                             int num_gpus, fastc_gpu_timing *timing) {
+  auto t0 = std::chrono::steady_clock::now();
+  if (!jobs && num_jobs) return fail("null job list");
+  int ndev = device_count();
+  if (ndev <= 0) return fail("no CUDA device available (there is no CPU fallback)");
+  if (num_gpus <= 0) num_gpus = g_num_init > 0 ? g_num_init : 1;
+  num_gpus = std::max(1, std::min(num_gpus, ndev));
+  for (uint32_t j = 0; j < num_jobs; j++) {
+    if (check_dims(format, jobs[j].width, jobs[j].height)) return 1;
+    if (!jobs[j].rgba_host || !jobs[j].out_host) return fail("job %u has a null pointer", j);
+  }
+  int prev = 0;
+  cudaGetDevice(&prev);
+  // Whole textures are dealt round-robin to the GPUs; each job
+  // is an independent compression (its own watermark sequence), like one
+  // CompressImageData call per texture in the reference.
+  std::vector<fastc_gpu_timing> per(num_gpus);
+  std::vector<int> rcs(num_gpus, 0);
+  std::vector<std::string> errs(num_gpus);
+  auto worker = [&](int g) {
+    for (uint32_t j = g; j < num_jobs; j += num_gpus) {
+      Shard s;
+      s.dev = g;
+      s.first_block = 0;
+      s.num_blocks = (jobs[j].width / 4) * (jobs[j].height / 4);
+      if (run_shard(s, format, jobs[j].rgba_host, jobs[j].width, jobs[j].height, jobs[j].out_host, quality,
+                    seed + ((uint64_t)j << 40), 0)) {
+        rcs[g] = 1;
+        errs[g] = tl_error;
+        return;
+      }
+      per[g].kernel_ms += s.kernel_ms;
+      per[g].kernel_launches += s.launches;
+      per[g].h2d_bytes += s.h2d;
+      per[g].d2h_bytes += s.d2h;
+    }
+  };
+  if (num_gpus == 1) {
+    worker(0);
+  } else {
+    std::vector<std::thread> th;
+    for (int g = 0; g < num_gpus; g++) th.emplace_back(worker, g);
+    for (auto &t : th) t.join();
+  }
+  cudaSetDevice(prev);
+  fastc_gpu_timing tm = {};
+  for (int g = 0; g < num_gpus; g++) {
+    if (rcs[g]) return fail("GPU %d: %s", g, errs[g].c_str());
+    tm.kernel_ms = std::max(tm.kernel_ms, per[g].kernel_ms);
+    tm.kernel_launches += per[g].kernel_launches;
+    tm.h2d_bytes += per[g].h2d_bytes;
+    tm.d2h_bytes += per[g].d2h_bytes;
+  }
+  tm.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  if (timing) *timing = tm;
+  return 0;
+}
+
+int fastc_gpu_bc7_counters(uint64_t *qe_calls, uint64_t *pixel_bucket_evals) {
+  int dev = 0;
+  CU_TRY(cudaGetDevice(&dev));
+  DeviceCtx &c = g_ctx[dev];
+  std::lock_guard<std::mutex> lk(c.mu);
+  CU_TRY(bc7_read_counters(c.bc7ws[kPipeDepth], qe_calls, pixel_bucket_evals));
+  return 0;
+}
+
+const char *fastc_gpu_last_error(void) { return tl_error; }
+
+}  // extern "C"

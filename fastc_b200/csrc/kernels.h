@@ -1,0 +1,42 @@
+// Internal launcher interface between the C ABI (capi.cu) and the per-format
+// kernels.  Not part of the public boundary (that is include/fastc_gpu.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fastc {
+
+// Per-device one-time constant uploads.
+cudaError_t dxt_upload_tables();
+cudaError_t etc1_upload_tables();
+cudaError_t bc7_upload_tables();
+
+cudaError_t launch_dxt(bool dxt5, const void *rgba_dev, uint32_t width, uint32_t first_block,
+                       uint32_t num_blocks, void *out_dev, cudaStream_t stream);
+
+cudaError_t launch_etc1(const void *rgba_dev, uint32_t width, uint32_t first_block, uint32_t num_blocks,
+                        void *out_dev, cudaStream_t stream);
+
+// Scratch for the multi-kernel BC7 pipeline (chain records, per-block
+// selections, prefix counters).  Owned by the per-device context, grown on
+// demand, reused across calls.
+struct Bc7Workspace {
+  void *base = nullptr;
+  size_t bytes = 0;
+  uint32_t *host_count = nullptr;  // pinned, 1 word (count_solid result)
+};
+void bc7_free_workspace(Bc7Workspace &ws);
+
+// block_index_base: raster index (in the full texture) of the buffer's block 0;
+// keys the per-chain RNG streams so sharded / chunked runs are bit-identical to
+// a single submission.  wm_base: solid blocks preceding first_block.
+cudaError_t launch_bc7(Bc7Workspace &ws, const void *rgba_dev, uint32_t width, uint32_t height,
+                       uint32_t first_block, uint32_t num_blocks, void *out_dev, int quality, uint64_t seed,
+                       uint32_t wm_base, uint32_t block_index_base, cudaStream_t stream, uint32_t *launches);
+
+cudaError_t bc7_count_solid(Bc7Workspace &ws, const void *rgba_dev, uint32_t width, uint32_t first_block,
+                            uint32_t num_blocks, cudaStream_t stream, uint32_t *count_out);
+
+cudaError_t bc7_read_counters(Bc7Workspace &ws, uint64_t *qe_calls, uint64_t *pbe);
+
+}  // namespace fastc

@@ -1,0 +1,121 @@
+/* fastc_gpu.h -- C ABI of the B200 (sm_100a) block-compression library
+ * (libfastc_gpu.so).  Plain pointers and sizes only: no C++/torch types.
+ *
+ * This is the boundary the reference's host code binds to.  Each entry point
+ * names the reference interface it replaces (paths relative to the reference
+ * tree, GammaUNC/FasTC @ 0f8cef65):
+ *
+ *   fastc_gpu_compress         <- bool CompressImageData(data, w, h, cmpData, cmpDataSz, settings)
+ *                                 Core/include/FasTC/TexComp.h:82-89, Core/src/TexComp.cpp:427-525
+ *                                 and, via first_block/num_blocks, one CompressionFunc call
+ *                                 `void(*)(const FasTC::CompressionJob&)` Core/src/CompressionFuncs.h:29
+ *                                 (BPTCC::Compress BPTCEncoder/src/Compressor.cpp:1473,
+ *                                  DXTC::CompressImageDXT1/5 DXTEncoder/src/Compressor.cpp:47/74,
+ *                                  ETCC::Compress_RG ETCEncoder/src/Compressor.cpp:26)
+ *   fastc_gpu_compress_batch   <- FasTC::CompressionJobList (Base/include/FasTC/CompressionJob.h:172-209)
+ *                                 / BPTCC::CompressAtomic (BPTCEncoder/src/Compressor.cpp:1542-1574)
+ *   fastc_gpu_compress_device  <- the same CompressionFunc, with device-resident
+ *   fastc_gpu_count_solid_device  buffers (kernel-only timing; multi-process sharding)
+ *   fastc_gpu_compressed_size  <- CompressedImage::GetCompressedSize (Core/src/CompressedImage.cpp:136-149)
+ *   fastc_gpu_last_error       <- ReportError()'s "TexComp -- %s" message (Core/src/TexComp.cpp:157-159)
+ *
+ * Conventions: every function returns 0 on success and non-zero on failure
+ * (message via fastc_gpu_last_error(), thread-local).  Nothing is allocated
+ * that the caller must free.  There is NO CPU fallback: if no CUDA device is
+ * usable the call fails.
+ *
+ * Pixel layout: row-major RGBA8, R in the lowest byte, pitch = width*4
+ * (RGBAEndpoints.h:64-72, Pixel.cpp:165-179).  Block i (raster order over
+ * width/4 x height/4 blocks) is written at out + i*block_bytes, exactly like
+ * the reference's encoder loops.
+ */
+#ifndef FASTC_GPU_H_
+#define FASTC_GPU_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum fastc_gpu_format {
+  FASTC_GPU_DXT1 = 0, /* FasTC::eCompressionFormat_DXT1, 8 B/block  */
+  FASTC_GPU_DXT5 = 1, /* FasTC::eCompressionFormat_DXT5, 16 B/block */
+  FASTC_GPU_ETC1 = 2, /* FasTC::eCompressionFormat_ETC1, 8 B/block (rg_etc1 cLowQuality) */
+  FASTC_GPU_BPTC = 3  /* FasTC::eCompressionFormat_BPTC, 16 B/block (BC7) */
+};
+
+/* One texture of a batch submission (CompressionJob: Base/include/FasTC/CompressionJob.h:40-140). */
+typedef struct fastc_gpu_job {
+  const uint8_t *rgba_host; /* width*height*4 bytes */
+  uint8_t *out_host;        /* >= fastc_gpu_compressed_size() bytes */
+  uint32_t width, height;   /* multiples of 4 */
+} fastc_gpu_job;
+
+/* Timing breakdown returned by the host-pointer entry points (milliseconds). */
+typedef struct fastc_gpu_timing {
+  double kernel_ms; /* max over GPUs of the summed kernel time (CUDA events)   */
+  double total_ms;  /* wall time of the whole call: H2D + kernels + D2H        */
+  uint64_t h2d_bytes, d2h_bytes;
+  uint32_t kernel_launches; /* number of our kernels launched by the call */
+} fastc_gpu_timing;
+
+/* Number of visible CUDA devices (<0 on error). Creates nothing. */
+int fastc_gpu_device_count(void);
+
+/* Optional: pre-create per-device contexts/streams/workspaces for devices
+ * [0, num_gpus).  num_gpus <= 0 means "all visible".  Called lazily otherwise. */
+int fastc_gpu_init(int num_gpus);
+void fastc_gpu_shutdown(void);
+
+uint32_t fastc_gpu_block_bytes(int format);
+uint64_t fastc_gpu_compressed_size(int format, uint32_t width, uint32_t height);
+
+/* Host -> host.  Encodes blocks [first_block, first_block+num_blocks) of the
+ * image (num_blocks == 0 means "to the end").  quality = SA steps (BPTC only;
+ * SCompressionSettings::iQuality), seed keys the per-block RNG streams,
+ * chunk_blocks = blocks per pipeline chunk (SCompressionSettings::iJobSize;
+ * 0 = auto), num_gpus = devices to shard block rows over (<=0: all
+ * initialised).  timing may be NULL. */
+int fastc_gpu_compress(int format, const uint8_t *rgba_host, uint32_t width, uint32_t height,
+                       uint32_t first_block, uint32_t num_blocks, uint8_t *out_host,
+                       int quality, uint64_t seed, uint32_t chunk_blocks, int num_gpus,
+                       fastc_gpu_timing *timing);
+
+/* N independent textures in one submission, whole textures dealt round-robin
+ * to the GPUs. */
+int fastc_gpu_compress_batch(int format, const fastc_gpu_job *jobs, uint32_t num_jobs,
+                             int quality, uint64_t seed, int num_gpus, fastc_gpu_timing *timing);
+
+/* Device -> device on the CURRENT device, asynchronous on `cuda_stream`
+ * (a cudaStream_t passed as void*; NULL = legacy default stream).
+ * rgba_dev/out_dev address the WHOLE image / whole output; only the block
+ * range is touched.  wm_base = number of solid-colour blocks that precede
+ * first_block in raster order (BC7 watermark sequence, Compressor.cpp:1457);
+ * ignored by the other formats.  block_index_base = raster index, in the full
+ * texture, of this buffer's block 0 when the buffer is a slab of a larger
+ * texture (0 otherwise): it keys the per-block RNG streams, so a sharded run is
+ * bit-identical to an unsharded one.  launches_out (may be NULL) receives the
+ * number of kernels enqueued. */
+int fastc_gpu_compress_device(int format, const void *rgba_dev, uint32_t width, uint32_t height,
+                              uint32_t first_block, uint32_t num_blocks, void *out_dev,
+                              int quality, uint64_t seed, uint32_t wm_base, uint32_t block_index_base,
+                              void *cuda_stream, uint32_t *launches_out);
+
+/* Counts solid-colour blocks in the range (needed to chain wm_base across
+ * shards).  Synchronous with respect to `cuda_stream`. */
+int fastc_gpu_count_solid_device(const void *rgba_dev, uint32_t width, uint32_t height,
+                                 uint32_t first_block, uint32_t num_blocks, void *cuda_stream,
+                                 uint32_t *count_out);
+
+/* BC7 work counters of the last BPTC call on this thread's device context
+ * (QuantizedError calls and pixel-bucket evaluations), only
+ * maintained when the library is built with -DFASTC_GPU_COUNTERS. */
+int fastc_gpu_bc7_counters(uint64_t *qe_calls, uint64_t *pixel_bucket_evals);
+
+const char *fastc_gpu_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FASTC_GPU_H_ */
