@@ -1,0 +1,1142 @@
+// TEST INFRASTRUCTURE ONLY -- CPU restatement (oracle) of the reference's BC7
+// (BPTC) block encoder.  Never linked into or called from the product path.
+//
+// Restates, operation for operation (same float types, same evaluation order,
+// no FMA: oracle/Makefile builds this with -ffp-contract=off and no -march):
+//   reference/BPTCEncoder/src/Compressor.cpp      (CompressBC7Block :1819, BoxSelection :1670,
+//       CompressClusters :1752, CompressionMode::Compress :1300, CompressCluster :921/:632,
+//       OptimizeEndpointsForCluster :538, PickBestNeighboringEndpoints :426, Pack :1096)
+//   reference/BPTCEncoder/src/RGBAEndpoints.{h,cpp} (RGBACluster, QuantizedError :190,
+//       GetPrincipalAxis :327, QuantizeChannel :126, ToPixel :167)
+//   reference/Base/include/FasTC/MatrixSquare.h:44-105 (PowerMethod), VectorBase.h (Dot/Length)
+// including the reference's bug-for-bug behaviours (SURVEY.md traps T1-T18).
+//
+// Pinned bit-for-bit against the compiled reference (oracle/_ref):
+//   * quality 0: deterministic, whole images incl. the watermark sequence;
+//   * quality > 0: rng_mode 0 replays the reference's global LCG (g_seed is set
+//     to a known value through oracle/ref_harness.cpp), so SA is pinned too.
+// rng_mode 1 is the keyed per-chain stream the CUDA path uses.
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+
+#include "bc7_tables.h"
+#include "oracle.h"
+
+namespace {
+using namespace bc7t;
+
+struct V4 {
+  float v[4];
+  float &operator[](int i) { return v[i]; }
+  const float &operator[](int i) const { return v[i]; }
+};
+inline V4 splat(float c) { return V4{{c, c, c, c}}; }
+inline V4 from_pixel(uint32_t p) {
+  return V4{{(float)(p & 0xFF), (float)((p >> 8) & 0xFF), (float)((p >> 16) & 0xFF), (float)((p >> 24) & 0xFF)}};
+}
+inline V4 add(const V4 &a, const V4 &b) { return V4{{a[0] + b[0], a[1] + b[1], a[2] + b[2], a[3] + b[3]}}; }
+inline V4 sub(const V4 &a, const V4 &b) { return V4{{a[0] - b[0], a[1] - b[1], a[2] - b[2], a[3] - b[3]}}; }
+inline V4 mul(const V4 &a, float s) { return V4{{a[0] * s, a[1] * s, a[2] * s, a[3] * s}}; }
+inline V4 divs(const V4 &a, float s) { return V4{{a[0] / s, a[1] / s, a[2] / s, a[3] / s}}; }
+inline bool eq(const V4 &a, const V4 &b) { return a[0] == b[0] && a[1] == b[1] && a[2] == b[2] && a[3] == b[3]; }
+// VectorBase::Dot (VectorBase.h:96-101): sum = 0; sum += a[i]*b[i], i ascending.
+inline float dot(const V4 &a, const V4 &b) {
+  float s = 0;
+  for (int i = 0; i < 4; i++) s += a[i] * b[i];
+  return s;
+}
+// VectorBase::Length (VectorBase.h:104-105)
+inline float length(const V4 &a) { return (float)sqrtl((long double)dot(a, a)); }
+inline V4 normalized(const V4 &a) {
+  float len = length(a);
+  return divs(a, len);
+}
+// std::min / std::max argument-order semantics (T6)
+inline float smin(float a, float b) { return (b < a) ? b : a; }
+inline float smax(float a, float b) { return (a < b) ? b : a; }
+
+// ---------------------------------------------------------------------------
+// RNG (Compressor.cpp:355-362, 506-519).  fastrand() masks with RAND_MAX, which is
+// 0x7FFFFFFF on glibc (the reference's COMPILE_ASSERT(RAND_MAX == 0x7FFF) is a
+// zero-length extern array and compiles silently), so a draw is the full upper
+// 16 bits of the state.  frand() then ORs bit 15 of the draw into the exponent's
+// (already set) low bit: the mantissa gets draw[14:0] << 8 | draw >> 7.
+struct Rng {
+  uint32_t *state;
+  uint32_t next() {
+    *state = 214013u * *state + 2531011u;
+    return (*state >> 16) & 0x7FFFFFFFu;
+  }
+  float frand() {
+    const uint16_t r = (uint16_t)next();
+    const uint32_t m = ((uint32_t)r << 8) | (r >> 7);
+    union { uint32_t u; float f; } x = {(127u << 23) | m};
+    return x.f - 1.0f;
+  }
+};
+
+inline uint32_t fmix32(uint32_t h) {
+  h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+  return h;
+}
+// Keyed per-chain stream (the CUDA path's scheme, fastc_b200/csrc/bc7.cu chain_seed()).
+inline uint32_t chain_seed(uint64_t seed, uint32_t block, uint32_t chain) {
+  const uint32_t h = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x9E3779B9u);
+  return fmix32(h + fmix32(block * 64u + chain));
+}
+
+struct Ctx {
+  int sa_steps;
+  int rng_mode;       // 0 global LCG, 1 keyed per chain
+  uint32_t *global;   // rng_mode 0
+  uint64_t seed;      // rng_mode 1
+  uint32_t block;     // global raster block index (rng_mode 1 key)
+  uint32_t local;     // current chain's state (rng_mode 1)
+  uint64_t qe_calls = 0, pbe = 0;
+};
+
+// ---------------------------------------------------------------------------
+// QuantizeChannel / ToPixel (RGBAEndpoints.cpp:126-177)
+inline int popcount8(uint32_t m) { return __builtin_popcount(m & 0xFF); }
+
+uint8_t quantize_channel(uint8_t val, uint8_t mask, int pbit) {
+  if (mask == 0xFF) return val;
+  if (mask == 0x0) return 0xFF;
+  uint32_t prec = popcount8(mask);
+  const uint32_t step = 1u << (8 - prec);
+  uint32_t lval = val & mask;
+  uint32_t hval = lval + step;
+  if (pbit >= 0) {
+    prec++;
+    lval |= (uint32_t)(!!pbit) << (8 - prec);
+    hval |= (uint32_t)(!!pbit) << (8 - prec);
+  }
+  if (lval > val) {
+    lval -= step;
+    hval -= step;
+  }
+  lval |= lval >> prec;
+  hval |= hval >> prec;
+  // sad<uint8>(val, lval): arguments are truncated to uint8 first
+  const uint8_t l8 = (uint8_t)lval, h8 = (uint8_t)hval;
+  const uint8_t dl = (val > l8) ? (uint8_t)(val - l8) : (uint8_t)(l8 - val);
+  const uint8_t dh = (val > h8) ? (uint8_t)(val - h8) : (uint8_t)(h8 - val);
+  return (dl < dh) ? (uint8_t)lval : (uint8_t)hval;
+}
+
+// uint32(x + 0.5) & 0xFF with the x86 result for NaN (cvttsd2si "integer indefinite" -> low bits 0)
+inline uint32_t round_byte(float x) {
+  const double d = (double)x + 0.5;
+  if (!(d == d)) return 0;
+  return (uint32_t)(int64_t)d & 0xFF;
+}
+
+uint32_t to_pixel(const V4 &p, uint32_t mask = 0xFFFFFFFFu, int pbit = -1) {
+  const uint32_t r0 = quantize_channel((uint8_t)round_byte(p[0]), mask & 0xFF, pbit);
+  const uint32_t r1 = quantize_channel((uint8_t)round_byte(p[1]), (mask >> 8) & 0xFF, pbit);
+  const uint32_t r2 = quantize_channel((uint8_t)round_byte(p[2]), (mask >> 16) & 0xFF, pbit);
+  const uint32_t r3 = quantize_channel((uint8_t)round_byte(p[3]), (mask >> 24) & 0xFF, pbit);
+  return r0 | (r1 << 8) | (r2 << 16) | (r3 << 24);
+}
+
+void clamp_endpoints(V4 &p1, V4 &p2) {  // RGBAEndpoints.cpp:107-110, 436-441
+  for (int i = 0; i < 4; i++) {
+    p1[i] = (p1[i] < 0.0f) ? 0.0f : ((p1[i] > 255.0f) ? 255.0f : p1[i]);
+    p2[i] = (p2[i] < 0.0f) ? 0.0f : ((p2[i] > 255.0f) ? 255.0f : p2[i]);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// RGBACluster (RGBAEndpoints.h:104-227)
+struct Cluster {
+  int n;
+  int nparts, part, shape;
+  V4 avg, mn, mx;
+  V4 pts[16];        // m_DataPoints
+  uint32_t pix[16];  // m_DataPixels
+  uint8_t map[16];   // m_PointMap
+
+  explicit Cluster(const uint32_t pixels[16]) {
+    n = 0; nparts = 1; part = 0; shape = 0;
+    avg = splat(0.0f);
+    mn = splat(FLT_MAX);
+    mx = splat(-FLT_MAX);
+    for (int i = 0; i < 16; i++) {
+      V4 p = from_pixel(pixels[i]);
+      avg = add(avg, p);
+      map[n] = (uint8_t)i;
+      pix[n] = to_pixel(p);
+      pts[n++] = p;
+      for (int c = 0; c < 4; c++) {
+        mn[c] = smin(p[c], mn[c]);
+        mx[c] = smax(p[c], mx[c]);
+      }
+    }
+    avg = divs(avg, (float)n);
+  }
+  const V4 &point(int i) const { return pts[map[i]]; }
+  V4 &point_mut(int i) { return pts[map[i]]; }
+  uint32_t pixel(int i) const { return pix[map[i]]; }
+  bool all_same() const { return eq(mx, mn); }
+  void set_shape(int s, int np) { shape = s; nparts = np; }
+  void set_partition(int p) {  // Recalculate (RGBAEndpoints.h:205-226)
+    part = p;
+    n = 0;
+    avg = splat(0.0f);
+    mn = splat(FLT_MAX);
+    mx = splat(-FLT_MAX);
+    int m = 0;
+    for (int idx = 0; idx < 16; idx++) {
+      if (subset_of(idx, shape, nparts) != part) continue;
+      n++;
+      avg = add(avg, pts[idx]);
+      map[m++] = (uint8_t)idx;
+      for (int c = 0; c < 4; c++) {
+        mn[c] = smin(pts[idx][c], mn[c]);
+        mx[c] = smax(pts[idx][c], mx[c]);
+      }
+    }
+    avg = divs(avg, (float)n);
+  }
+};
+
+// RGBACluster::QuantizedError (RGBAEndpoints.cpp:190-310)
+double quantized_error(Ctx &cx, const Cluster &c, const V4 &p1, const V4 &p2, int nbuckets, uint32_t bitmask,
+                       const V4 &metric, const int *pbits, uint8_t *indices) {
+  const int prec = nbuckets == 4 ? 2 : nbuckets == 8 ? 3 : 4;
+  const uint32_t(*interp)[2] = kInterp[prec - 1];
+  uint32_t qp1, qp2;
+  if (pbits) {
+    qp1 = to_pixel(p1, bitmask, pbits[0]);
+    qp2 = to_pixel(p2, bitmask, pbits[1]);
+  } else {
+    qp1 = to_pixel(p1, bitmask);
+    qp2 = to_pixel(p2, bitmask);
+  }
+  const V4 uqp1 = from_pixel(qp1), uqp2 = from_pixel(qp2);
+  const V4 d12 = sub(uqp1, uqp2);
+  const float uqplsq = dot(d12, d12);
+  const V4 uqpdir = sub(uqp2, uqp1);
+  uint8_t e1[4], e2[4];
+  for (int k = 0; k < 4; k++) { e1[k] = (qp1 >> (8 * k)) & 0xFF; e2[k] = (qp2 >> (8 * k)) & 0xFF; }
+  cx.qe_calls++;
+
+  float total = 0.0f;
+  if (uqplsq == 0) {
+    for (int i = 0; i < c.n; i++) {
+      const uint32_t pixel = c.pixel(i);
+      V4 ev = splat(0.0f);
+      for (int k = 0; k < 4; k++) {
+        const uint32_t ip = ((e1[k] * interp[0][0] + e2[k] * interp[0][1] + 32) >> 6) & 0xFF;
+        const uint8_t pb = (pixel >> (8 * k)) & 0xFF;
+        const uint8_t ip8 = (uint8_t)ip;
+        const uint8_t dist = (pb > ip8) ? (uint8_t)(pb - ip8) : (uint8_t)(ip8 - pb);
+        ev[k] = (float)dist * metric[k];
+      }
+      total += dot(ev, ev);
+      cx.pbe++;
+      if (indices) indices[i] = 0;
+    }
+    return total;
+  }
+  for (int i = 0; i < c.n; i++) {
+    const V4 pt = c.point(i);
+    const float pct = dot(sub(pt, uqp1), uqpdir) / uqplsq;
+    int j1 = (int)floor(pct * (float)(nbuckets - 1));  // float product promoted to double for floor/ceil
+    int j2 = (int)ceil(pct * (float)(nbuckets - 1));
+    j1 = (j1 < 0) ? 0 : j1;                // std::max(0, j1)
+    j1 = (nbuckets - 1 < j1) ? nbuckets - 1 : j1;  // std::min(.., nBuckets-1)
+    j2 = (nbuckets - 1 < j2) ? nbuckets - 1 : j2;
+    const uint32_t pixel = c.pixel(i);
+    float min_err = FLT_MAX;
+    uint8_t best = 0;
+    int j = j1;
+    do {
+      V4 ev = splat(0.0f);
+      for (int k = 0; k < 4; k++) {
+        const uint32_t ip = ((e1[k] * interp[j][0] + e2[k] * interp[j][1] + 32) >> 6) & 0xFF;
+        const uint8_t pb = (pixel >> (8 * k)) & 0xFF;
+        const uint8_t ip8 = (uint8_t)ip;
+        const uint8_t dist = (pb > ip8) ? (uint8_t)(pb - ip8) : (uint8_t)(ip8 - pb);
+        ev[k] = (float)dist * metric[k];
+      }
+      cx.pbe++;
+      const float err = dot(ev, ev);
+      if (err < min_err) {
+        min_err = err;
+        best = (uint8_t)j;
+      } else if (err > min_err) {
+        break;
+      }
+    } while (++j <= j2);
+    total += min_err;
+    if (indices) indices[i] = best;
+  }
+  return total;
+}
+
+// MatrixSquare::PowerMethod (MatrixSquare.h:44-105) for the 4x4 float case,
+// eigVal == NULL, kMaxNumIterations = 5.
+void power_method(const float m[4][4], V4 &eig) {
+  V4 b = splat(1.0f / sqrtf(4.0f));
+  bool bad = false, fixed = false;
+  int it = 0;
+  while (!fixed && ++it < 5) {
+    V4 nb;
+    for (int j = 0; j < 4; j++) {  // MatrixVectorMultiply (MatrixBase.h:136-146)
+      float r = 0;
+      for (int i = 0; i < 4; i++) r += m[j][i] * b[i];
+      nb[j] = r;
+    }
+    const float len = length(nb);
+    if (len < 1e-10) {
+      if (bad) {
+        eig = b;
+        return;
+      }
+      for (int i = 0; i < 2; i++) b[i] = 1;
+      b = normalized(b);
+      bad = true;
+      continue;
+    }
+    nb = normalized(nb);
+    if (fabs(1.0f - dot(b, nb)) < 1e-8) fixed = true;
+    b = nb;
+  }
+  eig = b;
+}
+
+// RGBACluster::GetPrincipalAxis (RGBAEndpoints.cpp:327-428), eigOne = eigTwo = NULL.
+void principal_axis(const Cluster &c, V4 &axis) {
+  V4 to_pts[16];
+  for (int i = 0; i < c.n; i++) to_pts[i] = sub(c.point(i), c.avg);
+  V4 upts[16];
+  for (int i = 0; i < 16; i++) upts[i] = splat(-1.0f);  // default-constructed RGBAVector (T7)
+  int nu = 0;
+  for (int i = 0; i < c.n; i++) {
+    bool has = false;
+    for (int j = 0; j < nu; j++)
+      if (eq(upts[j], c.point(i))) has = true;
+    if (!has) upts[nu++] = c.point(i);
+  }
+  if (nu == 1) {
+    axis = splat(0.0f);
+    return;
+  }
+  const V4 dir = normalized(sub(upts[1], upts[0]));
+  bool collinear = true;
+  for (int i = 2; i < c.n; i++) {  // T7: runs to GetNumPoints(), not to the unique count
+    const V4 v = sub(upts[i], upts[0]);
+    if (fabs(fabs((double)dot(v, dir)) - (double)length(v)) > 1e-7) {
+      collinear = false;
+      break;
+    }
+  }
+  if (collinear) {
+    axis = dir;
+    return;
+  }
+  float cov[4][4];
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j <= i; j++) {
+      float sum = 0.0f;
+      for (int k = 0; k < c.n; k++) sum += to_pts[k][i] * to_pts[k][j];
+      cov[i][j] = sum / 3.0f;  // T8
+      cov[j][i] = cov[i][j];
+    }
+  power_method(cov, axis);
+}
+
+// ---------------------------------------------------------------------------
+// CompressionMode (CompressionMode.h, Compressor.cpp)
+const int kPBits[4][2] = {{0, 0}, {0, 1}, {1, 0}, {1, 1}};
+
+struct Params {
+  V4 p1[3], p2[3];
+  uint8_t indices[3][16];
+  uint8_t alpha_indices[16];
+  uint8_t pbit_combo[3];
+  int rotation, index_mode, shape;
+  void init(int s) {
+    rotation = -1; index_mode = -1; shape = s;
+    memset(indices, 0xFF, sizeof(indices));
+    memset(alpha_indices, 0xFF, sizeof(alpha_indices));
+    memset(pbit_combo, 0xFF, sizeof(pbit_combo));
+    for (int i = 0; i < 3; i++) p1[i] = p2[i] = splat(-1.0f);
+  }
+};
+
+struct Mode {
+  Ctx &cx;
+  int mode;
+  const ModeAttr &A;
+  int rot = 0, idx_mode = 0;
+  int chain_slot = 0;  // shape slot (0/1) of the candidate being fitted; part of the RNG key
+  Mode(Ctx &c, int m) : cx(c), mode(m), A(kModes[m]) {}
+
+  bool opaque() const { return mode < 4; }  // m_IsOpaque
+  int rotation() const { return A.has_rotation ? rot : 0; }
+  int index_bits() const { return idx_mode == 0 ? A.index_bits : A.alpha_index_bits; }
+  int alpha_index_bits() const { return idx_mode == 0 ? A.alpha_index_bits : A.index_bits; }
+  V4 metric() const { return splat(1.0f); }  // eErrorMetric_Uniform under any rotation
+  uint32_t qmask() const {                   // GetQuantizationMask (CompressionMode.h:212-232)
+    const int32_t seed = (int32_t)0x80000000;
+    const uint32_t cbits = A.color_bits - 1, abits = A.alpha_bits - 1;
+    if (A.alpha_bits > 0)
+      return (uint32_t)(((seed >> (24 + cbits)) & 0xFF) | ((seed >> (16 + cbits)) & 0xFF00) |
+                        ((seed >> (8 + cbits)) & 0xFF0000) | ((seed >> abits) & 0xFF000000));
+    return (uint32_t)((((seed >> (24 + cbits)) & 0xFF) | ((seed >> (16 + cbits)) & 0xFF00) |
+                       ((seed >> (8 + cbits)) & 0xFF0000)) & 0x00FFFFFF);
+  }
+  int num_pbit_combos() const { return A.pbit_type == kPbitShared ? 2 : A.pbit_type == kPbitPerEndpoint ? 4 : 1; }
+  const int *pbit_combo(int idx) const {
+    if (A.pbit_type == kPbitShared) return idx ? kPBits[3] : kPBits[0];
+    if (A.pbit_type == kPbitPerEndpoint) return kPBits[idx % 4];
+    return kPBits[0];
+  }
+
+  // ClampEndpointsToGrid (Compressor.cpp:212-250)
+  void clamp_to_grid(V4 &p1, V4 &p2, uint8_t &best_combo) const {
+    const int ncombos = num_pbit_combos();
+    const bool has = ncombos > 1;
+    const uint32_t qm = qmask();
+    clamp_endpoints(p1, p2);
+    float min_dist = FLT_MAX;
+    V4 bp1 = splat(-1.0f), bp2 = splat(-1.0f);
+    for (int i = 0; i < ncombos; i++) {
+      uint32_t qp1, qp2;
+      if (has) {
+        qp1 = to_pixel(p1, qm, pbit_combo(i)[0]);
+        qp2 = to_pixel(p2, qm, pbit_combo(i)[1]);
+      } else {
+        qp1 = to_pixel(p1, qm);
+        qp2 = to_pixel(p2, qm);
+      }
+      const V4 np1 = from_pixel(qp1), np2 = from_pixel(qp2);
+      const V4 d1 = sub(np1, p1), d2 = sub(np2, p2);
+      const float dist = dot(d1, d1) + dot(d2, d2);
+      if (dist < min_dist) {
+        min_dist = dist;
+        bp1 = np1; bp2 = np2;
+        best_combo = (uint8_t)i;
+      }
+    }
+    p1 = bp1;
+    p2 = bp2;
+  }
+
+  // CompressSingleColor (Compressor.cpp:252-353)
+  double single_color(const V4 &p, V4 &p1, V4 &p2, uint8_t &best_combo) const {
+    const uint32_t pixel = to_pixel(p);
+    float best_error = FLT_MAX;
+    for (int pbi = 0; pbi < num_pbit_combos(); pbi++) {
+      const int *combo = pbit_combo(pbi);
+      uint32_t dist[4] = {0, 0, 0, 0};
+      uint32_t best_i[4], best_j[4];
+      memset(best_i, 0xFF, sizeof(best_i));
+      memset(best_j, 0xFF, sizeof(best_j));
+      for (int ci = 0; ci < 4; ci++) {
+        const uint8_t val = (pixel >> (ci * 8)) & 0xFF;
+        int nbits = ci == 3 ? A.alpha_bits : A.color_bits;
+        if (nbits == 0) {
+          best_i[ci] = best_j[ci] = 0xFF;
+          const uint32_t d = 0xFFu - val;
+          dist[ci] = dist[ci] < d ? d : dist[ci];
+          continue;
+        }
+        const int nvals = 1 << nbits;
+        int vals_h[256], vals_l[256];
+        const bool have_pbit = A.pbit_type != kPbitNone;
+        if (have_pbit) nbits++;
+        for (int i = 0; i < nvals; i++) {
+          int vh = i, vl = i;
+          if (have_pbit) {
+            vh = (vh << 1) | combo[1];
+            vl = (vl << 1) | combo[0];
+          }
+          vals_h[i] = vh << (8 - nbits);
+          vals_h[i] |= vals_h[i] >> nbits;
+          vals_l[i] = vl << (8 - nbits);
+          vals_l[i] |= vals_l[i] >> nbits;
+        }
+        const int bpi = index_bits() - 1;
+        const uint32_t w0 = kInterp[bpi][1][0], w1 = kInterp[bpi][1][1];
+        uint32_t best_d = 0xFF;
+        for (int i = 0; best_d > 0 && i < nvals; i++)
+          for (int j = 0; best_d > 0 && j < nvals; j++) {
+            const uint32_t v1 = vals_l[i], v2 = vals_h[j];
+            const uint32_t combo_v = (w0 * v1 + w1 * v2 + 32) >> 6;
+            const uint32_t err = combo_v > val ? combo_v - val : val - combo_v;
+            if (err < best_d) {
+              best_d = err;
+              best_i[ci] = v1;
+              best_j[ci] = v2;
+            }
+          }
+        dist[ci] = best_d < dist[ci] ? dist[ci] : best_d;
+      }
+      float error = 0.0f;
+      for (int i = 0; i < 4; i++) {
+        const float e = (float)dist[i] * 1.0f;
+        error += e * e;
+      }
+      if (error < best_error) {
+        best_error = error;
+        best_combo = (uint8_t)pbi;
+        for (int ci = 0; ci < 4; ci++) {
+          p1[ci] = (float)best_i[ci];
+          p2[ci] = (float)best_j[ci];
+        }
+      }
+    }
+    return best_error;
+  }
+
+  // PickBestNeighboringEndpoints (Compressor.cpp:426-498), stepSz = 1, nVisited = 1.
+  void pick_neighbor(Rng &rng, const V4 &p1, const V4 &p2, int cur_combo, V4 &np1, V4 &np2, int &ncombo,
+                     const V4 &vis1, const V4 &vis2, int vis_combo) const {
+    float step[4] = {(float)(1 << (8 - A.color_bits)), (float)(1 << (8 - A.color_bits)),
+                     (float)(1 << (8 - A.color_bits)), (float)(1 << (8 - A.alpha_bits))};
+    if (opaque()) step[(rotation() + 3) % 4] = 0.0f;
+    const bool has = A.pbit_type != kPbitNone;
+    if (has) ncombo = A.pbit_type == kPbitShared ? (cur_combo + 1) % 2 : 3 - cur_combo;
+    bool visited = true;
+    int guard = -1;
+    while (visited && ++guard < 16) {
+      for (int pt = 0; pt < 2; pt++) {
+        const V4 &p = pt ? p1 : p2;
+        V4 &np = pt ? np1 : np2;
+        np = p;
+        const uint32_t dir = rng.next() % 16;
+        if (has) {
+          const int old = pbit_combo(cur_combo)[pt];
+          for (int ch = 0; ch < 4; ch++) {
+            const bool neg = (dir >> ch) & 1;
+            if (neg && old == 0) np[ch] -= step[ch];
+            else if (!neg && old == 1) np[ch] += step[ch];
+          }
+        } else {
+          for (int ch = 0; ch < 4; ch++) {
+            if ((dir >> ch) & 1) np[ch] -= step[ch];
+            else np[ch] += step[ch];
+          }
+        }
+        for (int ch = 0; ch < 4; ch++) np[ch] = smin(smax(np[ch], 0.0f), 255.0f);
+      }
+      visited = eq(vis1, np1) && eq(vis2, np2) && vis_combo == ncombo;
+    }
+  }
+
+  // OptimizeEndpointsForCluster (Compressor.cpp:538-630)
+  double optimize(const Cluster &c, V4 &p1, V4 &p2, uint8_t *best_indices, uint8_t &best_combo, int chain_id) {
+    const int nbuckets = 1 << index_bits();
+    const uint32_t qm = qmask();
+    const V4 met = metric();
+    double cur_error = quantized_error(cx, c, p1, p2, nbuckets, qm, met, pbit_combo(best_combo), best_indices);
+    int cur_combo = best_combo;
+    double best_error = cur_error;
+    uint32_t qp1, qp2;
+    if (A.pbit_type != kPbitNone) {
+      qp1 = to_pixel(p1, qm, pbit_combo(best_combo)[0]);
+      qp2 = to_pixel(p2, qm, pbit_combo(best_combo)[1]);
+    } else {
+      qp1 = to_pixel(p1, qm);
+      qp2 = to_pixel(p2, qm);
+    }
+    p1 = from_pixel(qp1);
+    p2 = from_pixel(qp2);
+    V4 bp1 = p1, bp2 = p2;
+    V4 vis1 = p1, vis2 = p2;
+    int vis_combo = cur_combo;
+
+    uint32_t *st = cx.global;
+    if (cx.rng_mode == 1) {
+      cx.local = chain_seed(cx.seed, cx.block, (uint32_t)chain_id);
+      st = &cx.local;
+    }
+    Rng rng{st};
+
+    const int max_energy = cx.sa_steps;
+    for (int energy = 0; best_error > 0 && energy < max_energy; energy++) {
+      const float temp = (float)energy / (float)(max_energy - 1);
+      uint8_t indices[16];
+      V4 np1 = splat(-1.0f), np2 = splat(-1.0f);
+      int ncombo = 0;
+      pick_neighbor(rng, p1, p2, cur_combo, np1, np2, ncombo, vis1, vis2, vis_combo);
+      const double error = quantized_error(cx, c, np1, np2, nbuckets, qm, met, pbit_combo(ncombo), indices);
+      // AcceptNewEndpointError (Compressor.cpp:524-536)
+      bool accept;
+      if (error < cur_error) {
+        accept = true;
+      } else {
+        const double p = exp((0.1f * (cur_error - error)) / temp);
+        const double r = rng.frand();
+        accept = r < p;
+      }
+      if (accept) {
+        cur_error = error;
+        p1 = np1;
+        p2 = np2;
+        cur_combo = ncombo;
+      }
+      if (error < best_error) {
+        memcpy(best_indices, indices, sizeof(indices));
+        bp1 = np1;
+        bp2 = np2;
+        best_combo = (uint8_t)ncombo;
+        best_error = error;
+        vis1 = np1; vis2 = np2; vis_combo = ncombo;
+        energy = 0;  // restart (the loop increment makes it 1)
+      }
+    }
+    p1 = bp1;
+    p2 = bp2;
+    return best_error;
+  }
+
+  // CompressCluster, rgb variant (Compressor.cpp:921-1094)
+  double compress_cluster(const Cluster &c, V4 &p1, V4 &p2, uint8_t *best_indices, uint8_t &best_combo,
+                          int chain_id) {
+    if (c.all_same()) {
+      const V4 p = c.point(0);
+      const double e = single_color(p, p1, p2, best_combo);
+      for (int i = 0; i < c.n; i++) best_indices[i] = 1;
+      return c.n * e;
+    }
+    const int nbuckets = 1 << index_bits();
+    V4 axis;
+    principal_axis(c, axis);
+    float mindp = FLT_MAX, maxdp = -FLT_MAX;
+    for (int i = 0; i < c.n; i++) {
+      const float dp = dot(sub(c.point(i), c.avg), axis);
+      if (dp < mindp) mindp = dp;
+      if (dp > maxdp) maxdp = dp;
+    }
+    p1 = add(c.avg, mul(axis, mindp));
+    p2 = add(c.avg, mul(axis, maxdp));
+    clamp_endpoints(p1, p2);
+
+    V4 pts[16];
+    uint32_t num_pts[16];
+    for (int i = 0; i < nbuckets; i++) {
+      const float s = (float)i / (float)(nbuckets - 1);
+      pts[i] = add(mul(p1, 1.0f - s), mul(p2, s));
+    }
+    uint32_t bucket_idx[16] = {0};
+    bool fixed = false;
+    while (!fixed) {
+      V4 new_pts[16];
+      for (int i = 0; i < c.n; i++) {
+        int min_bucket = -1;
+        float min_dist = FLT_MAX;
+        for (int j = 0; j < nbuckets; j++) {
+          const V4 v = sub(c.point(i), pts[j]);
+          const float d = dot(v, v);
+          if (d < min_dist) {
+            min_dist = d;
+            min_bucket = j;
+          }
+        }
+        bucket_idx[i] = (uint32_t)min_bucket;
+      }
+      for (int i = 0; i < nbuckets; i++) {
+        num_pts[i] = 0;
+        new_pts[i] = splat(0.0f);
+        for (int j = 0; j < c.n; j++)
+          if (bucket_idx[j] == (uint32_t)i) {
+            num_pts[i]++;
+            new_pts[i] = add(new_pts[i], c.point(j));
+          }
+        if (num_pts[i] != 0) new_pts[i] = divs(new_pts[i], (float)num_pts[i]);  // T15: empty -> origin
+      }
+      fixed = true;
+      for (int i = 0; i < nbuckets; i++)
+        if (!eq(pts[i], new_pts[i])) fixed = false;
+      for (int i = 0; i < nbuckets; i++) pts[i] = new_pts[i];
+    }
+    int filled = 0, last_filled = -1;
+    for (int i = 0; i < nbuckets; i++)
+      if (num_pts[i] > 0) {
+        filled++;
+        last_filled = i;
+      }
+    if (filled == 1) {
+      const V4 p = pts[last_filled];
+      const double e = single_color(p, p1, p2, best_combo);
+      for (int i = 0; i < c.n; i++) best_indices[i] = 1;
+      return c.n * e;
+    }
+    float asq = 0.0f, bsq = 0.0f, ab = 0.0f;
+    V4 ax = splat(0.0f), bx = splat(0.0f);
+    for (int i = 0; i < nbuckets; i++) {
+      const V4 x = pts[i];
+      const float fbi = (float)(nbuckets - 1 - i), fb = (float)(nbuckets - 1), fi = (float)i;
+      const float fn = (float)(int)num_pts[i];
+      const float a = fbi / fb, b = fi / fb;
+      asq += fn * a * a;
+      bsq += fn * b * b;
+      ab += fn * a * b;
+      ax = add(ax, mul(mul(x, a), fn));
+      bx = add(bx, mul(mul(x, b), fn));
+    }
+    const float f = 1.0f / (asq * bsq - ab * ab);
+    p1 = mul(sub(mul(ax, bsq), mul(bx, ab)), f);
+    p2 = mul(sub(mul(bx, asq), mul(ax, ab)), f);
+    clamp_to_grid(p1, p2, best_combo);
+    return optimize(c, p1, p2, best_indices, best_combo, chain_id);
+  }
+
+  // CompressCluster, alpha variant for modes 4/5 (Compressor.cpp:632-919)
+  double compress_cluster_alpha(const Cluster &cluster, V4 &p1, V4 &p2, uint8_t *best_indices,
+                                uint8_t *alpha_indices, int chain_id) {
+    // (AllSamePoint branch is unreachable: solid blocks are handled earlier; kept for parity.)
+    if (cluster.all_same()) {
+      const V4 p = cluster.point(0);
+      uint8_t dummy = 0;
+      const double e = single_color(p, p1, p2, dummy);
+      for (int i = 0; i < cluster.n; i++) best_indices[i] = alpha_indices[i] = 1;
+      return cluster.n * e;
+    }
+    Cluster rgb(cluster);  // memberwise copy: avg/min/max/pix stay those of the original block (T16)
+    float alpha_vals[16] = {0};
+    float amin = FLT_MAX, amax = -FLT_MAX;
+    for (int i = 0; i < rgb.n; i++) {
+      V4 &v = rgb.point_mut(i);
+      float t;
+      switch (rotation()) {
+        case 1: t = v[0]; v[0] = v[3]; v[3] = t; break;
+        case 2: t = v[1]; v[1] = v[3]; v[3] = t; break;
+        case 3: t = v[2]; v[2] = v[3]; v[3] = t; break;
+        default: break;
+      }
+      alpha_vals[i] = v[3];
+      v[3] = 255.0f;
+      amin = smin(alpha_vals[i], amin);
+      amax = smax(alpha_vals[i], amax);
+    }
+    uint8_t dummy = 0;
+    V4 rgbp1 = splat(-1.0f), rgbp2 = splat(-1.0f);
+    const double rgb_error = compress_cluster(rgb, rgbp1, rgbp2, best_indices, dummy, chain_id);
+
+    float a1 = amin, a2 = amax;
+    double alpha_error = DBL_MAX;
+    const int abits = alpha_index_bits();
+    const uint32_t(*interp)[2] = kInterp[abits - 1];
+    const float weight = 1.0f;
+    const int nbuckets = 1 << abits;
+    if (a1 == a2) {
+      const uint8_t a1be = (uint8_t)a1, a2be = (uint8_t)a2;
+      if (mode == 5) {
+        for (int i = 0; i < 16; i++) alpha_indices[i] = 0;
+        alpha_error = 0.0;
+      } else {
+        const uint8_t *t1 = kOpt6Dxt1 + 6 * a1be, *t2 = kOpt6Dxt1 + 6 * a2be;  // [v][2][3]
+        if (t1[0]) {
+          a1 = (float)((t1[3 + 1] << 2) | (t1[1] >> 4));
+          a2 = (float)((t2[3 + 2] << 2) | (t2[1] >> 4));
+        } else {
+          a1 = (float)((t1[1] << 2) | (t1[1] >> 4));
+          a2 = (float)((t2[2] << 2) | (t2[1] >> 4));
+        }
+        for (int i = 0; i < 16; i++) alpha_indices[i] = idx_mode == 1 ? 1 : 2;
+        const uint32_t w0 = interp[alpha_indices[0] & 0xFF][0], w1 = interp[alpha_indices[0] & 0xFF][1];
+        const uint32_t a1i = (uint32_t)a1, a2i = (uint32_t)a2;
+        const uint8_t ip = (uint8_t)(((a1i * w0 + a2i * w1 + 32) >> 6) & 0xFF);
+        float px = weight * (float)((a1be > ip) ? a1be - ip : ip - a1be);
+        px *= px;
+        alpha_error = 16 * px;
+      }
+    } else {
+      float vals[8];
+      memset(vals, 0, sizeof(vals));
+      uint32_t buckets[16];
+      for (int i = 0; i < 16; i++) buckets[i] = 0;  // (reference leaves them uninitialised; always assigned below
+                                                    //  unless every |alpha - val| >= 255, impossible here)
+      for (int i = 0; i < nbuckets; i++) {
+        const float fi = (float)i, fb = (float)(nbuckets - 1);
+        vals[i] = amin + (fi / fb) * (amax - amin);
+      }
+      for (int i = 0; i < 16; i++) {
+        float md = 255.0f;
+        for (int j = 0; j < nbuckets; j++) {
+          const float d = fabsf(alpha_vals[i] - vals[j]);
+          if (d < md) { md = d; buckets[i] = j; }
+        }
+      }
+      float npts[8];
+      bool fixed = false;
+      while (!fixed) {
+        memset(npts, 0, sizeof(npts));
+        float avg[8];
+        memset(avg, 0, sizeof(avg));
+        for (int i = 0; i < nbuckets; i++) {
+          for (int j = 0; j < 16; j++)
+            if (buckets[j] == (uint32_t)i) {
+              avg[i] += alpha_vals[j];
+              npts[i] += 1.0f;
+            }
+          if (npts[i] > 0.0f) avg[i] /= npts[i];
+        }
+        fixed = true;
+        for (int i = 0; i < nbuckets; i++) fixed = fixed && (avg[i] == vals[i]);
+        memcpy(vals, avg, sizeof(vals));
+        for (int i = 0; i < 16; i++) {
+          float md = 255.0f;
+          for (int j = 0; j < nbuckets; j++) {
+            const float d = fabsf(alpha_vals[i] - vals[j]);
+            if (d < md) { md = d; buckets[i] = j; }
+          }
+        }
+      }
+      float asq = 0.0f, bsq = 0.0f, ab = 0.0f, ax = 0.0f, bx = 0.0f;
+      for (int i = 0; i < nbuckets; i++) {
+        const float fbi = (float)(nbuckets - 1 - i), fb = (float)(nbuckets - 1), fi = (float)i;
+        const float a = fbi / fb, b = fi / fb;
+        const float n = npts[i], x = vals[i];
+        asq += n * a * a;
+        bsq += n * b * b;
+        ab += n * a * b;
+        ax += x * a * n;
+        bx += x * b * n;
+      }
+      const float f = 1.0f / (asq * bsq - ab * ab);
+      a1 = f * (ax * bsq - bx * ab);
+      a2 = f * (bx * asq - ax * ab);
+      a1 = smin(255.0f, smax(0.0f, a1));
+      a2 = smin(255.0f, smax(0.0f, a2));
+      const int8_t mask_seed = -0x7F;
+      const uint8_t qmask8 = (uint8_t)(mask_seed >> (A.alpha_bits - 1));
+      const uint8_t a1b = quantize_channel((uint8_t)a1, qmask8, -1);
+      const uint8_t a2b = quantize_channel((uint8_t)a2, qmask8, -1);
+      alpha_error = 0.0;
+      for (int i = 0; i < 16; i++) {
+        const uint8_t val = (uint8_t)alpha_vals[i];
+        float min_error = FLT_MAX;
+        int best = -1;
+        for (int j = 0; j < nbuckets; j++) {
+          const uint8_t ip = (uint8_t)((((uint32_t)a1b * interp[j][0] + (uint32_t)a2b * interp[j][1] + 32) >> 6) & 0xFF);
+          float px = weight * (float)((val > ip) ? val - ip : ip - val);
+          px *= px;
+          if (px < min_error) { min_error = px; best = j; }
+        }
+        alpha_error += min_error;
+        alpha_indices[i] = (uint8_t)best;
+      }
+    }
+    for (int i = 0; i < 4; i++) {
+      p1[i] = (i == 3) ? a1 : rgbp1[i];
+      p2[i] = (i == 3) ? a2 : rgbp2[i];
+    }
+    return rgb_error + alpha_error;
+  }
+
+  // CompressionMode::Compress (Compressor.cpp:1300-1371)
+  double compress(Params &params, int shape_idx, Cluster &cluster) {
+    params.init(shape_idx);
+    double total = 0.0;
+    for (int cidx = 0; cidx < A.subsets; cidx++) {
+      uint8_t indices[16] = {0};
+      cluster.set_partition(cidx);
+      if (A.has_rotation) {
+        uint8_t alpha_indices[16];
+        double best = DBL_MAX;
+        for (int r = 0; r < 4; r++) {
+          rot = r;
+          const int nim = mode == 4 ? 2 : 1;
+          for (int im = 0; im < nim; im++) {
+            idx_mode = im;
+            V4 v1 = splat(-1.0f), v2 = splat(-1.0f);
+            const int chain_id = mode * 8 + (mode == 4 ? r * 2 + im : r);
+            const double err = compress_cluster_alpha(cluster, v1, v2, indices, alpha_indices, chain_id);
+            if (err < best) {
+              best = err;
+              memcpy(params.indices[cidx], indices, 16);
+              memcpy(params.alpha_indices, alpha_indices, 16);
+              params.rotation = r;
+              params.index_mode = im;
+              params.p1[cidx] = v1;
+              params.p2[cidx] = v2;
+            }
+          }
+        }
+        total += best;
+      } else {
+        const int chain_id = mode * 8 + chain_slot * 4 + cidx;
+        total += compress_cluster(cluster, params.p1[cidx], params.p2[cidx], indices, params.pbit_combo[cidx],
+                                  chain_id);
+        int k = 0;
+        for (int i = 0; i < 16; i++)
+          if (subset_of(i, shape_idx, A.subsets) == cidx) params.indices[cidx][i] = indices[k++];
+      }
+    }
+    return total;
+  }
+};
+
+// LSB-first bit writer (Base/include/FasTC/BitStream.h:46-99)
+struct BitWriter {
+  uint8_t *p;
+  int pos = 0;
+  explicit BitWriter(uint8_t *out) : p(out) { memset(out, 0, 16); }
+  void write(uint32_t v, int n) {
+    for (int i = 0; i < n; i++, pos++)
+      if ((v >> i) & 1) p[pos >> 3] |= (uint8_t)(1u << (pos & 7));
+  }
+};
+
+// CompressionMode::Pack (Compressor.cpp:1096-1298)
+void pack(Mode &M, Params &P, uint8_t *out) {
+  const ModeAttr &A = M.A;
+  BitWriter s(out);
+  s.write(1u << M.mode, M.mode + 1);
+  s.write((uint32_t)P.shape, A.partition_bits);
+  s.write((uint32_t)P.rotation, A.has_rotation ? 2 : 0);
+  s.write((uint32_t)P.index_mode, A.has_idx_mode ? 1 : 0);
+  const uint32_t qm = M.qmask();
+  uint32_t px1[3], px2[3];
+  for (int i = 0; i < A.subsets; i++) {
+    if (A.pbit_type == kPbitNone) {
+      px1[i] = to_pixel(P.p1[i], qm);
+      px2[i] = to_pixel(P.p2[i], qm);
+    } else {
+      px1[i] = to_pixel(P.p1[i], qm, M.pbit_combo(P.pbit_combo[i])[0]);
+      px2[i] = to_pixel(P.p2[i], qm, M.pbit_combo(P.pbit_combo[i])[1]);
+    }
+  }
+  const int im = P.index_mode;  // int8 in the reference; <0 means "use the mode's current"
+  auto nbits_index = [&](int m) { return (m < 0 ? M.idx_mode : m) == 0 ? A.index_bits : A.alpha_index_bits; };
+  auto nbits_alpha = [&](int m) { return (m < 0 ? M.idx_mode : m) == 0 ? A.alpha_index_bits : A.index_bits; };
+  for (int sidx = 0; sidx < A.subsets; sidx++) {
+    const int anchor = anchor_of(sidx, P.shape, A.subsets);
+    const int nab = nbits_alpha(im), nib = nbits_index(im);
+    if (P.indices[sidx][anchor] >> (nib - 1)) {
+      uint32_t t = px1[sidx]; px1[sidx] = px2[sidx]; px2[sidx] = t;
+      const int nvals = 1 << nib;
+      for (int i = 0; i < 16; i++) P.indices[sidx][i] = (uint8_t)((nvals - 1) - P.indices[sidx][i]);
+      const int navals = 1 << nab;
+      if (A.has_rotation)
+        for (int i = 0; i < 16; i++) P.alpha_indices[i] = (uint8_t)((navals - 1) - P.alpha_indices[i]);
+    }
+    const bool rotated = nab > 0 ? ((P.alpha_indices[anchor] >> (nab - 1)) > 0) : false;
+    if (A.has_rotation && rotated) {
+      const uint32_t a1 = px1[sidx] & 0xFF000000u, a2 = px2[sidx] & 0xFF000000u;
+      px1[sidx] = (px1[sidx] & 0x00FFFFFFu) | a2;
+      px2[sidx] = (px2[sidx] & 0x00FFFFFFu) | a1;
+      const int navals = 1 << nab;
+      for (int i = 0; i < 16; i++) P.alpha_indices[i] = (uint8_t)((navals - 1) - P.alpha_indices[i]);
+    }
+  }
+  for (int ch = 0; ch < 3; ch++)
+    for (int i = 0; i < A.subsets; i++) {
+      s.write(((px1[i] >> (8 * ch)) & 0xFF) >> (8 - A.color_bits), A.color_bits);
+      s.write(((px2[i] >> (8 * ch)) & 0xFF) >> (8 - A.color_bits), A.color_bits);
+    }
+  for (int i = 0; i < A.subsets; i++) {
+    s.write(((px1[i] >> 24) & 0xFF) >> (8 - A.alpha_bits), A.alpha_bits);
+    s.write(((px2[i] >> 24) & 0xFF) >> (8 - A.alpha_bits), A.alpha_bits);
+  }
+  if (A.pbit_type != kPbitNone)
+    for (int i = 0; i < A.subsets; i++) {
+      const int *pb = M.pbit_combo(P.pbit_combo[i]);  // T17: not swapped with the endpoints
+      s.write(pb[0], 1);
+      if (A.pbit_type != kPbitShared) s.write(pb[1], 1);
+    }
+  if (A.has_idx_mode && P.index_mode == 1) {
+    for (int i = 0; i < 16; i++) s.write(P.alpha_indices[i], i == 0 ? 1 : 2);
+    for (int i = 0; i < 16; i++) s.write(P.indices[0][i], i == 0 ? 2 : 3);
+  } else {
+    for (int i = 0; i < 16; i++) {
+      const int subs = subset_of(i, P.shape, A.subsets);
+      const int anchor = anchor_of(subs, P.shape, A.subsets);
+      const int nb = nbits_index(im);
+      s.write(P.indices[subs][i], i == anchor ? nb - 1 : nb);
+    }
+    if (A.has_rotation)
+      for (int i = 0; i < 16; i++) {
+        const int nb = nbits_alpha(im);
+        s.write(P.alpha_indices[i], i == 0 ? nb - 1 : nb);
+      }
+  }
+}
+
+// EstimateTwo/ThreeClusterError (Compressor.cpp:1626-1655)
+double estimate_error(Ctx &cx, const Cluster &c, int nbuckets) {
+  const V4 d = sub(c.mx, c.mn);
+  if (dot(d, d) == 0) return 0.0;
+  double e = 0.0001;
+  e += quantized_error(cx, c, c.mn, c.mx, nbuckets, 0xFFFFFFFFu, splat(1.0f), nullptr, nullptr);
+  return e;
+}
+
+struct Selection {
+  int num_shapes = 0;
+  int shape_idx[2] = {0, 0};
+  int shape_parts[2] = {0, 0};
+  uint32_t modes = 0xFF;
+};
+
+// BoxSelection (Compressor.cpp:1670-1750)
+Selection box_selection(Ctx &cx, const uint32_t pixels[16]) {
+  Selection r;
+  bool opaque = true;
+  for (int i = 0; i < 16; i++) opaque = opaque && (((pixels[i] >> 24) & 0xFF) >= 250);
+  double best[2] = {std::numeric_limits<double>::max(), std::numeric_limits<double>::max()};
+  Cluster c(pixels);
+  r.num_shapes = 1;
+  for (int i = 0; i < 64; i++) {
+    c.set_shape(i, 2);
+    double err = 0.0;
+    for (int ci = 0; ci < 2; ci++) {
+      c.set_partition(ci);
+      err += estimate_error(cx, c, 8);
+    }
+    if (err < best[0]) {
+      best[0] = err;
+      r.shape_idx[0] = i;
+      r.shape_parts[0] = 2;
+    }
+    if (err < 1e-9) {
+      r.modes = 0x02 | 0x08 | 0x80;  // kTwoPartitionModes
+      return r;
+    }
+  }
+  if (!opaque) {
+    r.modes &= (0x10 | 0x20 | 0x40 | 0x80);  // kAlphaModes
+    return r;
+  }
+  r.modes &= ~(0x10u | 0x20u);
+  r.num_shapes++;
+  for (int i = 0; i < 64; i++) {
+    c.set_shape(i, 3);
+    double err = 0.0;
+    for (int ci = 0; ci < 3; ci++) {
+      c.set_partition(ci);
+      err += estimate_error(cx, c, 4);
+    }
+    if (err < best[1]) {
+      best[1] = err;
+      r.shape_idx[1] = i;
+      r.shape_parts[1] = 3;
+    }
+    if (err < 1e-9) {
+      r.modes = 0x01 | 0x04;  // kThreePartitionModes
+      return r;
+    }
+  }
+  return r;
+}
+
+// CompressClusters (Compressor.cpp:1752-1817)
+void compress_clusters(Ctx &cx, const Selection &sel, const uint32_t pixels[16], uint8_t *out) {
+  Cluster cluster(pixels);
+  double best_error = std::numeric_limits<double>::max();
+  static const int order[8] = {0, 2, 1, 3, 7, 4, 5, 6};
+  int best_mode = 8;
+  Params best_params;
+  best_params.init(0);
+  uint32_t selected = sel.modes;
+  int nshapes = sel.num_shapes < 5 ? sel.num_shapes : 5;
+  if (nshapes == 0) {
+    nshapes = 1;
+    selected &= ~(0x02u | 0x08u | 0x80u | 0x01u | 0x04u);
+  }
+  for (int mi = 0; mi < 8; mi++) {
+    const int mode = order[mi];
+    if ((selected & (1u << mode)) == 0) continue;
+    for (int si = 0; si < nshapes; si++) {
+      const int nparts = kModes[mode].subsets;
+      if (nparts != 1 && nparts != sel.shape_parts[si]) continue;
+      if (sel.shape_idx[si] >= 16 && mode == 0) continue;
+      const int idx = sel.shape_idx[si];
+      cluster.set_shape(idx, nparts);
+      Params params;
+      Mode M(cx, mode);
+      M.chain_slot = si;
+      const double err = M.compress(params, idx, cluster);
+      if (err < best_error) {
+        best_error = err;
+        best_mode = mode;
+        best_params = params;
+      }
+    }
+  }
+  if (best_mode >= 8) {  // unreachable with the default mode mask
+    memset(out, 0, 16);
+    return;
+  }
+  Mode M(cx, best_mode);
+  pack(M, best_params, out);
+}
+
+// CompressBC7Block (Compressor.cpp:1819-1860) incl. the two fast paths
+// (CompressOptimalColorBC7 :1424-1458, WriteTransparentBlock :1416-1421).
+// Returns true if the block took the solid-colour path (consumes a watermark word).
+bool compress_block(Ctx &cx, const uint32_t block[16], uint8_t *out, uint32_t wm_index) {
+  bool solid = true;
+  for (int i = 1; i < 16; i++)
+    if (block[i] != block[0]) { solid = false; break; }
+  if (solid) {
+    BitWriter s(out);
+    const uint32_t px = block[0];
+    s.write(1u << 5, 6);
+    s.write(0, 2);
+    for (int ch = 0; ch < 3; ch++) {
+      const uint8_t v = (px >> (8 * ch)) & 0xFF;
+      s.write(kOpt7Mode5[2 * v], 7);
+      s.write(kOpt7Mode5[2 * v + 1], 7);
+    }
+    s.write(px >> 24, 8);
+    s.write(px >> 24, 8);
+    s.write(0xaaaaaaabu, 31);
+    s.write(kWatermark[wm_index % 9], 31);  // T1
+    return true;
+  }
+  bool transparent = true;
+  for (int i = 0; i < 16; i++)
+    if ((block[i] >> 24) != 0) { transparent = false; break; }
+  if (transparent) {
+    BitWriter s(out);
+    s.write(1u << 6, 7);
+    return false;
+  }
+  const Selection sel = box_selection(cx, block);
+  compress_clusters(cx, sel, block, out);
+  return false;
+}
+
+}  // namespace
+
+static uint64_t g_last_qe = 0, g_last_pbe = 0;
+
+extern "C" void fastc_oracle_bc7(const uint8_t *rgba, uint32_t width, uint32_t height, uint32_t first_block,
+                                 uint32_t num_blocks, uint8_t *out, int quality, int rng_mode,
+                                 uint32_t *lcg_state, uint64_t seed, uint32_t wm_base) {
+  (void)height;
+  const uint32_t bw = width / 4;
+  Ctx cx;
+  cx.sa_steps = quality;
+  cx.rng_mode = rng_mode;
+  cx.global = lcg_state;
+  cx.seed = seed;
+  cx.local = 0;
+  uint32_t wm = wm_base;
+  for (uint32_t n = 0; n < num_blocks; n++) {
+    const uint32_t bi = first_block + n, bx = bi % bw, by = bi / bw;
+    uint32_t block[16];
+    for (int j = 0; j < 4; j++)
+      memcpy(block + 4 * j, rgba + ((size_t)(by * 4 + j) * width + bx * 4) * 4, 16);
+    cx.block = bi;
+    if (compress_block(cx, block, out + (size_t)bi * 16, wm)) wm++;
+  }
+  g_last_qe = cx.qe_calls;
+  g_last_pbe = cx.pbe;
+}
+
+// Work counters of the last fastc_oracle_bc7 call (SURVEY.md §8d op model).
+extern "C" void fastc_oracle_bc7_counters(uint64_t *qe_calls, uint64_t *pbe) {
+  *qe_calls = g_last_qe;
+  *pbe = g_last_pbe;
+}
