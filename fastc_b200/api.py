@@ -76,6 +76,7 @@ class GpuLibrary:
         "fastc_gpu_device_count", "fastc_gpu_init", "fastc_gpu_shutdown", "fastc_gpu_block_bytes",
         "fastc_gpu_compressed_size", "fastc_gpu_compress", "fastc_gpu_compress_batch",
         "fastc_gpu_compress_device", "fastc_gpu_count_solid_device", "fastc_gpu_bc7_counters",
+        "fastc_gpu_debug_bc7_dump",
         "fastc_gpu_last_error",
     ]
 
@@ -99,6 +100,7 @@ class GpuLibrary:
                                                 C.POINTER(u32)]
         L.fastc_gpu_count_solid_device.argtypes = [vp, u32, u32, u32, u32, vp, C.POINTER(u32)]
         L.fastc_gpu_bc7_counters.argtypes = [C.POINTER(u64), C.POINTER(u64)]
+        L.fastc_gpu_debug_bc7_dump.argtypes = [u32, vp, vp]
         L.fastc_gpu_last_error.restype = C.c_char_p
 
     def error(self) -> str:

@@ -1,14 +1,1419 @@
-// placeholder until the BC7 kernels land (fails loudly, no fallback)
+// BC7 (BPTC) block encoder for sm_100a.
+//
+// Behavioural contract: the per-block search of the reference's BPTCEncoder
+//   reference/BPTCEncoder/src/Compressor.cpp   (CompressBC7Block :1819, BoxSelection :1670,
+//       CompressClusters :1752, CompressionMode::Compress :1300, CompressCluster :921 / :632,
+//       OptimizeEndpointsForCluster :538, PickBestNeighboringEndpoints :426, Pack :1096)
+//   reference/BPTCEncoder/src/RGBAEndpoints.cpp (QuantizedError :190, GetPrincipalAxis :327,
+//       QuantizeChannel :126)
+// replayed with the same float semantics (no FMA: this TU is built with
+// -fmad=false; IEEE div/sqrt), so that quality 0 is bit-identical to the
+// reference and quality > 0 runs the reference's annealing schedule on keyed
+// per-chain RNG streams (bit-identical to oracle/bc7_oracle.cpp rng_mode 1).
+//
+// B200 mapping (this is NOT how the reference is organised):
+//   bc7_classify   1 thread / block : solid / transparent flags, per-tile solid counts
+//   bc7_wm_scan    1 CTA            : exclusive scan of tile counts (watermark order, T1)
+//   bc7_select     1 warp / block   : lanes = the 64 partition shapes; bbox + 8/4-bucket
+//                                     error estimate per shape, warp argmin (first index wins)
+//   bc7_chains     1 thread / (block, endpoint-fit "chain"): PCA + k-means + LSQ start,
+//                                     then the serial annealing chain, all-integer inner loop
+//   bc7_pack       1 thread / block : best mode by total error in the reference's mode
+//                                     order, anchor fix-ups, 128-bit pack
+// The unit of parallelism for the expensive part is the *chain* (one subset of
+// one candidate mode/shape/rotation): ~14 independent serial chains per block.
+#include <cfloat>
+#include <cstdio>
+
+#include "bc7_tables.cuh"
+#include "common.cuh"
 #include "kernels.h"
+
 namespace fastc {
-cudaError_t bc7_upload_tables() { return cudaSuccess; }
-void bc7_free_workspace(Bc7Workspace &) {}
-cudaError_t launch_bc7(Bc7Workspace &, const void *, uint32_t, uint32_t, uint32_t, uint32_t, void *, int, uint64_t,
-                       uint32_t, uint32_t, cudaStream_t, uint32_t *) {
-  return cudaErrorNotSupported;
+namespace {
+
+// ------------------------------------------------------------------ tables
+__constant__ uint16_t c_shape2[64];
+__constant__ uint32_t c_shape3[64];
+__constant__ uint8_t c_anchor2[64], c_anchor3a[64], c_anchor3b[64];
+__constant__ uint8_t c_weight[64];  // [index_bits-1][16] weight of endpoint 2 (0..64)
+__constant__ uint8_t c_opt7[512];   // [v][2]
+__constant__ uint8_t c_opt6[1536];  // [v][2][3]
+__constant__ uint32_t c_wm[9];
+
+// Per-mode attributes (BC7 spec; reference kModeAttributes Compressor.cpp:170-203).
+struct ModeAttr {
+  uint8_t partition_bits, subsets, index_bits, alpha_index_bits, color_bits, alpha_bits, rotation, idx_mode, pbit;
+};
+enum { kPbitShared = 0, kPbitPerEndpoint = 1, kPbitNone = 2 };
+__constant__ ModeAttr c_modes[8] = {
+    {4, 3, 3, 0, 4, 0, 0, 0, 1}, {6, 2, 3, 0, 6, 0, 0, 0, 0}, {6, 3, 2, 0, 5, 0, 0, 0, 2}, {6, 2, 2, 0, 7, 0, 0, 0, 1},
+    {0, 1, 2, 3, 5, 6, 1, 1, 2}, {0, 1, 2, 2, 7, 8, 1, 0, 2}, {0, 1, 4, 0, 7, 7, 0, 0, 1}, {6, 2, 2, 0, 5, 5, 0, 0, 1},
+};
+
+// CompressSingleColor (Compressor.cpp:252-353) is a per-channel exhaustive search
+// that only depends on (mode, index mode, p-bit combo, channel class, byte value):
+// precomputed on the host with the reference's scan order (first strict minimum,
+// i-major / j-minor).  Entry = v1 | v2 << 8 | dist << 16.
+// index: ((((mode * 2 + idx_mode) * 4 + pbi) * 2 + is_alpha) * 256 + val)
+__device__ uint32_t g_single[8 * 2 * 4 * 2 * 256];
+
+// ------------------------------------------------------------------ layout of the scratch
+// sel word per block
+//  [0:5] best 2-subset shape  [6:11] best 3-subset shape  [12:19] mode mask
+//  [20:21] number of shapes   [22] layout B (alpha path)   [24:25] type
+enum { kTypeNormal = 0, kTypeSolid = 1, kTypeTransparent = 2 };
+constexpr int kSlots = 16;       // result slots per block
+constexpr int kResWords = 8;     // 32 B per chain result
+// result words: 0 err, 1 p1, 2 p2, 3 p-bit combo, 4-5 colour indices (4 bit each,
+// cluster-local order), 6-7 alpha indices (modes 4/5)
+constexpr int kTile = 256;       // blocks per watermark tile (= classify CTA)
+
+struct Ws {
+  uint32_t *sel;        // [nblocks]
+  uint32_t *tile_count; // [ntiles] solid blocks per tile, then exclusive-scanned in place
+  uint32_t *total_solid;
+  uint32_t *results;    // [nblocks][kSlots][kResWords]
+  const uint32_t *wm_running;    // watermark base of this chunk (device side, chunks chain without a host sync)
+  unsigned long long *counters;  // qe calls, pbe
+};
+
+// ------------------------------------------------------------------ small helpers
+__device__ __forceinline__ int chan(uint32_t p, int k) { return (p >> (8 * k)) & 0xFF; }
+
+__device__ __forceinline__ uint32_t fmix32(uint32_t h) {
+  h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+  return h;
 }
-cudaError_t bc7_count_solid(Bc7Workspace &, const void *, uint32_t, uint32_t, uint32_t, cudaStream_t, uint32_t *) {
-  return cudaErrorNotSupported;
+// Keyed per-chain RNG stream; identical to oracle/bc7_oracle.cpp chain_seed().
+__device__ __forceinline__ uint32_t chain_seed(uint64_t seed, uint32_t block, uint32_t chain) {
+  const uint32_t h = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x9E3779B9u);
+  return fmix32(h + fmix32(block * 64u + chain));
 }
-cudaError_t bc7_read_counters(Bc7Workspace &, uint64_t *, uint64_t *) { return cudaErrorNotSupported; }
+// reference fastrand() (Compressor.cpp:358-362): 16-bit draws on glibc (RAND_MAX = 2^31-1).
+__device__ __forceinline__ uint32_t lcg_next(uint32_t &s) {
+  s = 214013u * s + 2531011u;
+  return s >> 16;
+}
+
+__device__ __forceinline__ int subset_of(int idx, int shape, int nsub) {
+  if (nsub == 2) return (c_shape2[shape] >> idx) & 1;
+  if (nsub == 3) return (c_shape3[shape] >> (2 * idx)) & 3;
+  return 0;
+}
+__device__ __forceinline__ int anchor_of(int subset, int shape, int nsub) {
+  if (subset == 0) return 0;
+  if (subset == 1) return nsub == 2 ? c_anchor2[shape] : c_anchor3a[shape];
+  return c_anchor3b[shape];
+}
+
+// GetQuantizationMask (CompressionMode.h:212-232): per-channel mask of the kept top bits.
+__device__ __forceinline__ uint32_t quant_mask(const ModeAttr &A) {
+  const uint32_t cm = (0xFF00u >> A.color_bits) & 0xFF;
+  const uint32_t am = A.alpha_bits ? ((0xFF00u >> A.alpha_bits) & 0xFF) : 0u;
+  return cm | (cm << 8) | (cm << 16) | (am << 24);
+}
+
+// QuantizeChannel (RGBAEndpoints.cpp:126-165).  prec = number of mask bits.
+__device__ __forceinline__ uint32_t quantize_channel(uint32_t val, uint32_t mask, int pbit) {
+  if (mask == 0xFF) return val;
+  if (mask == 0) return 0xFF;
+  int prec = __popc(mask);
+  const uint32_t step = 1u << (8 - prec);
+  uint32_t lval = val & mask, hval = lval + step;
+  if (pbit >= 0) {
+    prec++;
+    lval |= (uint32_t)(pbit != 0) << (8 - prec);
+    hval |= (uint32_t)(pbit != 0) << (8 - prec);
+  }
+  if (lval > val) { lval -= step; hval -= step; }
+  lval |= lval >> prec;
+  hval |= hval >> prec;
+  const uint32_t l8 = lval & 0xFF, h8 = hval & 0xFF;  // sad<uint8>
+  const uint32_t dl = val > l8 ? val - l8 : l8 - val;
+  const uint32_t dh = val > h8 ? val - h8 : h8 - val;
+  return (dl < dh ? lval : hval) & 0xFF;
+}
+// ToPixel for endpoint bytes that are already integers (RGBAEndpoints.cpp:167-177).
+__device__ __forceinline__ uint32_t to_pixel_b(uint32_t p, uint32_t mask, int pbit) {
+  return quantize_channel(p & 0xFF, mask & 0xFF, pbit) | (quantize_channel((p >> 8) & 0xFF, (mask >> 8) & 0xFF, pbit) << 8) |
+         (quantize_channel((p >> 16) & 0xFF, (mask >> 16) & 0xFF, pbit) << 16) |
+         (quantize_channel(p >> 24, mask >> 24, pbit) << 24);
+}
+// uint32(x + 0.5) & 0xFF, x in [0, 255.5): exact without fp64 (x - floor(x) is exact).
+__device__ __forceinline__ uint32_t round_byte(float x) {
+  if (!(x == x)) return 0;  // x86 cvttsd2si of NaN -> low byte 0
+  const float f = floorf(x);
+  uint32_t r = (uint32_t)(int)f;
+  if (__fsub_rn(x, f) >= 0.5f) r++;
+  return r & 0xFF;
+}
+__device__ __forceinline__ uint32_t pack_round(const float p[4]) {
+  return round_byte(p[0]) | (round_byte(p[1]) << 8) | (round_byte(p[2]) << 16) | (round_byte(p[3]) << 24);
+}
+
+// p-bit pair of combo `idx` (CompressionMode.h:244-251): returns pb[0] | pb[1] << 1, or -1/-1 via has=false
+__device__ __forceinline__ void pbit_combo(int pbit_type, int idx, int &pb0, int &pb1) {
+  if (pbit_type == kPbitShared) { pb0 = pb1 = (idx ? 1 : 0); }
+  else if (pbit_type == kPbitPerEndpoint) { pb0 = (idx >> 1) & 1; pb1 = idx & 1; }
+  else { pb0 = pb1 = -1; }
+}
+
+// ------------------------------------------------------------------ QuantizedError, integer form
+// RGBACluster::QuantizedError (RGBAEndpoints.cpp:190-310) for the uniform metric.
+// With metric (1,1,1,1) every per-pixel error is an integer (sum of squared byte
+// differences <= 4*255^2) and every partial sum stays below 2^24, so the
+// reference's float accumulation is exact and an int32 sum reproduces it
+// bit-for-bit.  The projection uses the reference's float ops (one correctly
+// rounded division per pixel; the dot products are exact integers).
+//
+// pts: points used for the projection (== pix except in the rotated mode-4/5 fit),
+// pix: original pixel bytes the error is measured against (T16).
+struct QeEndpoints {
+  int e1[4], d[4];  // quantised endpoint 1 and (endpoint 2 - endpoint 1), per channel
+  int den;          // |e2 - e1|^2
+};
+__device__ __forceinline__ void qe_prepare(QeEndpoints &q, uint32_t q1, uint32_t q2) {
+  q.den = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    q.e1[k] = chan(q1, k);
+    q.d[k] = chan(q2, k) - q.e1[k];
+    q.den += q.d[k] * q.d[k];
+  }
+}
+// error of pixel bytes `pb` against bucket with weight w (0..64)
+__device__ __forceinline__ int qe_bucket_error(const QeEndpoints &q, const int pb[4], int w) {
+  int err = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int ip = q.e1[k] + ((q.d[k] * w + 32) >> 6);  // == ((64-w)*e1 + w*e2 + 32) >> 6
+    const int df = pb[k] - ip;
+    err += df * df;
+  }
+  return err;
+}
+// One pixel: returns min error; *best = chosen bucket.
+__device__ __forceinline__ int qe_pixel(const QeEndpoints &q, uint32_t pt, uint32_t px, int nbm1,
+                                        const uint8_t *__restrict__ wtab, int *best) {
+  int pb[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) pb[k] = chan(px, k);
+  if (q.den == 0) {
+    *best = 0;
+    return qe_bucket_error(q, pb, 0);
+  }
+  int num = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) num += (chan(pt, k) - q.e1[k]) * q.d[k];
+  const float pct = __fdiv_rn((float)num, (float)q.den);
+  const float t = __fmul_rn(pct, (float)nbm1);
+  int j1 = (int)floorf(t), j2 = (int)ceilf(t);
+  j1 = max(0, j1);
+  j1 = min(j1, nbm1);
+  j2 = min(j2, nbm1);
+  int e = qe_bucket_error(q, pb, wtab[j1]);
+  int b = j1;
+  if (j1 + 1 <= j2) {  // at most two candidates: floor and ceil of the projection
+    const int e2 = qe_bucket_error(q, pb, wtab[j1 + 1]);
+    if (e2 < e) { e = e2; b = j1 + 1; }
+  }
+  *best = b;
+  return e;
+}
+
+// ------------------------------------------------------------------ classify + watermark scan
+__device__ __forceinline__ uint32_t classify_block(const uint32_t px[16]) {
+  bool solid = true, transparent = true;
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    solid = solid && (px[i] == px[0]);
+    transparent = transparent && ((px[i] >> 24) == 0);
+  }
+  return solid ? kTypeSolid : (transparent ? kTypeTransparent : kTypeNormal);
+}
+
+__global__ void __launch_bounds__(kTile)
+bc7_classify(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, uint32_t first_block,
+             uint32_t num_blocks, uint32_t *__restrict__ sel, uint32_t *__restrict__ tile_count) {
+  const uint32_t t = blockIdx.x * kTile + threadIdx.x;
+  uint32_t type = kTypeNormal;
+  if (t < num_blocks) {
+    uint32_t px[16];
+    load_block(img, width, blocks_x, first_block + t, px);
+    type = classify_block(px);
+    if (sel) sel[t] = type << 24;
+  }
+  const int cnt = __syncthreads_count(type == kTypeSolid);
+  if (threadIdx.x == 0) tile_count[blockIdx.x] = cnt;
+}
+
+// Exclusive scan of the per-tile solid counts (single CTA; ntiles = nblocks/256).
+__global__ void __launch_bounds__(1024) bc7_wm_scan(uint32_t *tile_count, uint32_t ntiles, uint32_t *total) {
+  __shared__ uint32_t warp_sums[32];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < ntiles; base += 1024) {
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t v = i < ntiles ? tile_count[i] : 0;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if ((threadIdx.x & 31) >= o) x += y;
+    }
+    if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      uint32_t w = warp_sums[threadIdx.x];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
+        if (threadIdx.x >= o) w += y;
+      }
+      warp_sums[threadIdx.x] = w;
+    }
+    __syncthreads();
+    const uint32_t warp_off = (threadIdx.x >> 5) ? warp_sums[(threadIdx.x >> 5) - 1] : 0;
+    const uint32_t incl = carry + warp_off + x;
+    if (i < ntiles) tile_count[i] = incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+
+__global__ void bc7_set_u32(uint32_t *p, uint32_t v) { *p = v; }
+__global__ void bc7_add_u32(uint32_t *p, const uint32_t *v) { *p += *v; }
+
+// ------------------------------------------------------------------ shape selection
+// BoxSelection (Compressor.cpp:1670-1750).  One warp per block; lane l evaluates
+// shapes l and l+32.  Estimate for one shape = sum over its subsets of
+//   0 if the subset's bounding box is a point, else 0.0001 + QuantizedError(bbox min, bbox max,
+//   8 (two subsets) or 4 (three subsets) buckets, no quantisation)
+// accumulated in double exactly like the reference (the tie-break between shapes
+// with equal integer error depends on those roundings).
+template <int NSUB>
+__device__ __forceinline__ double estimate_shape(const uint32_t *__restrict__ px, int shape,
+                                                 const uint8_t *__restrict__ wtab) {
+  uint32_t mn[NSUB], mx[NSUB];
+#pragma unroll
+  for (int s = 0; s < NSUB; s++) { mn[s] = 0xFFFFFFFFu; mx[s] = 0; }
+  const uint32_t m2 = NSUB == 2 ? c_shape2[shape] : 0;
+  const uint32_t m3 = NSUB == 3 ? c_shape3[shape] : 0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    const int s = NSUB == 2 ? ((m2 >> i) & 1) : ((m3 >> (2 * i)) & 3);
+    const uint32_t p = px[i];
+#pragma unroll
+    for (int q = 0; q < NSUB; q++)
+      if (s == q) { mn[q] = __vminu4(mn[q], p); mx[q] = __vmaxu4(mx[q], p); }
+  }
+  QeEndpoints qe[NSUB];
+  int tot[NSUB];
+#pragma unroll
+  for (int s = 0; s < NSUB; s++) { qe_prepare(qe[s], mn[s], mx[s]); tot[s] = 0; }
+  constexpr int nbm1 = NSUB == 2 ? 7 : 3;
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    const int s = NSUB == 2 ? ((m2 >> i) & 1) : ((m3 >> (2 * i)) & 3);
+    const uint32_t p = px[i];
+    int b;
+#pragma unroll
+    for (int q = 0; q < NSUB; q++)
+      if (s == q && qe[q].den != 0) tot[q] += qe_pixel(qe[q], p, p, nbm1, wtab, &b);
+  }
+  double err = 0.0;
+#pragma unroll
+  for (int s = 0; s < NSUB; s++) {
+    // subsets that own no pixel cannot occur (every BC7 partition uses all its subsets)
+    const double e = qe[s].den == 0 ? 0.0 : __dadd_rn(0.0001, (double)tot[s]);
+    err = __dadd_rn(err, e);
+  }
+  return err;
+}
+
+// warp argmin with "first index wins" (strict < in scan order, T10)
+__device__ __forceinline__ void warp_argmin(double &err, int &idx) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double e2 = __shfl_xor_sync(0xffffffffu, err, o);
+    const int i2 = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (e2 < err || (e2 == err && i2 < idx)) { err = e2; idx = i2; }
+  }
+}
+
+constexpr int kSelWarps = 4;
+
+__global__ void __launch_bounds__(kSelWarps * 32)
+bc7_select(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, uint32_t first_block,
+           uint32_t num_blocks, uint32_t *__restrict__ sel) {
+  __shared__ uint32_t s_px[kSelWarps][16];
+  __shared__ uint8_t s_w[64];
+  if (threadIdx.x < 64) s_w[threadIdx.x] = c_weight[threadIdx.x];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t t = blockIdx.x * kSelWarps + warp;
+  const bool valid = t < num_blocks;
+  uint32_t type = kTypeNormal;
+  if (valid) {
+    type = sel[t] >> 24;
+    if (lane < 16) {
+      const uint32_t bi = first_block + t, bx = bi % blocks_x, by = bi / blocks_x;
+      s_px[warp][lane] = __ldg(img + (size_t)(by * 4 + (lane >> 2)) * width + bx * 4 + (lane & 3));
+    }
+  }
+  __syncthreads();
+  if (!valid || type != kTypeNormal) return;
+  const uint32_t *px = s_px[warp];
+
+  bool opaque = true;
+#pragma unroll
+  for (int i = 0; i < 16; i++) opaque = opaque && ((px[i] >> 24) >= 250);
+
+  // ---- two-subset shapes
+  double e0 = estimate_shape<2>(px, lane, s_w + 32);       // 8 buckets -> 3-bit weights
+  double e1 = estimate_shape<2>(px, lane + 32, s_w + 32);
+  // early-out: first shape (scan order) with estimate < 1e-9 (Compressor.cpp:1706-1710)
+  const uint32_t z0 = __ballot_sync(0xffffffffu, e0 < 1e-9), z1 = __ballot_sync(0xffffffffu, e1 < 1e-9);
+  uint32_t word;
+  if (z0 | z1) {
+    const int s = z0 ? (__ffs(z0) - 1) : (32 + __ffs(z1) - 1);
+    word = (uint32_t)s | (0x8Au << 12) | (1u << 20);  // modes {1,3,7}, one shape
+    if (lane == 0) sel[t] = word;
+    return;
+  }
+  double be = e0;
+  int bi2 = lane;
+  if (e1 < be) { be = e1; bi2 = lane + 32; }
+  warp_argmin(be, bi2);
+  if (!opaque) {
+    word = (uint32_t)bi2 | (0xF0u << 12) | (1u << 20) | (1u << 22);  // modes {4,5,6,7}, layout B
+    if (lane == 0) sel[t] = word;
+    return;
+  }
+  // ---- three-subset shapes (opaque blocks only)
+  e0 = estimate_shape<3>(px, lane, s_w + 16);              // 4 buckets -> 2-bit weights
+  e1 = estimate_shape<3>(px, lane + 32, s_w + 16);
+  const uint32_t y0 = __ballot_sync(0xffffffffu, e0 < 1e-9), y1 = __ballot_sync(0xffffffffu, e1 < 1e-9);
+  if (y0 | y1) {
+    const int s = y0 ? (__ffs(y0) - 1) : (32 + __ffs(y1) - 1);
+    word = (uint32_t)bi2 | ((uint32_t)s << 6) | (0x05u << 12) | (2u << 20);  // modes {0,2}
+    if (lane == 0) sel[t] = word;
+    return;
+  }
+  double be3 = e0;
+  int bi3 = lane;
+  if (e1 < be3) { be3 = e1; bi3 = lane + 32; }
+  warp_argmin(be3, bi3);
+  word = (uint32_t)bi2 | ((uint32_t)bi3 << 6) | (0xCFu << 12) | (2u << 20);  // all but modes 4,5
+  if (lane == 0) sel[t] = word;
+}
+
+// ------------------------------------------------------------------ chains
+// Decoded description of the chain a (block, slot) pair stands for.
+struct Chain {
+  int mode, shape, nsub, subset, rot, idx_mode, chain_id;
+  bool active;
+};
+
+__device__ __forceinline__ Chain decode_chain(uint32_t selw, int slot) {
+  Chain c;
+  c.active = false;
+  c.rot = 0; c.idx_mode = 0; c.subset = 0; c.shape = 0; c.nsub = 1; c.mode = 0; c.chain_id = 0;
+  if ((selw >> 24) != kTypeNormal) return c;
+  const int shape2 = selw & 63, shape3 = (selw >> 6) & 63;
+  const uint32_t modes = (selw >> 12) & 0xFF;
+  const int nshapes = (selw >> 20) & 3;
+  const bool layout_b = (selw >> 22) & 1;
+  int mode = -1, subset = 0, si = 0;
+  if (!layout_b) {
+    if (slot < 3) { mode = 0; subset = slot; si = 1; }
+    else if (slot < 6) { mode = 2; subset = slot - 3; si = 1; }
+    else if (slot < 8) { mode = 1; subset = slot - 6; }
+    else if (slot < 10) { mode = 3; subset = slot - 8; }
+    else if (slot < 12) { mode = 7; subset = slot - 10; }
+    else if (slot < 14) { mode = 6; si = slot - 12; }
+    else return c;
+  } else {
+    if (slot < 8) { mode = 4; c.rot = slot >> 1; c.idx_mode = slot & 1; }
+    else if (slot < 12) { mode = 5; c.rot = slot - 8; }
+    else if (slot == 12) { mode = 6; }
+    else if (slot < 15) { mode = 7; subset = slot - 13; }
+    else return c;
+  }
+  if (!((modes >> mode) & 1)) return c;
+  const int nsub = c_modes[mode].subsets;
+  if (si >= nshapes) return c;                       // needs the three-subset shape slot
+  if (nsub == 3 && mode == 0 && shape3 >= 16) return c;  // mode 0 has 4 partition bits (Compressor.cpp:1790)
+  c.mode = mode;
+  c.nsub = nsub;
+  c.subset = subset;
+  c.shape = nsub == 3 ? shape3 : (nsub == 2 ? shape2 : (si ? shape3 : shape2));
+  c.chain_id = (mode == 4) ? (32 + c.rot * 2 + c.idx_mode) : (mode == 5 ? 40 + c.rot : mode * 8 + si * 4 + subset);
+  c.active = true;
+  return c;
+}
+
+struct F4 { float v[4]; };
+__device__ __forceinline__ float dot4(const float a[4], const float b[4]) {
+  float s = __fmul_rn(a[0], b[0]);  // 0 + x == x
+  s = __fadd_rn(s, __fmul_rn(a[1], b[1]));
+  s = __fadd_rn(s, __fmul_rn(a[2], b[2]));
+  s = __fadd_rn(s, __fmul_rn(a[3], b[3]));
+  return s;
+}
+__device__ __forceinline__ float length4(const float a[4]) { return __fsqrt_rn(dot4(a, a)); }
+
+// single colour lookup (see g_single)
+__device__ __forceinline__ uint32_t single_color(int mode, int idx_mode, int npbit, uint32_t pixel, uint32_t &p1,
+                                                 uint32_t &p2, int &best_combo) {
+  uint32_t best_err = 0xFFFFFFFFu;
+  for (int pbi = 0; pbi < npbit; pbi++) {
+    uint32_t v1 = 0, v2 = 0, err = 0;
+#pragma unroll
+    for (int ci = 0; ci < 4; ci++) {
+      const uint32_t e = g_single[((((mode * 2 + idx_mode) * 4 + pbi) * 2 + (ci == 3)) << 8) + chan(pixel, ci)];
+      v1 |= (e & 0xFF) << (8 * ci);
+      v2 |= ((e >> 8) & 0xFF) << (8 * ci);
+      const uint32_t d = e >> 16;
+      err += d * d;
+    }
+    if (err < best_err) { best_err = err; best_combo = pbi; p1 = v1; p2 = v2; }
+  }
+  return best_err;
+}
+
+#ifdef FASTC_GPU_COUNTERS
+#define COUNT_QE(ws, ncalls, npbe) do { atomicAdd(&(ws).counters[0], (unsigned long long)(ncalls)); atomicAdd(&(ws).counters[1], (unsigned long long)(npbe)); } while (0)
+#else
+#define COUNT_QE(ws, ncalls, npbe) do { } while (0)
+#endif
+
+// Full QuantizedError over a cluster (returns the integer total; optionally the indices).
+__device__ __forceinline__ uint32_t qe_cluster(const uint32_t *pts, const uint32_t *pix, int n, uint32_t q1, uint32_t q2,
+                                               int nbm1, const uint8_t *__restrict__ wtab, unsigned long long *indices) {
+  QeEndpoints q;
+  qe_prepare(q, q1, q2);
+  uint32_t total = 0;
+  unsigned long long idx = 0;
+  for (int i = 0; i < n; i++) {
+    int b;
+    total += qe_pixel(q, pts[i], pix[i], nbm1, wtab, &b);
+    idx |= (unsigned long long)b << (4 * i);
+  }
+  if (indices) *indices = idx;
+  return total;
+}
+
+// The fit of one chain: CompressCluster (Compressor.cpp:921-1094) followed by
+// OptimizeEndpointsForCluster (:538-630).  pts/pix are this thread's private
+// copies of the cluster (n points).  avg/mn/mx are the cluster statistics the
+// reference would see (for the rotated mode-4/5 fit these are the STALE ones of
+// the un-rotated block, T16).  Returns the total error.
+struct FitResult {
+  uint32_t err, p1, p2;
+  int combo;
+  unsigned long long indices;
+};
+
+__device__ void fit_cluster(const Ws &ws, const ModeAttr &A, int mode, int idx_mode, int rot, const uint32_t *pts,
+                            const uint32_t *pix, int n, const float avg[4], bool all_same, int sa_steps,
+                            uint32_t rng, const uint8_t *__restrict__ s_w, FitResult &R) {
+  const int ibits = idx_mode == 0 ? A.index_bits : A.alpha_index_bits;
+  const int nb = 1 << ibits, nbm1 = nb - 1;
+  const uint8_t *wtab = s_w + 16 * (ibits - 1);
+  const int npbit = A.pbit == kPbitShared ? 2 : (A.pbit == kPbitPerEndpoint ? 4 : 1);
+  const uint32_t qm = quant_mask(A);
+
+  if (all_same) {  // AllSamePoint -> CompressSingleColor on point 0
+    int combo = 0;
+    uint32_t p1 = 0, p2 = 0;
+    const uint32_t e = single_color(mode, idx_mode, npbit, pts[0], p1, p2, combo);
+    R.err = (uint32_t)n * e;
+    R.p1 = p1; R.p2 = p2; R.combo = combo;
+    R.indices = 0x1111111111111111ull;
+    return;
+  }
+
+  // ---- GetPrincipalAxis (RGBAEndpoints.cpp:327-428)
+  float axis[4];
+  {
+    // unique points; entries past the unique count stay (-1,-1,-1,-1) (T7)
+    uint32_t upts[16];
+    int nu = 0;
+    for (int i = 0; i < n; i++) {
+      bool has = false;
+      for (int j = 0; j < nu; j++) has = has || (upts[j] == pts[i]);
+      if (!has) upts[nu++] = pts[i];
+    }
+    if (nu == 1) {
+      axis[0] = axis[1] = axis[2] = axis[3] = 0.0f;
+    } else {
+      float dir[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) dir[k] = (float)(chan(upts[1], k) - chan(upts[0], k));
+      {
+        const float len = length4(dir);
+#pragma unroll
+        for (int k = 0; k < 4; k++) dir[k] = __fdiv_rn(dir[k], len);
+      }
+      bool collinear = true;
+      for (int i = 2; i < n; i++) {
+        float v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          v[k] = i < nu ? (float)(chan(upts[i], k) - chan(upts[0], k)) : __fsub_rn(-1.0f, (float)chan(upts[0], k));
+        const double a = fabs((double)dot4(v, dir));
+        const double b = (double)length4(v);
+        if (fabs(a - b) > 1e-7) { collinear = false; break; }
+      }
+      if (collinear) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) axis[k] = dir[k];
+      } else {
+        // covariance of (pt - avg), divided by 3 (T8); lower triangle then mirrored
+        float cov[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int j = 0; j <= i; j++) {
+            float sum = 0.0f;
+            for (int k = 0; k < n; k++) {
+              const float a = __fsub_rn((float)chan(pts[k], i), avg[i]);
+              const float b = __fsub_rn((float)chan(pts[k], j), avg[j]);
+              sum = __fadd_rn(sum, __fmul_rn(a, b));
+            }
+            cov[i][j] = __fdiv_rn(sum, 3.0f);
+            cov[j][i] = cov[i][j];
+          }
+        // MatrixSquare::PowerMethod (MatrixSquare.h:44-105): <= 4 iterations from (.5,.5,.5,.5)
+        float b[4] = {0.5f, 0.5f, 0.5f, 0.5f};
+        bool bad = false, fixed = false;
+        int it = 0;
+        while (!fixed && ++it < 5) {
+          float nbv[4];
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            float r = __fmul_rn(cov[j][0], b[0]);
+            r = __fadd_rn(r, __fmul_rn(cov[j][1], b[1]));
+            r = __fadd_rn(r, __fmul_rn(cov[j][2], b[2]));
+            r = __fadd_rn(r, __fmul_rn(cov[j][3], b[3]));
+            nbv[j] = r;
+          }
+          const float len = length4(nbv);
+          if ((double)len < 1e-10) {
+            if (bad) break;
+            b[0] = 1.0f; b[1] = 1.0f;
+            const float l2 = length4(b);
+#pragma unroll
+            for (int k = 0; k < 4; k++) b[k] = __fdiv_rn(b[k], l2);
+            bad = true;
+            continue;
+          }
+#pragma unroll
+          for (int k = 0; k < 4; k++) nbv[k] = __fdiv_rn(nbv[k], len);
+          if (fabs((double)__fsub_rn(1.0f, dot4(b, nbv))) < 1e-8) fixed = true;
+#pragma unroll
+          for (int k = 0; k < 4; k++) b[k] = nbv[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) axis[k] = b[k];
+      }
+    }
+  }
+
+  // ---- endpoints along the axis (Compressor.cpp:946-959)
+  float p1[4], p2[4];
+  {
+    float mindp = FLT_MAX, maxdp = -FLT_MAX;
+    for (int i = 0; i < n; i++) {
+      float v[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) v[k] = __fsub_rn((float)chan(pts[i], k), avg[k]);
+      const float dp = dot4(v, axis);
+      if (dp < mindp) mindp = dp;
+      if (dp > maxdp) maxdp = dp;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      p1[k] = __fadd_rn(avg[k], __fmul_rn(axis[k], mindp));
+      p2[k] = __fadd_rn(avg[k], __fmul_rn(axis[k], maxdp));
+      p1[k] = (p1[k] < 0.0f) ? 0.0f : ((p1[k] > 255.0f) ? 255.0f : p1[k]);
+      p2[k] = (p2[k] < 0.0f) ? 0.0f : ((p2[k] > 255.0f) ? 255.0f : p2[k]);
+    }
+  }
+
+  // ---- k-means over the nb interpolation points until a fixed point (:961-1026, T15)
+  float cen[16][4];
+  int cnt[16];
+  for (int i = 0; i < nb; i++) {
+    const float s = __fdiv_rn((float)i, (float)nbm1);
+    const float oms = __fsub_rn(1.0f, s);
+#pragma unroll
+    for (int k = 0; k < 4; k++) cen[i][k] = __fadd_rn(__fmul_rn(p1[k], oms), __fmul_rn(p2[k], s));
+  }
+  {
+    uint8_t bucket[16];
+    bool fixed = false;
+    int guard = 0;
+    while (!fixed && guard++ < 4096) {
+      for (int i = 0; i < n; i++) {
+        float pf[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) pf[k] = (float)chan(pts[i], k);
+        int mb = 0;
+        float md = FLT_MAX;
+        for (int j = 0; j < nb; j++) {
+          float v[4];
+#pragma unroll
+          for (int k = 0; k < 4; k++) v[k] = __fsub_rn(pf[k], cen[j][k]);
+          const float d = dot4(v, v);
+          if (d < md) { md = d; mb = j; }
+        }
+        bucket[i] = (uint8_t)mb;
+      }
+      fixed = true;
+      for (int j = 0; j < nb; j++) {
+        int c = 0;
+        float sum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        for (int i = 0; i < n; i++)
+          if (bucket[i] == j) {
+            c++;
+#pragma unroll
+            for (int k = 0; k < 4; k++) sum[k] = __fadd_rn(sum[k], (float)chan(pts[i], k));
+          }
+        if (c != 0) {
+          const float fc = (float)c;
+#pragma unroll
+          for (int k = 0; k < 4; k++) sum[k] = __fdiv_rn(sum[k], fc);
+        }
+        cnt[j] = c;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          if (!(cen[j][k] == sum[k])) fixed = false;
+          cen[j][k] = sum[k];
+        }
+      }
+    }
+  }
+  int filled = 0, last = -1;
+  for (int j = 0; j < nb; j++)
+    if (cnt[j] > 0) { filled++; last = j; }
+  if (filled == 1) {  // one bucket -> CompressSingleColor on its centroid (:1038-1047)
+    int combo = 0;
+    uint32_t q1 = 0, q2 = 0;
+    const uint32_t e = single_color(mode, idx_mode, npbit, pack_round(cen[last]), q1, q2, combo);
+    R.err = (uint32_t)n * e;
+    R.p1 = q1; R.p2 = q2; R.combo = combo;
+    R.indices = 0x1111111111111111ull;
+    return;
+  }
+
+  // ---- least squares endpoints (:1053-1077)
+  {
+    float asq = 0.0f, bsq = 0.0f, ab = 0.0f;
+    float ax[4] = {0, 0, 0, 0}, bx[4] = {0, 0, 0, 0};
+    const float fb = (float)nbm1;
+    for (int i = 0; i < nb; i++) {
+      const float fn = (float)cnt[i];
+      const float a = __fdiv_rn((float)(nbm1 - i), fb), b = __fdiv_rn((float)i, fb);
+      asq = __fadd_rn(asq, __fmul_rn(__fmul_rn(fn, a), a));
+      bsq = __fadd_rn(bsq, __fmul_rn(__fmul_rn(fn, b), b));
+      ab = __fadd_rn(ab, __fmul_rn(__fmul_rn(fn, a), b));
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        ax[k] = __fadd_rn(ax[k], __fmul_rn(__fmul_rn(cen[i][k], a), fn));
+        bx[k] = __fadd_rn(bx[k], __fmul_rn(__fmul_rn(cen[i][k], b), fn));
+      }
+    }
+    const float f = __fdiv_rn(1.0f, __fsub_rn(__fmul_rn(asq, bsq), __fmul_rn(ab, ab)));
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      p1[k] = __fmul_rn(__fsub_rn(__fmul_rn(ax[k], bsq), __fmul_rn(bx[k], ab)), f);
+      p2[k] = __fmul_rn(__fsub_rn(__fmul_rn(bx[k], asq), __fmul_rn(ax[k], ab)), f);
+    }
+  }
+
+  // ---- ClampEndpointsToGrid (:212-250)
+  uint32_t c1, c2;  // current endpoints, integer bytes from here on
+  int combo = 0;
+  {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      p1[k] = (p1[k] < 0.0f) ? 0.0f : ((p1[k] > 255.0f) ? 255.0f : p1[k]);
+      p2[k] = (p2[k] < 0.0f) ? 0.0f : ((p2[k] > 255.0f) ? 255.0f : p2[k]);
+    }
+    const uint32_t r1 = pack_round(p1), r2 = pack_round(p2);
+    float md = FLT_MAX;
+    c1 = c2 = 0;
+    for (int i = 0; i < npbit; i++) {
+      int pb0, pb1;
+      pbit_combo(A.pbit, i, pb0, pb1);
+      const uint32_t q1 = to_pixel_b(r1, qm, pb0), q2 = to_pixel_b(r2, qm, pb1);
+      float d1[4], d2[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        d1[k] = __fsub_rn((float)chan(q1, k), p1[k]);
+        d2[k] = __fsub_rn((float)chan(q2, k), p2[k]);
+      }
+      const float dist = __fadd_rn(dot4(d1, d1), dot4(d2, d2));
+      if (dist < md) { md = dist; c1 = q1; c2 = q2; combo = i; }
+    }
+  }
+
+  // ---- OptimizeEndpointsForCluster (:538-630), integer state.
+  // Endpoints are bytes on the mode's grid; a step moves every channel by one
+  // grid step in a random direction (p-bit modes: the p-bit always flips).
+  // Reference quirk: QuantizedError always receives a non-NULL p-bit pair -- for the modes
+  // WITHOUT p-bits GetPBitCombo() returns {0,0} (CompressionMode.h:244-251), so inside the error
+  // evaluation (and only there) their endpoints are quantised as if a p-bit of 0 followed the
+  // colour bits.  The endpoint state itself and Pack quantise without a p-bit.
+  int pb0, pb1;
+  pbit_combo(A.pbit, combo, pb0, pb1);
+  const bool has_pbit = A.pbit != kPbitNone;
+  uint32_t cur1 = to_pixel_b(c1, qm, pb0), cur2 = to_pixel_b(c2, qm, pb1);  // idempotent: c1/c2 are on the grid
+  uint32_t cur_err = qe_cluster(pts, pix, n, to_pixel_b(c1, qm, has_pbit ? pb0 : 0),
+                                to_pixel_b(c2, qm, has_pbit ? pb1 : 0), nbm1, wtab, nullptr);
+  uint32_t best_err = cur_err, best1 = cur1, best2 = cur2;
+  int cur_combo = combo, best_combo = combo;
+  uint32_t ncalls = 1;
+
+  int step[4];
+  step[0] = step[1] = step[2] = 1 << (8 - A.color_bits);
+  step[3] = 1 << (8 - A.alpha_bits);  // alpha_bits == 0 -> 256, zeroed below for opaque modes
+  if (mode < 4) step[(rot + 3) & 3] = 0;
+  const float inv_tm1 = (float)(sa_steps - 1);
+
+  for (int energy = 0; best_err > 0 && energy < sa_steps; energy++) {
+    // PickBestNeighboringEndpoints (:426-498)
+    int ncombo = 0;
+    if (has_pbit) ncombo = A.pbit == kPbitShared ? ((cur_combo + 1) & 1) : 3 - cur_combo;
+    int opb0, opb1;
+    pbit_combo(A.pbit, cur_combo, opb0, opb1);
+    uint32_t n1 = 0, n2 = 0;
+    bool visited = true;
+    int guard = -1;
+    while (visited && ++guard < 16) {
+#pragma unroll
+      for (int pt = 0; pt < 2; pt++) {  // pt = 0 moves endpoint 2 first (and reads p-bit [0] for it, as the reference does)
+        const uint32_t src = pt ? cur1 : cur2;
+        const uint32_t dir = lcg_next(rng) & 15;
+        const int old = pt ? opb1 : opb0;
+        uint32_t np = 0;
+#pragma unroll
+        for (int ch = 0; ch < 4; ch++) {
+          int v = chan(src, ch);
+          const bool neg = (dir >> ch) & 1;
+          if (has_pbit) {
+            if (neg && old == 0) v -= step[ch];
+            else if (!neg && old == 1) v += step[ch];
+          } else {
+            v += neg ? -step[ch] : step[ch];
+          }
+          v = min(max(v, 0), 255);
+          np |= (uint32_t)v << (8 * ch);
+        }
+        if (pt) n1 = np; else n2 = np;
+      }
+      visited = (best1 == n1) && (best2 == n2) && (best_combo == ncombo);
+    }
+    int npb0, npb1;
+    pbit_combo(A.pbit, ncombo, npb0, npb1);
+    const uint32_t q1 = to_pixel_b(n1, qm, has_pbit ? npb0 : 0), q2 = to_pixel_b(n2, qm, has_pbit ? npb1 : 0);
+    const uint32_t err = qe_cluster(pts, pix, n, q1, q2, nbm1, wtab, nullptr);
+    ncalls++;
+
+    // AcceptNewEndpointError (:524-536)
+    bool accept;
+    if (err < cur_err) {
+      accept = true;
+    } else {
+      const float temp = __fdiv_rn((float)energy, inv_tm1);
+      const double x = ((double)0.1f * ((double)cur_err - (double)err)) / (double)temp;
+      const double p = exp(x);
+      const uint32_t r = lcg_next(rng) & 0xFFFF;
+      const uint32_t m = ((r << 8) | (r >> 7)) & 0x7FFFFF;
+      const float fr = __fsub_rn(__uint_as_float((127u << 23) | m), 1.0f);
+      accept = (double)fr < p;
+    }
+    if (accept) { cur_err = err; cur1 = n1; cur2 = n2; cur_combo = ncombo; }
+    if (err < best_err) {
+      best_err = err; best1 = n1; best2 = n2; best_combo = ncombo;
+      energy = 0;  // restart; the loop increment makes it 1
+    }
+  }
+  // indices belong to the evaluation that produced best_err (same quirky quantisation)
+  pbit_combo(A.pbit, best_combo, pb0, pb1);
+  const uint32_t f1 = to_pixel_b(best1, qm, has_pbit ? pb0 : 0), f2 = to_pixel_b(best2, qm, has_pbit ? pb1 : 0);
+  unsigned long long indices;
+  qe_cluster(pts, pix, n, f1, f2, nbm1, wtab, &indices);
+  COUNT_QE(ws, ncalls, 0);
+  R.err = best_err;
+  R.p1 = best1; R.p2 = best2; R.combo = best_combo;
+  R.indices = indices;
+}
+
+constexpr int kChainThreads = 128;
+
+__global__ void __launch_bounds__(kChainThreads)
+bc7_chains(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, uint32_t first_block,
+           uint32_t num_blocks, Ws ws, int sa_steps, uint64_t seed, uint32_t block_index_base) {
+  __shared__ uint8_t s_w[64];
+  if (threadIdx.x < 64) s_w[threadIdx.x] = c_weight[threadIdx.x];
+  __syncthreads();
+  const uint32_t gid = blockIdx.x * kChainThreads + threadIdx.x;
+  const uint32_t t = gid / kSlots;
+  const int slot = gid % kSlots;
+  if (t >= num_blocks) return;
+  const uint32_t selw = ws.sel[t];
+  const Chain c = decode_chain(selw, slot);
+  if (!c.active) return;
+  const ModeAttr A = c_modes[c.mode];
+
+  uint32_t blk[16];
+  load_block(img, width, blocks_x, first_block + t, blk);
+
+  // Cluster of this chain: points in raster order of the subset (m_PointMap).
+  uint32_t pts[16], pix[16];
+  int n = 0;
+  float sum[4] = {0, 0, 0, 0};
+  uint32_t mn = 0xFFFFFFFFu, mx = 0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    if (subset_of(i, c.shape, c.nsub) == c.subset) {
+      pix[n] = blk[i];
+      pts[n] = blk[i];
+      n++;
+#pragma unroll
+      for (int k = 0; k < 4; k++) sum[k] = __fadd_rn(sum[k], (float)chan(blk[i], k));  // exact integers
+      mn = __vminu4(mn, blk[i]);
+      mx = __vmaxu4(mx, blk[i]);
+    }
+  }
+  float avg[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) avg[k] = __fdiv_rn(sum[k], (float)n);
+  const bool all_same = mn == mx;
+  const uint32_t gblock = block_index_base + first_block + t;
+  const uint32_t rng = chain_seed(seed, gblock, (uint32_t)c.chain_id);
+
+  uint32_t *res = ws.results + ((size_t)t * kSlots + slot) * kResWords;
+  FitResult R;
+  if (!A.rotation) {
+    fit_cluster(ws, A, c.mode, 0, 0, pts, pix, n, avg, all_same, sa_steps, rng, s_w, R);
+    res[0] = R.err; res[1] = R.p1; res[2] = R.p2; res[3] = (uint32_t)R.combo;
+    res[4] = (uint32_t)R.indices; res[5] = (uint32_t)(R.indices >> 32);
+    return;
+  }
+
+  // ---- modes 4/5: CompressCluster alpha variant (Compressor.cpp:632-919), n == 16.
+  // Points are rotated and their alpha forced to 255, but avg / bounds / error
+  // pixels stay those of the original block (T16).
+  float alpha_vals[16];
+  float amin = FLT_MAX, amax = -FLT_MAX;
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    const uint32_t p = blk[i];
+    const uint32_t a = c.rot == 0 ? (p >> 24) : chan(p, c.rot - 1);
+    uint32_t q = p;
+    if (c.rot) q = (p & ~(0xFFu << (8 * (c.rot - 1)))) | ((p >> 24) << (8 * (c.rot - 1)));  // channel <- old alpha
+    pts[i] = q | 0xFF000000u;
+    alpha_vals[i] = (float)a;
+    amin = fminf(amin, (float)a);
+    amax = fmaxf(amax, (float)a);
+  }
+  fit_cluster(ws, A, c.mode, c.idx_mode, c.rot, pts, pix, 16, avg, all_same, sa_steps, rng, s_w, R);
+
+  const int abits = c.idx_mode == 0 ? A.alpha_index_bits : A.index_bits;
+  const int nba = 1 << abits;
+  const uint8_t *wa = s_w + 16 * (abits - 1);
+  float a1 = amin, a2 = amax;
+  uint32_t alpha_err = 0;
+  unsigned long long aidx = 0;
+  if (a1 == a2) {
+    const int a1be = (int)a1;
+    if (c.mode == 5) {
+      aidx = 0;
+      alpha_err = 0;
+    } else {
+      const uint8_t *t1 = c_opt6 + 6 * a1be;
+      if (t1[0]) {
+        a1 = (float)((t1[4] << 2) | (t1[1] >> 4));
+        a2 = (float)((t1[5] << 2) | (t1[1] >> 4));
+      } else {
+        a1 = (float)((t1[1] << 2) | (t1[1] >> 4));
+        a2 = (float)((t1[2] << 2) | (t1[1] >> 4));
+      }
+      const int ai = c.idx_mode == 1 ? 1 : 2;
+      aidx = ai * 0x1111111111111111ull;
+      const int w1 = wa[ai], w0 = 64 - w1;
+      const int ip = (((int)a1 * w0 + (int)a2 * w1 + 32) >> 6) & 0xFF;
+      const int d = a1be > ip ? a1be - ip : ip - a1be;
+      alpha_err = 16u * (uint32_t)(d * d);
+    }
+  } else {
+    // scalar k-means over the alpha interpolation points (:770-842)
+    float vals[8];
+    uint8_t bucket[16];
+    for (int i = 0; i < nba; i++)
+      vals[i] = __fadd_rn(amin, __fmul_rn(__fdiv_rn((float)i, (float)(nba - 1)), __fsub_rn(amax, amin)));
+    for (int i = 0; i < 16; i++) {
+      float md = 255.0f;
+      int b = 0;
+      for (int j = 0; j < nba; j++) {
+        const float d = fabsf(__fsub_rn(alpha_vals[i], vals[j]));
+        if (d < md) { md = d; b = j; }
+      }
+      bucket[i] = (uint8_t)b;
+    }
+    float npts[8];
+    bool fixed = false;
+    int guard = 0;
+    while (!fixed && guard++ < 4096) {
+      float av[8];
+      fixed = true;
+      for (int i = 0; i < nba; i++) {
+        float s = 0.0f, c2 = 0.0f;
+        for (int j = 0; j < 16; j++)
+          if (bucket[j] == i) { s = __fadd_rn(s, alpha_vals[j]); c2 = __fadd_rn(c2, 1.0f); }
+        if (c2 > 0.0f) s = __fdiv_rn(s, c2);
+        av[i] = s; npts[i] = c2;
+        fixed = fixed && (av[i] == vals[i]);
+      }
+      for (int i = 0; i < nba; i++) vals[i] = av[i];
+      for (int i = 0; i < 16; i++) {
+        float md = 255.0f;
+        int b = bucket[i];  // reference keeps the previous bucket when nothing is closer than 255
+        for (int j = 0; j < nba; j++) {
+          const float d = fabsf(__fsub_rn(alpha_vals[i], vals[j]));
+          if (d < md) { md = d; b = j; }
+        }
+        bucket[i] = (uint8_t)b;
+      }
+    }
+    float asq = 0.0f, bsq = 0.0f, ab = 0.0f, ax = 0.0f, bx = 0.0f;
+    const float fb = (float)(nba - 1);
+    for (int i = 0; i < nba; i++) {
+      const float a = __fdiv_rn((float)(nba - 1 - i), fb), b = __fdiv_rn((float)i, fb);
+      const float nn = npts[i], x = vals[i];
+      asq = __fadd_rn(asq, __fmul_rn(__fmul_rn(nn, a), a));
+      bsq = __fadd_rn(bsq, __fmul_rn(__fmul_rn(nn, b), b));
+      ab = __fadd_rn(ab, __fmul_rn(__fmul_rn(nn, a), b));
+      ax = __fadd_rn(ax, __fmul_rn(__fmul_rn(x, a), nn));
+      bx = __fadd_rn(bx, __fmul_rn(__fmul_rn(x, b), nn));
+    }
+    const float f = __fdiv_rn(1.0f, __fsub_rn(__fmul_rn(asq, bsq), __fmul_rn(ab, ab)));
+    a1 = __fmul_rn(f, __fsub_rn(__fmul_rn(ax, bsq), __fmul_rn(bx, ab)));
+    a2 = __fmul_rn(f, __fsub_rn(__fmul_rn(bx, asq), __fmul_rn(ax, ab)));
+    // std::min(255.0f, std::max(0.0f, a)) -- NaN maps to 0 through std::max's argument order
+    a1 = (a1 > 0.0f) ? a1 : 0.0f; a1 = (a1 < 255.0f) ? a1 : 255.0f;
+    a2 = (a2 > 0.0f) ? a2 : 0.0f; a2 = (a2 < 255.0f) ? a2 : 255.0f;
+    const uint32_t qmask8 = (0xFF00u >> A.alpha_bits) & 0xFF;
+    const int a1b = (int)quantize_channel((uint32_t)(int)a1, qmask8, -1);  // uint8(a1): truncation
+    const int a2b = (int)quantize_channel((uint32_t)(int)a2, qmask8, -1);
+    for (int i = 0; i < 16; i++) {
+      const int val = (int)alpha_vals[i];
+      int me = 0x7fffffff, bb = 0;
+      for (int j = 0; j < nba; j++) {
+        const int w1 = wa[j], w0 = 64 - w1;
+        const int ip = ((a1b * w0 + a2b * w1 + 32) >> 6) & 0xFF;
+        const int d = val - ip;
+        const int e = d * d;
+        if (e < me) { me = e; bb = j; }
+      }
+      alpha_err += (uint32_t)me;
+      aidx |= (unsigned long long)bb << (4 * i);
+    }
+  }
+  // endpoints handed to Pack: rgb from the fit, alpha = the float a1/a2 (Pack rounds them)
+  const uint32_t e1 = (R.p1 & 0x00FFFFFFu) | (round_byte(a1) << 24);
+  const uint32_t e2 = (R.p2 & 0x00FFFFFFu) | (round_byte(a2) << 24);
+  res[0] = R.err + alpha_err; res[1] = e1; res[2] = e2; res[3] = 0;
+  res[4] = (uint32_t)R.indices; res[5] = (uint32_t)(R.indices >> 32);
+  res[6] = (uint32_t)aidx; res[7] = (uint32_t)(aidx >> 32);
+}
+
+// ------------------------------------------------------------------ pack
+struct BitWriter {
+  uint32_t w[4] = {0, 0, 0, 0};
+  int pos = 0;
+  __device__ __forceinline__ void write(uint32_t v, int n) {  // LSB first (BitStream.h:65-94)
+    if (n == 0) return;
+    v &= (n >= 32) ? 0xFFFFFFFFu : ((1u << n) - 1);
+    const int word = pos >> 5, off = pos & 31;
+    w[word] |= v << off;
+    if (off + n > 32 && word < 3) w[word + 1] |= v >> (32 - off);
+    pos += n;
+  }
+};
+
+__global__ void __launch_bounds__(128)
+bc7_pack(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, uint32_t first_block,
+         uint32_t num_blocks, Ws ws, uint8_t *__restrict__ out) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= num_blocks) return;
+  const uint32_t bi = first_block + t;
+  const uint32_t selw = ws.sel[t];
+  const uint32_t type = selw >> 24;
+  BitWriter s;
+  if (type == kTypeSolid) {
+    // CompressOptimalColorBC7 (Compressor.cpp:1424-1458) + watermark order (T1): word index =
+    // number of solid blocks before this one = tile prefix + solid blocks earlier in the tile.
+    const uint32_t px = __ldg(img + (size_t)(bi / blocks_x) * 4 * width + (size_t)(bi % blocks_x) * 4);
+    uint32_t before = *ws.wm_running + ws.tile_count[t / kTile];
+    for (uint32_t j = (t / kTile) * kTile; j < t; j++) before += ((ws.sel[j] >> 24) == kTypeSolid);
+    s.write(1u << 5, 6);
+    s.write(0, 2);
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) {
+      const int v = chan(px, ch);
+      s.write(c_opt7[2 * v], 7);
+      s.write(c_opt7[2 * v + 1], 7);
+    }
+    s.write(px >> 24, 8);
+    s.write(px >> 24, 8);
+    s.write(0xaaaaaaabu, 31);
+    s.write(c_wm[before % 9], 31);
+    reinterpret_cast<uint4 *>(out)[bi] = make_uint4(s.w[0], s.w[1], s.w[2], s.w[3]);
+    return;
+  }
+  if (type == kTypeTransparent) {  // WriteTransparentBlock (:1416-1421)
+    reinterpret_cast<uint4 *>(out)[bi] = make_uint4(1u << 6, 0, 0, 0);
+    return;
+  }
+
+  // ---- CompressClusters' selection (:1771-1808): modes in the order {0,2,1,3,7,4,5,6},
+  // shape slots ascending, strict <.
+  const uint32_t *res = ws.results + (size_t)t * kSlots * kResWords;
+  const bool layout_b = (selw >> 22) & 1;
+  unsigned long long best_err = ~0ull;
+  int best_mode = -1, best_si = 0, best_first = 0;  // best_first: first slot of the winning candidate
+  const int order[8] = {0, 2, 1, 3, 7, 4, 5, 6};
+  for (int mi = 0; mi < 8; mi++) {
+    const int mode = order[mi];
+    for (int si = 0; si < 2; si++) {
+      // slots of candidate (mode, si)
+      int first = -1, count = 0;
+      if (!layout_b) {
+        if (mode == 0 && si == 1) { first = 0; count = 3; }
+        else if (mode == 2 && si == 1) { first = 3; count = 3; }
+        else if (mode == 1 && si == 0) { first = 6; count = 2; }
+        else if (mode == 3 && si == 0) { first = 8; count = 2; }
+        else if (mode == 7 && si == 0) { first = 10; count = 2; }
+        else if (mode == 6) { first = 12 + si; count = 1; }
+      } else if (si == 0) {
+        if (mode == 4) { first = 0; count = 8; }
+        else if (mode == 5) { first = 8; count = 4; }
+        else if (mode == 6) { first = 12; count = 1; }
+        else if (mode == 7) { first = 13; count = 2; }
+      }
+      if (first < 0) continue;
+      if (!decode_chain(selw, first).active) continue;
+      unsigned long long err;
+      int pick = first;
+      if (mode == 4 || mode == 5) {  // best rotation / index mode, strict < in loop order (:1320-1348)
+        unsigned long long be = ~0ull;
+        for (int k = 0; k < count; k++) {
+          const unsigned long long e = res[(first + k) * kResWords];
+          if (e < be) { be = e; pick = first + k; }
+        }
+        err = be;
+      } else {
+        err = 0;
+        for (int k = 0; k < count; k++) err += res[(first + k) * kResWords];
+      }
+      if (err < best_err) { best_err = err; best_mode = mode; best_si = si; best_first = pick; }
+    }
+  }
+  if (best_mode < 0) {  // unreachable with the default mode mask
+    reinterpret_cast<uint4 *>(out)[bi] = make_uint4(0, 0, 0, 0);
+    return;
+  }
+
+  // ---- CompressionMode::Pack (:1096-1298)
+  const ModeAttr A = c_modes[best_mode];
+  const int shape = A.subsets == 3 ? ((selw >> 6) & 63) : (A.subsets == 2 ? (selw & 63) : (best_si ? ((selw >> 6) & 63) : (selw & 63)));
+  int rot = 0, idx_mode = 0;
+  if (best_mode == 4) { rot = best_first >> 1; idx_mode = best_first & 1; }
+  if (best_mode == 5) { rot = best_first - 8; }
+  const uint32_t qm = quant_mask(A);
+
+  uint32_t px1[3], px2[3];
+  int combo[3];
+  uint8_t idx[16], aidx[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) { idx[i] = 0; aidx[i] = 0; }
+  for (int sub = 0; sub < A.subsets; sub++) {
+    const uint32_t *r = res + (best_first + sub) * kResWords;
+    int pb0, pb1;
+    combo[sub] = (int)r[3];
+    pbit_combo(A.pbit, combo[sub], pb0, pb1);
+    px1[sub] = to_pixel_b(r[1], qm, pb0);
+    px2[sub] = to_pixel_b(r[2], qm, pb1);
+    const unsigned long long ci = (unsigned long long)r[4] | ((unsigned long long)r[5] << 32);
+    const unsigned long long ai = (unsigned long long)r[6] | ((unsigned long long)r[7] << 32);
+    int k = 0;
+    for (int i = 0; i < 16; i++)
+      if (subset_of(i, shape, A.subsets) == sub) {
+        idx[i] = (ci >> (4 * k)) & 15;
+        if (A.rotation) aidx[i] = (ai >> (4 * k)) & 15;
+        k++;
+      }
+  }
+  const int nib = idx_mode == 0 ? A.index_bits : A.alpha_index_bits;
+  const int nab = idx_mode == 0 ? A.alpha_index_bits : A.index_bits;
+  for (int sub = 0; sub < A.subsets; sub++) {
+    const int anchor = anchor_of(sub, shape, A.subsets);
+    if (idx[anchor] >> (nib - 1)) {
+      const uint32_t tmp = px1[sub]; px1[sub] = px2[sub]; px2[sub] = tmp;
+      for (int i = 0; i < 16; i++)
+        if (subset_of(i, shape, A.subsets) == sub) idx[i] = (uint8_t)(((1 << nib) - 1) - idx[i]);
+      if (A.rotation)
+        for (int i = 0; i < 16; i++) aidx[i] = (uint8_t)(((1 << nab) - 1) - aidx[i]);
+    }
+    if (A.rotation && (aidx[anchor] >> (nab - 1))) {
+      const uint32_t a1 = px1[sub] & 0xFF000000u, a2 = px2[sub] & 0xFF000000u;
+      px1[sub] = (px1[sub] & 0x00FFFFFFu) | a2;
+      px2[sub] = (px2[sub] & 0x00FFFFFFu) | a1;
+      for (int i = 0; i < 16; i++) aidx[i] = (uint8_t)(((1 << nab) - 1) - aidx[i]);
+    }
+  }
+  s.write(1u << best_mode, best_mode + 1);
+  s.write((uint32_t)shape, A.partition_bits);
+  if (A.rotation) s.write((uint32_t)rot, 2);
+  if (A.idx_mode) s.write((uint32_t)idx_mode, 1);
+  for (int ch = 0; ch < 3; ch++)
+    for (int sub = 0; sub < A.subsets; sub++) {
+      s.write(chan(px1[sub], ch) >> (8 - A.color_bits), A.color_bits);
+      s.write(chan(px2[sub], ch) >> (8 - A.color_bits), A.color_bits);
+    }
+  if (A.alpha_bits)
+    for (int sub = 0; sub < A.subsets; sub++) {
+      s.write((px1[sub] >> 24) >> (8 - A.alpha_bits), A.alpha_bits);
+      s.write((px2[sub] >> 24) >> (8 - A.alpha_bits), A.alpha_bits);
+    }
+  if (A.pbit != kPbitNone)
+    for (int sub = 0; sub < A.subsets; sub++) {
+      int pb0, pb1;
+      pbit_combo(A.pbit, combo[sub], pb0, pb1);  // T17: original order even if the endpoints were swapped
+      s.write((uint32_t)pb0, 1);
+      if (A.pbit != kPbitShared) s.write((uint32_t)pb1, 1);
+    }
+  if (A.idx_mode && idx_mode == 1) {
+    for (int i = 0; i < 16; i++) s.write(aidx[i], i == 0 ? 1 : 2);
+    for (int i = 0; i < 16; i++) s.write(idx[i], i == 0 ? 2 : 3);
+  } else {
+    for (int i = 0; i < 16; i++) {
+      const int sub = subset_of(i, shape, A.subsets);
+      s.write(idx[i], i == anchor_of(sub, shape, A.subsets) ? nib - 1 : nib);
+    }
+    if (A.rotation)
+      for (int i = 0; i < 16; i++) s.write(aidx[i], i == 0 ? nab - 1 : nab);
+  }
+  reinterpret_cast<uint4 *>(out)[bi] = make_uint4(s.w[0], s.w[1], s.w[2], s.w[3]);
+}
+
+// ------------------------------------------------------------------ host side
+// CompressSingleColor's per-channel search (Compressor.cpp:268-332), run once on
+// the host for every (mode, index mode, p-bit combo, channel class, value).
+void build_single_table(uint32_t *tab) {
+  static const int kAttr[8][9] = {{4, 3, 3, 0, 4, 0, 0, 0, 1}, {6, 2, 3, 0, 6, 0, 0, 0, 0}, {6, 3, 2, 0, 5, 0, 0, 0, 2},
+                                  {6, 2, 2, 0, 7, 0, 0, 0, 1}, {0, 1, 2, 3, 5, 6, 1, 1, 2}, {0, 1, 2, 2, 7, 8, 1, 0, 2},
+                                  {0, 1, 4, 0, 7, 7, 0, 0, 1}, {6, 2, 2, 0, 5, 5, 0, 0, 1}};
+  static const int kPB[4][2] = {{0, 0}, {0, 1}, {1, 0}, {1, 1}};
+  for (int mode = 0; mode < 8; mode++)
+    for (int im = 0; im < 2; im++)
+      for (int pbi = 0; pbi < 4; pbi++)
+        for (int al = 0; al < 2; al++) {
+          const int pbt = kAttr[mode][8];
+          const int *combo = pbt == kPbitShared ? (pbi ? kPB[3] : kPB[0]) : (pbt == kPbitPerEndpoint ? kPB[pbi] : kPB[0]);
+          int nbits = al ? kAttr[mode][5] : kAttr[mode][4];
+          const int ibits = im == 0 ? kAttr[mode][2] : kAttr[mode][3];
+          uint32_t *row = tab + ((((mode * 2 + im) * 4 + pbi) * 2 + al) << 8);
+          if (nbits == 0 || ibits == 0) {
+            for (int v = 0; v < 256; v++) row[v] = 0xFF | (0xFF << 8) | ((uint32_t)(0xFF - v) << 16);
+            continue;
+          }
+          const int nvals = 1 << nbits;
+          const bool have = pbt != kPbitNone;
+          if (have) nbits++;
+          int vh[256], vl[256];
+          for (int i = 0; i < nvals; i++) {
+            int h = i, l = i;
+            if (have) { h = (h << 1) | combo[1]; l = (l << 1) | combo[0]; }
+            vh[i] = h << (8 - nbits); vh[i] |= vh[i] >> nbits;
+            vl[i] = l << (8 - nbits); vl[i] |= vl[i] >> nbits;
+          }
+          const uint32_t w1 = bc7tab::kWeight[(ibits - 1) * 16 + 1], w0 = 64 - w1;
+          for (int v = 0; v < 256; v++) {
+            uint32_t best = 0xFF, b1 = 0xFF, b2 = 0xFF;  // memset(0xFF) leaves 0xFFFFFFFF; only the low byte is ever used
+            for (int i = 0; best > 0 && i < nvals; i++)
+              for (int j = 0; best > 0 && j < nvals; j++) {
+                const uint32_t c = (w0 * vl[i] + w1 * vh[j] + 32) >> 6;
+                const uint32_t e = c > (uint32_t)v ? c - v : v - c;
+                if (e < best) { best = e; b1 = vl[i]; b2 = vh[j]; }
+              }
+            row[v] = (b1 & 0xFF) | ((b2 & 0xFF) << 8) | (best << 16);
+          }
+        }
+}
+
+size_t ws_bytes(uint32_t nblocks) {
+  const size_t ntiles = (nblocks + kTile - 1) / kTile;
+  size_t b = 0;
+  b += ((size_t)nblocks * 4 + 255) & ~(size_t)255;               // sel
+  b += ((ntiles + 1) * 4 + 255) & ~(size_t)255;                  // tile counts
+  b += 256;                                                      // total
+  b += (size_t)nblocks * kSlots * kResWords * 4;                 // results
+  return b;
+}
+
+Ws carve(void *base, uint32_t nblocks) {
+  const size_t ntiles = (nblocks + kTile - 1) / kTile;
+  uint8_t *p = static_cast<uint8_t *>(base);
+  Ws w;
+  w.sel = reinterpret_cast<uint32_t *>(p); p += ((size_t)nblocks * 4 + 255) & ~(size_t)255;
+  w.tile_count = reinterpret_cast<uint32_t *>(p); p += ((ntiles + 1) * 4 + 255) & ~(size_t)255;
+  w.total_solid = reinterpret_cast<uint32_t *>(p); p += 256;
+  w.counters = nullptr;
+  w.wm_running = nullptr;
+  w.results = reinterpret_cast<uint32_t *>(p);
+  return w;
+}
+
+cudaError_t ensure_ws(Bc7Workspace &ws, size_t bytes) {
+  if (!ws.host_count) {
+    cudaError_t e = cudaMallocHost(reinterpret_cast<void **>(&ws.host_count), 64);
+    if (e != cudaSuccess) return e;
+    e = cudaMalloc(reinterpret_cast<void **>(&ws.wm_running), 64);
+    if (e != cudaSuccess) return e;
+    e = cudaMalloc(reinterpret_cast<void **>(&ws.counters), 64);
+    if (e != cudaSuccess) return e;
+    e = cudaMemset(ws.counters, 0, 64);
+    if (e != cudaSuccess) return e;
+  }
+  if (ws.bytes >= bytes) return cudaSuccess;
+  if (ws.base) {
+    cudaError_t e = cudaFree(ws.base);
+    if (e != cudaSuccess) return e;
+    ws.base = nullptr; ws.bytes = 0;
+  }
+  cudaError_t e = cudaMalloc(&ws.base, bytes);
+  if (e != cudaSuccess) return e;
+  ws.bytes = bytes;
+  return cudaSuccess;
+}
+
+}  // namespace
+
+cudaError_t bc7_upload_tables() {
+  using namespace bc7tab;
+  cudaError_t e;
+#define UP(sym, src) if ((e = cudaMemcpyToSymbol(sym, src, sizeof(src))) != cudaSuccess) return e
+  UP(c_shape2, kShape2); UP(c_shape3, kShape3); UP(c_anchor2, kAnchor2); UP(c_anchor3a, kAnchor3a);
+  UP(c_anchor3b, kAnchor3b); UP(c_weight, kWeight); UP(c_opt7, kOpt7Mode5); UP(c_opt6, kOpt6Dxt1);
+  UP(c_wm, kWatermark);
+#undef UP
+  static uint32_t host_single[8 * 2 * 4 * 2 * 256];
+  static bool built = false;
+  if (!built) { build_single_table(host_single); built = true; }
+  return cudaMemcpyToSymbol(g_single, host_single, sizeof(host_single));
+}
+
+void bc7_free_workspace(Bc7Workspace &ws) {
+  if (ws.base) cudaFree(ws.base);
+  if (ws.host_count) cudaFreeHost(ws.host_count);
+  if (ws.wm_running) cudaFree(ws.wm_running);
+  if (ws.counters) cudaFree(ws.counters);
+  ws.base = nullptr; ws.bytes = 0; ws.host_count = nullptr; ws.wm_running = nullptr; ws.counters = nullptr;
+}
+
+// Blocks per internal chunk: bounds the scratch (512 B of chain results per block).
+constexpr uint32_t kChunkBlocks = 1u << 19;
+
+cudaError_t launch_bc7(Bc7Workspace &wsp, const void *rgba_dev, uint32_t width, uint32_t height,
+                       uint32_t first_block, uint32_t num_blocks, void *out_dev, int quality, uint64_t seed,
+                       uint32_t wm_base, uint32_t block_index_base, cudaStream_t stream, uint32_t *launches) {
+  (void)height;
+  if (num_blocks == 0) return cudaSuccess;
+  const uint32_t chunk = num_blocks < kChunkBlocks ? num_blocks : kChunkBlocks;
+  cudaError_t e = ensure_ws(wsp, ws_bytes(chunk) + 256);
+  if (e != cudaSuccess) return e;
+  const uint32_t *img = static_cast<const uint32_t *>(rgba_dev);
+  const uint32_t bx = width / 4;
+  // The running watermark base lives on the device, so chunks chain without a host sync.
+  uint32_t n = 0;
+  Ws ws = carve(wsp.base, chunk);
+  ws.wm_running = wsp.wm_running;
+  ws.counters = wsp.counters;
+#ifdef FASTC_GPU_COUNTERS
+  cudaMemsetAsync(wsp.counters, 0, 16, stream);
+#endif
+  bc7_set_u32<<<1, 1, 0, stream>>>(wsp.wm_running, wm_base);
+  n++;
+  for (uint32_t off = 0; off < num_blocks; off += chunk) {
+    const uint32_t nb = num_blocks - off < chunk ? num_blocks - off : chunk;
+    const uint32_t fb = first_block + off;
+    const uint32_t ntiles = (nb + kTile - 1) / kTile;
+    bc7_classify<<<ntiles, kTile, 0, stream>>>(img, width, bx, fb, nb, ws.sel, ws.tile_count);
+    bc7_wm_scan<<<1, 1024, 0, stream>>>(ws.tile_count, ntiles, ws.total_solid);
+    bc7_select<<<(nb + kSelWarps - 1) / kSelWarps, kSelWarps * 32, 0, stream>>>(img, width, bx, fb, nb, ws.sel);
+    const uint64_t nthreads = (uint64_t)nb * kSlots;
+    bc7_chains<<<(uint32_t)((nthreads + kChainThreads - 1) / kChainThreads), kChainThreads, 0, stream>>>(
+        img, width, bx, fb, nb, ws, quality, seed, block_index_base);
+    bc7_pack<<<(nb + 127) / 128, 128, 0, stream>>>(img, width, bx, fb, nb, ws, static_cast<uint8_t *>(out_dev));
+    n += 5;
+    if (off + chunk < num_blocks) {
+      bc7_add_u32<<<1, 1, 0, stream>>>(wsp.wm_running, ws.total_solid);
+      n++;
+    }
+  }
+  if (launches) *launches = n;
+  return cudaGetLastError();
+}
+
+cudaError_t bc7_count_solid(Bc7Workspace &wsp, const void *rgba_dev, uint32_t width, uint32_t first_block,
+                            uint32_t num_blocks, cudaStream_t stream, uint32_t *count_out) {
+  *count_out = 0;
+  if (num_blocks == 0) return cudaSuccess;
+  const uint32_t ntiles = (num_blocks + kTile - 1) / kTile;
+  cudaError_t e = ensure_ws(wsp, ((size_t)(ntiles + 1) * 4 + 511) & ~(size_t)255);
+  if (e != cudaSuccess) return e;
+  uint32_t *tiles = static_cast<uint32_t *>(wsp.base);
+  uint32_t *total = tiles + ntiles;
+  bc7_classify<<<ntiles, kTile, 0, stream>>>(static_cast<const uint32_t *>(rgba_dev), width, width / 4, first_block,
+                                              num_blocks, nullptr, tiles);
+  bc7_wm_scan<<<1, 1024, 0, stream>>>(tiles, ntiles, total);
+  e = cudaMemcpyAsync(wsp.host_count, total, 4, cudaMemcpyDeviceToHost, stream);
+  if (e != cudaSuccess) return e;
+  e = cudaStreamSynchronize(stream);
+  if (e != cudaSuccess) return e;
+  *count_out = *wsp.host_count;
+  return cudaGetLastError();
+}
+
+cudaError_t bc7_debug_dump(Bc7Workspace &wsp, uint32_t nblocks, uint32_t *sel_out, uint32_t *results_out) {
+  if (!wsp.base) return cudaErrorInvalidValue;
+  Ws ws = carve(wsp.base, nblocks);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return e;
+  e = cudaMemcpy(sel_out, ws.sel, (size_t)nblocks * 4, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) return e;
+  return cudaMemcpy(results_out, ws.results, (size_t)nblocks * kSlots * kResWords * 4, cudaMemcpyDeviceToHost);
+}
+
+cudaError_t bc7_read_counters(Bc7Workspace &wsp, uint64_t *qe_calls, uint64_t *pbe) {
+  *qe_calls = 0;
+  *pbe = 0;
+  if (!wsp.counters) return cudaSuccess;
+  unsigned long long h[2] = {0, 0};
+  cudaError_t e = cudaMemcpy(h, wsp.counters, sizeof(h), cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) return e;
+  *qe_calls = h[0];
+  *pbe = h[1];
+  return cudaSuccess;
+}
+
 }  // namespace fastc

@@ -481,6 +481,15 @@ int fastc_gpu_bc7_counters(uint64_t *qe_calls, uint64_t *pixel_bucket_evals) {
   return 0;
 }
 
+int fastc_gpu_debug_bc7_dump(uint32_t nblocks, uint32_t *sel_out, uint32_t *results_out) {
+  int dev = 0;
+  CU_TRY(cudaGetDevice(&dev));
+  DeviceCtx &c = g_ctx[dev];
+  std::lock_guard<std::mutex> lk(c.mu);
+  CU_TRY(bc7_debug_dump(c.bc7ws[kPipeDepth], nblocks, sel_out, results_out));
+  return 0;
+}
+
 const char *fastc_gpu_last_error(void) { return tl_error; }
 
 }  // extern "C"

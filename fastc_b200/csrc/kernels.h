@@ -24,6 +24,8 @@ struct Bc7Workspace {
   void *base = nullptr;
   size_t bytes = 0;
   uint32_t *host_count = nullptr;  // pinned, 1 word (count_solid result)
+  uint32_t *wm_running = nullptr;  // device: watermark base of the chunk being packed
+  unsigned long long *counters = nullptr;  // device: [0] QuantizedError calls, [1] pixel-bucket evaluations
 };
 void bc7_free_workspace(Bc7Workspace &ws);
 
@@ -36,6 +38,9 @@ cudaError_t launch_bc7(Bc7Workspace &ws, const void *rgba_dev, uint32_t width, u
 
 cudaError_t bc7_count_solid(Bc7Workspace &ws, const void *rgba_dev, uint32_t width, uint32_t first_block,
                             uint32_t num_blocks, cudaStream_t stream, uint32_t *count_out);
+
+// Debug: copies sel[nblocks] then results[nblocks][16][8] of the last launch_bc7 (<= one chunk).
+cudaError_t bc7_debug_dump(Bc7Workspace &ws, uint32_t nblocks, uint32_t *sel_out, uint32_t *results_out);
 
 cudaError_t bc7_read_counters(Bc7Workspace &ws, uint64_t *qe_calls, uint64_t *pbe);
 

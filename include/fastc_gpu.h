@@ -113,6 +113,11 @@ int fastc_gpu_count_solid_device(const void *rgba_dev, uint32_t width, uint32_t 
  * maintained when the library is built with -DFASTC_GPU_COUNTERS. */
 int fastc_gpu_bc7_counters(uint64_t *qe_calls, uint64_t *pixel_bucket_evals);
 
+/* Diagnostics: after a BPTC fastc_gpu_compress_device call of nblocks (<= 2^19)
+ * blocks on this device, copies the per-block selection word and the per-chain
+ * fit results (nblocks x 16 slots x 8 words) out of the scratch. */
+int fastc_gpu_debug_bc7_dump(uint32_t nblocks, uint32_t *sel_out, uint32_t *results_out);
+
 const char *fastc_gpu_last_error(void);
 
 #ifdef __cplusplus

@@ -88,6 +88,11 @@ inline uint32_t chain_seed(uint64_t seed, uint32_t block, uint32_t chain) {
   return fmix32(h + fmix32(block * 64u + chain));
 }
 
+// debug: error of every chain of the most recently compressed block, by chain id
+static double g_dbg_chain_err[64];
+
+static uint64_t g_last_qe = 0, g_last_pbe = 0;
+
 struct Ctx {
   int sa_steps;
   int rng_mode;       // 0 global LCG, 1 keyed per chain
@@ -851,6 +856,7 @@ struct Mode {
             V4 v1 = splat(-1.0f), v2 = splat(-1.0f);
             const int chain_id = mode * 8 + (mode == 4 ? r * 2 + im : r);
             const double err = compress_cluster_alpha(cluster, v1, v2, indices, alpha_indices, chain_id);
+            g_dbg_chain_err[chain_id] = err;
             if (err < best) {
               best = err;
               memcpy(params.indices[cidx], indices, 16);
@@ -865,8 +871,10 @@ struct Mode {
         total += best;
       } else {
         const int chain_id = mode * 8 + chain_slot * 4 + cidx;
-        total += compress_cluster(cluster, params.p1[cidx], params.p2[cidx], indices, params.pbit_combo[cidx],
-                                  chain_id);
+        const double cerr = compress_cluster(cluster, params.p1[cidx], params.p2[cidx], indices,
+                                             params.pbit_combo[cidx], chain_id);
+        g_dbg_chain_err[chain_id] = cerr;
+        total += cerr;
         int k = 0;
         for (int i = 0; i < 16; i++)
           if (subset_of(i, shape_idx, A.subsets) == cidx) params.indices[cidx][i] = indices[k++];
@@ -1109,12 +1117,10 @@ bool compress_block(Ctx &cx, const uint32_t block[16], uint8_t *out, uint32_t wm
 
 }  // namespace
 
-static uint64_t g_last_qe = 0, g_last_pbe = 0;
 
-extern "C" void fastc_oracle_bc7(const uint8_t *rgba, uint32_t width, uint32_t height, uint32_t first_block,
-                                 uint32_t num_blocks, uint8_t *out, int quality, int rng_mode,
-                                 uint32_t *lcg_state, uint64_t seed, uint32_t wm_base) {
-  (void)height;
+static void run_bc7(const uint8_t *rgba, uint32_t width, uint32_t first_block, uint32_t num_blocks, uint8_t *out,
+                    int quality, int rng_mode, uint32_t *lcg_state, uint64_t seed, uint32_t wm_base,
+                    uint32_t block_index_base) {
   const uint32_t bw = width / 4;
   Ctx cx;
   cx.sa_steps = quality;
@@ -1128,15 +1134,40 @@ extern "C" void fastc_oracle_bc7(const uint8_t *rgba, uint32_t width, uint32_t h
     uint32_t block[16];
     for (int j = 0; j < 4; j++)
       memcpy(block + 4 * j, rgba + ((size_t)(by * 4 + j) * width + bx * 4) * 4, 16);
-    cx.block = bi;
+    cx.block = block_index_base + bi;
+    for (int k = 0; k < 64; k++) g_dbg_chain_err[k] = -1.0;
     if (compress_block(cx, block, out + (size_t)bi * 16, wm)) wm++;
   }
   g_last_qe = cx.qe_calls;
   g_last_pbe = cx.pbe;
 }
 
+extern "C" void fastc_oracle_bc7(const uint8_t *rgba, uint32_t width, uint32_t height, uint32_t first_block,
+                                 uint32_t num_blocks, uint8_t *out, int quality, int rng_mode,
+                                 uint32_t *lcg_state, uint64_t seed, uint32_t wm_base) {
+  (void)height;
+  run_bc7(rgba, width, first_block, num_blocks, out, quality, rng_mode, lcg_state, seed, wm_base, 0);
+}
+
+// Keyed-RNG variant for a buffer that is a slab of a larger texture: block_index_base
+// is the raster index of the buffer's block 0 in the full texture (same meaning as in
+// include/fastc_gpu.h).
+extern "C" void fastc_oracle_bc7_keyed(const uint8_t *rgba, uint32_t width, uint32_t height, uint32_t first_block,
+                                       uint32_t num_blocks, uint8_t *out, int quality, uint64_t seed,
+                                       uint32_t wm_base, uint32_t block_index_base) {
+  (void)height;
+  uint32_t dummy = 0;
+  run_bc7(rgba, width, first_block, num_blocks, out, quality, 1, &dummy, seed, wm_base, block_index_base);
+}
+
 // Work counters of the last fastc_oracle_bc7 call (SURVEY.md §8d op model).
 extern "C" void fastc_oracle_bc7_counters(uint64_t *qe_calls, uint64_t *pbe) {
   *qe_calls = g_last_qe;
   *pbe = g_last_pbe;
+}
+
+// Debug: per-chain errors (index = chain id, -1 = chain not run) of the LAST block of the
+// last fastc_oracle_bc7 call.
+extern "C" void fastc_oracle_bc7_chain_errors(double *out64) {
+  for (int k = 0; k < 64; k++) out64[k] = g_dbg_chain_err[k];
 }
