@@ -76,7 +76,7 @@ class GpuLibrary:
         "fastc_gpu_device_count", "fastc_gpu_init", "fastc_gpu_shutdown", "fastc_gpu_block_bytes",
         "fastc_gpu_compressed_size", "fastc_gpu_compress", "fastc_gpu_compress_batch",
         "fastc_gpu_compress_device", "fastc_gpu_count_solid_device", "fastc_gpu_bc7_counters",
-        "fastc_gpu_debug_bc7_dump",
+        "fastc_gpu_debug_bc7_dump", "fastc_gpu_bc7_stage_ms",
         "fastc_gpu_last_error",
     ]
 
@@ -101,6 +101,7 @@ class GpuLibrary:
         L.fastc_gpu_count_solid_device.argtypes = [vp, u32, u32, u32, u32, vp, C.POINTER(u32)]
         L.fastc_gpu_bc7_counters.argtypes = [C.POINTER(u64), C.POINTER(u64)]
         L.fastc_gpu_debug_bc7_dump.argtypes = [u32, vp, vp]
+        L.fastc_gpu_bc7_stage_ms.argtypes = [i, C.POINTER(C.c_double)]
         L.fastc_gpu_last_error.restype = C.c_char_p
 
     def error(self) -> str:
@@ -173,6 +174,14 @@ class GpuLibrary:
         self.check(self.cdll.fastc_gpu_count_solid_device(rgba_dev.data_ptr(), width, height, first_block,
                                                           num_blocks, stream, C.byref(n)))
         return n.value
+
+
+    def bc7_stage_ms(self, enable: bool = True, read: bool = True):
+        """Arms / reads the per-stage CUDA-event timing of the BC7 pipeline (ms):
+        {classify+scan, select, chains, pack, total} of the last device-API call."""
+        arr = (C.c_double * 5)()
+        self.check(self.cdll.fastc_gpu_bc7_stage_ms(int(enable), arr if read else None))
+        return dict(zip(("classify", "select", "chains", "pack", "total"), arr)) if read else None
 
 
 _lib: GpuLibrary | None = None

@@ -1327,6 +1327,9 @@ void bc7_free_workspace(Bc7Workspace &ws) {
   if (ws.host_count) cudaFreeHost(ws.host_count);
   if (ws.wm_running) cudaFree(ws.wm_running);
   if (ws.counters) cudaFree(ws.counters);
+  for (auto &row : ws.ev)
+    for (auto &evn : row)
+      if (evn) { cudaEventDestroy(evn); evn = nullptr; }
   ws.base = nullptr; ws.bytes = 0; ws.host_count = nullptr; ws.wm_running = nullptr; ws.counters = nullptr;
 }
 
@@ -1353,17 +1356,29 @@ cudaError_t launch_bc7(Bc7Workspace &wsp, const void *rgba_dev, uint32_t width, 
 #endif
   bc7_set_u32<<<1, 1, 0, stream>>>(wsp.wm_running, wm_base);
   n++;
+  wsp.timed_chunks = 0;
   for (uint32_t off = 0; off < num_blocks; off += chunk) {
     const uint32_t nb = num_blocks - off < chunk ? num_blocks - off : chunk;
     const uint32_t fb = first_block + off;
     const uint32_t ntiles = (nb + kTile - 1) / kTile;
+    cudaEvent_t *ev = nullptr;
+    if (wsp.timing && wsp.timed_chunks < Bc7Workspace::kMaxTimedChunks) {
+      ev = wsp.ev[wsp.timed_chunks++];
+      for (int k = 0; k < 5; k++)
+        if (!ev[k] && (e = cudaEventCreate(&ev[k])) != cudaSuccess) return e;
+      cudaEventRecord(ev[0], stream);
+    }
     bc7_classify<<<ntiles, kTile, 0, stream>>>(img, width, bx, fb, nb, ws.sel, ws.tile_count);
     bc7_wm_scan<<<1, 1024, 0, stream>>>(ws.tile_count, ntiles, ws.total_solid);
+    if (ev) cudaEventRecord(ev[1], stream);
     bc7_select<<<(nb + kSelWarps - 1) / kSelWarps, kSelWarps * 32, 0, stream>>>(img, width, bx, fb, nb, ws.sel);
+    if (ev) cudaEventRecord(ev[2], stream);
     const uint64_t nthreads = (uint64_t)nb * kSlots;
     bc7_chains<<<(uint32_t)((nthreads + kChainThreads - 1) / kChainThreads), kChainThreads, 0, stream>>>(
         img, width, bx, fb, nb, ws, quality, seed, block_index_base);
+    if (ev) cudaEventRecord(ev[3], stream);
     bc7_pack<<<(nb + 127) / 128, 128, 0, stream>>>(img, width, bx, fb, nb, ws, static_cast<uint8_t *>(out_dev));
+    if (ev) cudaEventRecord(ev[4], stream);
     n += 5;
     if (off + chunk < num_blocks) {
       bc7_add_u32<<<1, 1, 0, stream>>>(wsp.wm_running, ws.total_solid);
@@ -1402,6 +1417,25 @@ cudaError_t bc7_debug_dump(Bc7Workspace &wsp, uint32_t nblocks, uint32_t *sel_ou
   e = cudaMemcpy(sel_out, ws.sel, (size_t)nblocks * 4, cudaMemcpyDeviceToHost);
   if (e != cudaSuccess) return e;
   return cudaMemcpy(results_out, ws.results, (size_t)nblocks * kSlots * kResWords * 4, cudaMemcpyDeviceToHost);
+}
+
+cudaError_t bc7_stage_timing(Bc7Workspace &wsp, int enable, double *ms5) {
+  if (ms5) {
+    for (int k = 0; k < 5; k++) ms5[k] = 0.0;
+    for (int c = 0; c < wsp.timed_chunks; c++) {
+      cudaError_t e = cudaEventSynchronize(wsp.ev[c][4]);
+      if (e != cudaSuccess) return e;
+      for (int k = 0; k < 4; k++) {
+        float ms = 0;
+        e = cudaEventElapsedTime(&ms, wsp.ev[c][k], wsp.ev[c][k + 1]);
+        if (e != cudaSuccess) return e;
+        ms5[k] += ms;
+        ms5[4] += ms;
+      }
+    }
+  }
+  wsp.timing = enable != 0;
+  return cudaSuccess;
 }
 
 cudaError_t bc7_read_counters(Bc7Workspace &wsp, uint64_t *qe_calls, uint64_t *pbe) {

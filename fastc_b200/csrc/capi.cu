@@ -144,6 +144,41 @@ int enqueue(int dev, int ws_slot, int format, const void *rgba_dev, uint32_t wid
   return 0;
 }
 
+// Solid-colour blocks in the raster range [lo, hi) of a host image (64 B compare per
+// block, split over a few host threads).  Solid-ness depends on the input only, so
+// the BC7 watermark order (Compressor.cpp:135-140,1457) can be fixed before encoding.
+uint32_t host_count_solid(const uint8_t *rgba_host, uint32_t width, uint32_t lo, uint32_t hi) {
+  if (hi <= lo) return 0;
+  const uint32_t bx = width / 4;
+  const uint32_t *img = reinterpret_cast<const uint32_t *>(rgba_host);
+  auto count = [&](uint32_t a, uint32_t b) {
+    uint32_t cnt = 0;
+    for (uint32_t bi = a; bi < b; bi++) {
+      const uint32_t *p = img + (size_t)(bi / bx) * 4 * width + (size_t)(bi % bx) * 4;
+      const uint32_t v = p[0];
+      bool same = true;
+      for (int j = 0; j < 4 && same; j++)
+        for (int i = 0; i < 4; i++)
+          if (p[(size_t)j * width + i] != v) { same = false; break; }
+      cnt += same;
+    }
+    return cnt;
+  };
+  const uint32_t n = hi - lo;
+  const int nt = (int)std::min<uint32_t>(8, std::max<uint32_t>(1, n >> 16));
+  if (nt == 1) return count(lo, hi);
+  std::vector<uint32_t> part(nt, 0);
+  std::vector<std::thread> th;
+  for (int k = 0; k < nt; k++)
+    th.emplace_back([&, k] {
+      part[k] = count(lo + (uint32_t)((uint64_t)n * k / nt), lo + (uint32_t)((uint64_t)n * (k + 1) / nt));
+    });
+  for (auto &t : th) t.join();
+  uint32_t total = 0;
+  for (uint32_t c : part) total += c;
+  return total;
+}
+
 struct Shard {
   int dev;
   uint32_t first_block, num_blocks;  // within the image
@@ -168,14 +203,19 @@ int run_shard(Shard &s, int format, const uint8_t *rgba_host, uint32_t width, ui
   const uint32_t row0 = s.first_block / bx;
   const uint32_t row1 = (s.first_block + s.num_blocks + bx - 1) / bx;
   uint32_t rows_per_chunk;
-  if (chunk_blocks == 0) {
+  if (chunk_blocks == 0 && format == FASTC_GPU_BPTC) {
+    // BC7 is compute-bound (copies are ~1% of the time) and its watermark chain is kept
+    // on the device inside one submission: no host-side chunking unless asked for.
+    rows_per_chunk = row1 - row0;
+  } else if (chunk_blocks == 0) {
     // auto: ~4 Mi pixels per chunk keeps the copy engines busy without making the
-    // pipeline too coarse; BC7 is compute-bound so larger chunks are fine too.
+    // pipeline too coarse.
     rows_per_chunk = std::max<uint32_t>(1, (1u << 18) / bx);
   } else {
     rows_per_chunk = std::max<uint32_t>(1, chunk_blocks / bx);
   }
   const uint32_t total_rows = row1 - row0;
+  rows_per_chunk = std::max<uint32_t>(1, rows_per_chunk);
   const uint32_t nchunks = (total_rows + rows_per_chunk - 1) / rows_per_chunk;
   // BC7's watermark chain needs the solid-block count of every earlier chunk;
   // bc7 tracks that itself when the whole shard is submitted as one range, so
@@ -358,33 +398,19 @@ int fastc_gpu_compress(int format, const uint8_t *rgba_host, uint32_t width, uin
     shards[g].first_block = lo;
     shards[g].num_blocks = hi > lo ? hi - lo : 0;
   }
-  // BC7 watermark chain across shards: the word index of a solid block is the
-  // number of solid blocks before it in raster order (reference: process-global
-  // counter, Compressor.cpp:135-140,1457).  Solid-ness only depends on the
-  // input, so count on the host side of each later shard's predecessor cheaply:
-  // a 64 B compare per block, done by the shard threads below before encoding.
-  if (format == FASTC_GPU_BPTC && num_gpus > 1) {
-    std::vector<uint32_t> counts(num_gpus, 0);
-    std::vector<std::thread> th;
-    for (int g = 0; g + 1 < num_gpus; g++)
-      th.emplace_back([&, g] {
-        uint32_t cnt = 0;
-        const uint32_t *img = reinterpret_cast<const uint32_t *>(rgba_host);
-        for (uint32_t bi = shards[g].first_block; bi < shards[g].first_block + shards[g].num_blocks; bi++) {
-          const uint32_t *p = img + (size_t)(bi / bx) * 4 * width + (size_t)(bi % bx) * 4;
-          const uint32_t v = p[0];
-          bool same = true;
-          for (int j = 0; j < 4 && same; j++)
-            for (int i = 0; i < 4; i++)
-              if (p[(size_t)j * width + i] != v) { same = false; break; }
-          cnt += same;
-        }
-        counts[g] = cnt;
-      });
-    for (auto &t : th) t.join();
-    uint32_t run = 0;
-    for (int g = 0; g < num_gpus; g++) { shards[g].wm_base = run; run += counts[g]; }
+  // BC7 watermark order: the word index of a solid block is the number of solid blocks
+  // before it in raster order over the WHOLE image (the reference's single-threaded
+  // process-global counter, Compressor.cpp:135-140,1457).  Counting on the host keeps a
+  // sub-range / sharded submission bit-identical to the same bytes of a full submission.
+  if (format == FASTC_GPU_BPTC) {
+    uint32_t run = host_count_solid(rgba_host, width, 0, first_block);
+    for (int g = 0; g < num_gpus; g++) {
+      shards[g].wm_base = run;
+      if (g + 1 < num_gpus)
+        run += host_count_solid(rgba_host, width, shards[g].first_block, shards[g].first_block + shards[g].num_blocks);
+    }
   }
+  if (num_gpus == 1) cudaGetDevice(&shards[0].dev);  // one GPU: the caller's current device
 
   if (num_gpus == 1) {
     shards[0].rc = run_shard(shards[0], format, rgba_host, width, height, out_host, quality, seed, chunk_blocks);
@@ -437,6 +463,7 @@ int fastc_gpu_compress_batch(int format, const fastc_gpu_job *jobs, uint32_t num
     for (uint32_t j = g; j < num_jobs; j += num_gpus) {
       Shard s;
       s.dev = g;
+      if (num_gpus == 1) cudaGetDevice(&s.dev);
       s.first_block = 0;
       s.num_blocks = (jobs[j].width / 4) * (jobs[j].height / 4);
       if (run_shard(s, format, jobs[j].rgba_host, jobs[j].width, jobs[j].height, jobs[j].out_host, quality,
@@ -478,6 +505,15 @@ int fastc_gpu_bc7_counters(uint64_t *qe_calls, uint64_t *pixel_bucket_evals) {
   DeviceCtx &c = g_ctx[dev];
   std::lock_guard<std::mutex> lk(c.mu);
   CU_TRY(bc7_read_counters(c.bc7ws[kPipeDepth], qe_calls, pixel_bucket_evals));
+  return 0;
+}
+
+int fastc_gpu_bc7_stage_ms(int enable, double *ms5) {
+  int dev = 0;
+  CU_TRY(cudaGetDevice(&dev));
+  DeviceCtx &c = g_ctx[dev];
+  std::lock_guard<std::mutex> lk(c.mu);
+  CU_TRY(bc7_stage_timing(c.bc7ws[kPipeDepth], enable, ms5));
   return 0;
 }
 
