@@ -14,7 +14,7 @@ the compressed slabs gathered to rank 0 over NCCL/NVLink.
 `e2e`    = the same metric through the C ABI's host-pointer entry
            (fastc_gpu_compress: what FasTC's CompressImageData binds to) with
            pinned HOST buffers -- H2D and D2H inside the timed region.
-`roofline` describes the dominant kernel (bc7_chains).  BC7 is an ALU-issue
+`roofline` describes the dominant kernel (bc7_anneal).  BC7 is an ALU-issue
            bound per-block search, so besides the HBM figure the schema asks for
            we report lane-instruction throughput against the chip's issue peak.
 `cpu_baseline` = the UNMODIFIED reference (oracle/_ref/libfastc_ref.so, built from
@@ -232,7 +232,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         step_device()
         ev[k][1].record()
         st = g.bc7_stage_ms(enable=True, read=True)  # syncs on this step's stage events
-        chains_ms.append(st["chains"]); stage_tot.append(st)
+        chains_ms.append(st["anneal"]); stage_tot.append(st)
     barrier()
     t_wall = time.perf_counter() - t_wall0
     step_ms = [a.elapsed_time(b) for a, b in ev]
@@ -272,7 +272,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     value = mpix / (ms_per_step / 1e3)
     e2e_value = mpix / (e2e_s / args.steps)
 
-    # ---- roofline of the dominant kernel (bc7_chains), rank 0's slab
+    # ---- roofline of the dominant kernel (bc7_anneal), rank 0's slab
     hbm_peak, peak_src = load_peaks()
     k_ms = sum(chains_ms) / len(chains_ms)
     share = k_ms / (sum(s["total"] for s in stage_tot) / len(stage_tot))
@@ -280,12 +280,12 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     lane_ops = nblk * LANE_OPS_PER_BLOCK / (k_ms / 1e3)
     roofline = {
         "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-        "frac": achieved_gbs / hbm_peak, "traffic": None, "kernel": "bc7_chains",
+        "frac": achieved_gbs / hbm_peak, "traffic": None, "kernel": "bc7_anneal",
         "kernel_ms": k_ms, "kernel_share_of_step": share, "peak_source": peak_src,
         "note": "BC7 is ALU-issue bound, not HBM bound (SURVEY 8d): see alu_issue",
         "alu_issue": {"achieved_lane_ops_per_s": lane_ops, "peak_lane_ops_per_s": ALU_PEAK_LANE_OPS,
                       "frac": lane_ops / ALU_PEAK_LANE_OPS,
-                      "model": "1.2e6 lane-ops per block at -q 50 (SURVEY 8d op model) / bc7_chains time; "
+                      "model": "1.2e6 lane-ops per block at -q 50 (SURVEY 8d op model) / bc7_anneal time; "
                                "peak = 148 SM x 128 lanes x 1.965 GHz"},
         "stages_ms": {k: sum(s[k] for s in stage_tot) / len(stage_tot) for k in stage_tot[0]},
     }
@@ -341,7 +341,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--size", type=int, default=8192,
+                    help="profiling only: square texture size (the reported benchmark is the default 8192)")
     args = ap.parse_args()
+    global WIDTH, HEIGHT
+    WIDTH = HEIGHT = args.size
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

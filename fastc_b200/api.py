@@ -178,10 +178,10 @@ class GpuLibrary:
 
     def bc7_stage_ms(self, enable: bool = True, read: bool = True):
         """Arms / reads the per-stage CUDA-event timing of the BC7 pipeline (ms):
-        {classify+scan, select, chains, pack, total} of the last device-API call."""
-        arr = (C.c_double * 5)()
+        {classify+scan, select, setup(+sort), anneal, pack, total} of the last device-API call."""
+        arr = (C.c_double * 6)()
         self.check(self.cdll.fastc_gpu_bc7_stage_ms(int(enable), arr if read else None))
-        return dict(zip(("classify", "select", "chains", "pack", "total"), arr)) if read else None
+        return dict(zip(("classify", "select", "setup", "anneal", "pack", "total"), arr)) if read else None
 
 
 _lib: GpuLibrary | None = None

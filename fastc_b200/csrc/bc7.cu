@@ -74,6 +74,9 @@ struct Ws {
   uint32_t *tile_count; // [ntiles] solid blocks per tile, then exclusive-scanned in place
   uint32_t *total_solid;
   uint32_t *results;    // [nblocks][kSlots][kResWords]
+  uint32_t *states;     // [nblocks][kSlots][kStateWords] annealing start states
+  uint32_t *order;      // [nblocks*kSlots] chain ids sorted by descending cluster size
+  uint32_t *bins;       // histogram / offsets / cursors (see bc7_bin_offsets)
   const uint32_t *wm_running;    // watermark base of this chunk (device side, chunks chain without a host sync)
   unsigned long long *counters;  // qe calls, pbe
 };
@@ -516,11 +519,13 @@ struct FitResult {
   uint32_t err, p1, p2;
   int combo;
   unsigned long long indices;
+  bool need_sa;  // true: (p1, p2, combo, err) is the START state of the annealing chain
 };
 
 __device__ void fit_cluster(const Ws &ws, const ModeAttr &A, int mode, int idx_mode, int rot, const uint32_t *pts,
                             const uint32_t *pix, int n, const float avg[4], bool all_same, int sa_steps,
-                            uint32_t rng, const uint8_t *__restrict__ s_w, FitResult &R) {
+                            const uint8_t *__restrict__ s_w, FitResult &R) {
+  R.need_sa = false;
   const int ibits = idx_mode == 0 ? A.index_bits : A.alpha_index_bits;
   const int nb = 1 << ibits, nbm1 = nb - 1;
   const uint8_t *wtab = s_w + 16 * (ibits - 1);
@@ -776,90 +781,43 @@ __device__ void fit_cluster(const Ws &ws, const ModeAttr &A, int mode, int idx_m
   uint32_t cur1 = to_pixel_b(c1, qm, pb0), cur2 = to_pixel_b(c2, qm, pb1);  // idempotent: c1/c2 are on the grid
   uint32_t cur_err = qe_cluster(pts, pix, n, to_pixel_b(c1, qm, has_pbit ? pb0 : 0),
                                 to_pixel_b(c2, qm, has_pbit ? pb1 : 0), nbm1, wtab, nullptr);
-  uint32_t best_err = cur_err, best1 = cur1, best2 = cur2;
-  int cur_combo = combo, best_combo = combo;
-  uint32_t ncalls = 1;
-
-  int step[4];
-  step[0] = step[1] = step[2] = 1 << (8 - A.color_bits);
-  step[3] = 1 << (8 - A.alpha_bits);  // alpha_bits == 0 -> 256, zeroed below for opaque modes
-  if (mode < 4) step[(rot + 3) & 3] = 0;
-  const float inv_tm1 = (float)(sa_steps - 1);
-
-  for (int energy = 0; best_err > 0 && energy < sa_steps; energy++) {
-    // PickBestNeighboringEndpoints (:426-498)
-    int ncombo = 0;
-    if (has_pbit) ncombo = A.pbit == kPbitShared ? ((cur_combo + 1) & 1) : 3 - cur_combo;
-    int opb0, opb1;
-    pbit_combo(A.pbit, cur_combo, opb0, opb1);
-    uint32_t n1 = 0, n2 = 0;
-    bool visited = true;
-    int guard = -1;
-    while (visited && ++guard < 16) {
-#pragma unroll
-      for (int pt = 0; pt < 2; pt++) {  // pt = 0 moves endpoint 2 first (and reads p-bit [0] for it, as the reference does)
-        const uint32_t src = pt ? cur1 : cur2;
-        const uint32_t dir = lcg_next(rng) & 15;
-        const int old = pt ? opb1 : opb0;
-        uint32_t np = 0;
-#pragma unroll
-        for (int ch = 0; ch < 4; ch++) {
-          int v = chan(src, ch);
-          const bool neg = (dir >> ch) & 1;
-          if (has_pbit) {
-            if (neg && old == 0) v -= step[ch];
-            else if (!neg && old == 1) v += step[ch];
-          } else {
-            v += neg ? -step[ch] : step[ch];
-          }
-          v = min(max(v, 0), 255);
-          np |= (uint32_t)v << (8 * ch);
-        }
-        if (pt) n1 = np; else n2 = np;
-      }
-      visited = (best1 == n1) && (best2 == n2) && (best_combo == ncombo);
-    }
-    int npb0, npb1;
-    pbit_combo(A.pbit, ncombo, npb0, npb1);
-    const uint32_t q1 = to_pixel_b(n1, qm, has_pbit ? npb0 : 0), q2 = to_pixel_b(n2, qm, has_pbit ? npb1 : 0);
-    const uint32_t err = qe_cluster(pts, pix, n, q1, q2, nbm1, wtab, nullptr);
-    ncalls++;
-
-    // AcceptNewEndpointError (:524-536)
-    bool accept;
-    if (err < cur_err) {
-      accept = true;
-    } else {
-      const float temp = __fdiv_rn((float)energy, inv_tm1);
-      const double x = ((double)0.1f * ((double)cur_err - (double)err)) / (double)temp;
-      const double p = exp(x);
-      const uint32_t r = lcg_next(rng) & 0xFFFF;
-      const uint32_t m = ((r << 8) | (r >> 7)) & 0x7FFFFF;
-      const float fr = __fsub_rn(__uint_as_float((127u << 23) | m), 1.0f);
-      accept = (double)fr < p;
-    }
-    if (accept) { cur_err = err; cur1 = n1; cur2 = n2; cur_combo = ncombo; }
-    if (err < best_err) {
-      best_err = err; best1 = n1; best2 = n2; best_combo = ncombo;
-      energy = 0;  // restart; the loop increment makes it 1
-    }
+  COUNT_QE(ws, 1, 0);
+  if (sa_steps > 0 && cur_err > 0) {  // hand over to bc7_anneal
+    R.need_sa = true;
+    R.err = cur_err;
+    R.p1 = cur1; R.p2 = cur2; R.combo = combo;
+    R.indices = 0;
+    return;
   }
-  // indices belong to the evaluation that produced best_err (same quirky quantisation)
-  pbit_combo(A.pbit, best_combo, pb0, pb1);
-  const uint32_t f1 = to_pixel_b(best1, qm, has_pbit ? pb0 : 0), f2 = to_pixel_b(best2, qm, has_pbit ? pb1 : 0);
+  // no annealing: indices of the evaluation above (same quirky quantisation)
   unsigned long long indices;
-  qe_cluster(pts, pix, n, f1, f2, nbm1, wtab, &indices);
-  COUNT_QE(ws, ncalls, 0);
-  R.err = best_err;
-  R.p1 = best1; R.p2 = best2; R.combo = best_combo;
+  qe_cluster(pts, pix, n, to_pixel_b(c1, qm, has_pbit ? pb0 : 0), to_pixel_b(c2, qm, has_pbit ? pb1 : 0), nbm1, wtab,
+             &indices);
+  R.err = cur_err;
+  R.p1 = cur1; R.p2 = cur2; R.combo = combo;
   R.indices = indices;
 }
 
 constexpr int kChainThreads = 128;
 
+// Start state of one annealing chain (8 words), written by bc7_setup, read by bc7_anneal.
+//  w0: subset pixel mask [0:15] | mode [16:18] | rot [19:20] | idx_mode [21] | combo [22:23] | n [24:28] | valid [31]
+//  w1/w2: start endpoints (bytes on the grid)   w3: start error   w4: RNG state
+//  w5: alpha error (modes 4/5)   w6: rounded alpha endpoint bytes a1 | a2 << 8 (modes 4/5)
+constexpr int kStateWords = 8;
+
+__device__ __forceinline__ void write_state(const Ws &ws, uint32_t gid, uint32_t mask, const Chain &c, int n,
+                                            const FitResult &R, uint32_t rng, uint32_t alpha_err, uint32_t abytes) {
+  uint32_t *st = ws.states + (size_t)gid * kStateWords;
+  st[1] = R.p1; st[2] = R.p2; st[3] = R.err; st[4] = rng; st[5] = alpha_err; st[6] = abytes;
+  st[0] = mask | ((uint32_t)c.mode << 16) | ((uint32_t)c.rot << 19) | ((uint32_t)c.idx_mode << 21) |
+          ((uint32_t)R.combo << 22) | ((uint32_t)n << 24) | (1u << 31);
+  atomicAdd(&ws.bins[n], 1u);  // histogram by cluster size: bc7_anneal runs chains sorted by n
+}
+
 __global__ void __launch_bounds__(kChainThreads)
-bc7_chains(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, uint32_t first_block,
-           uint32_t num_blocks, Ws ws, int sa_steps, uint64_t seed, uint32_t block_index_base) {
+bc7_setup(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, uint32_t first_block,
+          uint32_t num_blocks, Ws ws, int sa_steps, uint64_t seed, uint32_t block_index_base) {
   __shared__ uint8_t s_w[64];
   if (threadIdx.x < 64) s_w[threadIdx.x] = c_weight[threadIdx.x];
   __syncthreads();
@@ -867,6 +825,7 @@ bc7_chains(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
   const uint32_t t = gid / kSlots;
   const int slot = gid % kSlots;
   if (t >= num_blocks) return;
+  ws.states[(size_t)gid * kStateWords] = 0;  // not (yet) an annealing chain
   const uint32_t selw = ws.sel[t];
   const Chain c = decode_chain(selw, slot);
   if (!c.active) return;
@@ -878,6 +837,7 @@ bc7_chains(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
   // Cluster of this chain: points in raster order of the subset (m_PointMap).
   uint32_t pts[16], pix[16];
   int n = 0;
+  uint32_t mask = 0;
   float sum[4] = {0, 0, 0, 0};
   uint32_t mn = 0xFFFFFFFFu, mx = 0;
 #pragma unroll
@@ -886,6 +846,7 @@ bc7_chains(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
       pix[n] = blk[i];
       pts[n] = blk[i];
       n++;
+      mask |= 1u << i;
 #pragma unroll
       for (int k = 0; k < 4; k++) sum[k] = __fadd_rn(sum[k], (float)chan(blk[i], k));  // exact integers
       mn = __vminu4(mn, blk[i]);
@@ -902,7 +863,11 @@ bc7_chains(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
   uint32_t *res = ws.results + ((size_t)t * kSlots + slot) * kResWords;
   FitResult R;
   if (!A.rotation) {
-    fit_cluster(ws, A, c.mode, 0, 0, pts, pix, n, avg, all_same, sa_steps, rng, s_w, R);
+    fit_cluster(ws, A, c.mode, 0, 0, pts, pix, n, avg, all_same, sa_steps, s_w, R);
+    if (R.need_sa) {
+      write_state(ws, gid, mask, c, n, R, rng, 0, 0);
+      return;
+    }
     res[0] = R.err; res[1] = R.p1; res[2] = R.p2; res[3] = (uint32_t)R.combo;
     res[4] = (uint32_t)R.indices; res[5] = (uint32_t)(R.indices >> 32);
     return;
@@ -924,7 +889,7 @@ bc7_chains(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
     amin = fminf(amin, (float)a);
     amax = fmaxf(amax, (float)a);
   }
-  fit_cluster(ws, A, c.mode, c.idx_mode, c.rot, pts, pix, 16, avg, all_same, sa_steps, rng, s_w, R);
+  fit_cluster(ws, A, c.mode, c.idx_mode, c.rot, pts, pix, 16, avg, all_same, sa_steps, s_w, R);
 
   const int abits = c.idx_mode == 0 ? A.alpha_index_bits : A.index_bits;
   const int nba = 1 << abits;
@@ -1028,11 +993,280 @@ bc7_chains(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
     }
   }
   // endpoints handed to Pack: rgb from the fit, alpha = the float a1/a2 (Pack rounds them)
+  res[6] = (uint32_t)aidx; res[7] = (uint32_t)(aidx >> 32);
+  if (R.need_sa) {
+    write_state(ws, gid, 0xFFFFu, c, 16, R, rng, alpha_err, round_byte(a1) | (round_byte(a2) << 8));
+    return;
+  }
   const uint32_t e1 = (R.p1 & 0x00FFFFFFu) | (round_byte(a1) << 24);
   const uint32_t e2 = (R.p2 & 0x00FFFFFFu) | (round_byte(a2) << 24);
   res[0] = R.err + alpha_err; res[1] = e1; res[2] = e2; res[3] = 0;
   res[4] = (uint32_t)R.indices; res[5] = (uint32_t)(R.indices >> 32);
-  res[6] = (uint32_t)aidx; res[7] = (uint32_t)(aidx >> 32);
+}
+
+// ------------------------------------------------------------------ annealing
+// bins layout (uint32): [0..16] chains per cluster size n, [32..48] start offset of bin n in the
+// sorted order (descending n), [64..80] scatter cursors, [96] total, [97] fetch cursor
+__global__ void bc7_bin_offsets(uint32_t *bins) {
+  uint32_t off = 0;
+  for (int n = 16; n >= 1; n--) {
+    bins[32 + n] = off;
+    off += bins[n];
+    bins[64 + n] = 0;
+  }
+  bins[96] = off;
+  bins[97] = 0;
+}
+
+__global__ void __launch_bounds__(256) bc7_scatter(Ws ws, uint32_t num_blocks) {
+  const uint32_t gid = blockIdx.x * 256 + threadIdx.x;
+  if (gid >= num_blocks * kSlots) return;
+  const uint32_t w0 = ws.states[(size_t)gid * kStateWords];
+  if (!(w0 >> 31)) return;
+  const uint32_t n = (w0 >> 24) & 31;
+  const uint32_t p = ws.bins[32 + n] + atomicAdd(&ws.bins[64 + n], 1u);
+  ws.order[p] = gid;
+}
+
+constexpr int kSaThreads = 128;
+constexpr int kSaCtasPerSm = 6;
+
+// OptimizeEndpointsForCluster (Compressor.cpp:538-630) as an all-integer state machine, one
+// chain per lane.  Lanes fetch the next chain from the n-sorted list as soon as theirs ends,
+// so a warp stays full until the list runs dry (the reference's chains have very uneven
+// lengths: every new best restarts the schedule).
+//
+// Per evaluation (QuantizedError, RGBAEndpoints.cpp:190-310) the work is arranged as
+//   palette[j] = interpolated colour of bucket j (packed bytes), B2[j] = |palette[j]|^2
+//   error(pixel, j) = |pixel|^2 + B2[j] - 2 * dp4a(pixel, palette[j])          (exact integers)
+// and the projection that picks the two candidate buckets uses one float multiply by a
+// per-call reciprocal; whenever that product lands within 2^-16 of an integer (where the
+// reference's own rounding could fall on the other side) the reference's exact division
+// sequence is replayed instead.
+struct SaConst {
+  uint32_t qm, stepb;  // quantisation mask; per-channel step bytes
+  int n, nbm1, woff, pbit, has_pbit;
+};
+
+__device__ __forceinline__ uint32_t move_endpoint(uint32_t src, uint32_t dir, int old_pbit, int has_pbit,
+                                                  uint32_t stepb) {
+  uint32_t np = 0;
+#pragma unroll
+  for (int ch = 0; ch < 4; ch++) {
+    int v = chan(src, ch);
+    const int st = chan(stepb, ch);
+    const bool neg = (dir >> ch) & 1;
+    int delta;
+    if (has_pbit) delta = (neg && old_pbit == 0) ? -st : ((!neg && old_pbit == 1) ? st : 0);
+    else delta = neg ? -st : st;
+    v = min(max(v + delta, 0), 255);
+    np |= (uint32_t)v << (8 * ch);
+  }
+  return np;
+}
+
+// Evaluate one cluster against quantised endpoints q1/q2.  WITH_IDX also returns the indices.
+template <bool WITH_IDX>
+__device__ __forceinline__ uint32_t sa_eval(uint32_t (*s_pix)[kSaThreads], uint32_t (*s_pts)[kSaThreads],
+                                            uint32_t (*s_pal)[kSaThreads], uint32_t (*s_b2)[kSaThreads],
+                                            const uint8_t *__restrict__ s_w, int tid, const SaConst &K, uint32_t q1,
+                                            uint32_t q2, unsigned long long *indices) {
+  int e1[4], d[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) { e1[k] = chan(q1, k); d[k] = chan(q2, k) - e1[k]; }
+  const uint32_t d11 = __dp4a(q1, q1, 0u), d12 = __dp4a(q1, q2, 0u), d22 = __dp4a(q2, q2, 0u);
+  const int cq = (int)d12 - (int)d11;                       // e1 . (e2 - e1)
+  const int den = (int)d22 - 2 * (int)d12 + (int)d11;       // |e2 - e1|^2
+  for (int j = 0; j <= K.nbm1; j++) {
+    const int w = s_w[K.woff + j];
+    uint32_t pal = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) pal |= (uint32_t)((e1[k] + ((d[k] * w + 32) >> 6)) & 0xFF) << (8 * k);
+    s_pal[j][tid] = pal;
+    s_b2[j][tid] = __dp4a(pal, pal, 0u);
+  }
+  const float fden = (float)den, fnb = (float)K.nbm1;
+  const float inv16 = den ? __fdiv_rn(__fmul_rn(65536.0f, fnb), fden) : 0.0f;
+  uint32_t total = 0;
+  unsigned long long idx = 0;
+  for (int i = 0; i < K.n; i++) {
+    const uint32_t px = s_pix[i][tid], pt = s_pts[i][tid];
+    const int num = (int)__dp4a(pt, q2, 0u) - (int)__dp4a(pt, q1, 0u) - cq;  // (pt - e1) . (e2 - e1), exact
+    const float fnum = (float)num;
+    const int v = __float2int_rd(__fmul_rn(fnum, inv16));
+    int j1 = v >> 16;
+    const int fb = v & 0xFFFF;
+    bool two = (j1 >= 0) && (j1 < K.nbm1);
+    int ja = min(max(j1, 0), K.nbm1);
+    if (den == 0) {
+      ja = 0; two = false;  // both endpoints equal: bucket 0 (RGBAEndpoints.cpp:226-251)
+    } else if ((fb == 0 || fb == 0xFFFF) && j1 >= -1 && j1 <= K.nbm1) {
+      // too close to a bucket boundary for the fast product: replay the reference's float sequence
+      const float t = __fmul_rn(__fdiv_rn(fnum, fden), fnb);
+      int x1 = (int)floorf(t), x2 = (int)ceilf(t);
+      x1 = min(max(0, x1), K.nbm1);
+      x2 = min(x2, K.nbm1);
+      ja = x1;
+      two = x1 + 1 <= x2;
+    }
+    const int jb = min(ja + 1, K.nbm1);
+    const uint32_t a2 = __dp4a(px, px, 0u);
+    const uint32_t ea = a2 + s_b2[ja][tid] - 2u * __dp4a(px, s_pal[ja][tid], 0u);
+    const uint32_t eb = a2 + s_b2[jb][tid] - 2u * __dp4a(px, s_pal[jb][tid], 0u);
+    const bool pick_b = two && (eb < ea);
+    total += pick_b ? eb : ea;
+    if (WITH_IDX) idx |= (unsigned long long)(pick_b ? jb : ja) << (4 * i);
+  }
+  if (WITH_IDX) *indices = idx;
+  return total;
+}
+
+__global__ void __launch_bounds__(kSaThreads)
+bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, uint32_t first_block, Ws ws,
+           int sa_steps) {
+  __shared__ uint32_t s_pix[16][kSaThreads], s_pts[16][kSaThreads], s_pal[16][kSaThreads], s_b2[16][kSaThreads];
+  __shared__ uint8_t s_w[64];
+  if (threadIdx.x < 64) s_w[threadIdx.x] = c_weight[threadIdx.x];
+  __syncthreads();
+  const int tid = threadIdx.x;
+  const uint32_t total = ws.bins[96];
+  const float f_tm1 = (float)(sa_steps - 1);
+
+  bool have = false, dry = false;
+  SaConst K = {0, 0, 0, 0, 0, kPbitNone, 0};
+  uint32_t gid = 0, cur1 = 0, cur2 = 0, best1 = 0, best2 = 0, cur_err = 0, best_err = 0, rng = 0;
+  uint32_t alpha_err = 0, abytes = 0;
+  int cur_combo = 0, best_combo = 0, energy = 0, rotation = 0;
+#ifdef FASTC_GPU_COUNTERS
+  uint32_t ncalls = 0, npbe = 0;
+#endif
+
+  for (;;) {
+    if (!have && !dry) {
+      const uint32_t pos = atomicAdd(&ws.bins[97], 1u);
+      if (pos >= total) {
+        dry = true;
+      } else {
+        // ---- load a chain: constants of its mode, its pixels, its start state
+        gid = ws.order[pos];
+        const uint32_t *st = ws.states + (size_t)gid * kStateWords;
+        const uint32_t w0 = st[0];
+        const int mode = (w0 >> 16) & 7, rot = (w0 >> 19) & 3, idx_mode = (w0 >> 21) & 1;
+        const ModeAttr A = c_modes[mode];
+        const int ibits = idx_mode == 0 ? A.index_bits : A.alpha_index_bits;
+        K.qm = quant_mask(A);
+        K.n = (w0 >> 24) & 31;
+        K.nbm1 = (1 << ibits) - 1;
+        K.woff = 16 * (ibits - 1);
+        K.pbit = A.pbit;
+        K.has_pbit = A.pbit != kPbitNone;
+        uint32_t sc = 1u << (8 - A.color_bits), sa = A.alpha_bits ? (1u << (8 - A.alpha_bits)) : 0u;
+        K.stepb = sc | (sc << 8) | (sc << 16) | (sa << 24);
+        if (mode < 4) K.stepb &= ~(0xFFu << (8 * ((rot + 3) & 3)));  // opaque modes never move alpha (T3)
+        rotation = A.rotation;
+        cur1 = best1 = st[1]; cur2 = best2 = st[2];
+        cur_err = best_err = st[3];
+        rng = st[4]; alpha_err = st[5]; abytes = st[6];
+        cur_combo = best_combo = (w0 >> 22) & 3;
+        energy = 0;
+        const uint32_t t = gid / kSlots, bi = first_block + t;
+        const uint32_t *base = img + (size_t)(bi / blocks_x) * 4 * width + (size_t)(bi % blocks_x) * 4;
+        int k = 0;
+        for (int i = 0; i < 16; i++)
+          if ((w0 >> i) & 1) {
+            const uint32_t p = __ldg(base + (size_t)(i >> 2) * width + (i & 3));
+            uint32_t q = p;
+            if (rotation) {  // rotated point with alpha forced to 255; the error still uses p (T16)
+              if (rot) q = (p & ~(0xFFu << (8 * (rot - 1)))) | ((p >> 24) << (8 * (rot - 1)));
+              q |= 0xFF000000u;
+            }
+            s_pix[k][tid] = p;
+            s_pts[k][tid] = q;
+            k++;
+          }
+        have = true;
+      }
+    }
+    if (!__any_sync(0xffffffffu, have)) break;
+    if (!have) continue;
+
+    // ---- one annealing step
+    bool done = !(best_err > 0 && energy < sa_steps);
+    if (!done) {
+      // PickBestNeighboringEndpoints (:426-498)
+      int ncombo = 0;
+      if (K.has_pbit) ncombo = K.pbit == kPbitShared ? (cur_combo ^ 1) : 3 - cur_combo;
+      int opb0, opb1;
+      pbit_combo(K.pbit, cur_combo, opb0, opb1);
+      uint32_t n1, n2;
+      int guard = -1;
+      bool visited;
+      do {
+        // pt = 0 moves endpoint 2 first and (as the reference does) tests p-bit [0] for it
+        n2 = move_endpoint(cur2, lcg_next(rng) & 15, opb0, K.has_pbit, K.stepb);
+        n1 = move_endpoint(cur1, lcg_next(rng) & 15, opb1, K.has_pbit, K.stepb);
+        visited = (best1 == n1) && (best2 == n2) && (best_combo == ncombo);
+      } while (visited && ++guard < 15);
+      int npb0, npb1;
+      pbit_combo(K.pbit, ncombo, npb0, npb1);
+      // modes without p-bits evaluate with a zero p-bit (reference quirk, see fit_cluster)
+      const uint32_t q1 = to_pixel_b(n1, K.qm, K.has_pbit ? npb0 : 0), q2 = to_pixel_b(n2, K.qm, K.has_pbit ? npb1 : 0);
+      const uint32_t err = sa_eval<false>(s_pix, s_pts, s_pal, s_b2, s_w, tid, K, q1, q2, nullptr);
+#ifdef FASTC_GPU_COUNTERS
+      ncalls++; npbe += K.n;
+#endif
+      // AcceptNewEndpointError (:524-536)
+      bool accept;
+      if (err < cur_err) {
+        accept = true;
+      } else {
+        const uint32_t r = lcg_next(rng) & 0xFFFF;
+        const uint32_t m = ((r << 8) | (r >> 7)) & 0x7FFFFF;
+        const float fr = __fsub_rn(__uint_as_float((127u << 23) | m), 1.0f);
+        if (energy == 0) {
+          accept = false;  // temp == 0: exp(-inf) = 0, exp(NaN) = NaN -> never accepted
+        } else {
+          const float temp = __fdiv_rn((float)energy, f_tm1);
+          const float diff = (float)((int)cur_err - (int)err);  // exact (|.| < 2^24)
+          const float pf = __expf(__fdividef(0.1f * diff, temp));
+          if (fr < pf * (1.0f - 3e-5f)) accept = true;
+          else if (fr > pf * (1.0f + 3e-5f)) accept = false;
+          else {  // within the fast exponential's error band: the reference's double expression
+            const double x = ((double)0.1f * ((double)cur_err - (double)err)) / (double)temp;
+            accept = (double)fr < exp(x);
+          }
+        }
+      }
+      if (accept) { cur_err = err; cur1 = n1; cur2 = n2; cur_combo = ncombo; }
+      if (err < best_err) {
+        best_err = err; best1 = n1; best2 = n2; best_combo = ncombo;
+        energy = 0;  // restart; the increment below makes it 1
+      }
+      energy++;
+      done = !(best_err > 0 && energy < sa_steps);
+    }
+    if (done) {
+      // indices of the evaluation that produced best_err
+      int pb0, pb1;
+      pbit_combo(K.pbit, best_combo, pb0, pb1);
+      const uint32_t f1 = to_pixel_b(best1, K.qm, K.has_pbit ? pb0 : 0), f2 = to_pixel_b(best2, K.qm, K.has_pbit ? pb1 : 0);
+      unsigned long long indices;
+      sa_eval<true>(s_pix, s_pts, s_pal, s_b2, s_w, tid, K, f1, f2, &indices);
+      uint32_t *res = ws.results + (size_t)gid * kResWords;
+      uint32_t o1 = best1, o2 = best2;
+      if (rotation) {
+        o1 = (o1 & 0x00FFFFFFu) | ((abytes & 0xFF) << 24);
+        o2 = (o2 & 0x00FFFFFFu) | (((abytes >> 8) & 0xFF) << 24);
+      }
+      res[0] = best_err + alpha_err; res[1] = o1; res[2] = o2; res[3] = (uint32_t)best_combo;
+      res[4] = (uint32_t)indices; res[5] = (uint32_t)(indices >> 32);
+      have = false;
+    }
+  }
+#ifdef FASTC_GPU_COUNTERS
+  atomicAdd(&ws.counters[0], (unsigned long long)ncalls);
+  atomicAdd(&ws.counters[1], (unsigned long long)npbe);
+#endif
 }
 
 // ------------------------------------------------------------------ pack
@@ -1267,6 +1501,9 @@ size_t ws_bytes(uint32_t nblocks) {
   b += ((ntiles + 1) * 4 + 255) & ~(size_t)255;                  // tile counts
   b += 256;                                                      // total
   b += (size_t)nblocks * kSlots * kResWords * 4;                 // results
+  b += (size_t)nblocks * kSlots * 8 * 4;                         // states
+  b += (size_t)nblocks * kSlots * 4;                             // order
+  b += 512;                                                      // bins
   return b;
 }
 
@@ -1279,7 +1516,10 @@ Ws carve(void *base, uint32_t nblocks) {
   w.total_solid = reinterpret_cast<uint32_t *>(p); p += 256;
   w.counters = nullptr;
   w.wm_running = nullptr;
-  w.results = reinterpret_cast<uint32_t *>(p);
+  w.results = reinterpret_cast<uint32_t *>(p); p += (size_t)nblocks * kSlots * kResWords * 4;
+  w.states = reinterpret_cast<uint32_t *>(p); p += (size_t)nblocks * kSlots * 8 * 4;
+  w.order = reinterpret_cast<uint32_t *>(p); p += (size_t)nblocks * kSlots * 4;
+  w.bins = reinterpret_cast<uint32_t *>(p);
   return w;
 }
 
@@ -1330,6 +1570,8 @@ void bc7_free_workspace(Bc7Workspace &ws) {
   for (auto &row : ws.ev)
     for (auto &evn : row)
       if (evn) { cudaEventDestroy(evn); evn = nullptr; }
+  for (auto &evn : ws.ev_mid)
+    if (evn) { cudaEventDestroy(evn); evn = nullptr; }
   ws.base = nullptr; ws.bytes = 0; ws.host_count = nullptr; ws.wm_running = nullptr; ws.counters = nullptr;
 }
 
@@ -1357,6 +1599,10 @@ cudaError_t launch_bc7(Bc7Workspace &wsp, const void *rgba_dev, uint32_t width, 
   bc7_set_u32<<<1, 1, 0, stream>>>(wsp.wm_running, wm_base);
   n++;
   wsp.timed_chunks = 0;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const uint32_t sa_grid = (uint32_t)sms * kSaCtasPerSm;  // persistent lanes: a multiple of the SM count
   for (uint32_t off = 0; off < num_blocks; off += chunk) {
     const uint32_t nb = num_blocks - off < chunk ? num_blocks - off : chunk;
     const uint32_t fb = first_block + off;
@@ -1366,6 +1612,7 @@ cudaError_t launch_bc7(Bc7Workspace &wsp, const void *rgba_dev, uint32_t width, 
       ev = wsp.ev[wsp.timed_chunks++];
       for (int k = 0; k < 5; k++)
         if (!ev[k] && (e = cudaEventCreate(&ev[k])) != cudaSuccess) return e;
+      if (!wsp.ev_mid[wsp.timed_chunks - 1] && (e = cudaEventCreate(&wsp.ev_mid[wsp.timed_chunks - 1])) != cudaSuccess) return e;
       cudaEventRecord(ev[0], stream);
     }
     bc7_classify<<<ntiles, kTile, 0, stream>>>(img, width, bx, fb, nb, ws.sel, ws.tile_count);
@@ -1374,12 +1621,23 @@ cudaError_t launch_bc7(Bc7Workspace &wsp, const void *rgba_dev, uint32_t width, 
     bc7_select<<<(nb + kSelWarps - 1) / kSelWarps, kSelWarps * 32, 0, stream>>>(img, width, bx, fb, nb, ws.sel);
     if (ev) cudaEventRecord(ev[2], stream);
     const uint64_t nthreads = (uint64_t)nb * kSlots;
-    bc7_chains<<<(uint32_t)((nthreads + kChainThreads - 1) / kChainThreads), kChainThreads, 0, stream>>>(
+    cudaMemsetAsync(ws.bins, 0, 512, stream);
+    bc7_setup<<<(uint32_t)((nthreads + kChainThreads - 1) / kChainThreads), kChainThreads, 0, stream>>>(
         img, width, bx, fb, nb, ws, quality, seed, block_index_base);
+    n++;
+    if (quality > 0) {
+      bc7_bin_offsets<<<1, 1, 0, stream>>>(ws.bins);
+      bc7_scatter<<<(uint32_t)((nthreads + 255) / 256), 256, 0, stream>>>(ws, nb);
+      if (ev) cudaEventRecord(wsp.ev_mid[wsp.timed_chunks - 1], stream);
+      bc7_anneal<<<sa_grid, kSaThreads, 0, stream>>>(img, width, bx, fb, ws, quality);
+      n += 3;
+    } else if (ev) {
+      cudaEventRecord(wsp.ev_mid[wsp.timed_chunks - 1], stream);
+    }
     if (ev) cudaEventRecord(ev[3], stream);
     bc7_pack<<<(nb + 127) / 128, 128, 0, stream>>>(img, width, bx, fb, nb, ws, static_cast<uint8_t *>(out_dev));
     if (ev) cudaEventRecord(ev[4], stream);
-    n += 5;
+    n += 4;
     if (off + chunk < num_blocks) {
       bc7_add_u32<<<1, 1, 0, stream>>>(wsp.wm_running, ws.total_solid);
       n++;
@@ -1419,18 +1677,20 @@ cudaError_t bc7_debug_dump(Bc7Workspace &wsp, uint32_t nblocks, uint32_t *sel_ou
   return cudaMemcpy(results_out, ws.results, (size_t)nblocks * kSlots * kResWords * 4, cudaMemcpyDeviceToHost);
 }
 
-cudaError_t bc7_stage_timing(Bc7Workspace &wsp, int enable, double *ms5) {
-  if (ms5) {
-    for (int k = 0; k < 5; k++) ms5[k] = 0.0;
+cudaError_t bc7_stage_timing(Bc7Workspace &wsp, int enable, double *ms6) {
+  // ms6 = {classify+scan, select, setup(+sort), anneal, pack, total}
+  if (ms6) {
+    for (int k = 0; k < 6; k++) ms6[k] = 0.0;
     for (int c = 0; c < wsp.timed_chunks; c++) {
       cudaError_t e = cudaEventSynchronize(wsp.ev[c][4]);
       if (e != cudaSuccess) return e;
-      for (int k = 0; k < 4; k++) {
+      cudaEvent_t seq[6] = {wsp.ev[c][0], wsp.ev[c][1], wsp.ev[c][2], wsp.ev_mid[c], wsp.ev[c][3], wsp.ev[c][4]};
+      for (int k = 0; k < 5; k++) {
         float ms = 0;
-        e = cudaEventElapsedTime(&ms, wsp.ev[c][k], wsp.ev[c][k + 1]);
+        e = cudaEventElapsedTime(&ms, seq[k], seq[k + 1]);
         if (e != cudaSuccess) return e;
-        ms5[k] += ms;
-        ms5[4] += ms;
+        ms6[k] += ms;
+        ms6[5] += ms;
       }
     }
   }

@@ -508,12 +508,12 @@ int fastc_gpu_bc7_counters(uint64_t *qe_calls, uint64_t *pixel_bucket_evals) {
   return 0;
 }
 
-int fastc_gpu_bc7_stage_ms(int enable, double *ms5) {
+int fastc_gpu_bc7_stage_ms(int enable, double *ms6) {
   int dev = 0;
   CU_TRY(cudaGetDevice(&dev));
   DeviceCtx &c = g_ctx[dev];
   std::lock_guard<std::mutex> lk(c.mu);
-  CU_TRY(bc7_stage_timing(c.bc7ws[kPipeDepth], enable, ms5));
+  CU_TRY(bc7_stage_timing(c.bc7ws[kPipeDepth], enable, ms6));
   return 0;
 }
 

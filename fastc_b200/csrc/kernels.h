@@ -30,7 +30,8 @@ struct Bc7Workspace {
   bool timing = false;
   int timed_chunks = 0;
   static constexpr int kMaxTimedChunks = 64;
-  cudaEvent_t ev[kMaxTimedChunks][5] = {};  // device: [0] QuantizedError calls, [1] pixel-bucket evaluations
+  cudaEvent_t ev[kMaxTimedChunks][5] = {};
+  cudaEvent_t ev_mid[kMaxTimedChunks] = {};  // between setup(+sort) and anneal  // device: [0] QuantizedError calls, [1] pixel-bucket evaluations
 };
 void bc7_free_workspace(Bc7Workspace &ws);
 
@@ -47,7 +48,7 @@ cudaError_t bc7_count_solid(Bc7Workspace &ws, const void *rgba_dev, uint32_t wid
 // Debug: copies sel[nblocks] then results[nblocks][16][8] of the last launch_bc7 (<= one chunk).
 cudaError_t bc7_debug_dump(Bc7Workspace &ws, uint32_t nblocks, uint32_t *sel_out, uint32_t *results_out);
 
-cudaError_t bc7_stage_timing(Bc7Workspace &ws, int enable, double *ms5);
+cudaError_t bc7_stage_timing(Bc7Workspace &ws, int enable, double *ms6);
 
 cudaError_t bc7_read_counters(Bc7Workspace &ws, uint64_t *qe_calls, uint64_t *pbe);
 

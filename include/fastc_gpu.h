@@ -115,10 +115,10 @@ int fastc_gpu_bc7_counters(uint64_t *qe_calls, uint64_t *pixel_bucket_evals);
 
 /* Per-stage device time of the BC7 pipeline on this device's device-API context:
  * enable != 0 arms CUDA-event recording around each stage of subsequent
- * fastc_gpu_compress_device(BPTC) calls on their stream; ms5 (may be NULL) receives
- * the summed milliseconds of the LAST call's stages {classify+scan, select, chains,
- * pack, total}, synchronising on its events. */
-int fastc_gpu_bc7_stage_ms(int enable, double *ms5);
+ * fastc_gpu_compress_device(BPTC) calls on their stream; ms6 (may be NULL) receives
+ * the summed milliseconds of the LAST call's stages {classify+scan, select,
+ * setup(+sort), anneal, pack, total}, synchronising on its events. */
+int fastc_gpu_bc7_stage_ms(int enable, double *ms6);
 
 /* Diagnostics: after a BPTC fastc_gpu_compress_device call of nblocks (<= 2^19)
  * blocks on this device, copies the per-block selection word and the per-chain
