@@ -1,8 +1,381 @@
-// placeholder until the ETC1 kernel lands (fails loudly, no fallback)
+// ETC1 block encoder for sm_100a.
+//
+// Behavioural contract: bit-identical to rg_etc1 v1.04 driven the way the
+// reference drives it (cLowQuality, no dithering):
+//   reference/ETCEncoder/src/Compressor.cpp:26-54       block loop
+//   reference/ETCEncoder/src/rg_etc1.cpp:2192-2451      pack_etc1_block
+//   reference/ETCEncoder/src/rg_etc1.cpp:1483-1672      etc1_optimizer::compute / init
+//   reference/ETCEncoder/src/rg_etc1.cpp:1767-1885      evaluate_solution_fast
+//   reference/ETCEncoder/src/rg_etc1.cpp:1951-2033      pack_etc1_block_solid_color
+//
+// B200 mapping (not how the reference is organised): the reference walks the
+// four (flip, 444/555) candidates of a block one after the other with a
+// running-best early-out; the candidates are independent, so here a QUAD of
+// lanes owns a block and lane q evaluates candidate q (both sub-blocks, the
+// second constrained to the first's base colour in 555 differential mode).  A
+// quad shuffle-argmin with "lowest candidate index wins ties" reproduces the
+// reference's strict-< scan order, and the winning lane packs and stores the
+// 8 bytes.  Two observations remove the reference's data-dependent control flow:
+//   * evaluate_solution_fast's sorted-luma walk assigns pixel p the selector
+//     (2*luma_p >= mid0) + (2*luma_p >= mid1) + (2*luma_p >= mid2) because the
+//     midpoints are non-decreasing -- no sort is needed, only min / max luma for
+//     the two "skip this table" tests;
+//   * squared RGB distances are evaluated as |p|^2 + |c|^2 - 2 dp4a(p, c) on
+//     packed bytes (exact integers).
+// A CTA of 128 threads stages its 32 blocks (2 KiB) through shared memory with
+// 16 B coalesced row loads; stores are 8 B per block, contiguous per warp.
+#include <vector>
+
+#include "common.cuh"
 #include "kernels.h"
+
 namespace fastc {
-cudaError_t etc1_upload_tables() { return cudaSuccess; }
-cudaError_t launch_etc1(const void *, uint32_t, uint32_t, uint32_t, void *, cudaStream_t) {
-  return cudaErrorNotSupported;
+namespace {
+
+// ETC1 specification: intensity modifier tables (rg_etc1.cpp:371-375).
+__constant__ int c_inten[8][4] = {{-8, -2, 2, 8},     {-17, -5, 5, 17},   {-29, -9, 9, 29},    {-42, -13, 13, 42},
+                                  {-60, -18, 18, 60}, {-80, -24, 24, 80}, {-106, -33, 33, 106}, {-183, -47, 47, 183}};
+
+// Solid-colour tables (rg_etc1.cpp:385-507 and :1905-1936), derived on the host by
+// the rule the reference's arrays follow (see build_solid_tables) and uploaded once.
+constexpr int kMaxCfg = 4096;
+__device__ uint16_t g_cfg_off[257];
+__device__ uint16_t g_cfg[kMaxCfg];
+__device__ uint16_t g_inverse[64 * 256];
+
+__device__ __forceinline__ int clamp255(int v) { return min(max(v, 0), 255); }
+
+struct Sol {
+  uint32_t err;    // total squared error of the sub-block
+  uint32_t color;  // unscaled base colour r | g << 8 | b << 16
+  uint32_t sel;    // 8 x 2-bit selector indices, sub-block pixel order
+  int inten;
+};
+
+__device__ __forceinline__ uint32_t scale_color(uint32_t c, bool color4) {
+  // per byte: 4-bit -> c | c << 4, 5-bit -> c >> 2 | c << 3
+  return color4 ? (c | (c << 4)) : (((c >> 2) & 0x07070707u) | (c << 3));
 }
+
+// evaluate_solution_fast (rg_etc1.cpp:1767-1885) for base colour `color` (unscaled).
+// px: 8 packed pixels (alpha cleared), p2: their squared norms, luma2: 2 * (r+g+b).
+__device__ __forceinline__ void evaluate(const uint32_t (&px)[8], const uint32_t (&p2)[8], const uint32_t (&luma2)[8],
+                                         uint32_t lmin, uint32_t lmax, uint32_t color, bool color4, Sol &trial) {
+  const uint32_t base = scale_color(color, color4);
+  const int b0 = base & 0xFF, b1 = (base >> 8) & 0xFF, b2 = (base >> 16) & 0xFF;
+  trial.err = 0xFFFFFFFFu;
+  trial.color = color;
+  trial.inten = 0;
+  trial.sel = 0;
+#pragma unroll 1
+  for (int it = 7; it >= 0; --it) {
+    uint32_t bc[4], bc2[4], bi[4];
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+      const int yd = c_inten[it][s];
+      const uint32_t r = clamp255(b0 + yd), g = clamp255(b1 + yd), b = clamp255(b2 + yd);
+      bc[s] = r | (g << 8) | (b << 16);
+      bi[s] = r + g + b;
+      bc2[s] = __dp4a(bc[s], bc[s], 0u);
+    }
+    const uint32_t mid0 = bi[0] + bi[1], mid1 = bi[1] + bi[2], mid2 = bi[2] + bi[3];
+    // the two "all pixels beyond one end" cases may skip the table (rg_etc1.cpp:1809-1836)
+    if (lmax * 2 < mid0) {
+      if (bi[0] > lmax && bi[0] - lmax >= trial.err) continue;
+    } else if (lmin * 2 >= mid2) {
+      if (lmin > bi[3] && lmin - bi[3] >= trial.err) continue;
+    }
+    uint32_t total = 0, sel = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const bool g0 = luma2[i] >= mid0, g1 = luma2[i] >= mid1, g2 = luma2[i] >= mid2;
+      const uint32_t c = g2 ? bc[3] : (g1 ? bc[2] : (g0 ? bc[1] : bc[0]));
+      const uint32_t c2 = g2 ? bc2[3] : (g1 ? bc2[2] : (g0 ? bc2[1] : bc2[0]));
+      total += p2[i] + c2 - 2u * __dp4a(px[i], c, 0u);
+      sel |= ((uint32_t)g0 + (uint32_t)g1 + (uint32_t)g2) << (2 * i);
+    }
+    if (total < trial.err) {
+      trial.err = total;
+      trial.inten = it;
+      trial.sel = sel;
+      if (!total) break;
+    }
+  }
+}
+
+// etc1_optimizer::init + compute (rg_etc1.cpp:1627-1672, 1483-1625) for one 8-pixel
+// sub-block at cLowQuality (scan delta {0}: one lattice point, <= 2 refinement trials).
+// constrain: differential mode's second sub-block, base5 = first sub-block's colour.
+__device__ __forceinline__ bool optimize(const uint32_t (&px)[8], bool color4, bool constrain, uint32_t base5, Sol &best) {
+  const int limit = color4 ? 15 : 31;
+  uint32_t p2[8], luma2[8];
+  uint32_t sr = 0, sg = 0, sb = 0, lmin = 0xFFFFFFFFu, lmax = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const uint32_t r = px[i] & 0xFF, g = (px[i] >> 8) & 0xFF, b = px[i] >> 16;
+    sr += r; sg += g; sb += b;
+    const uint32_t l = r + g + b;
+    lmin = min(lmin, l);
+    lmax = max(lmax, l);
+    luma2[i] = 2 * l;
+    p2[i] = __dp4a(px[i], px[i], 0u);
+  }
+  const float flimit = (float)limit;
+  const float avg[3] = {__fmul_rn((float)sr, 0.125f), __fmul_rn((float)sg, 0.125f), __fmul_rn((float)sb, 0.125f)};
+  int m[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++)
+    m[k] = min(max(__float2int_rz(__fadd_rn(__fdiv_rn(__fmul_rn(avg[k], flimit), 255.0f), 0.5f)), 0), limit);
+
+  auto allowed = [&](int r, int g, int b) {
+    if (!constrain) return true;
+    const int dr = r - (int)(base5 & 0xFF), dg = g - (int)((base5 >> 8) & 0xFF), db = b - (int)(base5 >> 16);
+    return min(dr, min(dg, db)) >= -4 && max(dr, max(dg, db)) <= 3;
+  };
+
+  best.err = 0xFFFFFFFFu;
+  if (!allowed(m[0], m[1], m[2])) return false;
+  evaluate(px, p2, luma2, lmin, lmax, (uint32_t)m[0] | ((uint32_t)m[1] << 8) | ((uint32_t)m[2] << 16), color4, best);
+
+#pragma unroll 1
+  for (int trial = 0; trial < 2; trial++) {
+    const uint32_t base = scale_color(best.color, color4);
+    // sum of the clamped intensity deltas actually applied under the best selectors
+    int cnt[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const uint32_t s = (best.sel >> (2 * i)) & 3;
+#pragma unroll
+      for (int q = 0; q < 4; q++) cnt[q] += (s == (uint32_t)q);
+    }
+    int ds[3] = {0, 0, 0};
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+      const int yd = c_inten[best.inten][s];
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const int bk = (base >> (8 * k)) & 0xFF;
+        ds[k] += cnt[s] * (clamp255(bk + yd) - bk);
+      }
+    }
+    if (!ds[0] && !ds[1] && !ds[2]) break;
+    int n1[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const float ad = __fdiv_rn((float)ds[k], 8.0f);
+      const float f = __fadd_rn(__fdiv_rn(__fmul_rn(__fsub_rn(avg[k], ad), flimit), 255.0f), 0.5f);
+      n1[k] = min(max(__float2int_rz(f), 0), limit);  // x86 cvttss2si, then clamp<int>
+    }
+    if (n1[0] == m[0] && n1[1] == m[1] && n1[2] == m[2]) break;
+    const uint32_t ncol = (uint32_t)n1[0] | ((uint32_t)n1[1] << 8) | ((uint32_t)n1[2] << 16);
+    if (ncol == best.color) break;
+    if (!allowed(n1[0], n1[1], n1[2])) break;
+    Sol t;
+    evaluate(px, p2, luma2, lmin, lmax, ncol, color4, t);
+    if (t.err < best.err) best = t;
+    else break;
+  }
+  return true;
+}
+
+// pack_etc1_block_solid_color (rg_etc1.cpp:1951-2033)
+__device__ uint2 pack_solid(uint32_t pixel) {
+  const int col[3] = {(int)(pixel & 0xFF), (int)((pixel >> 8) & 0xFF), (int)((pixel >> 16) & 0xFF)};
+  const int next_comp[4] = {1, 2, 0, 1};
+  uint32_t best_error = 0xFFFFFFFFu, best_x = 0, best_c1 = 0, best_c2 = 0;
+  int best_i = 0;
+  bool perfect = false;
+  for (int i = 0; i < 3 && !perfect; i++) {
+    const int c1 = col[next_comp[i]], c2 = col[next_comp[i + 1]];
+    for (int delta = -1; delta <= 1 && !perfect; delta++) {
+      const int cpd = clamp255(col[i] + delta);
+      const int d0 = cpd - col[i];
+      for (uint32_t k = g_cfg_off[cpd]; k < g_cfg_off[cpd + 1]; k++) {
+        const uint32_t x = g_cfg[k];
+        const uint32_t p1 = g_inverse[(x & 0xFF) * 256 + c1], p2 = g_inverse[(x & 0xFF) * 256 + c2];
+        const uint32_t err = (uint32_t)(d0 * d0) + (p1 >> 8) * (p1 >> 8) + (p2 >> 8) * (p2 >> 8);
+        if (err < best_error) {
+          best_error = err; best_x = x; best_c1 = p1 & 0xFF; best_c2 = p2 & 0xFF; best_i = i;
+          if (!err) { perfect = true; break; }
+        }
+      }
+    }
+  }
+  const uint32_t diff = best_x & 1, inten = (best_x >> 1) & 7;
+  const uint32_t e = (0x4B >> (2 * ((best_x >> 4) & 3))) & 3;  // selector index -> ETC1 code {3,2,0,1}
+  uint32_t bytes[3];
+  const uint32_t vals[3] = {(best_x >> 8) & 255, best_c1, best_c2};
+  const int where[3] = {best_i, next_comp[best_i], next_comp[best_i + 1]};
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const uint32_t v = diff ? (vals[k] << 3) : (vals[k] | (vals[k] << 4));
+#pragma unroll
+    for (int w = 0; w < 3; w++)
+      if (where[k] == w) bytes[w] = v & 0xFF;
+  }
+  const uint32_t b3 = ((inten | (inten << 3)) << 2) | (diff << 1);
+  uint2 o;
+  o.x = bytes[0] | (bytes[1] << 8) | (bytes[2] << 16) | (b3 << 24);
+  o.y = ((e & 2) ? 0x0000FFFFu : 0u) | ((e & 1) ? 0xFFFF0000u : 0u);
+  return o;
+}
+
+constexpr int kEtcThreads = 128;
+constexpr int kEtcBlocksPerCta = kEtcThreads / 4;
+
+__global__ void __launch_bounds__(kEtcThreads)
+etc1_encode_kernel(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, uint32_t first_block,
+                   uint32_t num_blocks, uint2 *__restrict__ out) {
+  __shared__ uint32_t s_px[kEtcBlocksPerCta][17];  // +1 word: quads of a warp hit distinct banks
+  const int q = threadIdx.x >> 2, cand = threadIdx.x & 3;
+  const uint32_t t = blockIdx.x * kEtcBlocksPerCta + q;
+  const bool valid = t < num_blocks;
+  const uint32_t bi = first_block + (valid ? t : 0);
+  if (valid) {
+    // lane `cand` of the quad loads row `cand` of the block: 16 B, contiguous across the warp's quads
+    const uint32_t bx = bi % blocks_x, by = bi / blocks_x;
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(img + (size_t)(by * 4 + cand) * width + (size_t)bx * 4));
+    s_px[q][4 * cand + 0] = v.x; s_px[q][4 * cand + 1] = v.y; s_px[q][4 * cand + 2] = v.z; s_px[q][4 * cand + 3] = v.w;
+  }
+  __syncwarp();
+  if (!valid) return;  // whole quads leave together
+
+  uint32_t blk[16];
+  bool solid = true;
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    blk[i] = s_px[q][i];
+    solid = solid && (blk[i] == blk[0]);  // includes the alpha byte
+  }
+  if (solid) {
+    if (cand == 0) out[bi] = pack_solid(blk[0]);
+    return;
+  }
+
+  // ---- candidate `cand`: flip = cand >> 1, 444 mode = cand & 1 (reference loop order, rg_etc1.cpp:2251-2254)
+  const bool flip = cand >> 1, color4 = cand & 1;
+  Sol res[2] = {{0xFFFFFFFFu, 0, 0, 0}, {0xFFFFFFFFu, 0, 0, 0}};
+  bool ok = true;
+  uint32_t total = 0;
+#pragma unroll
+  for (int sb = 0; sb < 2; sb++) {
+    uint32_t sub[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      // flipped: rows 2*sb, 2*sb+1 in raster order; else columns 2*sb, 2*sb+1, column-major
+      const uint32_t a = blk[sb * 8 + i], b = blk[sb * 2 + (i >> 2) + 4 * (i & 3)];
+      sub[i] = (flip ? a : b) & 0x00FFFFFFu;
+    }
+    if (ok) {
+      ok = optimize(sub, color4, !color4 && sb == 1, res[0].color, res[sb]);
+      if (ok) total += res[sb].err;
+    }
+  }
+  // strict-< scan over the candidates in index order == min over (error, index)
+  uint32_t key = ok ? ((total << 2) | (uint32_t)cand) : 0xFFFFFFFFu;
+  const uint32_t qmask = 0xFu << ((threadIdx.x & 31) & ~3);
+  uint32_t best = key;
+  best = min(best, __shfl_xor_sync(qmask, best, 1));
+  best = min(best, __shfl_xor_sync(qmask, best, 2));
+  if (best != key) return;
+
+  // ---- pack (rg_etc1.cpp:2369-2448)
+  const uint32_t c0 = res[0].color, c1 = res[1].color;
+  uint32_t bytes[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const int a = (c0 >> (8 * k)) & 0xFF, b = (c1 >> (8 * k)) & 0xFF;
+    if (color4) bytes[k] = (uint32_t)(b | (a << 4));
+    else bytes[k] = (uint32_t)((a << 3) | ((b - a) & 7));
+  }
+  const uint32_t b3 = ((uint32_t)res[1].inten << 2) | ((uint32_t)res[0].inten << 5) | ((color4 ? 0u : 1u) << 1) | (flip ? 1u : 0u);
+  uint32_t lsb = 0, msb = 0;
+#pragma unroll
+  for (int y = 0; y < 4; y++)
+#pragma unroll
+    for (int x = 0; x < 4; x++) {
+      const int sbf = y >> 1, kf = (y & 1) * 4 + x;  // flipped
+      const int sbn = x >> 1, kn = (x & 1) * 4 + y;  // not flipped
+      const uint32_t sf = (res[sbf].sel >> (2 * kf)) & 3, sn = (res[sbn].sel >> (2 * kn)) & 3;
+      const uint32_t s = flip ? sf : sn;
+      const uint32_t e = (0x4B >> (2 * s)) & 3;  // selector index -> ETC1 code {3,2,0,1}
+      lsb |= (e & 1) << (x * 4 + y);
+      msb |= (e >> 1) << (x * 4 + y);
+    }
+  uint2 o;
+  o.x = bytes[0] | (bytes[1] << 8) | (bytes[2] << 16) | (b3 << 24);
+  o.y = (msb >> 8) | ((msb & 0xFF) << 8) | ((lsb >> 8) << 16) | ((lsb & 0xFF) << 24);
+  out[bi] = o;
+}
+
+// rg_etc1.cpp:1887-1901
+int decode_value(int diff, int inten, int selector, int packed_c) {
+  static const int kInten[8][4] = {{-8, -2, 2, 8},     {-17, -5, 5, 17},   {-29, -9, 9, 29},    {-42, -13, 13, 42},
+                                   {-60, -18, 18, 60}, {-80, -24, 24, 80}, {-106, -33, 33, 106}, {-183, -47, 47, 183}};
+  int c = diff ? ((packed_c >> 2) | (packed_c << 3)) : (packed_c | (packed_c << 4));
+  c += kInten[inten][selector];
+  return c < 0 ? 0 : (c > 255 ? 255 : c);
+}
+
+// Host construction of the solid-colour tables.
+//   inverse[diff | inten << 1 | selector << 4][v] = best base | abs error << 8, first strict
+//     minimum over ascending bases (pack_etc1_block_init, rg_etc1.cpp:1905-1936);
+//   config list of value v = every (diff, inten, selector) that reproduces v exactly, with
+//     the smallest such base, ordered by (diff, inten, base, selector) -- the order of the
+//     reference's literal arrays (rg_etc1.cpp:385-507), which decides ties in the search.
+void build_solid_tables(std::vector<uint16_t> &off, std::vector<uint16_t> &cfg, std::vector<uint16_t> &inverse) {
+  inverse.assign(64 * 256, 0);
+  for (int diff = 0; diff < 2; diff++)
+    for (int inten = 0; inten < 8; inten++)
+      for (int sel = 0; sel < 4; sel++)
+        for (int v = 0; v < 256; v++) {
+          uint32_t best = 0xFFFFFFFFu, best_c = 0;
+          for (int pc = 0; pc < (diff ? 32 : 16); pc++) {
+            const int d = decode_value(diff, inten, sel, pc) - v;
+            const uint32_t err = (uint32_t)(d < 0 ? -d : d);
+            if (err < best) { best = err; best_c = (uint32_t)pc; if (!best) break; }
+          }
+          inverse[(diff + (inten << 1) + (sel << 4)) * 256 + v] = (uint16_t)(best_c | (best << 8));
+        }
+  off.assign(257, 0);
+  cfg.clear();
+  for (int v = 0; v < 256; v++) {
+    off[v] = (uint16_t)cfg.size();
+    for (int diff = 0; diff < 2; diff++)
+      for (int inten = 0; inten < 8; inten++) {
+        // entries of this (diff, inten), by ascending base then selector
+        for (int pc = 0; pc < (diff ? 32 : 16); pc++)
+          for (int sel = 0; sel < 4; sel++) {
+            if (decode_value(diff, inten, sel, pc) != v) continue;
+            bool smaller = false;  // a smaller base already reproduces v with this selector
+            for (int p2 = 0; p2 < pc; p2++) smaller = smaller || decode_value(diff, inten, sel, p2) == v;
+            if (!smaller) cfg.push_back((uint16_t)(diff | (inten << 1) | (sel << 4) | (pc << 8)));
+          }
+      }
+  }
+  off[256] = (uint16_t)cfg.size();
+}
+
+}  // namespace
+
+cudaError_t etc1_upload_tables() {
+  static std::vector<uint16_t> off, cfg, inverse;
+  if (off.empty()) build_solid_tables(off, cfg, inverse);
+  if (cfg.size() > (size_t)kMaxCfg) return cudaErrorInvalidValue;
+  cudaError_t e = cudaMemcpyToSymbol(g_cfg_off, off.data(), off.size() * 2);
+  if (e != cudaSuccess) return e;
+  e = cudaMemcpyToSymbol(g_cfg, cfg.data(), cfg.size() * 2);
+  if (e != cudaSuccess) return e;
+  return cudaMemcpyToSymbol(g_inverse, inverse.data(), inverse.size() * 2);
+}
+
+cudaError_t launch_etc1(const void *rgba_dev, uint32_t width, uint32_t first_block, uint32_t num_blocks,
+                        void *out_dev, cudaStream_t stream) {
+  if (num_blocks == 0) return cudaSuccess;
+  const uint32_t grid = (num_blocks + kEtcBlocksPerCta - 1) / kEtcBlocksPerCta;
+  etc1_encode_kernel<<<grid, kEtcThreads, 0, stream>>>(static_cast<const uint32_t *>(rgba_dev), width, width / 4,
+                                                       first_block, num_blocks, static_cast<uint2 *>(out_dev));
+  return cudaGetLastError();
+}
+
 }  // namespace fastc

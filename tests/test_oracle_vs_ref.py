@@ -31,6 +31,54 @@ def test_dxt_oracle_equals_reference_random(oracle, reference, fmt):
     assert _bad(a, b, fmt) == 0
 
 
+@pytest.mark.parametrize("w,h,seed,kw", [(256, 256, 1, {}), (128, 512, 2, {"noise_mask": 63}),
+                                         (256, 64, 3, {"opaque": True})])
+def test_etc1_oracle_equals_reference(oracle, reference, w, h, seed, kw):
+    img = synth_rgba(w, h, seed, **kw)
+    a, _ = oracle.compress("ETC1", img)
+    b, _ = reference.compress("ETC1", img)
+    assert _bad(a, b, "ETC1") == 0
+
+
+def test_etc1_oracle_equals_reference_random_lowvariance_solid(oracle, reference):
+    rng = np.random.default_rng(5)
+    noise = rng.integers(0, 256, (64, 256, 4), dtype=np.uint8)
+    base = rng.integers(0, 256, (16, 64, 1, 1, 4))
+    low = (base + rng.integers(-6, 7, (16, 64, 4, 4, 4))).clip(0, 255).astype(np.uint8)
+    low = low.transpose(0, 2, 1, 3, 4).reshape(64, 256, 4)
+    cols = rng.integers(0, 256, (64, 64, 4), dtype=np.uint8)
+    cols[0, :8, :3] = 0
+    cols[0, 8:16, :3] = 255
+    solid = np.repeat(np.repeat(cols, 4, 0), 4, 1)
+    img = np.ascontiguousarray(np.concatenate([noise, low, solid], 0))
+    a, _ = oracle.compress("ETC1", img)
+    b, _ = reference.compress("ETC1", img)
+    assert _bad(a, b, "ETC1") == 0
+
+
+def test_bc7_oracle_equals_reference_q0_config1(oracle, reference):
+    """BASELINE config 1: 256x256 RGBA, -q 0, single thread: bit-identical incl. the
+    watermark sequence of the solid-colour blocks (T1)."""
+    img = synth_rgba(256, 256, 1)
+    a, _ = oracle.compress("BPTC", img, quality=0, rng_mode=0)
+    b, _ = reference.compress("BPTC", img, quality=0)
+    assert _bad(a, b, "BPTC") == 0
+
+
+@pytest.mark.parametrize("q,seed", [(1, 7), (2, 99), (5, 12345), (50, 1), (200, 31337)])
+def test_bc7_oracle_equals_reference_annealing_pinned_lcg(oracle, reference, q, seed):
+    """quality > 0 with the reference's process-global LCG pinned to `seed` (single thread):
+    the restatement draws the same random numbers in the same order -> identical bytes and
+    identical LCG state afterwards."""
+    img = np.ascontiguousarray(synth_rgba(256, 256, 1)[96:128, 32:160])  # alpha, opaque and solid tiles
+    if q >= 50:
+        img = img[:16, :64]
+    a, lcg = oracle.compress("BPTC", img, quality=q, rng_mode=0, lcg_state=seed)
+    b, _ = reference.compress("BPTC", img, quality=q, seed=seed)
+    assert _bad(a, b, "BPTC") == 0
+    assert lcg == reference.get_seed()
+
+
 @pytest.mark.parametrize("fmt", ["DXT1", "DXT5", "ETC1", "BPTC"])
 def test_decoders_and_psnr_equal_reference(oracle, reference, fmt):
     img = synth_rgba(128, 128, 4)
