@@ -77,6 +77,7 @@ class GpuLibrary:
         "fastc_gpu_compressed_size", "fastc_gpu_compress", "fastc_gpu_compress_batch",
         "fastc_gpu_compress_device", "fastc_gpu_count_solid_device", "fastc_gpu_bc7_counters",
         "fastc_gpu_debug_bc7_dump", "fastc_gpu_bc7_stage_ms",
+        "fastc_gpu_decompress", "fastc_gpu_decompress_device", "fastc_gpu_psnr", "fastc_gpu_psnr_device",
         "fastc_gpu_last_error",
     ]
 
@@ -102,6 +103,10 @@ class GpuLibrary:
         L.fastc_gpu_bc7_counters.argtypes = [C.POINTER(u64), C.POINTER(u64)]
         L.fastc_gpu_debug_bc7_dump.argtypes = [u32, vp, vp]
         L.fastc_gpu_bc7_stage_ms.argtypes = [i, C.POINTER(C.c_double)]
+        L.fastc_gpu_decompress.argtypes = [i, vp, u32, u32, vp, C.POINTER(_Timing)]
+        L.fastc_gpu_decompress_device.argtypes = [i, vp, u32, u32, vp, vp]
+        L.fastc_gpu_psnr.argtypes = [vp, vp, u32, u32, C.POINTER(C.c_double)]
+        L.fastc_gpu_psnr_device.argtypes = [vp, vp, u32, u32, vp, C.POINTER(C.c_double)]
         L.fastc_gpu_last_error.restype = C.c_char_p
 
     def error(self) -> str:
@@ -176,6 +181,42 @@ class GpuLibrary:
         return n.value
 
 
+    # ---- decoders + PSNR (the step after the encode path) -----------------------
+    def decompress(self, fmt: int, cmp: np.ndarray, width: int, height: int) -> np.ndarray:
+        cmp = np.ascontiguousarray(cmp, dtype=np.uint8)
+        need = int(self.cdll.fastc_gpu_compressed_size(int(fmt), width, height))
+        if cmp.nbytes < need:
+            raise FastcGpuError("compressed buffer smaller than the image needs")
+        out = np.empty((height, width, 4), dtype=np.uint8)
+        self.check(self.cdll.fastc_gpu_decompress(int(fmt), cmp.ctypes.data, width, height, out.ctypes.data, None))
+        return out
+
+    def decompress_device(self, fmt: int, cmp_dev, rgba_dev, *, width: int, height: int, stream: int | None = None):
+        import torch
+        if stream is None:
+            stream = torch.cuda.current_stream().cuda_stream
+        self.check(self.cdll.fastc_gpu_decompress_device(int(fmt), cmp_dev.data_ptr(), width, height,
+                                                         rgba_dev.data_ptr(), stream))
+
+    def psnr(self, a: np.ndarray, b: np.ndarray) -> float:
+        a = np.ascontiguousarray(a, dtype=np.uint8)
+        b = np.ascontiguousarray(b, dtype=np.uint8)
+        if a.shape != b.shape:
+            raise FastcGpuError("PSNR needs two images of the same size")
+        h, w = a.shape[:2]
+        r = C.c_double(0)
+        self.check(self.cdll.fastc_gpu_psnr(a.ctypes.data, b.ctypes.data, w, h, C.byref(r)))
+        return r.value
+
+    def psnr_device(self, a_dev, b_dev, *, width: int, height: int, stream: int | None = None) -> float:
+        import torch
+        if stream is None:
+            stream = torch.cuda.current_stream().cuda_stream
+        r = C.c_double(0)
+        self.check(self.cdll.fastc_gpu_psnr_device(a_dev.data_ptr(), b_dev.data_ptr(), width, height, stream,
+                                                   C.byref(r)))
+        return r.value
+
     def bc7_stage_ms(self, enable: bool = True, read: bool = True):
         """Arms / reads the per-stage CUDA-event timing of the BC7 pipeline (ms):
         {classify+scan, select, setup(+sort), anneal, pack, total} of the last device-API call."""
@@ -216,7 +257,7 @@ def CompressImageData(data: np.ndarray, width: int, height: int, cmpData: np.nda
     `TexComp -- <msg>` to stderr) on failure, prints `Compression time: %0.3f ms`
     to stdout on success.  `data`: width*height*4 RGBA bytes; `cmpData`: output."""
     if settings.bUseSIMD:
-        _report_error("Platform does not support SIMD!")  # TexComp.cpp:440-445 (D7)
+        _report_error("Platform does not support SIMD!\n")  # TexComp.cpp:440-445 (D7)
         return False
     try:
         fmt = ECompressionFormat(settings.format)
@@ -224,7 +265,7 @@ def CompressImageData(data: np.ndarray, width: int, height: int, cmpData: np.nda
         _report_error("Unknown compression format")
         return False
     if width % 4 or height % 4 or width == 0 or height == 0:
-        _report_error("Image dimensions must be multiples of the block size")  # TexComp.cpp:472-476
+        _report_error("ERROR - CompressImageData: width or height is not multiple of block dimension")  # TexComp.cpp:472-476
         return False
     if cmpDataSz < CompressedImage.GetCompressedSize(width, height, fmt):
         _report_error("Not enough space for compressed data!")  # TexComp.cpp:493-496

@@ -56,6 +56,7 @@ struct DeviceCtx {
   // slot i for pipeline slot i of the host path, slot kPipeDepth for the device API;
   // grown on demand, reused across calls
   Bc7Workspace bc7ws[kPipeDepth + 1];
+  unsigned long long *psnr_sum = nullptr, *psnr_host = nullptr;  // device / pinned accumulators of fastc_gpu_psnr*
   std::mutex mu;
 };
 
@@ -77,6 +78,7 @@ int ensure_tables(int dev) {
   CU_TRY(dxt_upload_tables());
   CU_TRY(etc1_upload_tables());
   CU_TRY(bc7_upload_tables());
+  CU_TRY(decode_upload_tables());
   c.tables_ready = true;
   return 0;
 }
@@ -318,6 +320,9 @@ void fastc_gpu_shutdown(void) {
       c.in_buf[i] = c.out_buf[i] = nullptr; c.in_cap[i] = c.out_cap[i] = 0;
     }
     for (int i = 0; i <= kPipeDepth; i++) bc7_free_workspace(c.bc7ws[i]);
+    if (c.psnr_sum) cudaFree(c.psnr_sum);
+    if (c.psnr_host) cudaFreeHost(c.psnr_host);
+    c.psnr_sum = c.psnr_host = nullptr;
     c.ready = false;
   }
   g_num_init = 0;
@@ -497,6 +502,96 @@ int fastc_gpu_compress_batch(int format, const fastc_gpu_job *jobs, uint32_t num
   tm.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   if (timing) *timing = tm;
   return 0;
+}
+
+int fastc_gpu_decompress_device(int format, const void *cmp_dev, uint32_t width, uint32_t height, void *rgba_out_dev,
+                                void *cuda_stream) {
+  if (check_dims(format, width, height)) return 1;
+  if (!cmp_dev || !rgba_out_dev) return fail("null device pointer");
+  int dev = 0;
+  CU_TRY(cudaGetDevice(&dev));
+  if (dev >= kMaxDevices) return fail("device index %d not supported", dev);
+  if (ensure_tables(dev)) return 1;
+  CU_TRY(launch_decode(format, cmp_dev, width, 0, (width / 4) * (height / 4), rgba_out_dev,
+                       static_cast<cudaStream_t>(cuda_stream)));
+  return 0;
+}
+
+int fastc_gpu_decompress(int format, const uint8_t *cmp_host, uint32_t width, uint32_t height, uint8_t *rgba_out_host,
+                         fastc_gpu_timing *timing) {
+  auto t0 = std::chrono::steady_clock::now();
+  if (check_dims(format, width, height)) return 1;
+  if (!cmp_host || !rgba_out_host) return fail("null host pointer");
+  int dev = 0;
+  CU_TRY(cudaGetDevice(&dev));
+  if (dev >= kMaxDevices) return fail("device index %d not supported", dev);
+  if (ensure_ctx(dev)) return 1;
+  DeviceCtx &c = g_ctx[dev];
+  const size_t cmp_bytes = fastc_gpu_compressed_size(format, width, height);
+  const size_t out_bytes = (size_t)width * height * 4;
+  cudaStream_t st = c.streams[0];
+  // staging slot 0: the image buffer holds the decoded pixels, the output buffer the blocks
+  CU_TRY(cudaStreamSynchronize(st));
+  if (grow(&c.in_buf[0], &c.in_cap[0], out_bytes)) return 1;
+  if (grow(&c.out_buf[0], &c.out_cap[0], cmp_bytes)) return 1;
+  CU_TRY(cudaMemcpyAsync(c.out_buf[0], cmp_host, cmp_bytes, cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaEventRecord(c.ev_start[0], st));
+  CU_TRY(launch_decode(format, c.out_buf[0], width, 0, (width / 4) * (height / 4), c.in_buf[0], st));
+  CU_TRY(cudaEventRecord(c.ev_stop[0], st));
+  CU_TRY(cudaMemcpyAsync(rgba_out_host, c.in_buf[0], out_bytes, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  if (timing) {
+    float ms = 0;
+    CU_TRY(cudaEventElapsedTime(&ms, c.ev_start[0], c.ev_stop[0]));
+    *timing = fastc_gpu_timing{};
+    timing->kernel_ms = ms;
+    timing->h2d_bytes = cmp_bytes;
+    timing->d2h_bytes = out_bytes;
+    timing->kernel_launches = 1;
+    timing->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  }
+  return 0;
+}
+
+int fastc_gpu_psnr_device(const void *a_dev, const void *b_dev, uint32_t width, uint32_t height, void *cuda_stream,
+                          double *psnr_out) {
+  if (!a_dev || !b_dev || !psnr_out) return fail("null pointer");
+  if (width == 0 || height == 0) return fail("empty image");
+  int dev = 0;
+  CU_TRY(cudaGetDevice(&dev));
+  if (dev >= kMaxDevices) return fail("device index %d not supported", dev);
+  DeviceCtx &c = g_ctx[dev];
+  std::lock_guard<std::mutex> lk(c.mu);
+  if (!c.psnr_sum) {
+    CU_TRY(cudaMalloc(reinterpret_cast<void **>(&c.psnr_sum), 64));
+    CU_TRY(cudaMallocHost(reinterpret_cast<void **>(&c.psnr_host), 64));
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  const size_t n = (size_t)width * height;
+  CU_TRY(launch_psnr_sum(a_dev, b_dev, n, c.psnr_sum, st));
+  CU_TRY(cudaMemcpyAsync(c.psnr_host, c.psnr_sum, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  *psnr_out = psnr_from_sum(*c.psnr_host, n);
+  return 0;
+}
+
+int fastc_gpu_psnr(const uint8_t *a_host, const uint8_t *b_host, uint32_t width, uint32_t height, double *psnr_out) {
+  if (!a_host || !b_host || !psnr_out) return fail("null pointer");
+  if (width == 0 || height == 0) return fail("empty image");
+  int dev = 0;
+  CU_TRY(cudaGetDevice(&dev));
+  if (dev >= kMaxDevices) return fail("device index %d not supported", dev);
+  if (ensure_ctx(dev)) return 1;
+  DeviceCtx &c = g_ctx[dev];
+  const size_t bytes = (size_t)width * height * 4;
+  cudaStream_t st = c.streams[0];
+  CU_TRY(cudaStreamSynchronize(st));
+  if (grow(&c.in_buf[0], &c.in_cap[0], bytes)) return 1;
+  if (grow(&c.in_buf[1], &c.in_cap[1], bytes)) return 1;
+  CU_TRY(cudaStreamSynchronize(c.streams[1]));
+  CU_TRY(cudaMemcpyAsync(c.in_buf[0], a_host, bytes, cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaMemcpyAsync(c.in_buf[1], b_host, bytes, cudaMemcpyHostToDevice, st));
+  return fastc_gpu_psnr_device(c.in_buf[0], c.in_buf[1], width, height, st, psnr_out);
 }
 
 int fastc_gpu_bc7_counters(uint64_t *qe_calls, uint64_t *pixel_bucket_evals) {

@@ -10,12 +10,20 @@ namespace fastc {
 cudaError_t dxt_upload_tables();
 cudaError_t etc1_upload_tables();
 cudaError_t bc7_upload_tables();
+cudaError_t decode_upload_tables();
 
 cudaError_t launch_dxt(bool dxt5, const void *rgba_dev, uint32_t width, uint32_t first_block,
                        uint32_t num_blocks, void *out_dev, cudaStream_t stream);
 
 cudaError_t launch_etc1(const void *rgba_dev, uint32_t width, uint32_t first_block, uint32_t num_blocks,
                         void *out_dev, cudaStream_t stream);
+
+// Decoders + PSNR (decode.cu).  format: include/fastc_gpu.h numbering.
+cudaError_t launch_decode(int format, const void *cmp_dev, uint32_t width, uint32_t first_block, uint32_t num_blocks,
+                          void *rgba_dev, cudaStream_t stream);
+cudaError_t launch_psnr_sum(const void *a_dev, const void *b_dev, size_t num_pixels, unsigned long long *sum_dev,
+                            cudaStream_t stream);
+double psnr_from_sum(unsigned long long sum, size_t num_pixels);
 
 // Scratch for the multi-kernel BC7 pipeline (chain records, per-block
 // selections, prefix counters).  Owned by the per-device context, grown on

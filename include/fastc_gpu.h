@@ -16,6 +16,11 @@
  *                                 / BPTCC::CompressAtomic (BPTCEncoder/src/Compressor.cpp:1542-1574)
  *   fastc_gpu_compress_device  <- the same CompressionFunc, with device-resident
  *   fastc_gpu_count_solid_device  buffers (kernel-only timing; multi-process sharding)
+ *   fastc_gpu_decompress(_device) <- CompressedImage::DecompressImage (Core/src/CompressedImage.cpp:86-119):
+ *                                 BPTCC::Decompress BPTCEncoder/src/Decompressor.cpp:345,
+ *                                 DXTC::DecompressDXT1/5 DXTEncoder/src/Decompressor.cpp:98/127,
+ *                                 ETCC::Decompress ETCEncoder/src/Decompressor.cpp:27
+ *   fastc_gpu_psnr(_device)    <- FasTC::Image<Pixel>::ComputePSNR (Base/src/Image.cpp:205-255)
  *   fastc_gpu_compressed_size  <- CompressedImage::GetCompressedSize (Core/src/CompressedImage.cpp:136-149)
  *   fastc_gpu_last_error       <- ReportError()'s "TexComp -- %s" message (Core/src/TexComp.cpp:157-159)
  *
@@ -107,6 +112,21 @@ int fastc_gpu_compress_device(int format, const void *rgba_dev, uint32_t width, 
 int fastc_gpu_count_solid_device(const void *rgba_dev, uint32_t width, uint32_t height,
                                  uint32_t first_block, uint32_t num_blocks, void *cuda_stream,
                                  uint32_t *count_out);
+
+/* Decoders (bit-identical to the reference's, including its departures from the format
+ * specifications -- see fastc_b200/csrc/decode.cu).  Host -> host on the current device;
+ * the device variant is asynchronous on `cuda_stream`.  rgba_out: width*height*4 bytes. */
+int fastc_gpu_decompress(int format, const uint8_t *cmp_host, uint32_t width, uint32_t height,
+                         uint8_t *rgba_out_host, fastc_gpu_timing *timing);
+int fastc_gpu_decompress_device(int format, const void *cmp_dev, uint32_t width, uint32_t height,
+                                void *rgba_out_dev, void *cuda_stream);
+
+/* The reference's PSNR between two RGBA8 images of the same size (alpha-premultiplied RGB error,
+ * peak 3*255^2).  Identical images give +inf.  Both variants synchronise before returning. */
+int fastc_gpu_psnr(const uint8_t *a_host, const uint8_t *b_host, uint32_t width, uint32_t height,
+                   double *psnr_out);
+int fastc_gpu_psnr_device(const void *a_dev, const void *b_dev, uint32_t width, uint32_t height,
+                          void *cuda_stream, double *psnr_out);
 
 /* BC7 work counters of the last BPTC call on this thread's device context
  * (QuantizedError calls and pixel-bucket evaluations), only

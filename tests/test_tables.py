@@ -1,0 +1,94 @@
+"""CPU: the constant tables this repo GENERATES (tools/gen_bc7_tables.py for BC7; the
+derivation rule in oracle/etc1_oracle.cpp / fastc_b200/csrc/etc1.cu for rg_etc1's
+solid-colour lists) equal the reference's literal arrays.  Needs the reference tree
+(build container only); the oracle-vs-golden tests cover the same tables indirectly on
+the GPU box."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+REF = Path("/root/reference")
+
+pytestmark = pytest.mark.skipif(not (REF / "BPTCEncoder").exists(), reason="reference tree not present")
+
+
+def _array(text: str, name: str):
+    """All integer literals of the C array definition `name[...] = { ... };`."""
+    m = re.search(re.escape(name) + r"\s*(\[[^\]]*\]\s*)+=\s*\{", text)
+    assert m, name
+    end = text.index("};", m.end())
+    body = re.sub(r"//[^\n]*", "", text[m.end():end])
+    return [int(x, 0) for x in re.findall(r"0[xX][0-9a-fA-F]+|\d+", body)]
+
+
+def _ours(name: str, path: Path = ROOT / "oracle" / "bc7_tables.h"):
+    return _array(path.read_text().replace("u,", ",").replace("u\n", "\n"), name)
+
+
+def test_bc7_tables_equal_reference():
+    shapes = (REF / "BPTCEncoder/include/FasTC/Shapes.h").read_text()
+    anchors = (REF / "BPTCEncoder/src/AnchorTables.h").read_text()
+    luts = (REF / "BPTCEncoder/src/BCLookupTables.h").read_text()
+    comp = (REF / "BPTCEncoder/src/Compressor.cpp").read_text()
+    assert _ours("kShape2") == _array(shapes, "kShapeMask2")
+    s3 = _array(shapes, "kShapeMask3")
+    want3 = []
+    for a, b in zip(s3[0::2], s3[1::2]):  # (subset 1 or 2, subset 2) masks -> 2 bits per pixel
+        v = 0
+        for i in range(16):
+            sub = (1 + ((b >> i) & 1)) if (a >> i) & 1 else 0
+            v |= sub << (2 * i)
+        want3.append(v)
+    assert _ours("kShape3") == want3
+    assert _ours("kAnchor2") == _array(anchors, "kAnchorIdx2")
+    a3 = _array(anchors, "kAnchorIdx3")
+    assert _ours("kAnchor3a") == a3[:64] and _ours("kAnchor3b") == a3[64:]
+    assert _ours("kOpt7Mode5") == _array(luts, "Optimal7CompressBC7Mode5")
+    assert _ours("kOpt6Dxt1") == _array(luts, "Optimal6CompressDXT1")
+    assert _ours("kWatermark") == _array(comp, "kWMValues")
+    # the CUDA side's copy is generated from the same script
+    cu = ROOT / "fastc_b200" / "csrc" / "bc7_tables.cuh"
+    for name in ("kShape2", "kShape3", "kAnchor2", "kAnchor3a", "kAnchor3b", "kWeight", "kOpt7Mode5", "kOpt6Dxt1",
+                 "kWatermark"):
+        assert _ours(name) == _ours(name, cu), name
+
+
+def test_etc1_solid_colour_lists_equal_reference():
+    src = (REF / "ETCEncoder/src/rg_etc1.cpp").read_text()
+    t0 = _array(src, "g_color8_to_etc_block_config_0_255")
+    t1 = _array(src, "g_color8_to_etc_block_config_1_to_254")
+    want = {}
+    lists, cur = [], []
+    for v in t0 + t1:
+        if v == 0xFFFF:
+            lists.append(cur)
+            cur = []
+        else:
+            cur.append(v)
+    assert len(lists) == 256
+    want[0], want[255] = lists[0], lists[1]
+    for c in range(1, 255):
+        want[c] = lists[1 + c]
+    lib = C.CDLL(str(ROOT / "oracle" / "libfastc_oracle.so"))
+    lib.fastc_oracle_etc1_tables.restype = C.c_uint32
+    buf = (C.c_uint16 * 64)()
+    inv = (C.c_uint16 * (64 * 256))()
+    for c in range(256):
+        n = lib.fastc_oracle_etc1_tables(c, buf, inv)
+        assert list(buf[:n]) == want[c], c
+    # inverse lookup: spot-check its defining property (pack_etc1_block_init, rg_etc1.cpp:1905-1936)
+    inten = [[-8, -2, 2, 8], [-17, -5, 5, 17], [-29, -9, 9, 29], [-42, -13, 13, 42], [-60, -18, 18, 60],
+             [-80, -24, 24, 80], [-106, -33, 33, 106], [-183, -47, 47, 183]]
+    inv = np.frombuffer(inv, dtype=np.uint16).reshape(64, 256)
+    for idx in (0, 1, 0x1f, 0x2e, 0x3f):
+        diff, it, sel = idx & 1, (idx >> 1) & 7, idx >> 4
+        for v in (0, 1, 100, 254, 255):
+            errs = []
+            for pc in range(32 if diff else 16):
+                c = ((pc >> 2) | (pc << 3)) if diff else (pc | (pc << 4))
+                errs.append(abs(min(255, max(0, c + inten[it][sel])) - v))
+            assert inv[idx, v] >> 8 == min(errs) and inv[idx, v] & 0xFF == errs.index(min(errs))
