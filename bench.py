@@ -105,10 +105,9 @@ class ClockSampler:
 
 
 def shard_rows(rank: int, world: int):
-    """Contiguous block-row slab of rank `rank`."""
-    brows = HEIGHT // 4
-    a, b = brows * rank // world, brows * (rank + 1) // world
-    return a, b
+    """Contiguous block-row slab of rank `rank` (fastc_b200/sharding.py)."""
+    from fastc_b200.sharding import shard_block_rows
+    return shard_block_rows(HEIGHT // 4, rank, world)
 
 
 # --------------------------------------------------------------------------- reference arm
@@ -170,19 +169,15 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     h_out = torch.empty(nblk * 16, dtype=torch.uint8, pin_memory=True)
     torch.cuda.synchronize()
 
-    # watermark chain across ranks (8-int all-gather of solid-block counts)
+    # watermark chain across ranks (one integer per rank)
+    from fastc_b200.sharding import gather_slabs, watermark_base
     my_solid = g.count_solid_device(d_in, width=WIDTH, height=rows)
-    wm_base = 0
-    if multi:
-        counts = torch.zeros(world, dtype=torch.int64, device=dev)
-        counts[rank] = my_solid
-        dist.all_reduce(counts)
-        wm_base = int(counts[:rank].sum().item())
+    wm_base = watermark_base(my_solid, rank, world, device=dev)
     base_idx = r0 * (WIDTH // 4)
 
+    sizes = [(shard_rows(r, world)[1] - shard_rows(r, world)[0]) * (WIDTH // 4) * 16 for r in range(world)]
     gather_list = None
     if multi and rank == 0:
-        sizes = [(shard_rows(r, world)[1] - shard_rows(r, world)[0]) * (WIDTH // 4) * 16 for r in range(world)]
         gather_list = [torch.empty(s, dtype=torch.uint8, device=dev) for s in sizes]
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
@@ -195,15 +190,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                               wm_base=wm_base, block_index_base=base_idx)
         launches += n
         if multi:
-            # exchange step named by north_star: compressed slabs gathered to rank 0 over NVLink.
-            # Slabs can differ by one block row, so gather via send/recv of exact sizes.
-            if rank == 0:
-                gather_list[0].copy_(d_out)
-                reqs = [dist.irecv(gather_list[r], src=r) for r in range(1, world)]
-                for q in reqs:
-                    q.wait()
-            else:
-                dist.send(d_out, dst=0)
+            # exchange step named by north_star: compressed slabs gathered to rank 0 over NVLink
+            # (send/recv of exact sizes: slabs can differ by one block row)
+            gather_slabs(d_out, rank, world, sizes, gather_list)
 
     def barrier():
         if multi:

@@ -298,9 +298,52 @@ __global__ void bc7_add_u32(uint32_t *p, const uint32_t *v) { *p += *v; }
 //   8 (two subsets) or 4 (three subsets) buckets, no quantisation)
 // accumulated in double exactly like the reference (the tie-break between shapes
 // with equal integer error depends on those roundings).
+//
+// Lanes of a warp hold different shapes, so every per-pixel decision is a select, never a
+// branch: the pixel's subset picks (bbox min, extent, |extent|^2, min . extent, reciprocal) from
+// registers.  The endpoints are the bbox corners, hence extent >= 0 per byte and
+// 0 <= (p - min) . extent <= |extent|^2: the projection needs no clamping.  Bucket colours are
+// interpolated two channels per 32-bit multiply (a byte times a weight <= 64 fits 16 bits), the
+// squared error is |p|^2 + |c|^2 - 2 dp4a(p, c), and the bucket pair comes from one multiply by
+// a per-subset reciprocal; whenever that product lands within 2^-16 of an integer the
+// reference's own divide / multiply sequence decides (RGBAEndpoints.cpp:262-289).
+struct SubsetBox {
+  uint32_t mn, dlo, dhi, den, base;  // dlo/dhi: extent bytes 0,2 / 1,3 spread over 16-bit halves
+  float inv16, fden;
+};
+
+template <int NBM1>
+__device__ __forceinline__ uint32_t box_pixel_error(const SubsetBox &b, uint32_t p, uint32_t pp2, uint32_t d,
+                                                    const uint8_t *__restrict__ wtab) {
+  const uint32_t num = __dp4a(p, d, 0u) - b.base;  // (p - min) . extent, exact
+  const float fnum = (float)num;
+  const int v = __float2int_rd(__fmul_rn(fnum, b.inv16));
+  int ja = min(v >> 16, NBM1);
+  const int fb = v & 0xFFFF;
+  bool two = ja < NBM1;
+  if (num == 0 || num == b.den) {
+    two = false;  // pct is exactly 0 or 1: floor == ceil
+    ja = num ? NBM1 : 0;
+  } else if (fb == 0 || fb == 0xFFFF) {
+    const float t = __fmul_rn(__fdiv_rn(fnum, b.fden), (float)NBM1);
+    const int x1 = min(max(0, (int)floorf(t)), NBM1), x2 = min((int)ceilf(t), NBM1);
+    ja = x1;
+    two = x1 + 1 <= x2;
+  }
+  const uint32_t wa = wtab[ja], wb = wtab[min(ja + 1, NBM1)];
+  const uint32_t ca = b.mn + ((((b.dlo * wa + 0x00200020u) >> 6) & 0x00FF00FFu) |
+                              ((((b.dhi * wa + 0x00200020u) >> 6) & 0x00FF00FFu) << 8));
+  const uint32_t cb = b.mn + ((((b.dlo * wb + 0x00200020u) >> 6) & 0x00FF00FFu) |
+                              ((((b.dhi * wb + 0x00200020u) >> 6) & 0x00FF00FFu) << 8));
+  const uint32_t ea = pp2 + __dp4a(ca, ca, 0u) - 2u * __dp4a(p, ca, 0u);
+  const uint32_t eb = pp2 + __dp4a(cb, cb, 0u) - 2u * __dp4a(p, cb, 0u);
+  return (two && eb < ea) ? eb : ea;
+}
+
 template <int NSUB>
-__device__ __forceinline__ double estimate_shape(const uint32_t *__restrict__ px, int shape,
-                                                 const uint8_t *__restrict__ wtab) {
+__device__ __forceinline__ double estimate_shape(const uint32_t *__restrict__ px, const uint32_t *__restrict__ pp2,
+                                                 int shape, const uint8_t *__restrict__ wtab) {
+  constexpr int NBM1 = NSUB == 2 ? 7 : 3;
   uint32_t mn[NSUB], mx[NSUB];
 #pragma unroll
   for (int s = 0; s < NSUB; s++) { mn[s] = 0xFFFFFFFFu; mx[s] = 0; }
@@ -311,28 +354,45 @@ __device__ __forceinline__ double estimate_shape(const uint32_t *__restrict__ px
     const int s = NSUB == 2 ? ((m2 >> i) & 1) : ((m3 >> (2 * i)) & 3);
     const uint32_t p = px[i];
 #pragma unroll
-    for (int q = 0; q < NSUB; q++)
-      if (s == q) { mn[q] = __vminu4(mn[q], p); mx[q] = __vmaxu4(mx[q], p); }
+    for (int q = 0; q < NSUB; q++) {
+      mn[q] = __vminu4(mn[q], s == q ? p : 0xFFFFFFFFu);
+      mx[q] = __vmaxu4(mx[q], s == q ? p : 0u);
+    }
   }
-  QeEndpoints qe[NSUB];
-  int tot[NSUB];
+  SubsetBox box[NSUB];
+  uint32_t dd[NSUB];
 #pragma unroll
-  for (int s = 0; s < NSUB; s++) { qe_prepare(qe[s], mn[s], mx[s]); tot[s] = 0; }
-  constexpr int nbm1 = NSUB == 2 ? 7 : 3;
+  for (int s = 0; s < NSUB; s++) {
+    const uint32_t d = mx[s] - mn[s];  // per byte mx >= mn: no borrow (every BC7 partition uses all its subsets)
+    dd[s] = d;
+    box[s].mn = mn[s];
+    box[s].dlo = d & 0x00FF00FFu;
+    box[s].dhi = (d >> 8) & 0x00FF00FFu;
+    box[s].den = __dp4a(d, d, 0u);
+    box[s].base = __dp4a(mn[s], d, 0u);
+    box[s].fden = (float)box[s].den;
+    box[s].inv16 = box[s].den ? __fdiv_rn(65536.0f * (float)NBM1, box[s].fden) : 0.0f;
+  }
+  uint32_t tot[NSUB];
+#pragma unroll
+  for (int s = 0; s < NSUB; s++) tot[s] = 0;
 #pragma unroll
   for (int i = 0; i < 16; i++) {
     const int s = NSUB == 2 ? ((m2 >> i) & 1) : ((m3 >> (2 * i)) & 3);
-    const uint32_t p = px[i];
-    int b;
+    SubsetBox b = box[0];
+    uint32_t d = dd[0];
 #pragma unroll
-    for (int q = 0; q < NSUB; q++)
-      if (s == q && qe[q].den != 0) tot[q] += qe_pixel(qe[q], p, p, nbm1, wtab, &b);
+    for (int q = 1; q < NSUB; q++)
+      if (s == q) { b = box[q]; d = dd[q]; }  // selects
+    // a point-sized box contributes nothing; its pixels evaluate to 0 anyway (p == min, extent 0)
+    const uint32_t e = box_pixel_error<NBM1>(b, px[i], pp2[i], d, wtab);
+#pragma unroll
+    for (int q = 0; q < NSUB; q++) tot[q] += (s == q) ? e : 0u;
   }
   double err = 0.0;
 #pragma unroll
   for (int s = 0; s < NSUB; s++) {
-    // subsets that own no pixel cannot occur (every BC7 partition uses all its subsets)
-    const double e = qe[s].den == 0 ? 0.0 : __dadd_rn(0.0001, (double)tot[s]);
+    const double e = box[s].den == 0 ? 0.0 : __dadd_rn(0.0001, (double)tot[s]);
     err = __dadd_rn(err, e);
   }
   return err;
@@ -353,7 +413,7 @@ constexpr int kSelWarps = 4;
 __global__ void __launch_bounds__(kSelWarps * 32)
 bc7_select(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, uint32_t first_block,
            uint32_t num_blocks, uint32_t *__restrict__ sel) {
-  __shared__ uint32_t s_px[kSelWarps][16];
+  __shared__ uint32_t s_px[kSelWarps][16], s_pp2[kSelWarps][16];
   __shared__ uint8_t s_w[64];
   if (threadIdx.x < 64) s_w[threadIdx.x] = c_weight[threadIdx.x];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -364,20 +424,22 @@ bc7_select(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
     type = sel[t] >> 24;
     if (lane < 16) {
       const uint32_t bi = first_block + t, bx = bi % blocks_x, by = bi / blocks_x;
-      s_px[warp][lane] = __ldg(img + (size_t)(by * 4 + (lane >> 2)) * width + bx * 4 + (lane & 3));
+      const uint32_t p = __ldg(img + (size_t)(by * 4 + (lane >> 2)) * width + bx * 4 + (lane & 3));
+      s_px[warp][lane] = p;
+      s_pp2[warp][lane] = __dp4a(p, p, 0u);
     }
   }
   __syncthreads();
   if (!valid || type != kTypeNormal) return;
-  const uint32_t *px = s_px[warp];
+  const uint32_t *px = s_px[warp], *pp2 = s_pp2[warp];
 
   bool opaque = true;
 #pragma unroll
   for (int i = 0; i < 16; i++) opaque = opaque && ((px[i] >> 24) >= 250);
 
   // ---- two-subset shapes
-  double e0 = estimate_shape<2>(px, lane, s_w + 32);       // 8 buckets -> 3-bit weights
-  double e1 = estimate_shape<2>(px, lane + 32, s_w + 32);
+  double e0 = estimate_shape<2>(px, pp2, lane, s_w + 32);       // 8 buckets -> 3-bit weights
+  double e1 = estimate_shape<2>(px, pp2, lane + 32, s_w + 32);
   // early-out: first shape (scan order) with estimate < 1e-9 (Compressor.cpp:1706-1710)
   const uint32_t z0 = __ballot_sync(0xffffffffu, e0 < 1e-9), z1 = __ballot_sync(0xffffffffu, e1 < 1e-9);
   uint32_t word;
@@ -397,8 +459,8 @@ bc7_select(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
     return;
   }
   // ---- three-subset shapes (opaque blocks only)
-  e0 = estimate_shape<3>(px, lane, s_w + 16);              // 4 buckets -> 2-bit weights
-  e1 = estimate_shape<3>(px, lane + 32, s_w + 16);
+  e0 = estimate_shape<3>(px, pp2, lane, s_w + 16);              // 4 buckets -> 2-bit weights
+  e1 = estimate_shape<3>(px, pp2, lane + 32, s_w + 16);
   const uint32_t y0 = __ballot_sync(0xffffffffu, e0 < 1e-9), y1 = __ballot_sync(0xffffffffu, e1 < 1e-9);
   if (y0 | y1) {
     const int s = y0 ? (__ffs(y0) - 1) : (32 + __ffs(y1) - 1);
@@ -806,13 +868,20 @@ constexpr int kChainThreads = 128;
 //  w5: alpha error (modes 4/5)   w6: rounded alpha endpoint bytes a1 | a2 << 8 (modes 4/5)
 constexpr int kStateWords = 8;
 
+// sort key of an annealing chain: (index bits - 2) * 17 + cluster size, < kSortKeys
+constexpr int kSortKeys = 51;
+__device__ __forceinline__ int sort_key(int ibits, int n) { return (ibits - 2) * 17 + n; }
+
 __device__ __forceinline__ void write_state(const Ws &ws, uint32_t gid, uint32_t mask, const Chain &c, int n,
                                             const FitResult &R, uint32_t rng, uint32_t alpha_err, uint32_t abytes) {
   uint32_t *st = ws.states + (size_t)gid * kStateWords;
   st[1] = R.p1; st[2] = R.p2; st[3] = R.err; st[4] = rng; st[5] = alpha_err; st[6] = abytes;
   st[0] = mask | ((uint32_t)c.mode << 16) | ((uint32_t)c.rot << 19) | ((uint32_t)c.idx_mode << 21) |
           ((uint32_t)R.combo << 22) | ((uint32_t)n << 24) | (1u << 31);
-  atomicAdd(&ws.bins[n], 1u);  // histogram by cluster size: bc7_anneal runs chains sorted by n
+  // histogram by (index precision, cluster size): bc7_anneal runs chains sorted by that key so the
+  // lanes of a warp build palettes of the same length and walk the same number of pixels
+  const int ibits = c.idx_mode == 0 ? c_modes[c.mode].index_bits : c_modes[c.mode].alpha_index_bits;
+  atomicAdd(&ws.bins[sort_key(ibits, n)], 1u);
 }
 
 __global__ void __launch_bounds__(kChainThreads)
@@ -821,11 +890,18 @@ bc7_setup(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, u
   __shared__ uint8_t s_w[64];
   if (threadIdx.x < 64) s_w[threadIdx.x] = c_weight[threadIdx.x];
   __syncthreads();
-  const uint32_t gid = blockIdx.x * kChainThreads + threadIdx.x;
-  const uint32_t t = gid / kSlots;
-  const int slot = gid % kSlots;
+  // A CTA owns ONE chain slot of 128 consecutive blocks: the lanes of a warp run the same
+  // mode / subset / index precision on neighbouring blocks, so the k-means and least-squares
+  // loops below have (nearly) uniform trip counts across the warp.  Consecutive CTAs walk the
+  // slots of the same 128 blocks, which keeps their pixels in L1/L2.  Slot 15 never holds a
+  // chain (decode_chain) and gets no CTA; the slot-14 thread clears its state word.
+  constexpr int kLiveSlots = kSlots - 1;
+  const uint32_t t = (blockIdx.x / kLiveSlots) * kChainThreads + threadIdx.x;
+  const int slot = blockIdx.x % kLiveSlots;
   if (t >= num_blocks) return;
+  const uint32_t gid = t * kSlots + slot;
   ws.states[(size_t)gid * kStateWords] = 0;  // not (yet) an annealing chain
+  if (slot == kLiveSlots - 1) ws.states[(size_t)(gid + 1) * kStateWords] = 0;
   const uint32_t selw = ws.sel[t];
   const Chain c = decode_chain(selw, slot);
   if (!c.active) return;
@@ -1005,17 +1081,18 @@ bc7_setup(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, u
 }
 
 // ------------------------------------------------------------------ annealing
-// bins layout (uint32): [0..16] chains per cluster size n, [32..48] start offset of bin n in the
-// sorted order (descending n), [64..80] scatter cursors, [96] total, [97] fetch cursor
+// bins layout (uint32): [0, 51) chains per sort key, [64, 115) start offset of each key in the
+// sorted order (descending key: 4-bit-index chains first, large clusters first), [128, 179)
+// scatter cursors, [192] total, [193] fetch cursor
 __global__ void bc7_bin_offsets(uint32_t *bins) {
   uint32_t off = 0;
-  for (int n = 16; n >= 1; n--) {
-    bins[32 + n] = off;
-    off += bins[n];
-    bins[64 + n] = 0;
+  for (int k = kSortKeys - 1; k >= 0; k--) {
+    bins[64 + k] = off;
+    off += bins[k];
+    bins[128 + k] = 0;
   }
-  bins[96] = off;
-  bins[97] = 0;
+  bins[192] = off;
+  bins[193] = 0;
 }
 
 __global__ void __launch_bounds__(256) bc7_scatter(Ws ws, uint32_t num_blocks) {
@@ -1023,74 +1100,86 @@ __global__ void __launch_bounds__(256) bc7_scatter(Ws ws, uint32_t num_blocks) {
   if (gid >= num_blocks * kSlots) return;
   const uint32_t w0 = ws.states[(size_t)gid * kStateWords];
   if (!(w0 >> 31)) return;
-  const uint32_t n = (w0 >> 24) & 31;
-  const uint32_t p = ws.bins[32 + n] + atomicAdd(&ws.bins[64 + n], 1u);
+  const int mode = (w0 >> 16) & 7, idx_mode = (w0 >> 21) & 1;
+  const int ibits = idx_mode == 0 ? c_modes[mode].index_bits : c_modes[mode].alpha_index_bits;
+  const int key = sort_key(ibits, (w0 >> 24) & 31);
+  const uint32_t p = ws.bins[64 + key] + atomicAdd(&ws.bins[128 + key], 1u);
   ws.order[p] = gid;
 }
 
 constexpr int kSaThreads = 128;
-constexpr int kSaCtasPerSm = 6;
+constexpr int kSaCtasPerSm = 8;
 
 // OptimizeEndpointsForCluster (Compressor.cpp:538-630) as an all-integer state machine, one
-// chain per lane.  Lanes fetch the next chain from the n-sorted list as soon as theirs ends,
+// chain per lane.  Lanes fetch the next chain from the sorted list as soon as theirs ends,
 // so a warp stays full until the list runs dry (the reference's chains have very uneven
 // lengths: every new best restarts the schedule).
 //
 // Per evaluation (QuantizedError, RGBAEndpoints.cpp:190-310) the work is arranged as
-//   palette[j] = interpolated colour of bucket j (packed bytes), B2[j] = |palette[j]|^2
-//   error(pixel, j) = |pixel|^2 + B2[j] - 2 * dp4a(pixel, palette[j])          (exact integers)
+//   palette[j] = interpolated colour of bucket j, two channels per 32-bit multiply
+//   error(pixel, j) = |pixel|^2 + |palette[j]|^2 - 2 * dp4a(pixel, palette[j])   (exact integers)
 // and the projection that picks the two candidate buckets uses one float multiply by a
 // per-call reciprocal; whenever that product lands within 2^-16 of an integer (where the
 // reference's own rounding could fall on the other side) the reference's exact division
 // sequence is replayed instead.
+// Endpoint moves are byte-wise saturating adds (PickBestNeighboringEndpoints moves every channel
+// by one grid step and clamps to [0, 255]); ToPixel's per-channel quantisation
+// (RGBAEndpoints.cpp:126-177) is a 256-entry table per (precision, p-bit) built in shared memory
+// from the same quantize_channel() the other kernels use.
 struct SaConst {
-  uint32_t qm, stepb;  // quantisation mask; per-channel step bytes
+  uint32_t stepb;           // per-channel step bytes
+  uint32_t keep, ormask;    // projection point = (pixel & keep) | (alpha << rsh, if rotated) | ormask
+  int rsh;                  // < 0: no channel swap
   int n, nbm1, woff, pbit, has_pbit;
+  int tab_c, tab_a;         // quantisation table rows (precision class) of colour / alpha
 };
 
-__device__ __forceinline__ uint32_t move_endpoint(uint32_t src, uint32_t dir, int old_pbit, int has_pbit,
-                                                  uint32_t stepb) {
-  uint32_t np = 0;
-#pragma unroll
-  for (int ch = 0; ch < 4; ch++) {
-    int v = chan(src, ch);
-    const int st = chan(stepb, ch);
-    const bool neg = (dir >> ch) & 1;
-    int delta;
-    if (has_pbit) delta = (neg && old_pbit == 0) ? -st : ((!neg && old_pbit == 1) ? st : 0);
-    else delta = neg ? -st : st;
-    v = min(max(v + delta, 0), 255);
-    np |= (uint32_t)v << (8 * ch);
+// quantisation tables: row = class * 3 + (pbit + 1), class 0..4 = 4..8 kept bits, class 5 = "no
+// bits kept" (the alpha of opaque modes: always 255)
+constexpr int kQuantRows = 18;
+__device__ __forceinline__ uint32_t sa_quantize(const uint8_t (*s_q)[256], const SaConst &K, uint32_t p, int pbit) {
+  const uint8_t *tc = s_q[K.tab_c + pbit + 1], *ta = s_q[K.tab_a + pbit + 1];
+  return (uint32_t)tc[p & 0xFF] | ((uint32_t)tc[(p >> 8) & 0xFF] << 8) | ((uint32_t)tc[(p >> 16) & 0xFF] << 16) |
+         ((uint32_t)ta[p >> 24] << 24);
+}
+
+// one endpoint move: dir bit c set = channel c steps down.  With p-bits the step is taken only
+// when it agrees with the p-bit flip (ChangePointForDirWithPbitChange, Compressor.cpp:364-418).
+__device__ __forceinline__ uint32_t move_endpoint(uint32_t src, uint32_t dir, int old_pbit, int has_pbit, uint32_t stepb) {
+  const uint32_t neg = (((dir & 15u) * 0x00204081u) & 0x01010101u) * 0xFFu;  // 0xFF in the bytes that step down
+  uint32_t sub = stepb & neg, add = stepb & ~neg;
+  if (has_pbit) {
+    if (old_pbit == 0) add = 0;
+    else sub = 0;
   }
-  return np;
+  return __vaddus4(__vsubus4(src, sub), add);
 }
 
 // Evaluate one cluster against quantised endpoints q1/q2.  WITH_IDX also returns the indices.
 template <bool WITH_IDX>
-__device__ __forceinline__ uint32_t sa_eval(uint32_t (*s_pix)[kSaThreads], uint32_t (*s_pts)[kSaThreads],
-                                            uint32_t (*s_pal)[kSaThreads], uint32_t (*s_b2)[kSaThreads],
+__device__ __forceinline__ uint32_t sa_eval(uint32_t (*s_pix)[kSaThreads], uint32_t (*s_pal)[kSaThreads],
                                             const uint8_t *__restrict__ s_w, int tid, const SaConst &K, uint32_t q1,
                                             uint32_t q2, unsigned long long *indices) {
-  int e1[4], d[4];
-#pragma unroll
-  for (int k = 0; k < 4; k++) { e1[k] = chan(q1, k); d[k] = chan(q2, k) - e1[k]; }
   const uint32_t d11 = __dp4a(q1, q1, 0u), d12 = __dp4a(q1, q2, 0u), d22 = __dp4a(q2, q2, 0u);
   const int cq = (int)d12 - (int)d11;                       // e1 . (e2 - e1)
   const int den = (int)d22 - 2 * (int)d12 + (int)d11;       // |e2 - e1|^2
+  const uint32_t e1lo = q1 & 0x00FF00FFu, e1hi = (q1 >> 8) & 0x00FF00FFu;
+  const uint32_t e2lo = q2 & 0x00FF00FFu, e2hi = (q2 >> 8) & 0x00FF00FFu;
   for (int j = 0; j <= K.nbm1; j++) {
-    const int w = s_w[K.woff + j];
-    uint32_t pal = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) pal |= (uint32_t)((e1[k] + ((d[k] * w + 32) >> 6)) & 0xFF) << (8 * k);
-    s_pal[j][tid] = pal;
-    s_b2[j][tid] = __dp4a(pal, pal, 0u);
+    const uint32_t w = s_w[K.woff + j], iw = 64u - w;
+    // ((64 - w) * e1 + w * e2 + 32) >> 6 per channel, channels 0,2 and 1,3 in 16-bit halves
+    const uint32_t lo = ((e1lo * iw + e2lo * w + 0x00200020u) >> 6) & 0x00FF00FFu;
+    const uint32_t hi = ((e1hi * iw + e2hi * w + 0x00200020u) >> 6) & 0x00FF00FFu;
+    s_pal[j][tid] = lo | (hi << 8);
   }
   const float fden = (float)den, fnb = (float)K.nbm1;
   const float inv16 = den ? __fdiv_rn(__fmul_rn(65536.0f, fnb), fden) : 0.0f;
   uint32_t total = 0;
   unsigned long long idx = 0;
   for (int i = 0; i < K.n; i++) {
-    const uint32_t px = s_pix[i][tid], pt = s_pts[i][tid];
+    const uint32_t px = s_pix[i][tid];
+    uint32_t pt = (px & K.keep) | K.ormask;
+    if (K.rsh >= 0) pt |= (px >> 24) << K.rsh;
     const int num = (int)__dp4a(pt, q2, 0u) - (int)__dp4a(pt, q1, 0u) - cq;  // (pt - e1) . (e2 - e1), exact
     const float fnum = (float)num;
     const int v = __float2int_rd(__fmul_rn(fnum, inv16));
@@ -1110,9 +1199,10 @@ __device__ __forceinline__ uint32_t sa_eval(uint32_t (*s_pix)[kSaThreads], uint3
       two = x1 + 1 <= x2;
     }
     const int jb = min(ja + 1, K.nbm1);
+    const uint32_t ca = s_pal[ja][tid], cb = s_pal[jb][tid];
     const uint32_t a2 = __dp4a(px, px, 0u);
-    const uint32_t ea = a2 + s_b2[ja][tid] - 2u * __dp4a(px, s_pal[ja][tid], 0u);
-    const uint32_t eb = a2 + s_b2[jb][tid] - 2u * __dp4a(px, s_pal[jb][tid], 0u);
+    const uint32_t ea = a2 + __dp4a(ca, ca, 0u) - 2u * __dp4a(px, ca, 0u);
+    const uint32_t eb = a2 + __dp4a(cb, cb, 0u) - 2u * __dp4a(px, cb, 0u);
     const bool pick_b = two && (eb < ea);
     total += pick_b ? eb : ea;
     if (WITH_IDX) idx |= (unsigned long long)(pick_b ? jb : ja) << (4 * i);
@@ -1124,16 +1214,22 @@ __device__ __forceinline__ uint32_t sa_eval(uint32_t (*s_pix)[kSaThreads], uint3
 __global__ void __launch_bounds__(kSaThreads)
 bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, uint32_t first_block, Ws ws,
            int sa_steps) {
-  __shared__ uint32_t s_pix[16][kSaThreads], s_pts[16][kSaThreads], s_pal[16][kSaThreads], s_b2[16][kSaThreads];
+  __shared__ uint32_t s_pix[16][kSaThreads], s_pal[16][kSaThreads];
+  __shared__ uint8_t s_q[kQuantRows][256];
   __shared__ uint8_t s_w[64];
   if (threadIdx.x < 64) s_w[threadIdx.x] = c_weight[threadIdx.x];
+  for (int e = threadIdx.x; e < kQuantRows * 256; e += kSaThreads) {
+    const int row = e >> 8, cls = row / 3, pbit = row % 3 - 1;
+    const uint32_t mask = cls == 5 ? 0u : ((0xFF00u >> (cls + 4)) & 0xFFu);
+    s_q[row][e & 255] = (uint8_t)quantize_channel((uint32_t)(e & 255), mask, pbit);
+  }
   __syncthreads();
   const int tid = threadIdx.x;
-  const uint32_t total = ws.bins[96];
+  const uint32_t total = ws.bins[192];
   const float f_tm1 = (float)(sa_steps - 1);
 
   bool have = false, dry = false;
-  SaConst K = {0, 0, 0, 0, 0, kPbitNone, 0};
+  SaConst K = {0, 0, 0, -1, 0, 0, 0, kPbitNone, 0, 0, 0};
   uint32_t gid = 0, cur1 = 0, cur2 = 0, best1 = 0, best2 = 0, cur_err = 0, best_err = 0, rng = 0;
   uint32_t alpha_err = 0, abytes = 0;
   int cur_combo = 0, best_combo = 0, energy = 0, rotation = 0;
@@ -1143,7 +1239,7 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
 
   for (;;) {
     if (!have && !dry) {
-      const uint32_t pos = atomicAdd(&ws.bins[97], 1u);
+      const uint32_t pos = atomicAdd(&ws.bins[193], 1u);
       if (pos >= total) {
         dry = true;
       } else {
@@ -1154,16 +1250,23 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
         const int mode = (w0 >> 16) & 7, rot = (w0 >> 19) & 3, idx_mode = (w0 >> 21) & 1;
         const ModeAttr A = c_modes[mode];
         const int ibits = idx_mode == 0 ? A.index_bits : A.alpha_index_bits;
-        K.qm = quant_mask(A);
         K.n = (w0 >> 24) & 31;
         K.nbm1 = (1 << ibits) - 1;
         K.woff = 16 * (ibits - 1);
         K.pbit = A.pbit;
         K.has_pbit = A.pbit != kPbitNone;
+        K.tab_c = (A.color_bits - 4) * 3;
+        K.tab_a = (A.alpha_bits ? A.alpha_bits - 4 : 5) * 3;
         uint32_t sc = 1u << (8 - A.color_bits), sa = A.alpha_bits ? (1u << (8 - A.alpha_bits)) : 0u;
         K.stepb = sc | (sc << 8) | (sc << 16) | (sa << 24);
         if (mode < 4) K.stepb &= ~(0xFFu << (8 * ((rot + 3) & 3)));  // opaque modes never move alpha (T3)
         rotation = A.rotation;
+        // rotated point with alpha forced to 255; the error still uses the pixel itself (T16)
+        K.keep = 0xFFFFFFFFu; K.ormask = 0; K.rsh = -1;
+        if (rotation) {
+          K.ormask = 0xFF000000u;
+          if (rot) { K.rsh = 8 * (rot - 1); K.keep = ~(0xFFu << K.rsh); }
+        }
         cur1 = best1 = st[1]; cur2 = best2 = st[2];
         cur_err = best_err = st[3];
         rng = st[4]; alpha_err = st[5]; abytes = st[6];
@@ -1173,17 +1276,7 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
         const uint32_t *base = img + (size_t)(bi / blocks_x) * 4 * width + (size_t)(bi % blocks_x) * 4;
         int k = 0;
         for (int i = 0; i < 16; i++)
-          if ((w0 >> i) & 1) {
-            const uint32_t p = __ldg(base + (size_t)(i >> 2) * width + (i & 3));
-            uint32_t q = p;
-            if (rotation) {  // rotated point with alpha forced to 255; the error still uses p (T16)
-              if (rot) q = (p & ~(0xFFu << (8 * (rot - 1)))) | ((p >> 24) << (8 * (rot - 1)));
-              q |= 0xFF000000u;
-            }
-            s_pix[k][tid] = p;
-            s_pts[k][tid] = q;
-            k++;
-          }
+          if ((w0 >> i) & 1) s_pix[k++][tid] = __ldg(base + (size_t)(i >> 2) * width + (i & 3));
         have = true;
       }
     }
@@ -1203,15 +1296,15 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
       bool visited;
       do {
         // pt = 0 moves endpoint 2 first and (as the reference does) tests p-bit [0] for it
-        n2 = move_endpoint(cur2, lcg_next(rng) & 15, opb0, K.has_pbit, K.stepb);
-        n1 = move_endpoint(cur1, lcg_next(rng) & 15, opb1, K.has_pbit, K.stepb);
+        n2 = move_endpoint(cur2, lcg_next(rng), opb0, K.has_pbit, K.stepb);
+        n1 = move_endpoint(cur1, lcg_next(rng), opb1, K.has_pbit, K.stepb);
         visited = (best1 == n1) && (best2 == n2) && (best_combo == ncombo);
       } while (visited && ++guard < 15);
       int npb0, npb1;
       pbit_combo(K.pbit, ncombo, npb0, npb1);
       // modes without p-bits evaluate with a zero p-bit (reference quirk, see fit_cluster)
-      const uint32_t q1 = to_pixel_b(n1, K.qm, K.has_pbit ? npb0 : 0), q2 = to_pixel_b(n2, K.qm, K.has_pbit ? npb1 : 0);
-      const uint32_t err = sa_eval<false>(s_pix, s_pts, s_pal, s_b2, s_w, tid, K, q1, q2, nullptr);
+      const uint32_t q1 = sa_quantize(s_q, K, n1, K.has_pbit ? npb0 : 0), q2 = sa_quantize(s_q, K, n2, K.has_pbit ? npb1 : 0);
+      const uint32_t err = sa_eval<false>(s_pix, s_pal, s_w, tid, K, q1, q2, nullptr);
 #ifdef FASTC_GPU_COUNTERS
       ncalls++; npbe += K.n;
 #endif
@@ -1249,9 +1342,9 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
       // indices of the evaluation that produced best_err
       int pb0, pb1;
       pbit_combo(K.pbit, best_combo, pb0, pb1);
-      const uint32_t f1 = to_pixel_b(best1, K.qm, K.has_pbit ? pb0 : 0), f2 = to_pixel_b(best2, K.qm, K.has_pbit ? pb1 : 0);
+      const uint32_t f1 = sa_quantize(s_q, K, best1, K.has_pbit ? pb0 : 0), f2 = sa_quantize(s_q, K, best2, K.has_pbit ? pb1 : 0);
       unsigned long long indices;
-      sa_eval<true>(s_pix, s_pts, s_pal, s_b2, s_w, tid, K, f1, f2, &indices);
+      sa_eval<true>(s_pix, s_pal, s_w, tid, K, f1, f2, &indices);
       uint32_t *res = ws.results + (size_t)gid * kResWords;
       uint32_t o1 = best1, o2 = best2;
       if (rotation) {
@@ -1503,7 +1596,7 @@ size_t ws_bytes(uint32_t nblocks) {
   b += (size_t)nblocks * kSlots * kResWords * 4;                 // results
   b += (size_t)nblocks * kSlots * 8 * 4;                         // states
   b += (size_t)nblocks * kSlots * 4;                             // order
-  b += 512;                                                      // bins
+  b += 1024;                                                     // bins
   return b;
 }
 
@@ -1621,8 +1714,8 @@ cudaError_t launch_bc7(Bc7Workspace &wsp, const void *rgba_dev, uint32_t width, 
     bc7_select<<<(nb + kSelWarps - 1) / kSelWarps, kSelWarps * 32, 0, stream>>>(img, width, bx, fb, nb, ws.sel);
     if (ev) cudaEventRecord(ev[2], stream);
     const uint64_t nthreads = (uint64_t)nb * kSlots;
-    cudaMemsetAsync(ws.bins, 0, 512, stream);
-    bc7_setup<<<(uint32_t)((nthreads + kChainThreads - 1) / kChainThreads), kChainThreads, 0, stream>>>(
+    cudaMemsetAsync(ws.bins, 0, 1024, stream);
+    bc7_setup<<<((nb + kChainThreads - 1) / kChainThreads) * (kSlots - 1), kChainThreads, 0, stream>>>(
         img, width, bx, fb, nb, ws, quality, seed, block_index_base);
     n++;
     if (quality > 0) {
