@@ -584,7 +584,7 @@ struct FitResult {
   bool need_sa;  // true: (p1, p2, combo, err) is the START state of the annealing chain
 };
 
-__device__ void fit_cluster(const Ws &ws, const ModeAttr &A, int mode, int idx_mode, int rot, const uint32_t *pts,
+__device__ __noinline__ void fit_cluster(const Ws &ws, const ModeAttr &A, int mode, int idx_mode, int rot, const uint32_t *pts,
                             const uint32_t *pix, int n, const float avg[4], bool all_same, int sa_steps,
                             const uint8_t *__restrict__ s_w, FitResult &R) {
   R.need_sa = false;
@@ -610,6 +610,7 @@ __device__ void fit_cluster(const Ws &ws, const ModeAttr &A, int mode, int idx_m
     // unique points; entries past the unique count stay (-1,-1,-1,-1) (T7)
     uint32_t upts[16];
     int nu = 0;
+#pragma unroll 1
     for (int i = 0; i < n; i++) {
       bool has = false;
       for (int j = 0; j < nu; j++) has = has || (upts[j] == pts[i]);
@@ -627,6 +628,7 @@ __device__ void fit_cluster(const Ws &ws, const ModeAttr &A, int mode, int idx_m
         for (int k = 0; k < 4; k++) dir[k] = __fdiv_rn(dir[k], len);
       }
       bool collinear = true;
+#pragma unroll 1
       for (int i = 2; i < n; i++) {
         float v[4];
 #pragma unroll
@@ -640,21 +642,31 @@ __device__ void fit_cluster(const Ws &ws, const ModeAttr &A, int mode, int idx_m
 #pragma unroll
         for (int k = 0; k < 4; k++) axis[k] = dir[k];
       } else {
-        // covariance of (pt - avg), divided by 3 (T8); lower triangle then mirrored
+        // covariance of (pt - avg), divided by 3 (T8): ten running sums (lower triangle), each
+        // accumulated over the points in order exactly like the reference's per-entry loops
+        float cs[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 1
+        for (int k = 0; k < n; k++) {
+          float a[4];
+#pragma unroll
+          for (int c2 = 0; c2 < 4; c2++) a[c2] = __fsub_rn((float)chan(pts[k], c2), avg[c2]);
+          int e = 0;
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j <= i; j++, e++) cs[e] = __fadd_rn(cs[e], __fmul_rn(a[i], a[j]));
+        }
         float cov[4][4];
+        {
+          int e = 0;
 #pragma unroll
-        for (int i = 0; i < 4; i++)
+          for (int i = 0; i < 4; i++)
 #pragma unroll
-          for (int j = 0; j <= i; j++) {
-            float sum = 0.0f;
-            for (int k = 0; k < n; k++) {
-              const float a = __fsub_rn((float)chan(pts[k], i), avg[i]);
-              const float b = __fsub_rn((float)chan(pts[k], j), avg[j]);
-              sum = __fadd_rn(sum, __fmul_rn(a, b));
+            for (int j = 0; j <= i; j++, e++) {
+              cov[i][j] = __fdiv_rn(cs[e], 3.0f);
+              cov[j][i] = cov[i][j];
             }
-            cov[i][j] = __fdiv_rn(sum, 3.0f);
-            cov[j][i] = cov[i][j];
-          }
+        }
         // MatrixSquare::PowerMethod (MatrixSquare.h:44-105): <= 4 iterations from (.5,.5,.5,.5)
         float b[4] = {0.5f, 0.5f, 0.5f, 0.5f};
         bool bad = false, fixed = false;
@@ -695,6 +707,7 @@ __device__ void fit_cluster(const Ws &ws, const ModeAttr &A, int mode, int idx_m
   float p1[4], p2[4];
   {
     float mindp = FLT_MAX, maxdp = -FLT_MAX;
+#pragma unroll 1
     for (int i = 0; i < n; i++) {
       float v[4];
 #pragma unroll
@@ -715,6 +728,7 @@ __device__ void fit_cluster(const Ws &ws, const ModeAttr &A, int mode, int idx_m
   // ---- k-means over the nb interpolation points until a fixed point (:961-1026, T15)
   float cen[16][4];
   int cnt[16];
+#pragma unroll 1
   for (int i = 0; i < nb; i++) {
     const float s = __fdiv_rn((float)i, (float)nbm1);
     const float oms = __fsub_rn(1.0f, s);
@@ -726,12 +740,14 @@ __device__ void fit_cluster(const Ws &ws, const ModeAttr &A, int mode, int idx_m
     bool fixed = false;
     int guard = 0;
     while (!fixed && guard++ < 4096) {
+#pragma unroll 1
       for (int i = 0; i < n; i++) {
         float pf[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) pf[k] = (float)chan(pts[i], k);
         int mb = 0;
         float md = FLT_MAX;
+#pragma unroll 1
         for (int j = 0; j < nb; j++) {
           float v[4];
 #pragma unroll
@@ -742,9 +758,11 @@ __device__ void fit_cluster(const Ws &ws, const ModeAttr &A, int mode, int idx_m
         bucket[i] = (uint8_t)mb;
       }
       fixed = true;
+#pragma unroll 1
       for (int j = 0; j < nb; j++) {
         int c = 0;
         float sum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll 1
         for (int i = 0; i < n; i++)
           if (bucket[i] == j) {
             c++;
@@ -766,6 +784,7 @@ __device__ void fit_cluster(const Ws &ws, const ModeAttr &A, int mode, int idx_m
     }
   }
   int filled = 0, last = -1;
+#pragma unroll 1
   for (int j = 0; j < nb; j++)
     if (cnt[j] > 0) { filled++; last = j; }
   if (filled == 1) {  // one bucket -> CompressSingleColor on its centroid (:1038-1047)
@@ -783,6 +802,7 @@ __device__ void fit_cluster(const Ws &ws, const ModeAttr &A, int mode, int idx_m
     float asq = 0.0f, bsq = 0.0f, ab = 0.0f;
     float ax[4] = {0, 0, 0, 0}, bx[4] = {0, 0, 0, 0};
     const float fb = (float)nbm1;
+#pragma unroll 1
     for (int i = 0; i < nb; i++) {
       const float fn = (float)cnt[i];
       const float a = __fdiv_rn((float)(nbm1 - i), fb), b = __fdiv_rn((float)i, fb);
@@ -815,6 +835,7 @@ __device__ void fit_cluster(const Ws &ws, const ModeAttr &A, int mode, int idx_m
     const uint32_t r1 = pack_round(p1), r2 = pack_round(p2);
     float md = FLT_MAX;
     c1 = c2 = 0;
+#pragma unroll 1
     for (int i = 0; i < npbit; i++) {
       int pb0, pb1;
       pbit_combo(A.pbit, i, pb0, pb1);
@@ -841,8 +862,11 @@ __device__ void fit_cluster(const Ws &ws, const ModeAttr &A, int mode, int idx_m
   pbit_combo(A.pbit, combo, pb0, pb1);
   const bool has_pbit = A.pbit != kPbitNone;
   uint32_t cur1 = to_pixel_b(c1, qm, pb0), cur2 = to_pixel_b(c2, qm, pb1);  // idempotent: c1/c2 are on the grid
-  uint32_t cur_err = qe_cluster(pts, pix, n, to_pixel_b(c1, qm, has_pbit ? pb0 : 0),
-                                to_pixel_b(c2, qm, has_pbit ? pb1 : 0), nbm1, wtab, nullptr);
+  // one evaluation serves both outcomes: its error starts the annealing chain, its indices are
+  // the result when there is no annealing (same quirky quantisation either way)
+  unsigned long long indices;
+  const uint32_t cur_err = qe_cluster(pts, pix, n, to_pixel_b(c1, qm, has_pbit ? pb0 : 0),
+                                      to_pixel_b(c2, qm, has_pbit ? pb1 : 0), nbm1, wtab, &indices);
   COUNT_QE(ws, 1, 0);
   if (sa_steps > 0 && cur_err > 0) {  // hand over to bc7_anneal
     R.need_sa = true;
@@ -851,10 +875,6 @@ __device__ void fit_cluster(const Ws &ws, const ModeAttr &A, int mode, int idx_m
     R.indices = 0;
     return;
   }
-  // no annealing: indices of the evaluation above (same quirky quantisation)
-  unsigned long long indices;
-  qe_cluster(pts, pix, n, to_pixel_b(c1, qm, has_pbit ? pb0 : 0), to_pixel_b(c2, qm, has_pbit ? pb1 : 0), nbm1, wtab,
-             &indices);
   R.err = cur_err;
   R.p1 = cur1; R.p2 = cur2; R.combo = combo;
   R.indices = indices;
@@ -916,7 +936,7 @@ bc7_setup(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, u
   uint32_t mask = 0;
   float sum[4] = {0, 0, 0, 0};
   uint32_t mn = 0xFFFFFFFFu, mx = 0;
-#pragma unroll
+#pragma unroll 1
   for (int i = 0; i < 16; i++) {
     if (subset_of(i, c.shape, c.nsub) == c.subset) {
       pix[n] = blk[i];
@@ -937,9 +957,27 @@ bc7_setup(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, u
   const uint32_t rng = chain_seed(seed, gblock, (uint32_t)c.chain_id);
 
   uint32_t *res = ws.results + ((size_t)t * kSlots + slot) * kResWords;
+  // ---- modes 4/5: CompressCluster alpha variant (Compressor.cpp:632-919), n == 16.
+  // Points are rotated and their alpha forced to 255, but avg / bounds / error
+  // pixels stay those of the original block (T16).
+  float alpha_vals[16];
+  float amin = FLT_MAX, amax = -FLT_MAX;
+  if (A.rotation) {
+#pragma unroll 1
+    for (int i = 0; i < 16; i++) {
+      const uint32_t p = blk[i];
+      const uint32_t a = c.rot == 0 ? (p >> 24) : chan(p, c.rot - 1);
+      uint32_t q = p;
+      if (c.rot) q = (p & ~(0xFFu << (8 * (c.rot - 1)))) | ((p >> 24) << (8 * (c.rot - 1)));  // channel <- old alpha
+      pts[i] = q | 0xFF000000u;
+      alpha_vals[i] = (float)a;
+      amin = fminf(amin, (float)a);
+      amax = fmaxf(amax, (float)a);
+    }
+  }
   FitResult R;
+  fit_cluster(ws, A, c.mode, c.idx_mode, c.rot, pts, pix, n, avg, all_same, sa_steps, s_w, R);  // the one call site
   if (!A.rotation) {
-    fit_cluster(ws, A, c.mode, 0, 0, pts, pix, n, avg, all_same, sa_steps, s_w, R);
     if (R.need_sa) {
       write_state(ws, gid, mask, c, n, R, rng, 0, 0);
       return;
@@ -948,24 +986,6 @@ bc7_setup(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, u
     res[4] = (uint32_t)R.indices; res[5] = (uint32_t)(R.indices >> 32);
     return;
   }
-
-  // ---- modes 4/5: CompressCluster alpha variant (Compressor.cpp:632-919), n == 16.
-  // Points are rotated and their alpha forced to 255, but avg / bounds / error
-  // pixels stay those of the original block (T16).
-  float alpha_vals[16];
-  float amin = FLT_MAX, amax = -FLT_MAX;
-#pragma unroll
-  for (int i = 0; i < 16; i++) {
-    const uint32_t p = blk[i];
-    const uint32_t a = c.rot == 0 ? (p >> 24) : chan(p, c.rot - 1);
-    uint32_t q = p;
-    if (c.rot) q = (p & ~(0xFFu << (8 * (c.rot - 1)))) | ((p >> 24) << (8 * (c.rot - 1)));  // channel <- old alpha
-    pts[i] = q | 0xFF000000u;
-    alpha_vals[i] = (float)a;
-    amin = fminf(amin, (float)a);
-    amax = fmaxf(amax, (float)a);
-  }
-  fit_cluster(ws, A, c.mode, c.idx_mode, c.rot, pts, pix, 16, avg, all_same, sa_steps, s_w, R);
 
   const int abits = c.idx_mode == 0 ? A.alpha_index_bits : A.index_bits;
   const int nba = 1 << abits;
@@ -998,11 +1018,14 @@ bc7_setup(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, u
     // scalar k-means over the alpha interpolation points (:770-842)
     float vals[8];
     uint8_t bucket[16];
+#pragma unroll 1
     for (int i = 0; i < nba; i++)
       vals[i] = __fadd_rn(amin, __fmul_rn(__fdiv_rn((float)i, (float)(nba - 1)), __fsub_rn(amax, amin)));
+#pragma unroll 1
     for (int i = 0; i < 16; i++) {
       float md = 255.0f;
       int b = 0;
+#pragma unroll 1
       for (int j = 0; j < nba; j++) {
         const float d = fabsf(__fsub_rn(alpha_vals[i], vals[j]));
         if (d < md) { md = d; b = j; }
@@ -1015,15 +1038,19 @@ bc7_setup(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, u
     while (!fixed && guard++ < 4096) {
       float av[8];
       fixed = true;
+#pragma unroll 1
       for (int i = 0; i < nba; i++) {
         float s = 0.0f, c2 = 0.0f;
+#pragma unroll 1
         for (int j = 0; j < 16; j++)
           if (bucket[j] == i) { s = __fadd_rn(s, alpha_vals[j]); c2 = __fadd_rn(c2, 1.0f); }
         if (c2 > 0.0f) s = __fdiv_rn(s, c2);
         av[i] = s; npts[i] = c2;
         fixed = fixed && (av[i] == vals[i]);
       }
+#pragma unroll 1
       for (int i = 0; i < nba; i++) vals[i] = av[i];
+#pragma unroll 1
       for (int i = 0; i < 16; i++) {
         float md = 255.0f;
         int b = bucket[i];  // reference keeps the previous bucket when nothing is closer than 255
@@ -1036,6 +1063,7 @@ bc7_setup(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, u
     }
     float asq = 0.0f, bsq = 0.0f, ab = 0.0f, ax = 0.0f, bx = 0.0f;
     const float fb = (float)(nba - 1);
+#pragma unroll 1
     for (int i = 0; i < nba; i++) {
       const float a = __fdiv_rn((float)(nba - 1 - i), fb), b = __fdiv_rn((float)i, fb);
       const float nn = npts[i], x = vals[i];
@@ -1054,9 +1082,11 @@ bc7_setup(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, u
     const uint32_t qmask8 = (0xFF00u >> A.alpha_bits) & 0xFF;
     const int a1b = (int)quantize_channel((uint32_t)(int)a1, qmask8, -1);  // uint8(a1): truncation
     const int a2b = (int)quantize_channel((uint32_t)(int)a2, qmask8, -1);
+#pragma unroll 1
     for (int i = 0; i < 16; i++) {
       const int val = (int)alpha_vals[i];
       int me = 0x7fffffff, bb = 0;
+#pragma unroll 1
       for (int j = 0; j < nba; j++) {
         const int w1 = wa[j], w0 = 64 - w1;
         const int ip = ((a1b * w0 + a2b * w1 + 32) >> 6) & 0xFF;
