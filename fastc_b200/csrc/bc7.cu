@@ -872,7 +872,7 @@ __device__ __noinline__ void fit_cluster(const Ws &ws, const ModeAttr &A, int mo
     R.need_sa = true;
     R.err = cur_err;
     R.p1 = cur1; R.p2 = cur2; R.combo = combo;
-    R.indices = 0;
+    R.indices = indices;  // of the start state: final if annealing never improves on it
     return;
   }
   R.err = cur_err;
@@ -977,6 +977,7 @@ bc7_setup(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, u
   }
   FitResult R;
   fit_cluster(ws, A, c.mode, c.idx_mode, c.rot, pts, pix, n, avg, all_same, sa_steps, s_w, R);  // the one call site
+  res[4] = (uint32_t)R.indices; res[5] = (uint32_t)(R.indices >> 32);
   if (!A.rotation) {
     if (R.need_sa) {
       write_state(ws, gid, mask, c, n, R, rng, 0, 0);
@@ -1113,16 +1114,36 @@ bc7_setup(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, u
 // ------------------------------------------------------------------ annealing
 // bins layout (uint32): [0, 51) chains per sort key, [64, 115) start offset of each key in the
 // sorted order (descending key: 4-bit-index chains first, large clusters first), [128, 179)
-// scatter cursors, [192] total, [193] fetch cursor
-__global__ void bc7_bin_offsets(uint32_t *bins) {
+// scatter cursors, [192] total, [193 + c] fetch cursor of precision class c (= index bits - 2),
+// [196 + c] end of class c's region, [200 + c] first CTA whose home class is c or lower.
+//
+// bc7_anneal gives every CTA a HOME class, in proportion to the class's estimated work, so that
+// the lanes of a warp build palettes of the same length (and, for the 4-bit class, walk the same
+// 16 pixels); a lane whose home queue is dry steals from the other classes.
+__global__ void bc7_bin_offsets(uint32_t *bins, uint32_t grid_ctas) {
   uint32_t off = 0;
+  float work[3] = {0.0f, 0.0f, 0.0f};
   for (int k = kSortKeys - 1; k >= 0; k--) {
+    const int cls = k / 17, n = k % 17;
+    if (n == 16) bins[193 + cls] = off;  // the class's region starts with its largest clusters
     bins[64 + k] = off;
     off += bins[k];
     bins[128 + k] = 0;
+    if (n == 0) bins[196 + cls] = off;
+    // instructions per annealing step ~ fixed part + palette entries + pixels
+    work[cls] += (float)bins[k] * (150.0f + 12.0f * (float)(4 << cls) + 40.0f * (float)n);
   }
   bins[192] = off;
-  bins[193] = 0;
+  const float tot = work[0] + work[1] + work[2];
+  // CTAs [0, b2) -> class 2, [b2, b1) -> class 1, [b1, grid) -> class 0
+  uint32_t b2 = tot > 0.0f ? (uint32_t)(work[2] / tot * (float)grid_ctas + 0.5f) : 0;
+  uint32_t b1 = tot > 0.0f ? (uint32_t)((work[2] + work[1]) / tot * (float)grid_ctas + 0.5f) : 0;
+  if (b2 > grid_ctas) b2 = grid_ctas;
+  if (b1 > grid_ctas) b1 = grid_ctas;
+  if (b1 < b2) b1 = b2;
+  bins[200 + 2] = 0;
+  bins[200 + 1] = b2;
+  bins[200 + 0] = b1;
 }
 
 __global__ void __launch_bounds__(256) bc7_scatter(Ws ws, uint32_t num_blocks) {
@@ -1158,8 +1179,8 @@ constexpr int kSaCtasPerSm = 8;
 // from the same quantize_channel() the other kernels use.
 struct SaConst {
   uint32_t stepb;           // per-channel step bytes
-  uint32_t keep, ormask;    // projection point = (pixel & keep) | (alpha << rsh, if rotated) | ormask
-  int rsh;                  // < 0: no channel swap
+  uint32_t keep, orm, ins;  // projection point = (pixel & keep) | orm | ((alpha << rsh) & ins)
+  int rsh;
   int n, nbm1, woff, pbit, has_pbit;
   int tab_c, tab_a;         // quantisation table rows (precision class) of colour / alpha
 };
@@ -1185,11 +1206,11 @@ __device__ __forceinline__ uint32_t move_endpoint(uint32_t src, uint32_t dir, in
   return __vaddus4(__vsubus4(src, sub), add);
 }
 
-// Evaluate one cluster against quantised endpoints q1/q2.  WITH_IDX also returns the indices.
-template <bool WITH_IDX>
+// Evaluate one cluster against quantised endpoints q1/q2: returns the total error and the
+// chosen bucket of every pixel (4 bits each, cluster-local order) in idx_lo / idx_hi.
 __device__ __forceinline__ uint32_t sa_eval(uint32_t (*s_pix)[kSaThreads], uint32_t (*s_pal)[kSaThreads],
                                             const uint8_t *__restrict__ s_w, int tid, const SaConst &K, uint32_t q1,
-                                            uint32_t q2, unsigned long long *indices) {
+                                            uint32_t q2, uint32_t &idx_lo, uint32_t &idx_hi) {
   const uint32_t d11 = __dp4a(q1, q1, 0u), d12 = __dp4a(q1, q2, 0u), d22 = __dp4a(q2, q2, 0u);
   const int cq = (int)d12 - (int)d11;                       // e1 . (e2 - e1)
   const int den = (int)d22 - 2 * (int)d12 + (int)d11;       // |e2 - e1|^2
@@ -1203,45 +1224,52 @@ __device__ __forceinline__ uint32_t sa_eval(uint32_t (*s_pix)[kSaThreads], uint3
     s_pal[j][tid] = lo | (hi << 8);
   }
   const float fden = (float)den, fnb = (float)K.nbm1;
+  // den == 0 (both endpoints equal): the zero reciprocal sends every pixel through the exact path below
   const float inv16 = den ? __fdiv_rn(__fmul_rn(65536.0f, fnb), fden) : 0.0f;
-  uint32_t total = 0;
-  unsigned long long idx = 0;
-  for (int i = 0; i < K.n; i++) {
-    const uint32_t px = s_pix[i][tid];
-    uint32_t pt = (px & K.keep) | K.ormask;
-    if (K.rsh >= 0) pt |= (px >> 24) << K.rsh;
-    const int num = (int)__dp4a(pt, q2, 0u) - (int)__dp4a(pt, q1, 0u) - cq;  // (pt - e1) . (e2 - e1), exact
-    const float fnum = (float)num;
-    const int v = __float2int_rd(__fmul_rn(fnum, inv16));
-    int j1 = v >> 16;
-    const int fb = v & 0xFFFF;
-    bool two = (j1 >= 0) && (j1 < K.nbm1);
-    int ja = min(max(j1, 0), K.nbm1);
-    if (den == 0) {
-      ja = 0; two = false;  // both endpoints equal: bucket 0 (RGBAEndpoints.cpp:226-251)
-    } else if ((fb == 0 || fb == 0xFFFF) && j1 >= -1 && j1 <= K.nbm1) {
-      // too close to a bucket boundary for the fast product: replay the reference's float sequence
-      const float t = __fmul_rn(__fdiv_rn(fnum, fden), fnb);
-      int x1 = (int)floorf(t), x2 = (int)ceilf(t);
-      x1 = min(max(0, x1), K.nbm1);
-      x2 = min(x2, K.nbm1);
-      ja = x1;
-      two = x1 + 1 <= x2;
+  uint32_t total = 0, word[2] = {0, 0};
+#pragma unroll
+  for (int half = 0; half < 2; half++) {
+    const int i0 = 8 * half, i1 = min(K.n, i0 + 8);
+    uint32_t acc = 0;
+    for (int i = i0; i < i1; i++) {
+      const uint32_t px = s_pix[i][tid];
+      // projection point: the pixel itself, or (modes 4/5) the rotated pixel with alpha forced to
+      // 255 -- the error below still uses the pixel (T16)
+      const uint32_t pt = ((px & K.keep) | K.orm) | (((px >> 24) << K.rsh) & K.ins);
+      const int num = (int)__dp4a(pt, q2, 0u) - (int)__dp4a(pt, q1, 0u) - cq;  // (pt - e1) . (e2 - e1), exact
+      const float fnum = (float)num;
+      const int v = __float2int_rd(__fmul_rn(fnum, inv16));
+      const int j1 = v >> 16;
+      int ja = min(max(j1, 0), K.nbm1);
+      bool two = (uint32_t)j1 < (uint32_t)K.nbm1;
+      if ((((uint32_t)v + 1u) & 0xFFFFu) <= 1u) {
+        // too close to a bucket boundary for the fast product: replay the reference's float sequence
+        if (den == 0) {
+          ja = 0; two = false;  // bucket 0 (RGBAEndpoints.cpp:226-251)
+        } else {
+          const float t = __fmul_rn(__fdiv_rn(fnum, fden), fnb);
+          const int x1 = min(max(0, (int)floorf(t)), K.nbm1), x2 = min((int)ceilf(t), K.nbm1);
+          ja = x1;
+          two = x1 + 1 <= x2;
+        }
+      }
+      const int jb = ja + (two ? 1 : 0);  // !two: the same bucket twice, never picked
+      const uint32_t da = __vabsdiffu4(s_pal[ja][tid], px), db = __vabsdiffu4(s_pal[jb][tid], px);
+      const uint32_t ea = __dp4a(da, da, 0u), eb = __dp4a(db, db, 0u);
+      total += min(ea, eb);
+      const uint32_t pick = (uint32_t)ja + (eb < ea ? 1u : 0u);
+      acc = __funnelshift_r(acc, pick, 4);  // nibbles enter at the top; aligned after the loop
     }
-    const int jb = min(ja + 1, K.nbm1);
-    const uint32_t ca = s_pal[ja][tid], cb = s_pal[jb][tid];
-    const uint32_t a2 = __dp4a(px, px, 0u);
-    const uint32_t ea = a2 + __dp4a(ca, ca, 0u) - 2u * __dp4a(px, ca, 0u);
-    const uint32_t eb = a2 + __dp4a(cb, cb, 0u) - 2u * __dp4a(px, cb, 0u);
-    const bool pick_b = two && (eb < ea);
-    total += pick_b ? eb : ea;
-    if (WITH_IDX) idx |= (unsigned long long)(pick_b ? jb : ja) << (4 * i);
+    const int cnt = max(i1 - i0, 0);
+    word[half] = cnt ? acc >> (4 * (8 - cnt)) : 0u;
   }
-  if (WITH_IDX) *indices = idx;
+  const uint32_t lo = word[0], hi = word[1];
+  idx_lo = lo;
+  idx_hi = hi;
   return total;
 }
 
-__global__ void __launch_bounds__(kSaThreads)
+__global__ void __launch_bounds__(kSaThreads, kSaCtasPerSm)
 bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, uint32_t first_block, Ws ws,
            int sa_steps) {
   __shared__ uint32_t s_pix[16][kSaThreads], s_pal[16][kSaThreads];
@@ -1255,22 +1283,34 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
   }
   __syncthreads();
   const int tid = threadIdx.x;
-  const uint32_t total = ws.bins[192];
   const float f_tm1 = (float)(sa_steps - 1);
+  const int home = blockIdx.x >= ws.bins[200 + 0] ? 0 : (blockIdx.x >= ws.bins[200 + 1] ? 1 : 2);
 
   bool have = false, dry = false;
-  SaConst K = {0, 0, 0, -1, 0, 0, 0, kPbitNone, 0, 0, 0};
+  SaConst K = {0, 0xFFFFFFFFu, 0, 0, 0, 0, 0, 0, kPbitNone, 0, 0, 0};
   uint32_t gid = 0, cur1 = 0, cur2 = 0, best1 = 0, best2 = 0, cur_err = 0, best_err = 0, rng = 0;
-  uint32_t alpha_err = 0, abytes = 0;
+  uint32_t alpha_err = 0, abytes = 0, best_lo = 0, best_hi = 0;
   int cur_combo = 0, best_combo = 0, energy = 0, rotation = 0;
+  bool improved = false;
 #ifdef FASTC_GPU_COUNTERS
   uint32_t ncalls = 0, npbe = 0;
 #endif
 
   for (;;) {
     if (!have && !dry) {
-      const uint32_t pos = atomicAdd(&ws.bins[193], 1u);
-      if (pos >= total) {
+      // next chain: the home class's queue first, then the others (longest steps first)
+      uint32_t pos = 0;
+      bool got = false;
+#pragma unroll
+      for (int a = 0; a < 3 && !got; a++) {
+        const int cls = a == 0 ? home : (2 - (a - 1) - ((2 - (a - 1)) <= home ? 1 : 0));
+        if (cls < 0) break;
+        if (ws.bins[193 + cls] < ws.bins[196 + cls]) {  // cheap look before the atomic
+          pos = atomicAdd(&ws.bins[193 + cls], 1u);
+          got = pos < ws.bins[196 + cls];
+        }
+      }
+      if (!got) {
         dry = true;
       } else {
         // ---- load a chain: constants of its mode, its pixels, its start state
@@ -1291,17 +1331,17 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
         K.stepb = sc | (sc << 8) | (sc << 16) | (sa << 24);
         if (mode < 4) K.stepb &= ~(0xFFu << (8 * ((rot + 3) & 3)));  // opaque modes never move alpha (T3)
         rotation = A.rotation;
-        // rotated point with alpha forced to 255; the error still uses the pixel itself (T16)
-        K.keep = 0xFFFFFFFFu; K.ormask = 0; K.rsh = -1;
+        K.keep = 0xFFFFFFFFu; K.orm = 0; K.ins = 0; K.rsh = 0;
         if (rotation) {
-          K.ormask = 0xFF000000u;
-          if (rot) { K.rsh = 8 * (rot - 1); K.keep = ~(0xFFu << K.rsh); }
+          K.orm = 0xFF000000u;
+          if (rot) { K.rsh = 8 * (rot - 1); K.ins = 0xFFu << K.rsh; K.keep = ~K.ins; }
         }
         cur1 = best1 = st[1]; cur2 = best2 = st[2];
         cur_err = best_err = st[3];
         rng = st[4]; alpha_err = st[5]; abytes = st[6];
         cur_combo = best_combo = (w0 >> 22) & 3;
         energy = 0;
+        improved = false;
         const uint32_t t = gid / kSlots, bi = first_block + t;
         const uint32_t *base = img + (size_t)(bi / blocks_x) * 4 * width + (size_t)(bi % blocks_x) * 4;
         int k = 0;
@@ -1334,7 +1374,8 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
       pbit_combo(K.pbit, ncombo, npb0, npb1);
       // modes without p-bits evaluate with a zero p-bit (reference quirk, see fit_cluster)
       const uint32_t q1 = sa_quantize(s_q, K, n1, K.has_pbit ? npb0 : 0), q2 = sa_quantize(s_q, K, n2, K.has_pbit ? npb1 : 0);
-      const uint32_t err = sa_eval<false>(s_pix, s_pal, s_w, tid, K, q1, q2, nullptr);
+      uint32_t ilo, ihi;
+      const uint32_t err = sa_eval(s_pix, s_pal, s_w, tid, K, q1, q2, ilo, ihi);
 #ifdef FASTC_GPU_COUNTERS
       ncalls++; npbe += K.n;
 #endif
@@ -1363,18 +1404,15 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
       if (accept) { cur_err = err; cur1 = n1; cur2 = n2; cur_combo = ncombo; }
       if (err < best_err) {
         best_err = err; best1 = n1; best2 = n2; best_combo = ncombo;
+        best_lo = ilo; best_hi = ihi; improved = true;
         energy = 0;  // restart; the increment below makes it 1
       }
       energy++;
       done = !(best_err > 0 && energy < sa_steps);
     }
     if (done) {
-      // indices of the evaluation that produced best_err
-      int pb0, pb1;
-      pbit_combo(K.pbit, best_combo, pb0, pb1);
-      const uint32_t f1 = sa_quantize(s_q, K, best1, K.has_pbit ? pb0 : 0), f2 = sa_quantize(s_q, K, best2, K.has_pbit ? pb1 : 0);
-      unsigned long long indices;
-      sa_eval<true>(s_pix, s_pal, s_w, tid, K, f1, f2, &indices);
+      // the indices belong to the evaluation that produced best_err: the start state's were
+      // stored by bc7_setup, an improved state's were kept when it was found
       uint32_t *res = ws.results + (size_t)gid * kResWords;
       uint32_t o1 = best1, o2 = best2;
       if (rotation) {
@@ -1382,7 +1420,7 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
         o2 = (o2 & 0x00FFFFFFu) | (((abytes >> 8) & 0xFF) << 24);
       }
       res[0] = best_err + alpha_err; res[1] = o1; res[2] = o2; res[3] = (uint32_t)best_combo;
-      res[4] = (uint32_t)indices; res[5] = (uint32_t)(indices >> 32);
+      if (improved) { res[4] = best_lo; res[5] = best_hi; }
       have = false;
     }
   }
@@ -1699,7 +1737,7 @@ void bc7_free_workspace(Bc7Workspace &ws) {
 }
 
 // Blocks per internal chunk: bounds the scratch (512 B of chain results per block).
-constexpr uint32_t kChunkBlocks = 1u << 19;
+constexpr uint32_t kChunkBlocks = 1u << 22;
 
 cudaError_t launch_bc7(Bc7Workspace &wsp, const void *rgba_dev, uint32_t width, uint32_t height,
                        uint32_t first_block, uint32_t num_blocks, void *out_dev, int quality, uint64_t seed,
@@ -1749,7 +1787,7 @@ cudaError_t launch_bc7(Bc7Workspace &wsp, const void *rgba_dev, uint32_t width, 
         img, width, bx, fb, nb, ws, quality, seed, block_index_base);
     n++;
     if (quality > 0) {
-      bc7_bin_offsets<<<1, 1, 0, stream>>>(ws.bins);
+      bc7_bin_offsets<<<1, 1, 0, stream>>>(ws.bins, sa_grid);
       bc7_scatter<<<(uint32_t)((nthreads + 255) / 256), 256, 0, stream>>>(ws, nb);
       if (ev) cudaEventRecord(wsp.ev_mid[wsp.timed_chunks - 1], stream);
       bc7_anneal<<<sa_grid, kSaThreads, 0, stream>>>(img, width, bx, fb, ws, quality);
