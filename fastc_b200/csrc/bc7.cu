@@ -313,63 +313,67 @@ struct SubsetBox {
 };
 
 template <int NBM1>
-__device__ __forceinline__ uint32_t box_pixel_error(const SubsetBox &b, uint32_t p, uint32_t pp2, uint32_t d,
+__device__ __forceinline__ uint32_t box_pixel_error(const SubsetBox &b, uint32_t p, uint32_t d,
                                                     const uint8_t *__restrict__ wtab) {
   const uint32_t num = __dp4a(p, d, 0u) - b.base;  // (p - min) . extent, exact
   const float fnum = (float)num;
   const int v = __float2int_rd(__fmul_rn(fnum, b.inv16));
   int ja = min(v >> 16, NBM1);
-  const int fb = v & 0xFFFF;
   bool two = ja < NBM1;
   if (num == 0 || num == b.den) {
     two = false;  // pct is exactly 0 or 1: floor == ceil
     ja = num ? NBM1 : 0;
-  } else if (fb == 0 || fb == 0xFFFF) {
+  } else if ((((uint32_t)v + 1u) & 0xFFFFu) <= 1u) {
     const float t = __fmul_rn(__fdiv_rn(fnum, b.fden), (float)NBM1);
     const int x1 = min(max(0, (int)floorf(t)), NBM1), x2 = min((int)ceilf(t), NBM1);
     ja = x1;
     two = x1 + 1 <= x2;
   }
-  const uint32_t wa = wtab[ja], wb = wtab[min(ja + 1, NBM1)];
+  const uint32_t wa = wtab[ja], wb = wtab[ja + (two ? 1 : 0)];  // !two: the same bucket twice
   const uint32_t ca = b.mn + ((((b.dlo * wa + 0x00200020u) >> 6) & 0x00FF00FFu) |
                               ((((b.dhi * wa + 0x00200020u) >> 6) & 0x00FF00FFu) << 8));
   const uint32_t cb = b.mn + ((((b.dlo * wb + 0x00200020u) >> 6) & 0x00FF00FFu) |
                               ((((b.dhi * wb + 0x00200020u) >> 6) & 0x00FF00FFu) << 8));
-  const uint32_t ea = pp2 + __dp4a(ca, ca, 0u) - 2u * __dp4a(p, ca, 0u);
-  const uint32_t eb = pp2 + __dp4a(cb, cb, 0u) - 2u * __dp4a(p, cb, 0u);
-  return (two && eb < ea) ? eb : ea;
+  const uint32_t da = __vabsdiffu4(ca, p), db = __vabsdiffu4(cb, p);
+  return min(__dp4a(da, da, 0u), __dp4a(db, db, 0u));
 }
 
 template <int NSUB>
-__device__ __forceinline__ double estimate_shape(const uint32_t *__restrict__ px, const uint32_t *__restrict__ pp2,
-                                                 int shape, const uint8_t *__restrict__ wtab) {
+__device__ __forceinline__ double estimate_shape(const uint32_t *__restrict__ px, const uint32_t *__restrict__ plo,
+                                                 const uint32_t *__restrict__ phi, int shape,
+                                                 const uint8_t *__restrict__ wtab) {
   constexpr int NBM1 = NSUB == 2 ? 7 : 3;
-  uint32_t mn[NSUB], mx[NSUB];
+  // bounding boxes on pixels spread over 16-bit halves (bytes 0,2 / 1,3): unsigned 16x2 min / max
+  // is one instruction on sm_100a, byte-wise min / max is not
+  uint32_t mnl[NSUB], mnh[NSUB], mxl[NSUB], mxh[NSUB];
 #pragma unroll
-  for (int s = 0; s < NSUB; s++) { mn[s] = 0xFFFFFFFFu; mx[s] = 0; }
+  for (int s = 0; s < NSUB; s++) { mnl[s] = mnh[s] = 0xFFFFFFFFu; mxl[s] = mxh[s] = 0; }
   const uint32_t m2 = NSUB == 2 ? c_shape2[shape] : 0;
   const uint32_t m3 = NSUB == 3 ? c_shape3[shape] : 0;
 #pragma unroll
   for (int i = 0; i < 16; i++) {
     const int s = NSUB == 2 ? ((m2 >> i) & 1) : ((m3 >> (2 * i)) & 3);
-    const uint32_t p = px[i];
+    const uint32_t l = plo[i], h = phi[i];
 #pragma unroll
     for (int q = 0; q < NSUB; q++) {
-      mn[q] = __vminu4(mn[q], s == q ? p : 0xFFFFFFFFu);
-      mx[q] = __vmaxu4(mx[q], s == q ? p : 0u);
+      mnl[q] = __vminu2(mnl[q], s == q ? l : 0xFFFFFFFFu);
+      mnh[q] = __vminu2(mnh[q], s == q ? h : 0xFFFFFFFFu);
+      mxl[q] = __vmaxu2(mxl[q], s == q ? l : 0u);
+      mxh[q] = __vmaxu2(mxh[q], s == q ? h : 0u);
     }
   }
   SubsetBox box[NSUB];
   uint32_t dd[NSUB];
 #pragma unroll
   for (int s = 0; s < NSUB; s++) {
-    const uint32_t d = mx[s] - mn[s];  // per byte mx >= mn: no borrow (every BC7 partition uses all its subsets)
+    // per byte mx >= mn: no borrow (every BC7 partition uses all its subsets)
+    box[s].dlo = mxl[s] - mnl[s];
+    box[s].dhi = mxh[s] - mnh[s];
+    const uint32_t d = box[s].dlo | (box[s].dhi << 8);
     dd[s] = d;
-    box[s].mn = mn[s];
-    box[s].dlo = d & 0x00FF00FFu;
-    box[s].dhi = (d >> 8) & 0x00FF00FFu;
+    box[s].mn = mnl[s] | (mnh[s] << 8);
     box[s].den = __dp4a(d, d, 0u);
-    box[s].base = __dp4a(mn[s], d, 0u);
+    box[s].base = __dp4a(box[s].mn, d, 0u);
     box[s].fden = (float)box[s].den;
     box[s].inv16 = box[s].den ? __fdiv_rn(65536.0f * (float)NBM1, box[s].fden) : 0.0f;
   }
@@ -385,7 +389,7 @@ __device__ __forceinline__ double estimate_shape(const uint32_t *__restrict__ px
     for (int q = 1; q < NSUB; q++)
       if (s == q) { b = box[q]; d = dd[q]; }  // selects
     // a point-sized box contributes nothing; its pixels evaluate to 0 anyway (p == min, extent 0)
-    const uint32_t e = box_pixel_error<NBM1>(b, px[i], pp2[i], d, wtab);
+    const uint32_t e = box_pixel_error<NBM1>(b, px[i], d, wtab);
 #pragma unroll
     for (int q = 0; q < NSUB; q++) tot[q] += (s == q) ? e : 0u;
   }
@@ -413,7 +417,7 @@ constexpr int kSelWarps = 4;
 __global__ void __launch_bounds__(kSelWarps * 32)
 bc7_select(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, uint32_t first_block,
            uint32_t num_blocks, uint32_t *__restrict__ sel) {
-  __shared__ uint32_t s_px[kSelWarps][16], s_pp2[kSelWarps][16];
+  __shared__ uint32_t s_px[kSelWarps][16], s_plo[kSelWarps][16], s_phi[kSelWarps][16];
   __shared__ uint8_t s_w[64];
   if (threadIdx.x < 64) s_w[threadIdx.x] = c_weight[threadIdx.x];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -426,20 +430,21 @@ bc7_select(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
       const uint32_t bi = first_block + t, bx = bi % blocks_x, by = bi / blocks_x;
       const uint32_t p = __ldg(img + (size_t)(by * 4 + (lane >> 2)) * width + bx * 4 + (lane & 3));
       s_px[warp][lane] = p;
-      s_pp2[warp][lane] = __dp4a(p, p, 0u);
+      s_plo[warp][lane] = p & 0x00FF00FFu;
+      s_phi[warp][lane] = (p >> 8) & 0x00FF00FFu;
     }
   }
   __syncthreads();
   if (!valid || type != kTypeNormal) return;
-  const uint32_t *px = s_px[warp], *pp2 = s_pp2[warp];
+  const uint32_t *px = s_px[warp], *plo = s_plo[warp], *phi = s_phi[warp];
 
   bool opaque = true;
 #pragma unroll
   for (int i = 0; i < 16; i++) opaque = opaque && ((px[i] >> 24) >= 250);
 
   // ---- two-subset shapes
-  double e0 = estimate_shape<2>(px, pp2, lane, s_w + 32);       // 8 buckets -> 3-bit weights
-  double e1 = estimate_shape<2>(px, pp2, lane + 32, s_w + 32);
+  double e0 = estimate_shape<2>(px, plo, phi, lane, s_w + 32);       // 8 buckets -> 3-bit weights
+  double e1 = estimate_shape<2>(px, plo, phi, lane + 32, s_w + 32);
   // early-out: first shape (scan order) with estimate < 1e-9 (Compressor.cpp:1706-1710)
   const uint32_t z0 = __ballot_sync(0xffffffffu, e0 < 1e-9), z1 = __ballot_sync(0xffffffffu, e1 < 1e-9);
   uint32_t word;
@@ -459,8 +464,8 @@ bc7_select(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
     return;
   }
   // ---- three-subset shapes (opaque blocks only)
-  e0 = estimate_shape<3>(px, pp2, lane, s_w + 16);              // 4 buckets -> 2-bit weights
-  e1 = estimate_shape<3>(px, pp2, lane + 32, s_w + 16);
+  e0 = estimate_shape<3>(px, plo, phi, lane, s_w + 16);              // 4 buckets -> 2-bit weights
+  e1 = estimate_shape<3>(px, plo, phi, lane + 32, s_w + 16);
   const uint32_t y0 = __ballot_sync(0xffffffffu, e0 < 1e-9), y1 = __ballot_sync(0xffffffffu, e1 < 1e-9);
   if (y0 | y1) {
     const int s = y0 ? (__ffs(y0) - 1) : (32 + __ffs(y1) - 1);
@@ -901,7 +906,13 @@ __device__ __forceinline__ void write_state(const Ws &ws, uint32_t gid, uint32_t
   // histogram by (index precision, cluster size): bc7_anneal runs chains sorted by that key so the
   // lanes of a warp build palettes of the same length and walk the same number of pixels
   const int ibits = c.idx_mode == 0 ? c_modes[c.mode].index_bits : c_modes[c.mode].alpha_index_bits;
-  atomicAdd(&ws.bins[sort_key(ibits, n)], 1u);
+  {
+    // one atomic per distinct key among the lanes that arrive here together
+    const int key = sort_key(ibits, n);
+    const unsigned act = __activemask();
+    const unsigned peers = __match_any_sync(act, key);
+    if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&ws.bins[key], (uint32_t)__popc(peers));
+  }
 }
 
 __global__ void __launch_bounds__(kChainThreads)
@@ -1146,16 +1157,29 @@ __global__ void bc7_bin_offsets(uint32_t *bins, uint32_t grid_ctas) {
   bins[200 + 0] = b1;
 }
 
+// Counting-sort scatter.  Ranks are taken in shared memory and each CTA reserves one range per
+// key with a single global atomic (51 hot counters would otherwise serialise ~10 chains/block).
 __global__ void __launch_bounds__(256) bc7_scatter(Ws ws, uint32_t num_blocks) {
+  __shared__ uint32_t s_cnt[kSortKeys], s_base[kSortKeys];
+  if (threadIdx.x < kSortKeys) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
   const uint32_t gid = blockIdx.x * 256 + threadIdx.x;
-  if (gid >= num_blocks * kSlots) return;
-  const uint32_t w0 = ws.states[(size_t)gid * kStateWords];
-  if (!(w0 >> 31)) return;
-  const int mode = (w0 >> 16) & 7, idx_mode = (w0 >> 21) & 1;
-  const int ibits = idx_mode == 0 ? c_modes[mode].index_bits : c_modes[mode].alpha_index_bits;
-  const int key = sort_key(ibits, (w0 >> 24) & 31);
-  const uint32_t p = ws.bins[64 + key] + atomicAdd(&ws.bins[128 + key], 1u);
-  ws.order[p] = gid;
+  int key = -1;
+  uint32_t rank = 0;
+  if (gid < num_blocks * kSlots) {
+    const uint32_t w0 = ws.states[(size_t)gid * kStateWords];
+    if (w0 >> 31) {
+      const int mode = (w0 >> 16) & 7, idx_mode = (w0 >> 21) & 1;
+      const int ibits = idx_mode == 0 ? c_modes[mode].index_bits : c_modes[mode].alpha_index_bits;
+      key = sort_key(ibits, (w0 >> 24) & 31);
+      rank = atomicAdd(&s_cnt[key], 1u);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < kSortKeys && s_cnt[threadIdx.x])
+    s_base[threadIdx.x] = ws.bins[64 + threadIdx.x] + atomicAdd(&ws.bins[128 + threadIdx.x], s_cnt[threadIdx.x]);
+  __syncthreads();
+  if (key >= 0) ws.order[s_base[key] + rank] = gid;
 }
 
 constexpr int kSaThreads = 128;
