@@ -591,7 +591,7 @@ struct FitResult {
 
 __device__ __noinline__ void fit_cluster(const Ws &ws, const ModeAttr &A, int mode, int idx_mode, int rot, const uint32_t *pts,
                             const uint32_t *pix, int n, const float avg[4], bool all_same, int sa_steps,
-                            const uint8_t *__restrict__ s_w, FitResult &R) {
+                            const uint8_t *__restrict__ s_w, uint32_t (*s_acc)[16][128], int tid, FitResult &R) {
   R.need_sa = false;
   const int ibits = idx_mode == 0 ? A.index_bits : A.alpha_index_bits;
   const int nb = 1 << ibits, nbm1 = nb - 1;
@@ -762,18 +762,24 @@ __device__ __noinline__ void fit_cluster(const Ws &ws, const ModeAttr &A, int mo
         }
         bucket[i] = (uint8_t)mb;
       }
+      // centroids: bucket sums are exact small integers (<= 16 * 255), so they are accumulated as
+      // packed 16-bit pairs per bucket in shared memory -- O(n) instead of the reference's
+      // O(n * buckets) scan -- and only the division is done in float, as the reference does
+#pragma unroll 1
+      for (int j = 0; j < nb; j++) { s_acc[0][j][tid] = 0; s_acc[1][j][tid] = 0; s_acc[2][j][tid] = 0; }
+#pragma unroll 1
+      for (int i = 0; i < n; i++) {
+        const int b = bucket[i];
+        s_acc[0][b][tid] += pts[i] & 0x00FF00FFu;
+        s_acc[1][b][tid] += (pts[i] >> 8) & 0x00FF00FFu;
+        s_acc[2][b][tid] += 1u;
+      }
       fixed = true;
 #pragma unroll 1
       for (int j = 0; j < nb; j++) {
-        int c = 0;
-        float sum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-#pragma unroll 1
-        for (int i = 0; i < n; i++)
-          if (bucket[i] == j) {
-            c++;
-#pragma unroll
-            for (int k = 0; k < 4; k++) sum[k] = __fadd_rn(sum[k], (float)chan(pts[i], k));
-          }
+        const uint32_t rb = s_acc[0][j][tid], ga = s_acc[1][j][tid];
+        const int c = (int)s_acc[2][j][tid];
+        float sum[4] = {(float)(rb & 0xFFFFu), (float)(ga & 0xFFFFu), (float)(rb >> 16), (float)(ga >> 16)};
         if (c != 0) {
           const float fc = (float)c;
 #pragma unroll
@@ -915,27 +921,17 @@ __device__ __forceinline__ void write_state(const Ws &ws, uint32_t gid, uint32_t
   }
 }
 
-__global__ void __launch_bounds__(kChainThreads)
-bc7_setup(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, uint32_t first_block,
-          uint32_t num_blocks, Ws ws, int sa_steps, uint64_t seed, uint32_t block_index_base) {
-  __shared__ uint8_t s_w[64];
-  if (threadIdx.x < 64) s_w[threadIdx.x] = c_weight[threadIdx.x];
-  __syncthreads();
-  // A CTA owns ONE chain slot of 128 consecutive blocks: the lanes of a warp run the same
-  // mode / subset / index precision on neighbouring blocks, so the k-means and least-squares
-  // loops below have (nearly) uniform trip counts across the warp.  Consecutive CTAs walk the
-  // slots of the same 128 blocks, which keeps their pixels in L1/L2.  Slot 15 never holds a
-  // chain (decode_chain) and gets no CTA; the slot-14 thread clears its state word.
-  constexpr int kLiveSlots = kSlots - 1;
-  const uint32_t t = (blockIdx.x / kLiveSlots) * kChainThreads + threadIdx.x;
-  const int slot = blockIdx.x % kLiveSlots;
-  if (t >= num_blocks) return;
+// One endpoint-fit chain: cluster statistics, CompressCluster's start (fit_cluster), and for
+// modes 4/5 the scalar alpha fit.  Writes either the finished result or the start state of the
+// annealing chain.
+__device__ __forceinline__ void setup_chain(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x,
+                                            uint32_t first_block, const Ws &ws, int sa_steps, uint64_t seed,
+                                            uint32_t block_index_base, uint32_t t, int slot,
+                                            const uint8_t *__restrict__ s_w, uint32_t (*s_acc)[16][128], int tid) {
   const uint32_t gid = t * kSlots + slot;
-  ws.states[(size_t)gid * kStateWords] = 0;  // not (yet) an annealing chain
-  if (slot == kLiveSlots - 1) ws.states[(size_t)(gid + 1) * kStateWords] = 0;
   const uint32_t selw = ws.sel[t];
   const Chain c = decode_chain(selw, slot);
-  if (!c.active) return;
+  if (!c.active) return;  // (the caller's list only holds live chains)
   const ModeAttr A = c_modes[c.mode];
 
   uint32_t blk[16];
@@ -987,7 +983,7 @@ bc7_setup(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, u
     }
   }
   FitResult R;
-  fit_cluster(ws, A, c.mode, c.idx_mode, c.rot, pts, pix, n, avg, all_same, sa_steps, s_w, R);  // the one call site
+  fit_cluster(ws, A, c.mode, c.idx_mode, c.rot, pts, pix, n, avg, all_same, sa_steps, s_w, s_acc, tid, R);  // the one call site
   res[4] = (uint32_t)R.indices; res[5] = (uint32_t)(R.indices >> 32);
   if (!A.rotation) {
     if (R.need_sa) {
@@ -1120,6 +1116,78 @@ bc7_setup(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, u
   const uint32_t e2 = (R.p2 & 0x00FFFFFFu) | (round_byte(a2) << 24);
   res[0] = R.err + alpha_err; res[1] = e1; res[2] = e2; res[3] = 0;
   res[4] = (uint32_t)R.indices; res[5] = (uint32_t)(R.indices >> 32);
+}
+
+// Number of pixels in the subset a chain fits (its cluster size), from the partition tables.
+__device__ __forceinline__ int chain_pixels(const Chain &c) {
+  if (c.nsub == 1) return 16;
+  if (c.nsub == 2) {
+    const int ones = __popc((uint32_t)c_shape2[c.shape]);
+    return c.subset ? ones : 16 - ones;
+  }
+  const uint32_t m = c_shape3[c.shape], lo = m & 0x55555555u, hi = (m >> 1) & 0x55555555u;
+  return c.subset == 0 ? 16 - __popc(lo | hi) : (c.subset == 1 ? __popc(lo & ~hi) : __popc(hi & ~lo));
+}
+
+// A CTA owns one GROUP of chain slots (the two or three subsets of one candidate mode) of 128
+// consecutive blocks.  It first compacts the live chains of those blocks into a shared list
+// sorted by cluster size, then its lanes walk the list: no lane idles on a dead slot (mode 0 is
+// only tried for a quarter of the shapes, solid / transparent blocks have no chains), and the
+// lanes of a warp fit clusters of (nearly) the same size with the same bucket count, so the
+// k-means / least-squares loops run with uniform trip counts.  Consecutive CTAs walk the groups
+// of the same 128 blocks, which keeps their pixels in L1/L2.
+constexpr int kSlotGroups = 6;
+__constant__ uint8_t c_group_first[kSlotGroups] = {0, 3, 6, 8, 10, 12};
+__constant__ uint8_t c_group_count[kSlotGroups] = {3, 3, 2, 2, 2, 4};  // the last group also owns the dead slot 15
+
+__global__ void __launch_bounds__(kChainThreads)
+bc7_setup(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, uint32_t first_block,
+          uint32_t num_blocks, Ws ws, int sa_steps, uint64_t seed, uint32_t block_index_base) {
+  __shared__ uint8_t s_w[64];
+  __shared__ uint32_t s_acc[3][16][kChainThreads];
+  __shared__ uint16_t s_list[4 * kChainThreads];
+  __shared__ uint32_t s_hist[17], s_cur[17];
+  const int tid = threadIdx.x;
+  if (tid < 64) s_w[tid] = c_weight[tid];
+  if (tid < 17) { s_hist[tid] = 0; s_cur[tid] = 0; }
+  __syncthreads();
+  const int group = blockIdx.x % kSlotGroups;
+  const uint32_t tile = blockIdx.x / kSlotGroups;
+  const int first = c_group_first[group], count = c_group_count[group];
+  const uint32_t t = tile * kChainThreads + tid;
+  const uint32_t selw = t < num_blocks ? ws.sel[t] : (uint32_t)kTypeSolid << 24;
+  // pass 1: histogram of the live chains by cluster size; every state word starts as "no chain"
+  int sizes[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    sizes[k] = 0;
+    if (k < count && t < num_blocks) {
+      ws.states[((size_t)t * kSlots + first + k) * kStateWords] = 0;
+      const Chain c = decode_chain(selw, first + k);
+      if (c.active) {
+        sizes[k] = chain_pixels(c);
+        atomicAdd(&s_hist[sizes[k]], 1u);
+      }
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {  // start offsets, largest clusters first
+    uint32_t off = 0;
+    for (int n = 16; n >= 0; n--) { const uint32_t c = s_hist[n]; s_hist[n] = off; off += c; }
+    s_cur[0] = off;  // total
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+    if (sizes[k]) s_list[s_hist[sizes[k]] + atomicAdd(&s_cur[sizes[k]], 1u)] = (uint16_t)((tid << 4) | (first + k));
+  __syncthreads();
+  const uint32_t total = s_cur[0] - 0u;  // s_cur[0] is only touched by size-0 chains, which do not exist
+  // pass 2: one chain per lane and trip
+  for (uint32_t e = tid; e < total; e += kChainThreads) {
+    const uint32_t entry = s_list[e];
+    setup_chain(img, width, blocks_x, first_block, ws, sa_steps, seed, block_index_base,
+                tile * kChainThreads + (entry >> 4), (int)(entry & 15), s_w, s_acc, tid);
+  }
 }
 
 // ------------------------------------------------------------------ annealing
@@ -1807,7 +1875,7 @@ cudaError_t launch_bc7(Bc7Workspace &wsp, const void *rgba_dev, uint32_t width, 
     if (ev) cudaEventRecord(ev[2], stream);
     const uint64_t nthreads = (uint64_t)nb * kSlots;
     cudaMemsetAsync(ws.bins, 0, 1024, stream);
-    bc7_setup<<<((nb + kChainThreads - 1) / kChainThreads) * (kSlots - 1), kChainThreads, 0, stream>>>(
+    bc7_setup<<<((nb + kChainThreads - 1) / kChainThreads) * kSlotGroups, kChainThreads, 0, stream>>>(
         img, width, bx, fb, nb, ws, quality, seed, block_index_base);
     n++;
     if (quality > 0) {
