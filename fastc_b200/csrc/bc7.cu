@@ -350,7 +350,7 @@ __device__ __forceinline__ double estimate_shape(const uint32_t *__restrict__ px
   for (int s = 0; s < NSUB; s++) { mnl[s] = mnh[s] = 0xFFFFFFFFu; mxl[s] = mxh[s] = 0; }
   const uint32_t m2 = NSUB == 2 ? c_shape2[shape] : 0;
   const uint32_t m3 = NSUB == 3 ? c_shape3[shape] : 0;
-#pragma unroll
+#pragma unroll 2
   for (int i = 0; i < 16; i++) {
     const int s = NSUB == 2 ? ((m2 >> i) & 1) : ((m3 >> (2 * i)) & 3);
     const uint32_t l = plo[i], h = phi[i];
@@ -380,7 +380,7 @@ __device__ __forceinline__ double estimate_shape(const uint32_t *__restrict__ px
   uint32_t tot[NSUB];
 #pragma unroll
   for (int s = 0; s < NSUB; s++) tot[s] = 0;
-#pragma unroll
+#pragma unroll 2
   for (int i = 0; i < 16; i++) {
     const int s = NSUB == 2 ? ((m2 >> i) & 1) : ((m3 >> (2 * i)) & 3);
     SubsetBox b = box[0];
@@ -443,8 +443,14 @@ bc7_select(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
   for (int i = 0; i < 16; i++) opaque = opaque && ((px[i] >> 24) >= 250);
 
   // ---- two-subset shapes
-  double e0 = estimate_shape<2>(px, plo, phi, lane, s_w + 32);       // 8 buckets -> 3-bit weights
-  double e1 = estimate_shape<2>(px, plo, phi, lane + 32, s_w + 32);
+  // the lane's two shapes go through ONE copy of the estimate code (rolled loop): the kernel is
+  // instruction-fetch bound otherwise
+  double e0 = 0.0, e1 = 0.0;
+#pragma unroll 1
+  for (int h = 0; h < 2; h++) {
+    const double e = estimate_shape<2>(px, plo, phi, lane + 32 * h, s_w + 32);  // 8 buckets -> 3-bit weights
+    if (h == 0) e0 = e; else e1 = e;
+  }
   // early-out: first shape (scan order) with estimate < 1e-9 (Compressor.cpp:1706-1710)
   const uint32_t z0 = __ballot_sync(0xffffffffu, e0 < 1e-9), z1 = __ballot_sync(0xffffffffu, e1 < 1e-9);
   uint32_t word;
@@ -464,8 +470,11 @@ bc7_select(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
     return;
   }
   // ---- three-subset shapes (opaque blocks only)
-  e0 = estimate_shape<3>(px, plo, phi, lane, s_w + 16);              // 4 buckets -> 2-bit weights
-  e1 = estimate_shape<3>(px, plo, phi, lane + 32, s_w + 16);
+#pragma unroll 1
+  for (int h = 0; h < 2; h++) {
+    const double e = estimate_shape<3>(px, plo, phi, lane + 32 * h, s_w + 16);  // 4 buckets -> 2-bit weights
+    if (h == 0) e0 = e; else e1 = e;
+  }
   const uint32_t y0 = __ballot_sync(0xffffffffu, e0 < 1e-9), y1 = __ballot_sync(0xffffffffu, e1 < 1e-9);
   if (y0 | y1) {
     const int s = y0 ? (__ffs(y0) - 1) : (32 + __ffs(y1) - 1);

@@ -148,3 +148,20 @@ def test_bc7_large_roundtrip_property(gpu, oracle):
     assert solid.sum() > 0 and (dblocks[solid] == blocks[solid]).all()
     transp = (blocks[..., 3] == 0).all(1) & ~solid
     assert transp.sum() > 0 and (dblocks[transp][..., 3] == 0).all()
+
+
+def test_multi_gpu_host_path_equals_single_gpu(gpu):
+    """fastc_gpu_compress with num_gpus = 2 (block-row slabs, one host thread + streams per GPU,
+    each GPU copying straight into its slice of the caller's buffer) == num_gpus = 1, for every
+    format.  Skipped on a single-GPU box."""
+    if gpu.cdll.fastc_gpu_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    img = synth_rgba(512, 512, 1)
+    for fmt, q in ((F.BPTC, 3), (F.BPTC, 0), (F.DXT1, 0), (F.DXT5, 0), (F.ETC1, 0)):
+        one, _ = gpu.compress(fmt, img, quality=q, seed=9, num_gpus=1)
+        two, tm = gpu.compress(fmt, img, quality=q, seed=9, num_gpus=2)
+        assert (one == two).all(), fmt
+    outs, _ = gpu.compress_batch(F.DXT5, [img, img[:256], img[128:]], num_gpus=2)
+    for o, im in zip(outs, [img, img[:256], img[128:]]):
+        ref, _ = gpu.compress(F.DXT5, np.ascontiguousarray(im))
+        assert (o == ref).all()
