@@ -1261,6 +1261,7 @@ __global__ void __launch_bounds__(256) bc7_scatter(Ws ws, uint32_t num_blocks) {
 
 constexpr int kSaThreads = 128;
 constexpr int kSaCtasPerSm = 8;
+constexpr int kPixStride = kSaThreads + 1;  // odd row stride: a warp's cooperative column store is conflict-free
 
 // OptimizeEndpointsForCluster (Compressor.cpp:538-630) as an all-integer state machine, one
 // chain per lane.  Lanes fetch the next chain from the sorted list as soon as theirs ends,
@@ -1269,21 +1270,28 @@ constexpr int kSaCtasPerSm = 8;
 //
 // Per evaluation (QuantizedError, RGBAEndpoints.cpp:190-310) the work is arranged as
 //   palette[j] = interpolated colour of bucket j, two channels per 32-bit multiply
-//   error(pixel, j) = |pixel|^2 + |palette[j]|^2 - 2 * dp4a(pixel, palette[j])   (exact integers)
+//   error(pixel, j) = sum of squared byte differences, VABSDIFF4 + DP4A   (exact integers)
 // and the projection that picks the two candidate buckets uses one float multiply by a
 // per-call reciprocal; whenever that product lands within 2^-16 of an integer (where the
-// reference's own rounding could fall on the other side) the reference's exact division
-// sequence is replayed instead.
+// reference's own rounding could fall on the other side) the pixel is flagged and, after the
+// branch-free main loop, re-evaluated with the reference's exact division sequence.
+// The pixel loops run to the warp's largest cluster with per-lane predicates (lanes run in
+// lock-step anyway), so their trip counts are warp-uniform and the loops unroll.
+// Modes 4/5 project the ROTATED pixel with alpha forced to 255 (T16); instead of rotating
+// every pixel the rotation is applied once per evaluation to the endpoint operands of the dot
+// products:  pt . q = px . q' + 255 * q[3]  with  q' = q, alpha byte <- the rotated channel's byte,
+// rotated channel's byte <- 0.
 // Endpoint moves are byte-wise saturating adds (PickBestNeighboringEndpoints moves every channel
 // by one grid step and clamps to [0, 255]); ToPixel's per-channel quantisation
 // (RGBAEndpoints.cpp:126-177) is a 256-entry table per (precision, p-bit) built in shared memory
 // from the same quantize_channel() the other kernels use.
 struct SaConst {
-  uint32_t stepb;           // per-channel step bytes
-  uint32_t keep, orm, ins;  // projection point = (pixel & keep) | orm | ((alpha << rsh) & ins)
-  int rsh;
+  uint32_t stepb;        // per-channel step bytes
+  uint32_t qkeep, qins;  // projection operand q' = (q & qkeep) | (((q >> qsh) << 24) & qins)
+  int qsh;
+  int calpha;            // 255 when the projected point's alpha is forced to 255 (modes 4/5), else 0
   int n, nbm1, woff, pbit, has_pbit;
-  int tab_c, tab_a;         // quantisation table rows (precision class) of colour / alpha
+  int tab_c, tab_a;      // quantisation table rows (precision class) of colour / alpha
 };
 
 // quantisation tables: row = class * 3 + (pbit + 1), class 0..4 = 4..8 kept bits, class 5 = "no
@@ -1309,71 +1317,115 @@ __device__ __forceinline__ uint32_t move_endpoint(uint32_t src, uint32_t dir, in
 
 // Evaluate one cluster against quantised endpoints q1/q2: returns the total error and the
 // chosen bucket of every pixel (4 bits each, cluster-local order) in idx_lo / idx_hi.
-__device__ __forceinline__ uint32_t sa_eval(uint32_t (*s_pix)[kSaThreads], uint32_t (*s_pal)[kSaThreads],
-                                            const uint8_t *__restrict__ s_w, int tid, const SaConst &K, uint32_t q1,
-                                            uint32_t q2, uint32_t &idx_lo, uint32_t &idx_hi) {
+// nmax / nbmax: the warp's largest cluster size / bucket count - 1 (warp-uniform loop bounds).
+__device__ __forceinline__ uint32_t sa_eval(uint32_t (*s_pix)[kPixStride], uint32_t (*s_pal)[kSaThreads],
+                                            const uint8_t *__restrict__ s_w, int tid, const SaConst &K, int nmax,
+                                            int nbmax, uint32_t q1, uint32_t q2, uint32_t &idx_lo, uint32_t &idx_hi) {
   const uint32_t d11 = __dp4a(q1, q1, 0u), d12 = __dp4a(q1, q2, 0u), d22 = __dp4a(q2, q2, 0u);
-  const int cq = (int)d12 - (int)d11;                       // e1 . (e2 - e1)
   const int den = (int)d22 - 2 * (int)d12 + (int)d11;       // |e2 - e1|^2
-  const uint32_t e1lo = q1 & 0x00FF00FFu, e1hi = (q1 >> 8) & 0x00FF00FFu;
-  const uint32_t e2lo = q2 & 0x00FF00FFu, e2hi = (q2 >> 8) & 0x00FF00FFu;
-  for (int j = 0; j <= K.nbm1; j++) {
-    const uint32_t w = s_w[K.woff + j], iw = 64u - w;
-    // ((64 - w) * e1 + w * e2 + 32) >> 6 per channel, channels 0,2 and 1,3 in 16-bit halves
-    const uint32_t lo = ((e1lo * iw + e2lo * w + 0x00200020u) >> 6) & 0x00FF00FFu;
-    const uint32_t hi = ((e1hi * iw + e2hi * w + 0x00200020u) >> 6) & 0x00FF00FFu;
-    s_pal[j][tid] = lo | (hi << 8);
+  {
+    // ((64 - w) * e1 + w * e2 + 32) >> 6 per channel == (64 * e1 + 32 + w * (e2 - e1)) >> 6, channels
+    // 0,2 and 1,3 in 16-bit halves; the packed difference may borrow across halves, the sum is
+    // exact modulo 2^32 and the true value has no carries
+    const uint32_t e1lo = q1 & 0x00FF00FFu, e1hi = (q1 >> 8) & 0x00FF00FFu;
+    const uint32_t dlo = (q2 & 0x00FF00FFu) - e1lo, dhi = ((q2 >> 8) & 0x00FF00FFu) - e1hi;
+    const uint32_t blo = e1lo * 64u + 0x00200020u, bhi = e1hi * 64u + 0x00200020u;
+    const uint8_t *wt = s_w + K.woff;
+#pragma unroll 4
+    for (int j = 0; j <= nbmax; j++) {  // rows past this lane's bucket count are never read by it
+      const uint32_t w = wt[j];
+      s_pal[j][tid] = (((blo + dlo * w) >> 6) & 0x00FF00FFu) | (((bhi + dhi * w) << 2) & 0xFF00FF00u);
+    }
   }
   const float fden = (float)den, fnb = (float)K.nbm1;
-  // den == 0 (both endpoints equal): the zero reciprocal sends every pixel through the exact path below
+  // den == 0 (both endpoints equal): the zero reciprocal flags every pixel for the exact path
   const float inv16 = den ? __fdiv_rn(__fmul_rn(65536.0f, fnb), fden) : 0.0f;
-  uint32_t total = 0, word[2] = {0, 0};
+  // projection operands with the rotation folded in (see above)
+  const uint32_t q1p = (q1 & K.qkeep) | (((q1 >> K.qsh) << 24) & K.qins);
+  const uint32_t q2p = (q2 & K.qkeep) | (((q2 >> K.qsh) << 24) & K.qins);
+  // num = (pt - e1) . (e2 - e1) = px . q2' - (px . q1' + cq),  cq = e1 . (e2 - e1) - 255 * (e2 - e1)[alpha]
+  const uint32_t cq = (uint32_t)((int)d12 - (int)d11 - K.calpha * ((int)(q2 >> 24) - (int)(q1 >> 24)));
+  const int n = K.n, nbm1 = K.nbm1;
+  const int n1 = n - 1, n2 = n - 2, n3 = n - 3;  // pixel i + k of a group of four is valid iff i < n - k
+  const uint32_t *pal = &s_pal[0][tid];
+  uint32_t total = 0, slow = 0, word[2];
+  // One pixel: adds its error unless it is flagged or past the lane's cluster, shifts the chosen
+  // bucket into ACC from the top, leaves the flag in FLAG.
+#define SA_PIXEL(PX, VALID, FLAG)                                                                          \
+  {                                                                                                        \
+    const uint32_t px_ = (PX);                                                                             \
+    const int num_ = (int)(__dp4a(px_, q2p, 0u) - __dp4a(px_, q1p, cq));                                   \
+    const int v_ = __float2int_rd(__fmul_rn((float)num_, inv16)); /* 16.16 fixed point bucket coordinate */ \
+    /* flagged: within 2^-16 of a bucket boundary (or past the cluster: those flags are masked off later) */ \
+    const bool ok_ = (VALID) && ((((uint32_t)v_ + 1u) & 0xFFFEu) != 0u);                                   \
+    FLAG = !ok_;                                                                                           \
+    const int j1_ = v_ >> 16;                                                                              \
+    const int ja_ = __vimin_s32_relu(j1_, nbm1), jb_ = __vimin_s32_relu(j1_ + 1, nbm1); /* floor / ceil */ \
+    const uint32_t da_ = __vabsdiffu4(pal[ja_ * kSaThreads], px_), db_ = __vabsdiffu4(pal[jb_ * kSaThreads], px_); \
+    const uint32_t ea_ = __dp4a(da_, da_, 0u), eb_ = __dp4a(db_, db_, 0u);                                 \
+    if (ok_) total += min(ea_, eb_);                                                                       \
+    acc = __funnelshift_r(acc, eb_ < ea_ ? jb_ : ja_, 4); /* jb == ja implies eb == ea */                  \
+  }
 #pragma unroll
   for (int half = 0; half < 2; half++) {
-    const int i0 = 8 * half, i1 = min(K.n, i0 + 8);
+    const int i0 = 8 * half, i1 = min(nmax, i0 + 8);
     uint32_t acc = 0;
-    for (int i = i0; i < i1; i++) {
-      const uint32_t px = s_pix[i][tid];
-      // projection point: the pixel itself, or (modes 4/5) the rotated pixel with alpha forced to
-      // 255 -- the error below still uses the pixel (T16)
-      const uint32_t pt = ((px & K.keep) | K.orm) | (((px >> 24) << K.rsh) & K.ins);
-      const int num = (int)__dp4a(pt, q2, 0u) - (int)__dp4a(pt, q1, 0u) - cq;  // (pt - e1) . (e2 - e1), exact
-      const float fnum = (float)num;
-      const int v = __float2int_rd(__fmul_rn(fnum, inv16));
-      const int j1 = v >> 16;
-      int ja = min(max(j1, 0), K.nbm1);
-      bool two = (uint32_t)j1 < (uint32_t)K.nbm1;
-      if ((((uint32_t)v + 1u) & 0xFFFFu) <= 1u) {
-        // too close to a bucket boundary for the fast product: replay the reference's float sequence
-        if (den == 0) {
-          ja = 0; two = false;  // bucket 0 (RGBAEndpoints.cpp:226-251)
-        } else {
-          const float t = __fmul_rn(__fdiv_rn(fnum, fden), fnb);
-          const int x1 = min(max(0, (int)floorf(t)), K.nbm1), x2 = min((int)ceilf(t), K.nbm1);
-          ja = x1;
-          two = x1 + 1 <= x2;
-        }
-      }
-      const int jb = ja + (two ? 1 : 0);  // !two: the same bucket twice, never picked
-      const uint32_t da = __vabsdiffu4(s_pal[ja][tid], px), db = __vabsdiffu4(s_pal[jb][tid], px);
-      const uint32_t ea = __dp4a(da, da, 0u), eb = __dp4a(db, db, 0u);
-      total += min(ea, eb);
-      const uint32_t pick = (uint32_t)ja + (eb < ea ? 1u : 0u);
-      acc = __funnelshift_r(acc, pick, 4);  // nibbles enter at the top; aligned after the loop
+    int i = i0;
+#pragma unroll 1
+    for (; i + 4 <= i1; i += 4) {
+      bool f0, f1, f2, f3;
+      SA_PIXEL(s_pix[i][tid], i < n, f0)
+      SA_PIXEL(s_pix[i + 1][tid], i < n1, f1)
+      SA_PIXEL(s_pix[i + 2][tid], i < n2, f2)
+      SA_PIXEL(s_pix[i + 3][tid], i < n3, f3)
+      slow = (slow << 4) | (f0 ? 8u : 0u) | (f1 ? 4u : 0u) | (f2 ? 2u : 0u) | (f3 ? 1u : 0u);
     }
-    const int cnt = max(i1 - i0, 0);
-    word[half] = cnt ? acc >> (4 * (8 - cnt)) : 0u;
+#pragma unroll 1
+    for (; i < i1; i++) {
+      bool f;
+      SA_PIXEL(s_pix[i][tid], i < n, f)
+      slow = slow + slow + (f ? 1u : 0u);
+    }
+    const int cnt = i1 - i0;
+    word[half] = cnt > 0 ? acc >> (4 * (8 - cnt)) : 0u;
   }
-  const uint32_t lo = word[0], hi = word[1];
-  idx_lo = lo;
-  idx_hi = hi;
+#undef SA_PIXEL
+  // pixel i sits at bit nmax - 1 - i of `slow`; drop the flags of pixels past the lane's cluster
+  slow &= 0xFFFFFFFFu << (nmax - n);
+  // flagged pixels: too close to a bucket boundary for the fast product -- replay the reference's
+  // float sequence (RGBAEndpoints.cpp:262-289), or bucket 0 when the endpoints coincide (:226-251)
+  while (slow) {
+    const int bit = __ffs(slow) - 1;
+    slow &= slow - 1u;
+    const int i = nmax - 1 - bit;
+    const uint32_t px = s_pix[i][tid];
+    int ja = 0;
+    bool two = false;
+    if (den != 0) {
+      const int num = (int)(__dp4a(px, q2p, 0u) - __dp4a(px, q1p, cq));
+      const float t = __fmul_rn(__fdiv_rn((float)num, fden), fnb);
+      const int x1 = min(max(0, (int)floorf(t)), nbm1), x2 = min((int)ceilf(t), nbm1);
+      ja = x1;
+      two = x1 + 1 <= x2;
+    }
+    const uint32_t da = __vabsdiffu4(pal[ja * kSaThreads], px), db = __vabsdiffu4(pal[(ja + (two ? 1 : 0)) * kSaThreads], px);
+    const uint32_t ea = __dp4a(da, da, 0u), eb = __dp4a(db, db, 0u);
+    total += min(ea, eb);
+    const uint32_t pick = (uint32_t)ja + (eb < ea ? 1u : 0u);
+    const int sh = 4 * (i & 7);
+    const uint32_t clr = ~(0xFu << sh), ins = pick << sh;
+    if (i < 8) word[0] = (word[0] & clr) | ins;
+    else word[1] = (word[1] & clr) | ins;
+  }
+  idx_lo = word[0];
+  idx_hi = word[1];
   return total;
 }
 
 __global__ void __launch_bounds__(kSaThreads, kSaCtasPerSm)
 bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, uint32_t first_block, Ws ws,
            int sa_steps) {
-  __shared__ uint32_t s_pix[16][kSaThreads], s_pal[16][kSaThreads];
+  __shared__ uint32_t s_pix[16][kPixStride], s_pal[16][kSaThreads];
   __shared__ uint8_t s_q[kQuantRows][256];
   __shared__ uint8_t s_w[64];
   if (threadIdx.x < 64) s_w[threadIdx.x] = c_weight[threadIdx.x];
@@ -1383,14 +1435,16 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
     s_q[row][e & 255] = (uint8_t)quantize_channel((uint32_t)(e & 255), mask, pbit);
   }
   __syncthreads();
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wbase = tid & ~31;
+  const unsigned full = 0xffffffffu;
   const float f_tm1 = (float)(sa_steps - 1);
+  const float c_x = __fmul_rn(0.1f, f_tm1);  // fast Metropolis exponent: 0.1 * diff / (energy / (steps - 1))
   const int home = blockIdx.x >= ws.bins[200 + 0] ? 0 : (blockIdx.x >= ws.bins[200 + 1] ? 1 : 2);
 
   bool have = false, dry = false;
   SaConst K = {0, 0xFFFFFFFFu, 0, 0, 0, 0, 0, 0, kPbitNone, 0, 0, 0};
   uint32_t gid = 0, cur1 = 0, cur2 = 0, best1 = 0, best2 = 0, cur_err = 0, best_err = 0, rng = 0;
-  uint32_t alpha_err = 0, abytes = 0, best_lo = 0, best_hi = 0;
+  uint32_t best_lo = 0, best_hi = 0;
   int cur_combo = 0, best_combo = 0, energy = 0, rotation = 0;
   bool improved = false;
 #ifdef FASTC_GPU_COUNTERS
@@ -1398,60 +1452,79 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
 #endif
 
   for (;;) {
-    if (!have && !dry) {
-      // next chain: the home class's queue first, then the others (longest steps first)
-      uint32_t pos = 0;
+    const bool need = !have && !dry;
+    if (__any_sync(full, need)) {
+      // ---- refill: every idle lane takes the next chain of its home class's queue (then of the
+      // others, longest steps first) ...
+      uint32_t w0 = 0;
       bool got = false;
+      if (need) {
+        uint32_t pos = 0;
 #pragma unroll
-      for (int a = 0; a < 3 && !got; a++) {
-        const int cls = a == 0 ? home : (2 - (a - 1) - ((2 - (a - 1)) <= home ? 1 : 0));
-        if (cls < 0) break;
-        if (ws.bins[193 + cls] < ws.bins[196 + cls]) {  // cheap look before the atomic
-          pos = atomicAdd(&ws.bins[193 + cls], 1u);
-          got = pos < ws.bins[196 + cls];
+        for (int a = 0; a < 3 && !got; a++) {
+          const int cls = a == 0 ? home : (2 - (a - 1) - ((2 - (a - 1)) <= home ? 1 : 0));
+          if (cls < 0) break;
+          if (ws.bins[193 + cls] < ws.bins[196 + cls]) {  // cheap look before the atomic
+            pos = atomicAdd(&ws.bins[193 + cls], 1u);
+            got = pos < ws.bins[196 + cls];
+          }
+        }
+        if (!got) {
+          dry = true;
+        } else {
+          // constants of the chain's mode and its start state
+          gid = ws.order[pos];
+          const uint32_t *st = ws.states + (size_t)gid * kStateWords;
+          const uint4 s0 = *reinterpret_cast<const uint4 *>(st);
+          w0 = s0.x;
+          const int mode = (w0 >> 16) & 7, rot = (w0 >> 19) & 3, idx_mode = (w0 >> 21) & 1;
+          const ModeAttr A = c_modes[mode];
+          const int ibits = idx_mode == 0 ? A.index_bits : A.alpha_index_bits;
+          K.n = (w0 >> 24) & 31;
+          K.nbm1 = (1 << ibits) - 1;
+          K.woff = 16 * (ibits - 1);
+          K.pbit = A.pbit;
+          K.has_pbit = A.pbit != kPbitNone;
+          K.tab_c = (A.color_bits - 4) * 3;
+          K.tab_a = (A.alpha_bits ? A.alpha_bits - 4 : 5) * 3;
+          uint32_t sc = 1u << (8 - A.color_bits), sa = A.alpha_bits ? (1u << (8 - A.alpha_bits)) : 0u;
+          K.stepb = sc | (sc << 8) | (sc << 16) | (sa << 24);
+          if (mode < 4) K.stepb &= ~(0xFFu << (8 * ((rot + 3) & 3)));  // opaque modes never move alpha (T3)
+          rotation = A.rotation;
+          K.qkeep = 0xFFFFFFFFu; K.qins = 0; K.qsh = 0; K.calpha = 0;
+          if (rotation) {
+            K.calpha = 255;
+            K.qkeep = 0x00FFFFFFu;
+            if (rot) { K.qsh = 8 * (rot - 1); K.qins = 0xFF000000u; K.qkeep &= ~(0xFFu << K.qsh); }
+          }
+          cur1 = best1 = s0.y; cur2 = best2 = s0.z;
+          cur_err = best_err = s0.w;
+          rng = st[4];
+          cur_combo = best_combo = (w0 >> 22) & 3;
+          energy = 0;
+          improved = false;
+          have = true;
         }
       }
-      if (!got) {
-        dry = true;
-      } else {
-        // ---- load a chain: constants of its mode, its pixels, its start state
-        gid = ws.order[pos];
-        const uint32_t *st = ws.states + (size_t)gid * kStateWords;
-        const uint32_t w0 = st[0];
-        const int mode = (w0 >> 16) & 7, rot = (w0 >> 19) & 3, idx_mode = (w0 >> 21) & 1;
-        const ModeAttr A = c_modes[mode];
-        const int ibits = idx_mode == 0 ? A.index_bits : A.alpha_index_bits;
-        K.n = (w0 >> 24) & 31;
-        K.nbm1 = (1 << ibits) - 1;
-        K.woff = 16 * (ibits - 1);
-        K.pbit = A.pbit;
-        K.has_pbit = A.pbit != kPbitNone;
-        K.tab_c = (A.color_bits - 4) * 3;
-        K.tab_a = (A.alpha_bits ? A.alpha_bits - 4 : 5) * 3;
-        uint32_t sc = 1u << (8 - A.color_bits), sa = A.alpha_bits ? (1u << (8 - A.alpha_bits)) : 0u;
-        K.stepb = sc | (sc << 8) | (sc << 16) | (sa << 24);
-        if (mode < 4) K.stepb &= ~(0xFFu << (8 * ((rot + 3) & 3)));  // opaque modes never move alpha (T3)
-        rotation = A.rotation;
-        K.keep = 0xFFFFFFFFu; K.orm = 0; K.ins = 0; K.rsh = 0;
-        if (rotation) {
-          K.orm = 0xFF000000u;
-          if (rot) { K.rsh = 8 * (rot - 1); K.ins = 0xFFu << K.rsh; K.keep = ~K.ins; }
+      // ... and the warp loads the new chains' pixels together: lane i < 16 fetches pixel i of the
+      // block and stores it at its rank within the subset mask, into the owner lane's column
+      unsigned gm = __ballot_sync(full, got);
+      while (gm) {
+        const int owner = __ffs(gm) - 1;
+        gm &= gm - 1;
+        const uint32_t g = __shfl_sync(full, gid, owner), m = __shfl_sync(full, w0, owner);
+        if (lane < 16 && ((m >> lane) & 1)) {
+          const uint32_t bi = first_block + g / kSlots;
+          const uint32_t *base = img + (size_t)(bi / blocks_x) * 4 * width + (size_t)(bi % blocks_x) * 4;
+          s_pix[__popc(m & ((1u << lane) - 1u))][wbase + owner] = __ldg(base + (size_t)(lane >> 2) * width + (lane & 3));
         }
-        cur1 = best1 = st[1]; cur2 = best2 = st[2];
-        cur_err = best_err = st[3];
-        rng = st[4]; alpha_err = st[5]; abytes = st[6];
-        cur_combo = best_combo = (w0 >> 22) & 3;
-        energy = 0;
-        improved = false;
-        const uint32_t t = gid / kSlots, bi = first_block + t;
-        const uint32_t *base = img + (size_t)(bi / blocks_x) * 4 * width + (size_t)(bi % blocks_x) * 4;
-        int k = 0;
-        for (int i = 0; i < 16; i++)
-          if ((w0 >> i) & 1) s_pix[k++][tid] = __ldg(base + (size_t)(i >> 2) * width + (i & 3));
-        have = true;
       }
+      __syncwarp();
     }
-    if (!__any_sync(0xffffffffu, have)) break;
+    if (!__any_sync(full, have)) break;
+    // warp-uniform loop bounds of this step's evaluation
+    const int nmax = __reduce_max_sync(full, have ? K.n : 0);
+    const int nbmax = __reduce_max_sync(full, have ? K.nbm1 : 0);
     if (!have) continue;
 
     // ---- one annealing step
@@ -1476,7 +1549,7 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
       // modes without p-bits evaluate with a zero p-bit (reference quirk, see fit_cluster)
       const uint32_t q1 = sa_quantize(s_q, K, n1, K.has_pbit ? npb0 : 0), q2 = sa_quantize(s_q, K, n2, K.has_pbit ? npb1 : 0);
       uint32_t ilo, ihi;
-      const uint32_t err = sa_eval(s_pix, s_pal, s_w, tid, K, q1, q2, ilo, ihi);
+      const uint32_t err = sa_eval(s_pix, s_pal, s_w, tid, K, nmax, nbmax, q1, q2, ilo, ihi);
 #ifdef FASTC_GPU_COUNTERS
       ncalls++; npbe += K.n;
 #endif
@@ -1491,12 +1564,13 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
         if (energy == 0) {
           accept = false;  // temp == 0: exp(-inf) = 0, exp(NaN) = NaN -> never accepted
         } else {
-          const float temp = __fdiv_rn((float)energy, f_tm1);
           const float diff = (float)((int)cur_err - (int)err);  // exact (|.| < 2^24)
-          const float pf = __expf(__fdividef(0.1f * diff, temp));
+          // exp(0.1 * diff / temp), temp = energy / (steps - 1), through fast reciprocal / exponential
+          const float pf = __expf(__fdividef(__fmul_rn(diff, c_x), (float)energy));
           if (fr < pf * (1.0f - 3e-5f)) accept = true;
           else if (fr > pf * (1.0f + 3e-5f)) accept = false;
-          else {  // within the fast exponential's error band: the reference's double expression
+          else {  // within the fast path's error band: the reference's double expression
+            const float temp = __fdiv_rn((float)energy, f_tm1);
             const double x = ((double)0.1f * ((double)cur_err - (double)err)) / (double)temp;
             accept = (double)fr < exp(x);
           }
@@ -1515,13 +1589,22 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
       // the indices belong to the evaluation that produced best_err: the start state's were
       // stored by bc7_setup, an improved state's were kept when it was found
       uint32_t *res = ws.results + (size_t)gid * kResWords;
-      uint32_t o1 = best1, o2 = best2;
+      uint32_t o1 = best1, o2 = best2, alpha_err = 0;
       if (rotation) {
+        const uint32_t *st = ws.states + (size_t)gid * kStateWords;
+        const uint32_t abytes = st[6];
+        alpha_err = st[5];
         o1 = (o1 & 0x00FFFFFFu) | ((abytes & 0xFF) << 24);
         o2 = (o2 & 0x00FFFFFFu) | (((abytes >> 8) & 0xFF) << 24);
       }
-      res[0] = best_err + alpha_err; res[1] = o1; res[2] = o2; res[3] = (uint32_t)best_combo;
-      if (improved) { res[4] = best_lo; res[5] = best_hi; }
+      *reinterpret_cast<uint4 *>(res) = make_uint4(best_err + alpha_err, o1, o2, (uint32_t)best_combo);
+      if (improved) {
+        // nibbles past the cluster size come from the warp's longer loops: clear them
+        const int n = K.n;
+        const uint32_t mlo = n >= 8 ? 0xFFFFFFFFu : ((1u << (4 * n)) - 1u);
+        const uint32_t mhi = n >= 16 ? 0xFFFFFFFFu : (n > 8 ? ((1u << (4 * (n - 8))) - 1u) : 0u);
+        *reinterpret_cast<uint2 *>(res + 4) = make_uint2(best_lo & mlo, best_hi & mhi);
+      }
       have = false;
     }
   }
