@@ -1290,7 +1290,9 @@ struct SaConst {
   uint32_t qkeep, qins;  // projection operand q' = (q & qkeep) | (((q >> qsh) << 24) & qins)
   int qsh;
   int calpha;            // 255 when the projected point's alpha is forced to 255 (modes 4/5), else 0
-  int n, nbm1, woff, pbit, has_pbit;
+  int n, nbm1, woff;
+  int xm, sh0;           // p-bit combos without branches: the flipped combo is combo ^ xm (shared 1, per
+                         // endpoint 3, none 0); p-bit of endpoint 1 = (combo >> sh0) & 1, of endpoint 2 = combo & 1
   int tab_c, tab_a;      // quantisation table rows (precision class) of colour / alpha
 };
 
@@ -1442,7 +1444,7 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
   const int home = blockIdx.x >= ws.bins[200 + 0] ? 0 : (blockIdx.x >= ws.bins[200 + 1] ? 1 : 2);
 
   bool have = false, dry = false;
-  SaConst K = {0, 0xFFFFFFFFu, 0, 0, 0, 0, 0, 0, kPbitNone, 0, 0, 0};
+  SaConst K = {0, 0xFFFFFFFFu, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   uint32_t gid = 0, cur1 = 0, cur2 = 0, best1 = 0, best2 = 0, cur_err = 0, best_err = 0, rng = 0;
   uint32_t best_lo = 0, best_hi = 0;
   int cur_combo = 0, best_combo = 0, energy = 0, rotation = 0;
@@ -1483,8 +1485,8 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
           K.n = (w0 >> 24) & 31;
           K.nbm1 = (1 << ibits) - 1;
           K.woff = 16 * (ibits - 1);
-          K.pbit = A.pbit;
-          K.has_pbit = A.pbit != kPbitNone;
+          K.xm = A.pbit == kPbitShared ? 1 : (A.pbit == kPbitPerEndpoint ? 3 : 0);
+          K.sh0 = A.pbit == kPbitPerEndpoint ? 1 : 0;
           K.tab_c = (A.color_bits - 4) * 3;
           K.tab_a = (A.alpha_bits ? A.alpha_bits - 4 : 5) * 3;
           uint32_t sc = 1u << (8 - A.color_bits), sa = A.alpha_bits ? (1u << (8 - A.alpha_bits)) : 0u;
@@ -1531,23 +1533,20 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
     bool done = !(best_err > 0 && energy < sa_steps);
     if (!done) {
       // PickBestNeighboringEndpoints (:426-498)
-      int ncombo = 0;
-      if (K.has_pbit) ncombo = K.pbit == kPbitShared ? (cur_combo ^ 1) : 3 - cur_combo;
-      int opb0, opb1;
-      pbit_combo(K.pbit, cur_combo, opb0, opb1);
+      const int has_pbit = K.xm != 0;
+      const int ncombo = cur_combo ^ K.xm;  // the p-bit always flips (shared: 0 <-> 1, per endpoint: c <-> 3 - c)
+      const int opb0 = (cur_combo >> K.sh0) & 1, opb1 = cur_combo & 1;
       uint32_t n1, n2;
       int guard = -1;
       bool visited;
       do {
         // pt = 0 moves endpoint 2 first and (as the reference does) tests p-bit [0] for it
-        n2 = move_endpoint(cur2, lcg_next(rng), opb0, K.has_pbit, K.stepb);
-        n1 = move_endpoint(cur1, lcg_next(rng), opb1, K.has_pbit, K.stepb);
+        n2 = move_endpoint(cur2, lcg_next(rng), opb0, has_pbit, K.stepb);
+        n1 = move_endpoint(cur1, lcg_next(rng), opb1, has_pbit, K.stepb);
         visited = (best1 == n1) && (best2 == n2) && (best_combo == ncombo);
       } while (visited && ++guard < 15);
-      int npb0, npb1;
-      pbit_combo(K.pbit, ncombo, npb0, npb1);
-      // modes without p-bits evaluate with a zero p-bit (reference quirk, see fit_cluster)
-      const uint32_t q1 = sa_quantize(s_q, K, n1, K.has_pbit ? npb0 : 0), q2 = sa_quantize(s_q, K, n2, K.has_pbit ? npb1 : 0);
+      // modes without p-bits evaluate with a zero p-bit (reference quirk, see fit_cluster): their combo is 0
+      const uint32_t q1 = sa_quantize(s_q, K, n1, (ncombo >> K.sh0) & 1), q2 = sa_quantize(s_q, K, n2, ncombo & 1);
       uint32_t ilo, ihi;
       const uint32_t err = sa_eval(s_pix, s_pal, s_w, tid, K, nmax, nbmax, q1, q2, ilo, ihi);
 #ifdef FASTC_GPU_COUNTERS
