@@ -1296,11 +1296,12 @@ struct SaConst {
   int tab_c, tab_a;      // quantisation table rows (precision class) of colour / alpha
 };
 
-// quantisation tables: row = class * 3 + (pbit + 1), class 0..4 = 4..8 kept bits, class 5 = "no
-// bits kept" (the alpha of opaque modes: always 255)
-constexpr int kQuantRows = 18;
+// quantisation tables: row = class * 2 + pbit, class 0..4 = 4..8 kept bits, class 5 = "no bits
+// kept" (the alpha of opaque modes: always 255).  The annealing loop only ever quantises with a
+// p-bit of 0 or 1 (modes without p-bits evaluate with a zero p-bit, see fit_cluster).
+constexpr int kQuantRows = 12;
 __device__ __forceinline__ uint32_t sa_quantize(const uint8_t (*s_q)[256], const SaConst &K, uint32_t p, int pbit) {
-  const uint8_t *tc = s_q[K.tab_c + pbit + 1], *ta = s_q[K.tab_a + pbit + 1];
+  const uint8_t *tc = s_q[K.tab_c + pbit], *ta = s_q[K.tab_a + pbit];
   return (uint32_t)tc[p & 0xFF] | ((uint32_t)tc[(p >> 8) & 0xFF] << 8) | ((uint32_t)tc[(p >> 16) & 0xFF] << 16) |
          ((uint32_t)ta[p >> 24] << 24);
 }
@@ -1317,12 +1318,71 @@ __device__ __forceinline__ uint32_t move_endpoint(uint32_t src, uint32_t dir, in
   return __vaddus4(__vsubus4(src, sub), add);
 }
 
+// The pixel loops of sa_eval.  UNI: every lane of the warp fits a cluster of nmax pixels (the
+// usual case, the work list is sorted by cluster size), so no pixel needs a validity test.
+template <bool UNI>
+__device__ __forceinline__ void sa_pixels(uint32_t (*s_pix)[kPixStride], const uint2 *pal, int tid, int n, int nbm1,
+                                          int nmax, uint32_t q1p, uint32_t q2p, uint32_t cq, float inv16,
+                                          uint32_t &total, uint32_t &slow, uint32_t (&word)[2]) {
+  const int n1 = n - 1, n2 = n - 2, n3 = n - 3;  // pixel i + k of a group of four is valid iff i < n - k
+  // One pixel: adds its error unless it is flagged or past the lane's cluster, shifts the chosen
+  // bucket into ACC from the top, leaves the flag in FLAG.
+#define SA_PIXEL(PX, VALID, FLAG)                                                                          \
+  {                                                                                                        \
+    const uint32_t px_ = (PX);                                                                             \
+    const int num_ = (int)(__dp4a(px_, q2p, 0u) - __dp4a(px_, q1p, cq));                                   \
+    const int v_ = __float2int_rd(__fmul_rn((float)num_, inv16)); /* 16.16 fixed point bucket coordinate */ \
+    /* flagged: within 2^-16 of a bucket boundary (or past the cluster: those flags are masked off later) */ \
+    const bool ok_ = (VALID) && ((((uint32_t)v_ + 1u) & 0xFFFEu) != 0u);                                   \
+    FLAG = !ok_;                                                                                           \
+    const int ja_ = __vimin_s32_relu(v_ >> 16, nbm1); /* floor, clamped */                                 \
+    const uint2 c_ = pal[ja_ * kSaThreads];                                                                \
+    const uint32_t da_ = __vabsdiffu4(c_.x, px_), db_ = __vabsdiffu4(c_.y, px_);                           \
+    const uint32_t ea_ = __dp4a(da_, da_, 0u), eb_ = __dp4a(db_, db_, 0u);                                 \
+    /* a projection before endpoint 1 only tests bucket 0; past endpoint 2 both colours are bucket nbm1 */ \
+    uint32_t e_, pick_;                                                                                    \
+    asm("{\n\t.reg .pred p, q;\n\tsetp.ge.s32 q, %4, 0;\n\tsetp.lt.and.u32 p, %3, %2, q;\n\t"              \
+        "selp.u32 %0, %3, %2, p;\n\tmov.u32 %1, %5;\n\t@p add.u32 %1, %1, 1;\n\t}"                           \
+        : "=r"(e_), "=&r"(pick_) : "r"(ea_), "r"(eb_), "r"(v_), "r"(ja_));                                 \
+    if (ok_) total += e_;                                                                                  \
+    acc = __funnelshift_r(acc, pick_, 4);                                                                  \
+  }
+#pragma unroll
+  for (int half = 0; half < 2; half++) {
+    const int i0 = 8 * half, i1 = min(nmax, i0 + 8);
+    uint32_t acc = 0;
+    int i = i0;
+#pragma unroll 1
+    for (; i + 4 <= i1; i += 4) {
+      bool f0, f1, f2, f3;
+      SA_PIXEL(s_pix[i][tid], UNI || i < n, f0)
+      SA_PIXEL(s_pix[i + 1][tid], UNI || i < n1, f1)
+      SA_PIXEL(s_pix[i + 2][tid], UNI || i < n2, f2)
+      SA_PIXEL(s_pix[i + 3][tid], UNI || i < n3, f3)
+      slow = (slow << 4) | (f0 ? 8u : 0u) | (f1 ? 4u : 0u) | (f2 ? 2u : 0u) | (f3 ? 1u : 0u);
+    }
+#pragma unroll 1
+    for (; i < i1; i++) {
+      bool f;
+      SA_PIXEL(s_pix[i][tid], UNI || i < n, f)
+      slow = slow + slow + (f ? 1u : 0u);
+    }
+    const int cnt = i1 - i0;
+    word[half] = cnt > 0 ? acc >> (4 * (8 - cnt)) : 0u;
+  }
+#undef SA_PIXEL
+}
+
 // Evaluate one cluster against quantised endpoints q1/q2: returns the total error and the
 // chosen bucket of every pixel (4 bits each, cluster-local order) in idx_lo / idx_hi.
 // nmax / nbmax: the warp's largest cluster size / bucket count - 1 (warp-uniform loop bounds).
-__device__ __forceinline__ uint32_t sa_eval(uint32_t (*s_pix)[kPixStride], uint32_t (*s_pal)[kSaThreads],
+// The palette is stored as PAIRS: row j of the lane's column holds (colour j, colour j + 1), the
+// last row (colour nbm1, colour nbm1) -- the weight table is padded with 64 -- so the two
+// candidate buckets of a pixel (floor and ceil of its projection) come from one 64-bit load.
+__device__ __forceinline__ uint32_t sa_eval(uint32_t (*s_pix)[kPixStride], uint2 (*s_pal)[kSaThreads],
                                             const uint8_t *__restrict__ s_w, int tid, const SaConst &K, int nmax,
-                                            int nbmax, uint32_t q1, uint32_t q2, uint32_t &idx_lo, uint32_t &idx_hi) {
+                                            int nbmax, bool uniform, uint32_t q1, uint32_t q2, uint32_t &idx_lo,
+                                            uint32_t &idx_hi) {
   const uint32_t d11 = __dp4a(q1, q1, 0u), d12 = __dp4a(q1, q2, 0u), d22 = __dp4a(q2, q2, 0u);
   const int den = (int)d22 - 2 * (int)d12 + (int)d11;       // |e2 - e1|^2
   {
@@ -1332,11 +1392,14 @@ __device__ __forceinline__ uint32_t sa_eval(uint32_t (*s_pix)[kPixStride], uint3
     const uint32_t e1lo = q1 & 0x00FF00FFu, e1hi = (q1 >> 8) & 0x00FF00FFu;
     const uint32_t dlo = (q2 & 0x00FF00FFu) - e1lo, dhi = ((q2 >> 8) & 0x00FF00FFu) - e1hi;
     const uint32_t blo = e1lo * 64u + 0x00200020u, bhi = e1hi * 64u + 0x00200020u;
-    const uint8_t *wt = s_w + K.woff;
+    const uint8_t *wt = s_w + K.woff + 1;
+    uint32_t cur = q1;  // colour 0 (weight 0) is endpoint 1 itself
 #pragma unroll 4
     for (int j = 0; j <= nbmax; j++) {  // rows past this lane's bucket count are never read by it
       const uint32_t w = wt[j];
-      s_pal[j][tid] = (((blo + dlo * w) >> 6) & 0x00FF00FFu) | (((bhi + dhi * w) << 2) & 0xFF00FF00u);
+      const uint32_t nxt = (((blo + dlo * w) >> 6) & 0x00FF00FFu) | (((bhi + dhi * w) << 2) & 0xFF00FF00u);
+      s_pal[j][tid] = make_uint2(cur, nxt);
+      cur = nxt;
     }
   }
   const float fden = (float)den, fnb = (float)K.nbm1;
@@ -1348,54 +1411,18 @@ __device__ __forceinline__ uint32_t sa_eval(uint32_t (*s_pix)[kPixStride], uint3
   // num = (pt - e1) . (e2 - e1) = px . q2' - (px . q1' + cq),  cq = e1 . (e2 - e1) - 255 * (e2 - e1)[alpha]
   const uint32_t cq = (uint32_t)((int)d12 - (int)d11 - K.calpha * ((int)(q2 >> 24) - (int)(q1 >> 24)));
   const int n = K.n, nbm1 = K.nbm1;
-  const int n1 = n - 1, n2 = n - 2, n3 = n - 3;  // pixel i + k of a group of four is valid iff i < n - k
-  const uint32_t *pal = &s_pal[0][tid];
+  const uint2 *pal = &s_pal[0][tid];
   uint32_t total = 0, slow = 0, word[2];
-  // One pixel: adds its error unless it is flagged or past the lane's cluster, shifts the chosen
-  // bucket into ACC from the top, leaves the flag in FLAG.
-#define SA_PIXEL(PX, VALID, FLAG)                                                                          \
-  {                                                                                                        \
-    const uint32_t px_ = (PX);                                                                             \
-    const int num_ = (int)(__dp4a(px_, q2p, 0u) - __dp4a(px_, q1p, cq));                                   \
-    const int v_ = __float2int_rd(__fmul_rn((float)num_, inv16)); /* 16.16 fixed point bucket coordinate */ \
-    /* flagged: within 2^-16 of a bucket boundary (or past the cluster: those flags are masked off later) */ \
-    const bool ok_ = (VALID) && ((((uint32_t)v_ + 1u) & 0xFFFEu) != 0u);                                   \
-    FLAG = !ok_;                                                                                           \
-    const int j1_ = v_ >> 16;                                                                              \
-    const int ja_ = __vimin_s32_relu(j1_, nbm1), jb_ = __vimin_s32_relu(j1_ + 1, nbm1); /* floor / ceil */ \
-    const uint32_t da_ = __vabsdiffu4(pal[ja_ * kSaThreads], px_), db_ = __vabsdiffu4(pal[jb_ * kSaThreads], px_); \
-    const uint32_t ea_ = __dp4a(da_, da_, 0u), eb_ = __dp4a(db_, db_, 0u);                                 \
-    if (ok_) total += min(ea_, eb_);                                                                       \
-    acc = __funnelshift_r(acc, eb_ < ea_ ? jb_ : ja_, 4); /* jb == ja implies eb == ea */                  \
-  }
-#pragma unroll
-  for (int half = 0; half < 2; half++) {
-    const int i0 = 8 * half, i1 = min(nmax, i0 + 8);
-    uint32_t acc = 0;
-    int i = i0;
-#pragma unroll 1
-    for (; i + 4 <= i1; i += 4) {
-      bool f0, f1, f2, f3;
-      SA_PIXEL(s_pix[i][tid], i < n, f0)
-      SA_PIXEL(s_pix[i + 1][tid], i < n1, f1)
-      SA_PIXEL(s_pix[i + 2][tid], i < n2, f2)
-      SA_PIXEL(s_pix[i + 3][tid], i < n3, f3)
-      slow = (slow << 4) | (f0 ? 8u : 0u) | (f1 ? 4u : 0u) | (f2 ? 2u : 0u) | (f3 ? 1u : 0u);
-    }
-#pragma unroll 1
-    for (; i < i1; i++) {
-      bool f;
-      SA_PIXEL(s_pix[i][tid], i < n, f)
-      slow = slow + slow + (f ? 1u : 0u);
-    }
-    const int cnt = i1 - i0;
-    word[half] = cnt > 0 ? acc >> (4 * (8 - cnt)) : 0u;
-  }
-#undef SA_PIXEL
+  if (uniform) sa_pixels<true>(s_pix, pal, tid, n, nbm1, nmax, q1p, q2p, cq, inv16, total, slow, word);
+  else sa_pixels<false>(s_pix, pal, tid, n, nbm1, nmax, q1p, q2p, cq, inv16, total, slow, word);
   // pixel i sits at bit nmax - 1 - i of `slow`; drop the flags of pixels past the lane's cluster
   slow &= 0xFFFFFFFFu << (nmax - n);
-  // flagged pixels: too close to a bucket boundary for the fast product -- replay the reference's
-  // float sequence (RGBAEndpoints.cpp:262-289), or bucket 0 when the endpoints coincide (:226-251)
+  // Flagged pixels: too close to a bucket boundary for the fast product.  Nearly all of them sit
+  // EXACTLY on one (num * nbm1 == k * den): the reference then computes fl(fl(k / nbm1) * nbm1),
+  // which is exactly k for every 0 <= k <= nbm1 and nbm1 in {3, 7, 15}, stays <= 0 for k <= 0 and
+  // >= nbm1 for k >= nbm1 (tests/test_tables.py::test_projection_exact_buckets), so floor == ceil
+  // and only bucket clamp(k) is tested.  The rest replay the reference's float sequence
+  // (RGBAEndpoints.cpp:262-289); coinciding endpoints test bucket 0 (:226-251).
   while (slow) {
     const int bit = __ffs(slow) - 1;
     slow &= slow - 1u;
@@ -1405,15 +1432,22 @@ __device__ __forceinline__ uint32_t sa_eval(uint32_t (*s_pix)[kPixStride], uint3
     bool two = false;
     if (den != 0) {
       const int num = (int)(__dp4a(px, q2p, 0u) - __dp4a(px, q1p, cq));
-      const float t = __fmul_rn(__fdiv_rn((float)num, fden), fnb);
-      const int x1 = min(max(0, (int)floorf(t)), nbm1), x2 = min((int)ceilf(t), nbm1);
-      ja = x1;
-      two = x1 + 1 <= x2;
+      const int k = (__float2int_rd(__fmul_rn((float)num, inv16)) + 0x8000) >> 16;
+      if (num * nbm1 == k * den) {
+        ja = __vimin_s32_relu(k, nbm1);
+      } else {
+        const float t = __fmul_rn(__fdiv_rn((float)num, fden), fnb);
+        const int x1 = min(max(0, (int)floorf(t)), nbm1), x2 = min((int)ceilf(t), nbm1);
+        ja = x1;
+        two = x1 + 1 <= x2;
+      }
     }
-    const uint32_t da = __vabsdiffu4(pal[ja * kSaThreads], px), db = __vabsdiffu4(pal[(ja + (two ? 1 : 0)) * kSaThreads], px);
+    const uint2 c = pal[ja * kSaThreads];
+    const uint32_t da = __vabsdiffu4(c.x, px), db = __vabsdiffu4(c.y, px);
     const uint32_t ea = __dp4a(da, da, 0u), eb = __dp4a(db, db, 0u);
-    total += min(ea, eb);
-    const uint32_t pick = (uint32_t)ja + (eb < ea ? 1u : 0u);
+    const bool up = two && eb < ea;
+    total += up ? eb : ea;
+    const uint32_t pick = (uint32_t)ja + (up ? 1u : 0u);
     const int sh = 4 * (i & 7);
     const uint32_t clr = ~(0xFu << sh), ins = pick << sh;
     if (i < 8) word[0] = (word[0] & clr) | ins;
@@ -1427,12 +1461,16 @@ __device__ __forceinline__ uint32_t sa_eval(uint32_t (*s_pix)[kPixStride], uint3
 __global__ void __launch_bounds__(kSaThreads, kSaCtasPerSm)
 bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, uint32_t first_block, Ws ws,
            int sa_steps) {
-  __shared__ uint32_t s_pix[16][kPixStride], s_pal[16][kSaThreads];
+  __shared__ uint2 s_pal[16][kSaThreads];
+  __shared__ uint32_t s_pix[16][kPixStride];
   __shared__ uint8_t s_q[kQuantRows][256];
-  __shared__ uint8_t s_w[64];
-  if (threadIdx.x < 64) s_w[threadIdx.x] = c_weight[threadIdx.x];
+  __shared__ uint8_t s_w[80];  // c_weight with every slot past a row's last weight (and [64..79]) set to 64
+  if (threadIdx.x < 80) {
+    const int row = threadIdx.x >> 4, k = threadIdx.x & 15;  // row = index bits - 1
+    s_w[threadIdx.x] = (row < 4 && k < (2 << row)) ? c_weight[threadIdx.x] : (uint8_t)64;
+  }
   for (int e = threadIdx.x; e < kQuantRows * 256; e += kSaThreads) {
-    const int row = e >> 8, cls = row / 3, pbit = row % 3 - 1;
+    const int row = e >> 8, cls = row >> 1, pbit = row & 1;
     const uint32_t mask = cls == 5 ? 0u : ((0xFF00u >> (cls + 4)) & 0xFFu);
     s_q[row][e & 255] = (uint8_t)quantize_channel((uint32_t)(e & 255), mask, pbit);
   }
@@ -1448,7 +1486,8 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
   uint32_t gid = 0, cur1 = 0, cur2 = 0, best1 = 0, best2 = 0, cur_err = 0, best_err = 0, rng = 0;
   uint32_t best_lo = 0, best_hi = 0;
   int cur_combo = 0, best_combo = 0, energy = 0, rotation = 0;
-  bool improved = false;
+  bool improved = false, uniform = false;
+  int nmax = 0, nbmax = 0;
 #ifdef FASTC_GPU_COUNTERS
   uint32_t ncalls = 0, npbe = 0;
 #endif
@@ -1487,8 +1526,8 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
           K.woff = 16 * (ibits - 1);
           K.xm = A.pbit == kPbitShared ? 1 : (A.pbit == kPbitPerEndpoint ? 3 : 0);
           K.sh0 = A.pbit == kPbitPerEndpoint ? 1 : 0;
-          K.tab_c = (A.color_bits - 4) * 3;
-          K.tab_a = (A.alpha_bits ? A.alpha_bits - 4 : 5) * 3;
+          K.tab_c = (A.color_bits - 4) * 2;
+          K.tab_a = (A.alpha_bits ? A.alpha_bits - 4 : 5) * 2;
           uint32_t sc = 1u << (8 - A.color_bits), sa = A.alpha_bits ? (1u << (8 - A.alpha_bits)) : 0u;
           K.stepb = sc | (sc << 8) | (sc << 16) | (sa << 24);
           if (mode < 4) K.stepb &= ~(0xFFu << (8 * ((rot + 3) & 3)));  // opaque modes never move alpha (T3)
@@ -1522,11 +1561,13 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
         }
       }
       __syncwarp();
+      // warp-uniform loop bounds of the evaluations: they only change here (a lane that ends its
+      // chain with the queue dry leaves them larger than needed, which is harmless)
+      nmax = __reduce_max_sync(full, have ? K.n : 0);
+      nbmax = __reduce_max_sync(full, have ? K.nbm1 : 0);
+      uniform = __all_sync(full, !have || K.n == nmax);
     }
     if (!__any_sync(full, have)) break;
-    // warp-uniform loop bounds of this step's evaluation
-    const int nmax = __reduce_max_sync(full, have ? K.n : 0);
-    const int nbmax = __reduce_max_sync(full, have ? K.nbm1 : 0);
     if (!have) continue;
 
     // ---- one annealing step
@@ -1548,7 +1589,7 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
       // modes without p-bits evaluate with a zero p-bit (reference quirk, see fit_cluster): their combo is 0
       const uint32_t q1 = sa_quantize(s_q, K, n1, (ncombo >> K.sh0) & 1), q2 = sa_quantize(s_q, K, n2, ncombo & 1);
       uint32_t ilo, ihi;
-      const uint32_t err = sa_eval(s_pix, s_pal, s_w, tid, K, nmax, nbmax, q1, q2, ilo, ihi);
+      const uint32_t err = sa_eval(s_pix, s_pal, s_w, tid, K, nmax, nbmax, uniform, q1, q2, ilo, ihi);
 #ifdef FASTC_GPU_COUNTERS
       ncalls++; npbe += K.n;
 #endif

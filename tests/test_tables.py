@@ -92,3 +92,21 @@ def test_etc1_solid_colour_lists_equal_reference():
                 c = ((pc >> 2) | (pc << 3)) if diff else (pc | (pc << 4))
                 errs.append(abs(min(255, max(0, c + inten[it][sel])) - v))
             assert inv[idx, v] >> 8 == min(errs) and inv[idx, v] & 0xFF == errs.index(min(errs))
+
+
+def test_projection_exact_buckets():
+    """bc7_anneal's exact-bucket shortcut (fastc_b200/csrc/bc7.cu: sa_eval slow path): when a pixel's
+    projection num/den * nbm1 is EXACTLY an integer k, the reference's float sequence
+    fl(fl(num / den) * nbm1) (RGBAEndpoints.cpp:262-268) yields exactly k for 0 <= k <= nbm1, stays
+    <= 0 for k <= 0 and >= nbm1 for k >= nbm1, so floor == ceil after clamping and one bucket is tested."""
+    f = np.float32
+    for m in (3, 7, 15):
+        for k in range(-70000, 70001):   # |num * nbm1 / den| <= 15 * 4 * 255^2 / 1 in principle; the clamp only needs the sign / >= nbm1
+            t = f(f(k) / f(m)) * f(m)
+            assert isinstance(t, np.float32)
+            if 0 <= k <= m:
+                assert t == f(k), (m, k, t)
+            elif k < 0:
+                assert t < 0, (m, k, t)
+            else:
+                assert t > f(m) - f(0.5) and np.ceil(t) >= m and np.floor(t) >= m, (m, k, t)
