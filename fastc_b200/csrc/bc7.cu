@@ -598,23 +598,23 @@ struct FitResult {
   bool need_sa;  // true: (p1, p2, combo, err) is the START state of the annealing chain
 };
 
-__device__ __noinline__ void fit_cluster(const Ws &ws, const ModeAttr &A, int mode, int idx_mode, int rot, const uint32_t *pts,
-                            const uint32_t *pix, int n, const float avg[4], bool all_same, int sa_steps,
-                            const uint8_t *__restrict__ s_w, uint32_t (*s_acc)[16][128], int tid, FitResult &R) {
-  R.need_sa = false;
-  const int ibits = idx_mode == 0 ? A.index_bits : A.alpha_index_bits;
-  const int nb = 1 << ibits, nbm1 = nb - 1;
-  const uint8_t *wtab = s_w + 16 * (ibits - 1);
-  const int npbit = A.pbit == kPbitShared ? 2 : (A.pbit == kPbitPerEndpoint ? 4 : 1);
-  const uint32_t qm = quant_mask(A);
+// The fit is split in two so that chains which share a cluster AND an index precision share the
+// expensive part (see twin_slot below):
+//   fit_core    mode-independent: PCA axis, k-means over the 2^ibits interpolation points,
+//               least-squares endpoints (float)                      (Compressor.cpp:936-1077)
+//   fit_finish  per mode: single-colour shortcuts, ClampEndpointsToGrid, first error evaluation
+struct FitCore {
+  int kind;        // 0: all points equal, 1: k-means left one bucket (colour in `single`), 2: p1/p2 valid
+  uint32_t single;
+  float p1[4], p2[4];
+};
 
-  if (all_same) {  // AllSamePoint -> CompressSingleColor on point 0
-    int combo = 0;
-    uint32_t p1 = 0, p2 = 0;
-    const uint32_t e = single_color(mode, idx_mode, npbit, pts[0], p1, p2, combo);
-    R.err = (uint32_t)n * e;
-    R.p1 = p1; R.p2 = p2; R.combo = combo;
-    R.indices = 0x1111111111111111ull;
+__device__ __noinline__ void fit_core(int ibits, const uint32_t *pts, int n, const float avg[4], bool all_same,
+                                      uint32_t (*s_acc)[16][128], int tid, FitCore &C) {
+  const int nb = 1 << ibits, nbm1 = nb - 1;
+  if (all_same) {  // AllSamePoint -> CompressSingleColor on point 0 (fit_finish)
+    C.kind = 0;
+    C.single = pts[0];
     return;
   }
 
@@ -807,13 +807,9 @@ __device__ __noinline__ void fit_cluster(const Ws &ws, const ModeAttr &A, int mo
 #pragma unroll 1
   for (int j = 0; j < nb; j++)
     if (cnt[j] > 0) { filled++; last = j; }
-  if (filled == 1) {  // one bucket -> CompressSingleColor on its centroid (:1038-1047)
-    int combo = 0;
-    uint32_t q1 = 0, q2 = 0;
-    const uint32_t e = single_color(mode, idx_mode, npbit, pack_round(cen[last]), q1, q2, combo);
-    R.err = (uint32_t)n * e;
-    R.p1 = q1; R.p2 = q2; R.combo = combo;
-    R.indices = 0x1111111111111111ull;
+  if (filled == 1) {  // one bucket -> CompressSingleColor on its centroid (:1038-1047, fit_finish)
+    C.kind = 1;
+    C.single = pack_round(cen[last]);
     return;
   }
 
@@ -838,10 +834,34 @@ __device__ __noinline__ void fit_cluster(const Ws &ws, const ModeAttr &A, int mo
     const float f = __fdiv_rn(1.0f, __fsub_rn(__fmul_rn(asq, bsq), __fmul_rn(ab, ab)));
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-      p1[k] = __fmul_rn(__fsub_rn(__fmul_rn(ax[k], bsq), __fmul_rn(bx[k], ab)), f);
-      p2[k] = __fmul_rn(__fsub_rn(__fmul_rn(bx[k], asq), __fmul_rn(ax[k], ab)), f);
+      C.p1[k] = __fmul_rn(__fsub_rn(__fmul_rn(ax[k], bsq), __fmul_rn(bx[k], ab)), f);
+      C.p2[k] = __fmul_rn(__fsub_rn(__fmul_rn(bx[k], asq), __fmul_rn(ax[k], ab)), f);
     }
   }
+  C.kind = 2;
+}
+
+__device__ __noinline__ void fit_finish(const Ws &ws, const ModeAttr &A, int mode, int idx_mode, const FitCore &C,
+                                        const uint32_t *pts, const uint32_t *pix, int n, int sa_steps,
+                                        const uint8_t *__restrict__ s_w, FitResult &R) {
+  R.need_sa = false;
+  const int ibits = idx_mode == 0 ? A.index_bits : A.alpha_index_bits;
+  const int nbm1 = (1 << ibits) - 1;
+  const uint8_t *wtab = s_w + 16 * (ibits - 1);
+  const int npbit = A.pbit == kPbitShared ? 2 : (A.pbit == kPbitPerEndpoint ? 4 : 1);
+  const uint32_t qm = quant_mask(A);
+  if (C.kind != 2) {  // CompressSingleColor (:252-353) on point 0 / on the only bucket's centroid
+    int combo = 0;
+    uint32_t q1 = 0, q2 = 0;
+    const uint32_t e = single_color(mode, idx_mode, npbit, C.single, q1, q2, combo);
+    R.err = (uint32_t)n * e;
+    R.p1 = q1; R.p2 = q2; R.combo = combo;
+    R.indices = 0x1111111111111111ull;
+    return;
+  }
+  float p1[4], p2[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) { p1[k] = C.p1[k]; p2[k] = C.p2[k]; }
 
   // ---- ClampEndpointsToGrid (:212-250)
   uint32_t c1, c2;  // current endpoints, integer bytes from here on
@@ -930,69 +950,32 @@ __device__ __forceinline__ void write_state(const Ws &ws, uint32_t gid, uint32_t
   }
 }
 
-// One endpoint-fit chain: cluster statistics, CompressCluster's start (fit_cluster), and for
-// modes 4/5 the scalar alpha fit.  Writes either the finished result or the start state of the
-// annealing chain.
-__device__ __forceinline__ void setup_chain(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x,
-                                            uint32_t first_block, const Ws &ws, int sa_steps, uint64_t seed,
-                                            uint32_t block_index_base, uint32_t t, int slot,
-                                            const uint8_t *__restrict__ s_w, uint32_t (*s_acc)[16][128], int tid) {
-  const uint32_t gid = t * kSlots + slot;
-  const uint32_t selw = ws.sel[t];
-  const Chain c = decode_chain(selw, slot);
-  if (!c.active) return;  // (the caller's list only holds live chains)
-  const ModeAttr A = c_modes[c.mode];
+// Chains that fit the SAME cluster with the SAME index precision share everything up to the
+// least-squares endpoints (fit_core); only the grid clamp and the first evaluation depend on the
+// mode.  The first chain of such a pair does the shared part once and finishes both:
+//   opaque layout : mode 3 subset s -> mode 7 subset s (slots 8,9 -> 10,11; same two-subset shape,
+//                   2-bit indices), mode 6 on shape slot 0 -> mode 6 on shape slot 1 (12 -> 13: the
+//                   reference fits mode 6 once per candidate shape, T12; only the RNG stream differs)
+//   alpha layout  : mode 4 rotation r, index mode 0 -> mode 5 rotation r (slots 0,2,4,6 -> 8..11:
+//                   same rotated points, 2-bit colour indices; the scalar alpha fits differ and
+//                   run per chain)
+__device__ __forceinline__ int twin_slot(int layout_b, int slot) {
+  if (!layout_b) return (slot == 8 || slot == 9) ? slot + 2 : (slot == 12 ? 13 : -1);
+  return (slot < 8 && !(slot & 1)) ? 8 + (slot >> 1) : -1;
+}
+__device__ __forceinline__ int primary_slot(int layout_b, int slot) {  // inverse of twin_slot, -1: not a twin
+  if (!layout_b) return (slot == 10 || slot == 11) ? slot - 2 : (slot == 13 ? 12 : -1);
+  return (slot >= 8 && slot < 12) ? (slot - 8) * 2 : -1;
+}
 
-  uint32_t blk[16];
-  load_block(img, width, blocks_x, first_block + t, blk);
-
-  // Cluster of this chain: points in raster order of the subset (m_PointMap).
-  uint32_t pts[16], pix[16];
-  int n = 0;
-  uint32_t mask = 0;
-  float sum[4] = {0, 0, 0, 0};
-  uint32_t mn = 0xFFFFFFFFu, mx = 0;
-#pragma unroll 1
-  for (int i = 0; i < 16; i++) {
-    if (subset_of(i, c.shape, c.nsub) == c.subset) {
-      pix[n] = blk[i];
-      pts[n] = blk[i];
-      n++;
-      mask |= 1u << i;
-#pragma unroll
-      for (int k = 0; k < 4; k++) sum[k] = __fadd_rn(sum[k], (float)chan(blk[i], k));  // exact integers
-      mn = __vminu4(mn, blk[i]);
-      mx = __vmaxu4(mx, blk[i]);
-    }
-  }
-  float avg[4];
-#pragma unroll
-  for (int k = 0; k < 4; k++) avg[k] = __fdiv_rn(sum[k], (float)n);
-  const bool all_same = mn == mx;
-  const uint32_t gblock = block_index_base + first_block + t;
-  const uint32_t rng = chain_seed(seed, gblock, (uint32_t)c.chain_id);
-
-  uint32_t *res = ws.results + ((size_t)t * kSlots + slot) * kResWords;
-  // ---- modes 4/5: CompressCluster alpha variant (Compressor.cpp:632-919), n == 16.
-  // Points are rotated and their alpha forced to 255, but avg / bounds / error
-  // pixels stay those of the original block (T16).
-  float alpha_vals[16];
-  float amin = FLT_MAX, amax = -FLT_MAX;
-  if (A.rotation) {
-#pragma unroll 1
-    for (int i = 0; i < 16; i++) {
-      const uint32_t p = blk[i];
-      const uint32_t a = c.rot == 0 ? (p >> 24) : chan(p, c.rot - 1);
-      uint32_t q = p;
-      if (c.rot) q = (p & ~(0xFFu << (8 * (c.rot - 1)))) | ((p >> 24) << (8 * (c.rot - 1)));  // channel <- old alpha
-      pts[i] = q | 0xFF000000u;
-      alpha_vals[i] = (float)a;
-      amin = fminf(amin, (float)a);
-      amax = fmaxf(amax, (float)a);
-    }
-  }
+// Per-mode tail of one chain: ClampEndpointsToGrid + first evaluation (fit_finish), the scalar alpha fit
+// of modes 4/5, and the result / annealing start state.
+__device__ __forceinline__ void setup_variant(const Ws &ws, const Chain &c, const ModeAttr &A, const FitCore &core,
+                                              const uint32_t *pts, const uint32_t *pix, int n, uint32_t mask,
+                                              int sa_steps, const uint8_t *__restrict__ s_w, uint32_t gid, uint32_t rng,
+                                              uint32_t *res, const float *alpha_vals, float amin, float amax) {
   FitResult R;
-  fit_cluster(ws, A, c.mode, c.idx_mode, c.rot, pts, pix, n, avg, all_same, sa_steps, s_w, s_acc, tid, R);  // the one call site
+  fit_finish(ws, A, c.mode, c.idx_mode, core, pts, pix, n, sa_steps, s_w, R);  // the one call site
   res[4] = (uint32_t)R.indices; res[5] = (uint32_t)(R.indices >> 32);
   if (!A.rotation) {
     if (R.need_sa) {
@@ -1127,6 +1110,82 @@ __device__ __forceinline__ void setup_chain(const uint32_t *__restrict__ img, ui
   res[4] = (uint32_t)R.indices; res[5] = (uint32_t)(R.indices >> 32);
 }
 
+// One endpoint-fit chain: cluster statistics, CompressCluster's start (fit_cluster), and for
+// modes 4/5 the scalar alpha fit.  Writes either the finished result or the start state of the
+// annealing chain.
+__device__ __forceinline__ void setup_chain(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x,
+                                            uint32_t first_block, const Ws &ws, int sa_steps, uint64_t seed,
+                                            uint32_t block_index_base, uint32_t t, int slot,
+                                            const uint8_t *__restrict__ s_w, uint32_t (*s_acc)[16][128], int tid) {
+  const uint32_t selw = ws.sel[t];
+  const Chain c = decode_chain(selw, slot), &c0 = c;
+  if (!c.active) return;  // (the caller's list only holds live chains)
+  const ModeAttr A0 = c_modes[c.mode];
+  int twin = twin_slot((selw >> 22) & 1, slot);
+  if (twin >= 0 && !decode_chain(selw, twin).active) twin = -1;
+
+  uint32_t blk[16];
+  load_block(img, width, blocks_x, first_block + t, blk);
+
+  // Cluster of this chain: points in raster order of the subset (m_PointMap).
+  uint32_t pts[16], pix[16];
+  int n = 0;
+  uint32_t mask = 0;
+  float sum[4] = {0, 0, 0, 0};
+  uint32_t mn = 0xFFFFFFFFu, mx = 0;
+#pragma unroll 1
+  for (int i = 0; i < 16; i++) {
+    if (subset_of(i, c.shape, c.nsub) == c.subset) {
+      pix[n] = blk[i];
+      pts[n] = blk[i];
+      n++;
+      mask |= 1u << i;
+#pragma unroll
+      for (int k = 0; k < 4; k++) sum[k] = __fadd_rn(sum[k], (float)chan(blk[i], k));  // exact integers
+      mn = __vminu4(mn, blk[i]);
+      mx = __vmaxu4(mx, blk[i]);
+    }
+  }
+  float avg[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) avg[k] = __fdiv_rn(sum[k], (float)n);
+  const bool all_same = mn == mx;
+  const uint32_t gblock = block_index_base + first_block + t;
+
+  // ---- modes 4/5: CompressCluster alpha variant (Compressor.cpp:632-919), n == 16.
+  // Points are rotated and their alpha forced to 255, but avg / bounds / error
+  // pixels stay those of the original block (T16).
+  float alpha_vals[16];
+  float amin = FLT_MAX, amax = -FLT_MAX;
+  if (A0.rotation) {
+#pragma unroll 1
+    for (int i = 0; i < 16; i++) {
+      const uint32_t p = blk[i];
+      const uint32_t a = c.rot == 0 ? (p >> 24) : chan(p, c.rot - 1);
+      uint32_t q = p;
+      if (c.rot) q = (p & ~(0xFFu << (8 * (c.rot - 1)))) | ((p >> 24) << (8 * (c.rot - 1)));  // channel <- old alpha
+      pts[i] = q | 0xFF000000u;
+      alpha_vals[i] = (float)a;
+      amin = fminf(amin, (float)a);
+      amax = fmaxf(amax, (float)a);
+    }
+  }
+  // the expensive, mode-independent part runs once for the chain and its twin
+  FitCore core;
+  fit_core(c0.idx_mode == 0 ? A0.index_bits : A0.alpha_index_bits, pts, n, avg, all_same, s_acc, tid, core);
+  const int nvariants = twin >= 0 ? 2 : 1;
+#pragma unroll 1
+  for (int variant = 0; variant < nvariants; variant++) {
+    const int vslot = variant == 0 ? slot : twin;
+    const Chain c = decode_chain(selw, vslot);
+    const ModeAttr A = c_modes[c.mode];
+    const uint32_t gid = t * kSlots + vslot;
+    const uint32_t rng = chain_seed(seed, gblock, (uint32_t)c.chain_id);
+    uint32_t *res = ws.results + (size_t)gid * kResWords;
+    setup_variant(ws, c, A, core, pts, pix, n, mask, sa_steps, s_w, gid, rng, res, alpha_vals, amin, amax);
+  }
+}
+
 // Number of pixels in the subset a chain fits (its cluster size), from the partition tables.
 __device__ __forceinline__ int chain_pixels(const Chain &c) {
   if (c.nsub == 1) return 16;
@@ -1145,9 +1204,9 @@ __device__ __forceinline__ int chain_pixels(const Chain &c) {
 // lanes of a warp fit clusters of (nearly) the same size with the same bucket count, so the
 // k-means / least-squares loops run with uniform trip counts.  Consecutive CTAs walk the groups
 // of the same 128 blocks, which keeps their pixels in L1/L2.
-constexpr int kSlotGroups = 6;
-__constant__ uint8_t c_group_first[kSlotGroups] = {0, 3, 6, 8, 10, 12};
-__constant__ uint8_t c_group_count[kSlotGroups] = {3, 3, 2, 2, 2, 4};  // the last group also owns the dead slot 15
+constexpr int kSlotGroups = 5;
+__constant__ uint8_t c_group_first[kSlotGroups] = {0, 3, 6, 8, 12};
+__constant__ uint8_t c_group_count[kSlotGroups] = {3, 3, 2, 4, 4};  // the last group also owns the dead slot 15
 
 __global__ void __launch_bounds__(kChainThreads)
 bc7_setup(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, uint32_t first_block,
@@ -1173,7 +1232,9 @@ bc7_setup(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, u
     if (k < count && t < num_blocks) {
       ws.states[((size_t)t * kSlots + first + k) * kStateWords] = 0;
       const Chain c = decode_chain(selw, first + k);
-      if (c.active) {
+      // a twin is fitted by its primary chain's lane (see twin_slot)
+      const int prim = primary_slot((selw >> 22) & 1, first + k);
+      if (c.active && !(prim >= 0 && decode_chain(selw, prim).active)) {
         sizes[k] = chain_pixels(c);
         atomicAdd(&s_hist[sizes[k]], 1u);
       }
