@@ -535,6 +535,16 @@ __device__ __forceinline__ Chain decode_chain(uint32_t selw, int slot) {
   return c;
 }
 
+// a / c for an integer a in [0, 4080] and a count c in [1, 16], correctly rounded like the
+// reference's float division, in three instructions: with rc = RN(1 / c), q = RN(a * rc),
+// r = a - q * c (exact in an FMA), RN(q + r * rc) is the correctly rounded quotient (Markstein);
+// tests/test_tables.py::test_small_division_exact checks every (a, c) of that domain.
+__device__ __forceinline__ float div_small(float a, float c, float rc) {
+  const float q = __fmul_rn(a, rc);
+  const float r = __fmaf_rn(-q, c, a);
+  return __fmaf_rn(r, rc, q);
+}
+
 struct F4 { float v[4]; };
 __device__ __forceinline__ float dot4(const float a[4], const float b[4]) {
   float s = __fmul_rn(a[0], b[0]);  // 0 + x == x
@@ -610,7 +620,7 @@ struct FitCore {
 };
 
 __device__ __noinline__ void fit_core(int ibits, const uint32_t *pts, int n, const float avg[4], bool all_same,
-                                      uint32_t (*s_acc)[16][128], int tid, FitCore &C) {
+                                      uint32_t (*s_acc)[16][128], const float *__restrict__ s_rcp, int tid, FitCore &C) {
   const int nb = 1 << ibits, nbm1 = nb - 1;
   if (all_same) {  // AllSamePoint -> CompressSingleColor on point 0 (fit_finish)
     C.kind = 0;
@@ -754,22 +764,31 @@ __device__ __noinline__ void fit_core(int ibits, const uint32_t *pts, int n, con
     bool fixed = false;
     int guard = 0;
     while (!fixed && guard++ < 4096) {
+      // two points per pass over the centroids: half the centroid loads and two independent
+      // dependency chains (an odd cluster's last point is paired with itself)
 #pragma unroll 1
-      for (int i = 0; i < n; i++) {
-        float pf[4];
+      for (int i = 0; i < n; i += 2) {
+        const int i1 = min(i + 1, n - 1);
+        float pa[4], pb[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) pf[k] = (float)chan(pts[i], k);
-        int mb = 0;
-        float md = FLT_MAX;
+        for (int k = 0; k < 4; k++) { pa[k] = (float)chan(pts[i], k); pb[k] = (float)chan(pts[i1], k); }
+        int mba = 0, mbb = 0;
+        float mda = FLT_MAX, mdb = FLT_MAX;
 #pragma unroll 1
         for (int j = 0; j < nb; j++) {
-          float v[4];
+          float va[4], vb[4];
 #pragma unroll
-          for (int k = 0; k < 4; k++) v[k] = __fsub_rn(pf[k], cen[j][k]);
-          const float d = dot4(v, v);
-          if (d < md) { md = d; mb = j; }
+          for (int k = 0; k < 4; k++) {
+            const float c = cen[j][k];
+            va[k] = __fsub_rn(pa[k], c);
+            vb[k] = __fsub_rn(pb[k], c);
+          }
+          const float da = dot4(va, va), db = dot4(vb, vb);
+          if (da < mda) { mda = da; mba = j; }
+          if (db < mdb) { mdb = db; mbb = j; }
         }
-        bucket[i] = (uint8_t)mb;
+        bucket[i] = (uint8_t)mba;
+        bucket[i1] = (uint8_t)mbb;
       }
       // centroids: bucket sums are exact small integers (<= 16 * 255), so they are accumulated as
       // packed 16-bit pairs per bucket in shared memory -- O(n) instead of the reference's
@@ -790,9 +809,9 @@ __device__ __noinline__ void fit_core(int ibits, const uint32_t *pts, int n, con
         const int c = (int)s_acc[2][j][tid];
         float sum[4] = {(float)(rb & 0xFFFFu), (float)(ga & 0xFFFFu), (float)(rb >> 16), (float)(ga >> 16)};
         if (c != 0) {
-          const float fc = (float)c;
+          const float fc = (float)c, rc = s_rcp[c];
 #pragma unroll
-          for (int k = 0; k < 4; k++) sum[k] = __fdiv_rn(sum[k], fc);
+          for (int k = 0; k < 4; k++) sum[k] = div_small(sum[k], fc, rc);
         }
         cnt[j] = c;
 #pragma unroll
@@ -972,8 +991,9 @@ __device__ __forceinline__ int primary_slot(int layout_b, int slot) {  // invers
 // of modes 4/5, and the result / annealing start state.
 __device__ __forceinline__ void setup_variant(const Ws &ws, const Chain &c, const ModeAttr &A, const FitCore &core,
                                               const uint32_t *pts, const uint32_t *pix, int n, uint32_t mask,
-                                              int sa_steps, const uint8_t *__restrict__ s_w, uint32_t gid, uint32_t rng,
-                                              uint32_t *res, const float *alpha_vals, float amin, float amax) {
+                                              int sa_steps, const uint8_t *__restrict__ s_w, const float *__restrict__ s_rcp,
+                                              uint32_t gid, uint32_t rng, uint32_t *res, const float *alpha_vals,
+                                              float amin, float amax) {
   FitResult R;
   fit_finish(ws, A, c.mode, c.idx_mode, core, pts, pix, n, sa_steps, s_w, R);  // the one call site
   res[4] = (uint32_t)R.indices; res[5] = (uint32_t)(R.indices >> 32);
@@ -1044,7 +1064,7 @@ __device__ __forceinline__ void setup_variant(const Ws &ws, const Chain &c, cons
 #pragma unroll 1
         for (int j = 0; j < 16; j++)
           if (bucket[j] == i) { s = __fadd_rn(s, alpha_vals[j]); c2 = __fadd_rn(c2, 1.0f); }
-        if (c2 > 0.0f) s = __fdiv_rn(s, c2);
+        if (c2 > 0.0f) s = div_small(s, c2, s_rcp[(int)c2]);
         av[i] = s; npts[i] = c2;
         fixed = fixed && (av[i] == vals[i]);
       }
@@ -1116,7 +1136,8 @@ __device__ __forceinline__ void setup_variant(const Ws &ws, const Chain &c, cons
 __device__ __forceinline__ void setup_chain(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x,
                                             uint32_t first_block, const Ws &ws, int sa_steps, uint64_t seed,
                                             uint32_t block_index_base, uint32_t t, int slot,
-                                            const uint8_t *__restrict__ s_w, uint32_t (*s_acc)[16][128], int tid) {
+                                            const uint8_t *__restrict__ s_w, const float *__restrict__ s_rcp,
+                                            uint32_t (*s_acc)[16][128], int tid) {
   const uint32_t selw = ws.sel[t];
   const Chain c = decode_chain(selw, slot), &c0 = c;
   if (!c.active) return;  // (the caller's list only holds live chains)
@@ -1172,7 +1193,7 @@ __device__ __forceinline__ void setup_chain(const uint32_t *__restrict__ img, ui
   }
   // the expensive, mode-independent part runs once for the chain and its twin
   FitCore core;
-  fit_core(c0.idx_mode == 0 ? A0.index_bits : A0.alpha_index_bits, pts, n, avg, all_same, s_acc, tid, core);
+  fit_core(c0.idx_mode == 0 ? A0.index_bits : A0.alpha_index_bits, pts, n, avg, all_same, s_acc, s_rcp, tid, core);
   const int nvariants = twin >= 0 ? 2 : 1;
 #pragma unroll 1
   for (int variant = 0; variant < nvariants; variant++) {
@@ -1182,7 +1203,7 @@ __device__ __forceinline__ void setup_chain(const uint32_t *__restrict__ img, ui
     const uint32_t gid = t * kSlots + vslot;
     const uint32_t rng = chain_seed(seed, gblock, (uint32_t)c.chain_id);
     uint32_t *res = ws.results + (size_t)gid * kResWords;
-    setup_variant(ws, c, A, core, pts, pix, n, mask, sa_steps, s_w, gid, rng, res, alpha_vals, amin, amax);
+    setup_variant(ws, c, A, core, pts, pix, n, mask, sa_steps, s_w, s_rcp, gid, rng, res, alpha_vals, amin, amax);
   }
 }
 
@@ -1215,9 +1236,10 @@ bc7_setup(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, u
   __shared__ uint32_t s_acc[3][16][kChainThreads];
   __shared__ uint16_t s_list[4 * kChainThreads];
   __shared__ uint32_t s_hist[17], s_cur[17];
+  __shared__ float s_rcp[17];  // RN(1 / c) for the bucket counts 1..16 (div_small)
   const int tid = threadIdx.x;
   if (tid < 64) s_w[tid] = c_weight[tid];
-  if (tid < 17) { s_hist[tid] = 0; s_cur[tid] = 0; }
+  if (tid < 17) { s_hist[tid] = 0; s_cur[tid] = 0; s_rcp[tid] = tid ? __frcp_rn((float)tid) : 0.0f; }
   __syncthreads();
   const int group = blockIdx.x % kSlotGroups;
   const uint32_t tile = blockIdx.x / kSlotGroups;
@@ -1256,7 +1278,7 @@ bc7_setup(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, u
   for (uint32_t e = tid; e < total; e += kChainThreads) {
     const uint32_t entry = s_list[e];
     setup_chain(img, width, blocks_x, first_block, ws, sa_steps, seed, block_index_base,
-                tile * kChainThreads + (entry >> 4), (int)(entry & 15), s_w, s_acc, tid);
+                tile * kChainThreads + (entry >> 4), (int)(entry & 15), s_w, s_rcp, s_acc, tid);
   }
 }
 

@@ -110,3 +110,26 @@ def test_projection_exact_buckets():
                 assert t < 0, (m, k, t)
             else:
                 assert t > f(m) - f(0.5) and np.ceil(t) >= m and np.floor(t) >= m, (m, k, t)
+
+
+def test_small_division_exact():
+    """bc7_setup's div_small (fastc_b200/csrc/bc7.cu): q = RN(a * rc), r = fma(-q, c, a), RN(fma(r, rc, q))
+    with rc = RN(1 / c) equals the reference's correctly rounded float division a / c
+    (k-means centroid = bucket sum / count, Compressor.cpp:1008-1013) for every integer bucket sum
+    a in [0, 16 * 255] and count c in [1, 16].  Exact rational arithmetic, float32 rounding to nearest even."""
+    from fractions import Fraction
+
+    def rn(fr):
+        if fr == 0:
+            return np.float32(0)
+        y = np.float32(float(fr))
+        cands = [y, np.nextafter(y, np.float32(np.inf)), np.nextafter(y, np.float32(-np.inf))]
+        return min(cands, key=lambda c: (abs(Fraction(float(c)) - fr), int(np.float32(c).view(np.uint32)) & 1))
+
+    for c in range(1, 17):
+        rc = Fraction(float(rn(Fraction(1, c))))
+        for a in range(0, 16 * 255 + 1):
+            q = Fraction(float(rn(a * rc)))
+            r = Fraction(float(rn(a - q * c)))          # the FMA's exact product, rounded once
+            assert r == a - q * c                       # ... and that remainder is exactly representable
+            assert rn(q + r * rc) == rn(Fraction(a, c)), (a, c)
