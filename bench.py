@@ -281,6 +281,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
     # ---- CPU baseline: the reference itself on this box's host cores, bounded slab (N = 1 only)
     cpu_baseline = None
+    quality_check = None
     if world == 1 and not args.no_cpu_baseline:
         sys.path.insert(0, str(ROOT / "tests"))
         from _checkers import Reference, Oracle
@@ -290,9 +291,18 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         if Reference.available():
             ref = Reference()
             threads = min(cores, 256)
-            _, ms = ref.compress("BPTC", img_s, quality=QUALITY, threads=threads, seed=None)
+            ref_cmp, ms = ref.compress("BPTC", img_s, quality=QUALITY, threads=threads, seed=None)
             kind = "reference"
             how = f"CompressImageData -t {threads}"
+            # the metric's "PSNR delta vs ref": both outputs of that slab decoded by the reference's own
+            # decompressor, PSNR by the reference's formula (Base/src/Image.cpp:205-255)
+            ours_cmp = h_out_np[: ref_cmp.size]  # rank 0's slab starts at block row 0
+            p_ref = ref.psnr(img_s, ref.decode("BPTC", ref_cmp, WIDTH, rows_s))
+            p_gpu = ref.psnr(img_s, ref.decode("BPTC", np.ascontiguousarray(ours_cmp), WIDTH, rows_s))
+            same = float((ours_cmp.reshape(-1, 16) == ref_cmp.reshape(-1, 16)).all(1).mean())
+            quality_check = {"psnr_gpu_db": p_gpu, "psnr_ref_db": p_ref, "delta_db": p_gpu - p_ref,
+                             "bit_identical_block_fraction": same, "tolerance_db": 0.05,
+                             "sample": f"top {WIDTH}x{rows_s} slab, decoded by the reference's decompressor"}
         else:  # reference .so did not travel: time the oracle port (single thread)
             t0 = time.perf_counter()
             Oracle().compress("BPTC", img_s, quality=QUALITY, rng_mode=0)
@@ -320,6 +330,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     }
     if cpu_baseline:
         line["cpu_baseline"] = cpu_baseline
+    if quality_check:
+        line["psnr_vs_reference"] = quality_check
     print(json.dumps(line), flush=True)
 
 

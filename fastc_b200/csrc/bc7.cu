@@ -75,7 +75,8 @@ struct Ws {
   uint32_t *total_solid;
   uint32_t *results;    // [nblocks][kSlots][kResWords]
   uint32_t *states;     // [nblocks][kSlots][kStateWords] annealing start states
-  uint32_t *order;      // [nblocks*kSlots] chain ids sorted by descending cluster size
+  uint4 *sorted;        // [nblocks*kSlots][2] the live chains' start states, sorted by descending
+                        // (index precision, cluster size); word 7 = the chain's id (block * kSlots + slot)
   uint32_t *bins;       // histogram / offsets / cursors (see bc7_bin_offsets)
   const uint32_t *wm_running;    // watermark base of this chunk (device side, chunks chain without a host sync)
   unsigned long long *counters;  // qe calls, pbe
@@ -1326,8 +1327,10 @@ __global__ void __launch_bounds__(256) bc7_scatter(Ws ws, uint32_t num_blocks) {
   const uint32_t gid = blockIdx.x * 256 + threadIdx.x;
   int key = -1;
   uint32_t rank = 0;
+  uint4 st0 = make_uint4(0, 0, 0, 0);
   if (gid < num_blocks * kSlots) {
-    const uint32_t w0 = ws.states[(size_t)gid * kStateWords];
+    st0 = *reinterpret_cast<const uint4 *>(ws.states + (size_t)gid * kStateWords);
+    const uint32_t w0 = st0.x;
     if (w0 >> 31) {
       const int mode = (w0 >> 16) & 7, idx_mode = (w0 >> 21) & 1;
       const int ibits = idx_mode == 0 ? c_modes[mode].index_bits : c_modes[mode].alpha_index_bits;
@@ -1339,7 +1342,14 @@ __global__ void __launch_bounds__(256) bc7_scatter(Ws ws, uint32_t num_blocks) {
   if (threadIdx.x < kSortKeys && s_cnt[threadIdx.x])
     s_base[threadIdx.x] = ws.bins[64 + threadIdx.x] + atomicAdd(&ws.bins[128 + threadIdx.x], s_cnt[threadIdx.x]);
   __syncthreads();
-  if (key >= 0) ws.order[s_base[key] + rank] = gid;
+  if (key >= 0) {
+    // the annealing kernel reads its work in sorted order: one indirection less on its refill path
+    uint4 st1 = *reinterpret_cast<const uint4 *>(ws.states + (size_t)gid * kStateWords + 4);
+    st1.w = gid;
+    uint4 *dst = ws.sorted + (size_t)(s_base[key] + rank) * 2;
+    dst[0] = st0;
+    dst[1] = st1;
+  }
 }
 
 constexpr int kSaThreads = 128;
@@ -1557,14 +1567,34 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
     const uint32_t mask = cls == 5 ? 0u : ((0xFF00u >> (cls + 4)) & 0xFFu);
     s_q[row][e & 255] = (uint8_t)quantize_channel((uint32_t)(e & 255), mask, pbit);
   }
+  // per (mode, index mode): the annealing constants of the mode, decoded once per CTA
+  //   x: per-channel step bytes (opaque modes never move alpha, T3)
+  //   y: nbm1 [0:3] | weight row offset [4:11] | p-bit flip mask [12:13] | p-bit shift [14] |
+  //      colour / alpha quantisation rows [15:18] [19:22] | rotation [23]
+  __shared__ uint2 s_mode[16];
+  __shared__ uint32_t s_end[3];
+  if (threadIdx.x < 16) {
+    const int mode = threadIdx.x >> 1, idx_mode = threadIdx.x & 1;
+    const ModeAttr A = c_modes[mode];
+    const int ibits = max(1, idx_mode == 0 ? A.index_bits : A.alpha_index_bits);
+    const uint32_t sc = 1u << (8 - A.color_bits), sa = (A.alpha_bits && mode >= 4) ? (1u << (8 - A.alpha_bits)) : 0u;
+    const uint32_t xm = A.pbit == kPbitShared ? 1u : (A.pbit == kPbitPerEndpoint ? 3u : 0u);
+    const uint32_t tab_c = (uint32_t)(A.color_bits - 4) * 2u, tab_a = (uint32_t)(A.alpha_bits ? A.alpha_bits - 4 : 5) * 2u;
+    s_mode[threadIdx.x] = make_uint2(sc | (sc << 8) | (sc << 16) | (sa << 24),
+                                     (uint32_t)((1 << ibits) - 1) | ((uint32_t)(16 * (ibits - 1)) << 4) | (xm << 12) |
+                                         ((A.pbit == kPbitPerEndpoint ? 1u : 0u) << 14) | (tab_c << 15) | (tab_a << 19) |
+                                         ((uint32_t)A.rotation << 23));
+  }
+  if (threadIdx.x < 3) s_end[threadIdx.x] = ws.bins[196 + threadIdx.x];
   __syncthreads();
   const int tid = threadIdx.x, lane = tid & 31, wbase = tid & ~31;
   const unsigned full = 0xffffffffu;
+  uint32_t drymask = 0;
   const float f_tm1 = (float)(sa_steps - 1);
   const float c_x = __fmul_rn(0.1f, f_tm1);  // fast Metropolis exponent: 0.1 * diff / (energy / (steps - 1))
   const int home = blockIdx.x >= ws.bins[200 + 0] ? 0 : (blockIdx.x >= ws.bins[200 + 1] ? 1 : 2);
 
-  bool have = false, dry = false;
+  bool have = false;  // (drymask == 7: every queue has run dry for this lane)
   SaConst K = {0, 0xFFFFFFFFu, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   uint32_t gid = 0, cur1 = 0, cur2 = 0, best1 = 0, best2 = 0, cur_err = 0, best_err = 0, rng = 0;
   uint32_t best_lo = 0, best_hi = 0;
@@ -1576,7 +1606,7 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
 #endif
 
   for (;;) {
-    const bool need = !have && !dry;
+    const bool need = !have && drymask != 7u;
     if (__any_sync(full, need)) {
       // ---- refill: every idle lane takes the next chain of its home class's queue (then of the
       // others, longest steps first) ...
@@ -1588,33 +1618,29 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
         for (int a = 0; a < 3 && !got; a++) {
           const int cls = a == 0 ? home : (2 - (a - 1) - ((2 - (a - 1)) <= home ? 1 : 0));
           if (cls < 0) break;
-          if (ws.bins[193 + cls] < ws.bins[196 + cls]) {  // cheap look before the atomic
+          if (!((drymask >> cls) & 1)) {  // a class this lane has seen run dry stays dry
             pos = atomicAdd(&ws.bins[193 + cls], 1u);
-            got = pos < ws.bins[196 + cls];
+            got = pos < s_end[cls];
+            if (!got) drymask |= 1u << cls;
           }
         }
-        if (!got) {
-          dry = true;
-        } else {
-          // constants of the chain's mode and its start state
-          gid = ws.order[pos];
-          const uint32_t *st = ws.states + (size_t)gid * kStateWords;
-          const uint4 s0 = *reinterpret_cast<const uint4 *>(st);
+        if (got) {
+          // the chain's start state (sorted copy: two independent 16-byte loads) and the constants
+          // of its mode (one table row)
+          const uint4 s0 = ws.sorted[(size_t)pos * 2], s1 = ws.sorted[(size_t)pos * 2 + 1];
+          gid = s1.w;
           w0 = s0.x;
           const int mode = (w0 >> 16) & 7, rot = (w0 >> 19) & 3, idx_mode = (w0 >> 21) & 1;
-          const ModeAttr A = c_modes[mode];
-          const int ibits = idx_mode == 0 ? A.index_bits : A.alpha_index_bits;
+          const uint2 mt = s_mode[mode * 2 + idx_mode];
           K.n = (w0 >> 24) & 31;
-          K.nbm1 = (1 << ibits) - 1;
-          K.woff = 16 * (ibits - 1);
-          K.xm = A.pbit == kPbitShared ? 1 : (A.pbit == kPbitPerEndpoint ? 3 : 0);
-          K.sh0 = A.pbit == kPbitPerEndpoint ? 1 : 0;
-          K.tab_c = (A.color_bits - 4) * 2;
-          K.tab_a = (A.alpha_bits ? A.alpha_bits - 4 : 5) * 2;
-          uint32_t sc = 1u << (8 - A.color_bits), sa = A.alpha_bits ? (1u << (8 - A.alpha_bits)) : 0u;
-          K.stepb = sc | (sc << 8) | (sc << 16) | (sa << 24);
-          if (mode < 4) K.stepb &= ~(0xFFu << (8 * ((rot + 3) & 3)));  // opaque modes never move alpha (T3)
-          rotation = A.rotation;
+          K.stepb = mt.x;
+          K.nbm1 = mt.y & 15;
+          K.woff = (mt.y >> 4) & 0xFF;
+          K.xm = (mt.y >> 12) & 3;
+          K.sh0 = (mt.y >> 14) & 1;
+          K.tab_c = (mt.y >> 15) & 15;
+          K.tab_a = (mt.y >> 19) & 15;
+          rotation = (mt.y >> 23) & 1;
           K.qkeep = 0xFFFFFFFFu; K.qins = 0; K.qsh = 0; K.calpha = 0;
           if (rotation) {
             K.calpha = 255;
@@ -1623,7 +1649,7 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
           }
           cur1 = best1 = s0.y; cur2 = best2 = s0.z;
           cur_err = best_err = s0.w;
-          rng = st[4];
+          rng = s1.x;
           cur_combo = best_combo = (w0 >> 22) & 3;
           energy = 0;
           improved = false;
@@ -1970,7 +1996,7 @@ size_t ws_bytes(uint32_t nblocks) {
   b += 256;                                                      // total
   b += (size_t)nblocks * kSlots * kResWords * 4;                 // results
   b += (size_t)nblocks * kSlots * 8 * 4;                         // states
-  b += (size_t)nblocks * kSlots * 4;                             // order
+  b += (size_t)nblocks * kSlots * kStateWords * 4;               // sorted states
   b += 1024;                                                     // bins
   return b;
 }
@@ -1986,7 +2012,7 @@ Ws carve(void *base, uint32_t nblocks) {
   w.wm_running = nullptr;
   w.results = reinterpret_cast<uint32_t *>(p); p += (size_t)nblocks * kSlots * kResWords * 4;
   w.states = reinterpret_cast<uint32_t *>(p); p += (size_t)nblocks * kSlots * 8 * 4;
-  w.order = reinterpret_cast<uint32_t *>(p); p += (size_t)nblocks * kSlots * 4;
+  w.sorted = reinterpret_cast<uint4 *>(p); p += (size_t)nblocks * kSlots * kStateWords * 4;
   w.bins = reinterpret_cast<uint32_t *>(p);
   return w;
 }
