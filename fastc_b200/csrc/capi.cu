@@ -218,7 +218,18 @@ int run_shard(Shard &s, int format, const uint8_t *rgba_host, uint32_t width, ui
   }
   const uint32_t total_rows = row1 - row0;
   rows_per_chunk = std::max<uint32_t>(1, rows_per_chunk);
-  const uint32_t nchunks = (total_rows + rows_per_chunk - 1) / rows_per_chunk;
+  // chunk k covers block rows [bounds[k], bounds[k + 1])
+  std::vector<uint32_t> bounds;
+  for (uint32_t r = row0; r < row1; r += rows_per_chunk) bounds.push_back(r);
+  bounds.push_back(row1);
+  if (chunk_blocks == 0 && format == FASTC_GPU_BPTC && total_rows >= 64) {
+    // BC7 auto: one small head chunk (1/16 of the rows) and the rest.  The big upload then runs
+    // under the head's kernels and the head's download under the big chunk's kernels; only the
+    // head's upload and the tail's download stay exposed, and the persistent annealing kernel
+    // still sees (almost) the whole shard at once.
+    bounds.assign({row0, row0 + total_rows / 16, row1});
+  }
+  const uint32_t nchunks = (uint32_t)bounds.size() - 1;
   // BC7's watermark chain needs the solid-block count of every earlier chunk;
   // bc7 tracks that itself when the whole shard is submitted as one range, so
   // BPTC shards are uploaded chunk-wise but encoded per chunk with a running base.
@@ -228,8 +239,7 @@ int run_shard(Shard &s, int format, const uint8_t *rgba_host, uint32_t width, ui
   for (uint32_t k = 0; k < nchunks; k++) {
     const int slot = k % kPipeDepth;
     cudaStream_t st = c.streams[slot];
-    const uint32_t r0 = row0 + k * rows_per_chunk;
-    const uint32_t r1 = std::min(row1, r0 + rows_per_chunk);
+    const uint32_t r0 = bounds[k], r1 = bounds[k + 1];
     const size_t in_bytes = (size_t)(r1 - r0) * 4 * width * 4;
     const size_t out_bytes = (size_t)(r1 - r0) * bx * bsz;
     // slot reuse: wait for the previous occupant (stream order guarantees it,
