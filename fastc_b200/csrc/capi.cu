@@ -56,6 +56,13 @@ struct DeviceCtx {
   // slot i for pipeline slot i of the host path, slot kPipeDepth for the device API;
   // grown on demand, reused across calls
   Bc7Workspace bc7ws[kPipeDepth + 1];
+  // host-path pipeline state: the slot rotation carries over from one submission to the next of a
+  // batch, so texture j+1 uploads while texture j encodes and texture j-1 downloads
+  uint64_t next_chunk = 0;
+  bool slot_busy[kPipeDepth] = {};
+  // one host-path submission (or batch) at a time per device: FasTC's ThreadGroup / WorkerQueue
+  // call a CompressionFunc from many threads at once (Core/src/ThreadGroup.cpp:146-188)
+  std::mutex host_mu;
   unsigned long long *psnr_sum = nullptr, *psnr_host = nullptr;  // device / pinned accumulators of fastc_gpu_psnr*
   std::mutex mu;
 };
@@ -195,8 +202,23 @@ struct Shard {
 // Host->host for one GPU's slab.  The slab is cut into chunks of whole block
 // rows; chunk k uses staging slot k % kPipeDepth, so its H2D overlaps the
 // kernels of chunk k-1 and the D2H of chunk k-2 (three copy/compute engines).
+// Waits for every chunk still in flight on the device's staging slots and books its kernel time.
+int drain_slots(DeviceCtx &c, double *kernel_ms) {
+  for (int slot = 0; slot < kPipeDepth; slot++) {
+    if (!c.slot_busy[slot]) continue;
+    CU_TRY(cudaStreamSynchronize(c.streams[slot]));
+    float ms = 0;
+    CU_TRY(cudaEventElapsedTime(&ms, c.ev_start[slot], c.ev_stop[slot]));
+    if (kernel_ms) *kernel_ms += ms;
+    c.slot_busy[slot] = false;
+  }
+  return 0;
+}
+
+// drain = false leaves the last chunks in flight (batch submissions: the caller drains once at
+// the end, so consecutive textures overlap).
 int run_shard(Shard &s, int format, const uint8_t *rgba_host, uint32_t width, uint32_t height,
-              uint8_t *out_host, int quality, uint64_t seed, uint32_t chunk_blocks) {
+              uint8_t *out_host, int quality, uint64_t seed, uint32_t chunk_blocks, bool drain = true) {
   if (ensure_ctx(s.dev)) return 1;
   DeviceCtx &c = g_ctx[s.dev];
   const uint32_t bx = width / 4;
@@ -235,9 +257,8 @@ int run_shard(Shard &s, int format, const uint8_t *rgba_host, uint32_t width, ui
   // BPTC shards are uploaded chunk-wise but encoded per chunk with a running base.
   uint32_t wm_base = s.wm_base;
 
-  std::vector<float> chunk_ms;
   for (uint32_t k = 0; k < nchunks; k++) {
-    const int slot = k % kPipeDepth;
+    const int slot = (int)(c.next_chunk++ % kPipeDepth);
     cudaStream_t st = c.streams[slot];
     const uint32_t r0 = bounds[k], r1 = bounds[k + 1];
     const size_t in_bytes = (size_t)(r1 - r0) * 4 * width * 4;
@@ -249,12 +270,13 @@ int run_shard(Shard &s, int format, const uint8_t *rgba_host, uint32_t width, ui
       if (grow(&c.in_buf[slot], &c.in_cap[slot], in_bytes)) return 1;
       if (grow(&c.out_buf[slot], &c.out_cap[slot], out_bytes)) return 1;
     }
-    if (k >= (uint32_t)kPipeDepth) {
+    if (c.slot_busy[slot]) {
       // collect the timing of the chunk that used this slot before we re-record
       CU_TRY(cudaEventSynchronize(c.ev_stop[slot]));
       float ms = 0;
       CU_TRY(cudaEventElapsedTime(&ms, c.ev_start[slot], c.ev_stop[slot]));
       s.kernel_ms += ms;
+      c.slot_busy[slot] = false;
     }
     CU_TRY(cudaMemcpyAsync(c.in_buf[slot], rgba_host + (size_t)r0 * 4 * width * 4, in_bytes,
                            cudaMemcpyHostToDevice, st));
@@ -275,19 +297,21 @@ int run_shard(Shard &s, int format, const uint8_t *rgba_host, uint32_t width, ui
                 seed, wm_base, r0 * bx, st, &s.launches))
       return 1;
     CU_TRY(cudaEventRecord(c.ev_stop[slot], st));
+    c.slot_busy[slot] = true;
     wm_base += solid;
     CU_TRY(cudaMemcpyAsync(out_host + ((size_t)r0 * bx + lo) * bsz, (uint8_t *)c.out_buf[slot] + (size_t)lo * bsz,
                            (size_t)(hi - lo) * bsz, cudaMemcpyDeviceToHost, st));
     s.d2h += (size_t)(hi - lo) * bsz;
   }
-  for (uint32_t k = (nchunks > (uint32_t)kPipeDepth ? nchunks - kPipeDepth : 0); k < nchunks; k++) {
-    const int slot = k % kPipeDepth;
-    CU_TRY(cudaStreamSynchronize(c.streams[slot]));
-    float ms = 0;
-    CU_TRY(cudaEventElapsedTime(&ms, c.ev_start[slot], c.ev_stop[slot]));
-    s.kernel_ms += ms;
-  }
+  if (drain && drain_slots(c, &s.kernel_ms)) return 1;
   return 0;
+}
+
+int run_shard_locked(Shard &s, int format, const uint8_t *rgba_host, uint32_t width, uint32_t height,
+                     uint8_t *out_host, int quality, uint64_t seed, uint32_t chunk_blocks) {
+  if (s.dev < 0 || s.dev >= kMaxDevices) return fail("bad device %d", s.dev);
+  std::lock_guard<std::mutex> lk(g_ctx[s.dev].host_mu);
+  return run_shard(s, format, rgba_host, width, height, out_host, quality, seed, chunk_blocks);
 }
 
 }  // namespace
@@ -428,14 +452,14 @@ int fastc_gpu_compress(int format, const uint8_t *rgba_host, uint32_t width, uin
   if (num_gpus == 1) cudaGetDevice(&shards[0].dev);  // one GPU: the caller's current device
 
   if (num_gpus == 1) {
-    shards[0].rc = run_shard(shards[0], format, rgba_host, width, height, out_host, quality, seed, chunk_blocks);
+    shards[0].rc = run_shard_locked(shards[0], format, rgba_host, width, height, out_host, quality, seed, chunk_blocks);
     if (shards[0].rc) snprintf(shards[0].err, sizeof(shards[0].err), "%s", tl_error);
   } else {
     std::vector<std::thread> th;
     for (int g = 0; g < num_gpus; g++)
       th.emplace_back([&, g] {
         if (shards[g].num_blocks == 0) return;
-        shards[g].rc = run_shard(shards[g], format, rgba_host, width, height, out_host, quality, seed, chunk_blocks);
+        shards[g].rc = run_shard_locked(shards[g], format, rgba_host, width, height, out_host, quality, seed, chunk_blocks);
         if (shards[g].rc) snprintf(shards[g].err, sizeof(shards[g].err), "%s", tl_error);
       });
     for (auto &t : th) t.join();
@@ -475,14 +499,19 @@ int fastc_gpu_compress_batch(int format, const fastc_gpu_job *jobs, uint32_t num
   std::vector<int> rcs(num_gpus, 0);
   std::vector<std::string> errs(num_gpus);
   auto worker = [&](int g) {
+    int last_dev = -1, dev = g;
+    if (num_gpus == 1) cudaGetDevice(&dev);
+    if (dev < 0 || dev >= kMaxDevices) { rcs[g] = 1; errs[g] = "bad device"; return; }
+    std::lock_guard<std::mutex> lk(g_ctx[dev].host_mu);
     for (uint32_t j = g; j < num_jobs; j += num_gpus) {
       Shard s;
-      s.dev = g;
-      if (num_gpus == 1) cudaGetDevice(&s.dev);
+      s.dev = dev;
       s.first_block = 0;
       s.num_blocks = (jobs[j].width / 4) * (jobs[j].height / 4);
+      // no drain between textures: the staging slots keep rotating across jobs
       if (run_shard(s, format, jobs[j].rgba_host, jobs[j].width, jobs[j].height, jobs[j].out_host, quality,
-                    seed + ((uint64_t)j << 40), 0)) {
+                    seed + ((uint64_t)j << 40), 0, /*drain=*/false)) {
+        drain_slots(g_ctx[s.dev], nullptr);
         rcs[g] = 1;
         errs[g] = tl_error;
         return;
@@ -491,6 +520,16 @@ int fastc_gpu_compress_batch(int format, const fastc_gpu_job *jobs, uint32_t num
       per[g].kernel_launches += s.launches;
       per[g].h2d_bytes += s.h2d;
       per[g].d2h_bytes += s.d2h;
+      last_dev = s.dev;
+    }
+    if (last_dev >= 0) {
+      double ms = 0;
+      if (drain_slots(g_ctx[last_dev], &ms)) {
+        rcs[g] = 1;
+        errs[g] = tl_error;
+        return;
+      }
+      per[g].kernel_ms += ms;
     }
   };
   if (num_gpus == 1) {

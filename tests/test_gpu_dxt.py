@@ -91,3 +91,55 @@ def test_dxt_device_path_large_roundtrip(gpu, oracle):
         assert (got == host).all()
         dec = oracle.decode(fmt, got, 1024, 1024)
         assert oracle.psnr(img, dec) > 30.0
+
+
+def test_dxt_config4_batch_of_1024_textures(gpu, oracle):
+    """BASELINE configs[3]: DXT1 and DXT5 on a batch of 256 synthetic 1024x1024 textures (seeds 1..256),
+    ONE batch submission (fastc_gpu_compress_batch, textures pipelined through the staging slots).
+    Every texture of the batch equals its own single-texture submission; the first 48 are also
+    compared with the CPU oracle bit for bit (the oracle needs ~75 ms per texture and format)."""
+    import torch
+    from fastc_b200.synth import synth_rgba_torch
+    imgs = [np.ascontiguousarray(synth_rgba_torch(1024, 1024, seed, device="cuda").cpu().numpy())
+            for seed in range(1, 257)]
+    assert (imgs[0] == synth_rgba(1024, 1024, 1)).all()   # the device generator is the numpy generator
+    for fmt in ("DXT1", "DXT5"):
+        outs, tm = gpu.compress_batch(F[fmt], imgs)
+        assert len(outs) == 256 and tm["kernel_launches"] >= 256
+        assert tm["h2d_bytes"] == 256 * 1024 * 1024 * 4
+        for k in range(0, 256, 5):
+            single, _ = gpu.compress(F[fmt], imgs[k])
+            assert _mismatch(outs[k], single, fmt) == 0, (fmt, k)
+        for k in range(48):
+            want, _ = oracle.compress(fmt, imgs[k])
+            assert _mismatch(outs[k], want, fmt) == 0, (fmt, k)
+
+
+@pytest.mark.parametrize("fmt", ["DXT1", "BPTC"])
+def test_concurrent_ranged_submissions_like_threadgroup(gpu, oracle, fmt):
+    """FasTC's ThreadGroup calls a CompressionFunc from N threads at once on disjoint block ranges of
+    the same buffers (Core/src/ThreadGroup.cpp:146-188): concurrent fastc_gpu_compress calls on one
+    device must serialise safely and give the bytes of one whole-image call."""
+    import threading
+    img = synth_rgba(256, 256, 9)
+    nblk = 64 * 64
+    whole, _ = gpu.compress(F[fmt], img, quality=0)
+    out = np.zeros_like(whole)
+    nthreads = 8
+    per = (nblk + nthreads - 1) // nthreads          # ceil split, as PrepareThreads does
+    errs = []
+
+    def work(t):
+        try:
+            first = t * per
+            gpu.compress(F[fmt], img, out, quality=0, first_block=first, num_blocks=min(per, nblk - first))
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(nthreads)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
+    assert _mismatch(out, whole, fmt) == 0
