@@ -139,12 +139,20 @@ class GpuLibrary:
                      "d2h_bytes": tm.d2h_bytes, "kernel_launches": tm.kernel_launches}
 
     def compress_batch(self, fmt: int, images: list[np.ndarray], *, quality: int = 50, seed: int = 0,
-                       num_gpus: int = 1):
+                       num_gpus: int = 1, outs: list[np.ndarray] | None = None):
+        """One submission for a list of textures (fastc_gpu_compress_batch).  `outs`: optional
+        preallocated output arrays (e.g. pinned memory), one per texture."""
         jobs = (_Job * len(images))()
-        outs = []
+        given, outs = outs, []
         for k, im in enumerate(images):
             h, w = im.shape[:2]
-            o = np.zeros(int(self.cdll.fastc_gpu_compressed_size(int(fmt), w, h)), dtype=np.uint8)
+            size = int(self.cdll.fastc_gpu_compressed_size(int(fmt), w, h))
+            if given is not None:
+                o = given[k]
+                if o.nbytes < size:
+                    raise FastcGpuError("Not enough space for compressed data!")
+            else:
+                o = np.zeros(size, dtype=np.uint8)
             outs.append(o)
             jobs[k] = _Job(im.ctypes.data, o.ctypes.data, w, h)
         tm = _Timing()

@@ -294,7 +294,7 @@ __device__ __forceinline__ uint2 compress_alpha_block(const uint32_t (&px)[16]) 
 }
 
 template <bool DXT5>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 dxt_encode_kernel(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x,
                   uint32_t first_block, uint32_t num_blocks, uint8_t *__restrict__ out) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;

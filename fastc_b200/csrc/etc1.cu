@@ -223,7 +223,7 @@ __device__ uint2 pack_solid(uint32_t pixel) {
 constexpr int kEtcThreads = 128;
 constexpr int kEtcBlocksPerCta = kEtcThreads / 4;
 
-__global__ void __launch_bounds__(kEtcThreads)
+__global__ void __launch_bounds__(kEtcThreads, 6)
 etc1_encode_kernel(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, uint32_t first_block,
                    uint32_t num_blocks, uint2 *__restrict__ out) {
   __shared__ uint32_t s_px[kEtcBlocksPerCta][17];  // +1 word: quads of a warp hit distinct banks

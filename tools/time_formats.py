@@ -68,9 +68,10 @@ def batch_config4(g, hbm):
         b.record()
         torch.cuda.synchronize()
         k_ms = a.elapsed_time(b)
-        g.compress_batch(F[fmt], host[:8])
+        pouts = [torch.empty(nblk * bpb, dtype=torch.uint8, pin_memory=True).numpy() for _ in range(n)]
+        g.compress_batch(F[fmt], host[:8], outs=pouts[:8])
         t0 = time.perf_counter()
-        _, tm = g.compress_batch(F[fmt], host)
+        _, tm = g.compress_batch(F[fmt], host, outs=pouts)
         e_ms = (time.perf_counter() - t0) * 1e3
         mpix = n * size * size / 1e6
         gbs = n * nblk * (64 + bpb) / (k_ms / 1e3) / 1e9
@@ -78,7 +79,7 @@ def batch_config4(g, hbm):
                           "kernel_mpix_s": mpix / (k_ms / 1e3), "algo_gbs": gbs, "hbm_peak_gbs": hbm,
                           "hbm_frac": gbs / hbm, "e2e_ms": e_ms, "e2e_mpix_s": mpix / (e_ms / 1e3),
                           "e2e_pcie_gbs": (tm["h2d_bytes"] + tm["d2h_bytes"]) / (e_ms / 1e3) / 1e9,
-                          "host_memory": "pinned input, pageable output"}))
+                          "host_memory": "pinned"}))
 
 
 if __name__ == "__main__":
