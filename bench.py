@@ -48,6 +48,29 @@ ALU_PEAK_LANE_OPS = 148 * 128 * 1.965e9
 ALGO_BYTES_PER_BLOCK = 64 + 16  # read one 4x4 RGBA block, write one 128-bit BC7 block (5 B/px)
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write banners to fd 1 (NCCL prints its
+    version there), so fd 1 is pointed at stderr for the whole run and the line is written to the
+    saved descriptor by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def load_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -141,7 +164,7 @@ def run_reference(args, rank: int, world: int):
         "e2e": {"value": val, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------- our arm
@@ -332,7 +355,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         line["cpu_baseline"] = cpu_baseline
     if quality_check:
         line["psnr_vs_reference"] = quality_check
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -350,6 +373,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args, rank, world)
         return

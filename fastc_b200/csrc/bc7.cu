@@ -16,8 +16,13 @@
 //   bc7_wm_scan    1 CTA            : exclusive scan of tile counts (watermark order, T1)
 //   bc7_select     1 warp / block   : lanes = the 64 partition shapes; bbox + 8/4-bucket
 //                                     error estimate per shape, warp argmin (first index wins)
-//   bc7_chains     1 thread / (block, endpoint-fit "chain"): PCA + k-means + LSQ start,
-//                                     then the serial annealing chain, all-integer inner loop
+//   bc7_setup      1 thread / endpoint-fit "chain": PCA + k-means + least squares + grid clamp +
+//                                     first evaluation; chains that share a cluster and an index
+//                                     precision share the fit (twin_slot); writes either a final
+//                                     result or the start state of the chain's annealing
+//   bc7_bin_offsets / bc7_scatter   : counting sort of the start states by (precision, cluster size)
+//   bc7_anneal     persistent lanes : 1 chain / lane, refilled from the sorted list; all-integer
+//                                     evaluation (paired palette rows, VABSDIFF4 + DP4A)
 //   bc7_pack       1 thread / block : best mode by total error in the reference's mode
 //                                     order, anchor fix-ups, 128-bit pack
 // The unit of parallelism for the expensive part is the *chain* (one subset of
@@ -948,9 +953,35 @@ constexpr int kChainThreads = 128;
 //  w5: alpha error (modes 4/5)   w6: rounded alpha endpoint bytes a1 | a2 << 8 (modes 4/5)
 constexpr int kStateWords = 8;
 
-// sort key of an annealing chain: (index bits - 2) * 17 + cluster size, < kSortKeys
-constexpr int kSortKeys = 51;
-__device__ __forceinline__ int sort_key(int ibits, int n) { return (ibits - 2) * 17 + n; }
+// Sort key of an annealing chain: ((index bits - 2) * 17 + cluster size) * 4 + expected-length level.
+// A chain runs until 50 (-q) consecutive steps bring no new best, so its length is unknown in
+// advance, but it correlates strongly with the start error per pixel (measured on the SURVEY 8d
+// image at -q 50: < 128 per pixel: 57 steps on average, at most ~270; 128..4096: ~170; above --
+// the mode 4/5 fits, whose error carries the stale-alpha term of T16 and which make up more than
+// half of all annealing steps -- 245 to 586 on average, the longest > 2500 steps: 10+ ms for one
+// lane, a sizeable part of the whole kernel on a 1/8 shard).  Chains are queued longest-expected
+// first within their (precision, size) bin, in eight levels, so that the later a chain is
+// dequeued the shorter its worst case: the kernel's tail shrinks.
+constexpr int kLenLevels = 8;
+constexpr int kSortKeys = 51 * kLenLevels;
+__device__ __forceinline__ int sort_key(int ibits, int n, uint32_t err) {
+  // start error per pixel: < 128 | < 4096 | < 8192 | < 16384 | < 32768 | < 49152 | < 65536 | above
+  const uint32_t e = err / (uint32_t)max(n, 1);
+  const int lvl = e < 4096u ? (e < 128u ? 0 : 1)
+                            : (e < 16384u ? (e < 8192u ? 2 : 3) : (e < 32768u ? 4 : (e < 49152u ? 5 : (e < 65536u ? 6 : 7))));
+  return ((ibits - 2) * 17 + n) * kLenLevels + lvl;
+}
+// mean steps of a chain of each level (same measurement), for the work estimate of bc7_bin_offsets
+__constant__ float c_level_steps[kLenLevels] = {57.0f, 170.0f, 245.0f, 297.0f, 372.0f, 437.0f, 500.0f, 586.0f};
+// bins layout (uint32 words)
+constexpr int kBinCount = 0;      // [kSortKeys] chains per key (histogram, bc7_setup)
+constexpr int kBinOffset = 512;   // [kSortKeys] start of each key's range in the sorted order
+constexpr int kBinCursor = 1024;  // [kSortKeys] scatter cursors
+constexpr int kBinTotal = 1536;
+constexpr int kBinFetch = 1537;   // [3] fetch cursor of precision class c (= index bits - 2)
+constexpr int kBinEnd = 1540;     // [3] end of class c's region
+constexpr int kBinHome = 1544;    // [3] first CTA whose home class is c or lower
+constexpr int kBinWords = 2048;
 
 __device__ __forceinline__ void write_state(const Ws &ws, uint32_t gid, uint32_t mask, const Chain &c, int n,
                                             const FitResult &R, uint32_t rng, uint32_t alpha_err, uint32_t abytes) {
@@ -963,10 +994,10 @@ __device__ __forceinline__ void write_state(const Ws &ws, uint32_t gid, uint32_t
   const int ibits = c.idx_mode == 0 ? c_modes[c.mode].index_bits : c_modes[c.mode].alpha_index_bits;
   {
     // one atomic per distinct key among the lanes that arrive here together
-    const int key = sort_key(ibits, n);
+    const int key = sort_key(ibits, n, R.err);
     const unsigned act = __activemask();
     const unsigned peers = __match_any_sync(act, key);
-    if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&ws.bins[key], (uint32_t)__popc(peers));
+    if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&ws.bins[kBinCount + key], (uint32_t)__popc(peers));
   }
 }
 
@@ -1284,10 +1315,8 @@ bc7_setup(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, u
 }
 
 // ------------------------------------------------------------------ annealing
-// bins layout (uint32): [0, 51) chains per sort key, [64, 115) start offset of each key in the
-// sorted order (descending key: 4-bit-index chains first, large clusters first), [128, 179)
-// scatter cursors, [192] total, [193 + c] fetch cursor of precision class c (= index bits - 2),
-// [196 + c] end of class c's region, [200 + c] first CTA whose home class is c or lower.
+// The sorted order is by descending key (see sort_key and the bins layout above): 4-bit-index
+// chains first, within a precision class large clusters first, within a bin long chains first.
 //
 // bc7_anneal gives every CTA a HOME class, in proportion to the class's estimated work, so that
 // the lanes of a warp build palettes of the same length (and, for the 4-bit class, walk the same
@@ -1296,16 +1325,21 @@ __global__ void bc7_bin_offsets(uint32_t *bins, uint32_t grid_ctas) {
   uint32_t off = 0;
   float work[3] = {0.0f, 0.0f, 0.0f};
   for (int k = kSortKeys - 1; k >= 0; k--) {
-    const int cls = k / 17, n = k % 17;
-    if (n == 16) bins[193 + cls] = off;  // the class's region starts with its largest clusters
-    bins[64 + k] = off;
-    off += bins[k];
-    bins[128 + k] = 0;
-    if (n == 0) bins[196 + cls] = off;
-    // instructions per annealing step ~ fixed part + palette entries + pixels
-    work[cls] += (float)bins[k] * (150.0f + 12.0f * (float)(4 << cls) + 40.0f * (float)n);
+    const int base = k / kLenLevels, lvl = k % kLenLevels;
+    const int cls = base / 17, n = base % 17;
+    if (n == 16 && lvl == kLenLevels - 1) bins[kBinFetch + cls] = off;  // the class's region starts with its largest clusters
+    bins[kBinOffset + k] = off;
+    off += bins[kBinCount + k];
+    bins[kBinCursor + k] = 0;
+    if (n == 0 && lvl == 0) bins[kBinEnd + cls] = off;
+    // expected steps of the level x instructions per step ~ fixed part + palette entries + pixels
+    work[cls] += (float)bins[kBinCount + k] * c_level_steps[lvl] * (300.0f + 9.0f * (float)(4 << cls) + 28.0f * (float)n);
   }
-  bins[192] = off;
+  bins[kBinTotal] = off;
+  // measured correction of the model per class (share of CTA time each class's queue really took
+  // on the SURVEY 8d image); lanes steal across classes once their queue is dry, so an imperfect
+  // split costs warp uniformity, not idle time
+  work[0] *= 1.3f; work[1] *= 0.62f; work[2] *= 0.67f;
   const float tot = work[0] + work[1] + work[2];
   // CTAs [0, b2) -> class 2, [b2, b1) -> class 1, [b1, grid) -> class 0
   uint32_t b2 = tot > 0.0f ? (uint32_t)(work[2] / tot * (float)grid_ctas + 0.5f) : 0;
@@ -1313,16 +1347,21 @@ __global__ void bc7_bin_offsets(uint32_t *bins, uint32_t grid_ctas) {
   if (b2 > grid_ctas) b2 = grid_ctas;
   if (b1 > grid_ctas) b1 = grid_ctas;
   if (b1 < b2) b1 = b2;
-  bins[200 + 2] = 0;
-  bins[200 + 1] = b2;
-  bins[200 + 0] = b1;
+  bins[kBinHome + 2] = 0;
+  bins[kBinHome + 1] = b2;
+  bins[kBinHome + 0] = b1;
+#ifdef FASTC_GPU_TAILSTATS
+  printf("anneal classes: work %.3g / %.3g / %.3g -> CTAs %u / %u / %u; chains %u / %u / %u\n", work[0], work[1], work[2],
+         grid_ctas - b1, b1 - b2, b2, bins[kBinEnd + 0] - bins[kBinFetch + 0], bins[kBinEnd + 1] - bins[kBinFetch + 1],
+         bins[kBinEnd + 2] - bins[kBinFetch + 2]);
+#endif
 }
 
 // Counting-sort scatter.  Ranks are taken in shared memory and each CTA reserves one range per
 // key with a single global atomic (51 hot counters would otherwise serialise ~10 chains/block).
 __global__ void __launch_bounds__(256) bc7_scatter(Ws ws, uint32_t num_blocks) {
   __shared__ uint32_t s_cnt[kSortKeys], s_base[kSortKeys];
-  if (threadIdx.x < kSortKeys) s_cnt[threadIdx.x] = 0;
+  for (int k = threadIdx.x; k < kSortKeys; k += 256) s_cnt[k] = 0;
   __syncthreads();
   const uint32_t gid = blockIdx.x * 256 + threadIdx.x;
   int key = -1;
@@ -1334,13 +1373,13 @@ __global__ void __launch_bounds__(256) bc7_scatter(Ws ws, uint32_t num_blocks) {
     if (w0 >> 31) {
       const int mode = (w0 >> 16) & 7, idx_mode = (w0 >> 21) & 1;
       const int ibits = idx_mode == 0 ? c_modes[mode].index_bits : c_modes[mode].alpha_index_bits;
-      key = sort_key(ibits, (w0 >> 24) & 31);
+      key = sort_key(ibits, (w0 >> 24) & 31, st0.w);
       rank = atomicAdd(&s_cnt[key], 1u);
     }
   }
   __syncthreads();
-  if (threadIdx.x < kSortKeys && s_cnt[threadIdx.x])
-    s_base[threadIdx.x] = ws.bins[64 + threadIdx.x] + atomicAdd(&ws.bins[128 + threadIdx.x], s_cnt[threadIdx.x]);
+  for (int k = threadIdx.x; k < kSortKeys; k += 256)
+    if (s_cnt[k]) s_base[k] = ws.bins[kBinOffset + k] + atomicAdd(&ws.bins[kBinCursor + k], s_cnt[k]);
   __syncthreads();
   if (key >= 0) {
     // the annealing kernel reads its work in sorted order: one indirection less on its refill path
@@ -1551,6 +1590,29 @@ __device__ __forceinline__ uint32_t sa_eval(uint32_t (*s_pix)[kPixStride], uint2
   return total;
 }
 
+#ifdef FASTC_GPU_TAILSTATS
+// debug build: when did the queues run dry, when did the lanes / CTAs end (ns, globaltimer)
+__device__ unsigned long long g_tail[12];  // 0 start(min) 1 first dry(min) 2 last dry(max) 3 end(max) 4 - 5 CTAs 6..8 class c first seen dry
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__global__ void bc7_tail_reset() {
+  g_tail[0] = g_tail[1] = g_tail[6] = g_tail[7] = g_tail[8] = ~0ull;
+  g_tail[2] = g_tail[3] = g_tail[4] = g_tail[5] = g_tail[9] = g_tail[10] = 0;
+}
+__global__ void bc7_tail_report() {
+  const double t0 = (double)g_tail[0];
+  printf("anneal tail: all dry first seen %.3f ms, last %.3f ms, end %.3f ms; class queues dry at %.3f / %.3f / %.3f ms\n",
+         ((double)g_tail[1] - t0) * 1e-6, ((double)g_tail[2] - t0) * 1e-6, ((double)g_tail[3] - t0) * 1e-6,
+         ((double)g_tail[6] - t0) * 1e-6, ((double)g_tail[7] - t0) * 1e-6, ((double)g_tail[8] - t0) * 1e-6);
+  printf("  last chain to finish: %llu steps, ran %llu us; longest chain: %llu steps, ran %llu us\n",
+         ((g_tail[9] >> 14) & 0x3FFull) * 4ull, (g_tail[9] & 0xFFFull) * 16ull, g_tail[10] >> 32, g_tail[10] & 0xFFFFFFFFull);
+  printf("  last chain: class %llu\n", (g_tail[9] >> 12) & 3ull);
+}
+#endif
+
 __global__ void __launch_bounds__(kSaThreads, kSaCtasPerSm)
 bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, uint32_t first_block, Ws ws,
            int sa_steps) {
@@ -1585,14 +1647,19 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
                                          ((A.pbit == kPbitPerEndpoint ? 1u : 0u) << 14) | (tab_c << 15) | (tab_a << 19) |
                                          ((uint32_t)A.rotation << 23));
   }
-  if (threadIdx.x < 3) s_end[threadIdx.x] = ws.bins[196 + threadIdx.x];
+  if (threadIdx.x < 3) s_end[threadIdx.x] = ws.bins[kBinEnd + threadIdx.x];
   __syncthreads();
   const int tid = threadIdx.x, lane = tid & 31, wbase = tid & ~31;
   const unsigned full = 0xffffffffu;
   uint32_t drymask = 0;
+#ifdef FASTC_GPU_TAILSTATS
+  if (threadIdx.x == 0) atomicMin(&g_tail[0], gtime());
+  uint32_t dbg_steps = 0;
+  unsigned long long dbg_start = 0;
+#endif
   const float f_tm1 = (float)(sa_steps - 1);
   const float c_x = __fmul_rn(0.1f, f_tm1);  // fast Metropolis exponent: 0.1 * diff / (energy / (steps - 1))
-  const int home = blockIdx.x >= ws.bins[200 + 0] ? 0 : (blockIdx.x >= ws.bins[200 + 1] ? 1 : 2);
+  const int home = blockIdx.x >= ws.bins[kBinHome + 0] ? 0 : (blockIdx.x >= ws.bins[kBinHome + 1] ? 1 : 2);
 
   bool have = false;  // (drymask == 7: every queue has run dry for this lane)
   SaConst K = {0, 0xFFFFFFFFu, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -1619,9 +1686,16 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
           const int cls = a == 0 ? home : (2 - (a - 1) - ((2 - (a - 1)) <= home ? 1 : 0));
           if (cls < 0) break;
           if (!((drymask >> cls) & 1)) {  // a class this lane has seen run dry stays dry
-            pos = atomicAdd(&ws.bins[193 + cls], 1u);
+            pos = atomicAdd(&ws.bins[kBinFetch + cls], 1u);
             got = pos < s_end[cls];
             if (!got) drymask |= 1u << cls;
+#ifdef FASTC_GPU_TAILSTATS
+            if (!got) {
+              const unsigned long long t = gtime();
+              atomicMin(&g_tail[6 + cls], t);
+              if (drymask == 7u) { atomicMin(&g_tail[1], t); atomicMax(&g_tail[2], t); }
+            }
+#endif
           }
         }
         if (got) {
@@ -1654,6 +1728,10 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
           energy = 0;
           improved = false;
           have = true;
+#ifdef FASTC_GPU_TAILSTATS
+          dbg_steps = 0;
+          dbg_start = gtime();
+#endif
         }
       }
       // ... and the warp loads the new chains' pixels together: lane i < 16 fetches pixel i of the
@@ -1734,6 +1812,19 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
       energy++;
       done = !(best_err > 0 && energy < sa_steps);
     }
+#ifdef FASTC_GPU_TAILSTATS
+    dbg_steps++;
+    if (done) {
+      const unsigned long long t = gtime();
+      const unsigned long long dur_us = (t - dbg_start) / 1000ull;
+      // finish time (ns, 40 bits) | steps (12 bits, saturated) | duration us (12 bits, saturated)
+      const unsigned long long cls_ = K.nbm1 == 3 ? 0ull : (K.nbm1 == 7 ? 1ull : 2ull);
+      const unsigned long long rec = ((t & 0xFFFFFFFFFFull) << 24) | ((unsigned long long)min(dbg_steps / 4u, 1023u) << 14) |
+                                     (cls_ << 12) | (unsigned long long)min(dur_us / 16ull, 4095ull);
+      atomicMax(&g_tail[9], rec);
+      atomicMax(&g_tail[10], ((unsigned long long)dbg_steps << 32) | (unsigned long long)(uint32_t)dur_us);
+    }
+#endif
     if (done) {
       // the indices belong to the evaluation that produced best_err: the start state's were
       // stored by bc7_setup, an improved state's were kept when it was found
@@ -1760,6 +1851,15 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
 #ifdef FASTC_GPU_COUNTERS
   atomicAdd(&ws.counters[0], (unsigned long long)ncalls);
   atomicAdd(&ws.counters[1], (unsigned long long)npbe);
+#endif
+#ifdef FASTC_GPU_TAILSTATS
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned long long t = gtime();
+    atomicMax(&g_tail[3], t);
+    atomicAdd(&g_tail[4], t);
+    atomicAdd(&g_tail[5], 1ull);
+  }
 #endif
 }
 
@@ -1997,7 +2097,7 @@ size_t ws_bytes(uint32_t nblocks) {
   b += (size_t)nblocks * kSlots * kResWords * 4;                 // results
   b += (size_t)nblocks * kSlots * 8 * 4;                         // states
   b += (size_t)nblocks * kSlots * kStateWords * 4;               // sorted states
-  b += 1024;                                                     // bins
+  b += kBinWords * 4;                                            // bins
   return b;
 }
 
@@ -2115,7 +2215,7 @@ cudaError_t launch_bc7(Bc7Workspace &wsp, const void *rgba_dev, uint32_t width, 
     bc7_select<<<(nb + kSelWarps - 1) / kSelWarps, kSelWarps * 32, 0, stream>>>(img, width, bx, fb, nb, ws.sel);
     if (ev) cudaEventRecord(ev[2], stream);
     const uint64_t nthreads = (uint64_t)nb * kSlots;
-    cudaMemsetAsync(ws.bins, 0, 1024, stream);
+    cudaMemsetAsync(ws.bins, 0, kBinWords * 4, stream);
     bc7_setup<<<((nb + kChainThreads - 1) / kChainThreads) * kSlotGroups, kChainThreads, 0, stream>>>(
         img, width, bx, fb, nb, ws, quality, seed, block_index_base);
     n++;
@@ -2123,7 +2223,13 @@ cudaError_t launch_bc7(Bc7Workspace &wsp, const void *rgba_dev, uint32_t width, 
       bc7_bin_offsets<<<1, 1, 0, stream>>>(ws.bins, sa_grid);
       bc7_scatter<<<(uint32_t)((nthreads + 255) / 256), 256, 0, stream>>>(ws, nb);
       if (ev) cudaEventRecord(wsp.ev_mid[wsp.timed_chunks - 1], stream);
+#ifdef FASTC_GPU_TAILSTATS
+      bc7_tail_reset<<<1, 1, 0, stream>>>();
+#endif
       bc7_anneal<<<sa_grid, kSaThreads, 0, stream>>>(img, width, bx, fb, ws, quality);
+#ifdef FASTC_GPU_TAILSTATS
+      bc7_tail_report<<<1, 1, 0, stream>>>();
+#endif
       n += 3;
     } else if (ev) {
       cudaEventRecord(wsp.ev_mid[wsp.timed_chunks - 1], stream);
