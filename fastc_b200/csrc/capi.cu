@@ -244,11 +244,13 @@ int run_shard(Shard &s, int format, const uint8_t *rgba_host, uint32_t width, ui
   std::vector<uint32_t> bounds;
   for (uint32_t r = row0; r < row1; r += rows_per_chunk) bounds.push_back(r);
   bounds.push_back(row1);
-  if (chunk_blocks == 0 && format == FASTC_GPU_BPTC && total_rows >= 64) {
+  if (chunk_blocks == 0 && format == FASTC_GPU_BPTC && total_rows >= 64 &&
+      (size_t)total_rows * 4 * width * 4 >= ((size_t)96 << 20)) {
     // BC7 auto: one small head chunk (1/16 of the rows) and the rest.  The big upload then runs
     // under the head's kernels and the head's download under the big chunk's kernels; only the
     // head's upload and the tail's download stay exposed, and the persistent annealing kernel
-    // still sees (almost) the whole shard at once.
+    // still sees (almost) the whole shard at once.  Only worth it for big uploads (>= 96 MiB, ~2 ms):
+    // every extra submission pays the annealing kernel's ~1.5 ms tail once more.
     bounds.assign({row0, row0 + total_rows / 16, row1});
   }
   const uint32_t nchunks = (uint32_t)bounds.size() - 1;

@@ -165,3 +165,38 @@ def test_multi_gpu_host_path_equals_single_gpu(gpu):
     for o, im in zip(outs, [img, img[:256], img[128:]]):
         ref, _ = gpu.compress(F.DXT5, np.ascontiguousarray(im))
         assert (o == ref).all()
+
+
+@pytest.mark.parametrize("size", [2048, 8192])
+def test_bc7_q50_at_config_sizes_matches_oracle_on_sampled_ranges(gpu, oracle, size):
+    """BASELINE configs[1] / configs[2] (BPTC -q 50 at 2048^2 / 8192^2) are too large for the CPU
+    oracle (~500 blocks/s), but every chain's RNG stream is keyed by the block's index in the full
+    texture and the watermark word by the number of solid blocks before it, so any block range of the
+    full-size GPU run must equal the oracle run on that range alone.  Ranges are picked to cross
+    opaque, alpha (modes 4-7), solid (watermark) and transparent tiles."""
+    import torch
+    from fastc_b200.synth import synth_rgba_torch
+    d_in = synth_rgba_torch(size, size, 1, device="cuda")
+    bx = size // 4
+    d_out = torch.zeros(bx * bx * 16, dtype=torch.uint8, device="cuda")
+    gpu.compress_device(F.BPTC, d_in, d_out, width=size, height=size, quality=50, seed=7)
+    torch.cuda.synchronize()
+    got = d_out.cpu().numpy().reshape(-1, 16)
+    img = np.ascontiguousarray(d_in.cpu().numpy())
+    blocks = img.reshape(bx, 4, bx, 4, 4).transpose(0, 2, 1, 3, 4).reshape(bx * bx, 64)
+    solid = (blocks.reshape(-1, 16, 4) == blocks.reshape(-1, 16, 4)[:, :1]).all((1, 2))
+    transparent = (blocks.reshape(-1, 16, 4)[..., 3] == 0).all(1) & ~solid
+    alpha = (blocks.reshape(-1, 16, 4)[..., 3] < 250).any(1) & ~solid & ~transparent
+    solid_before = np.concatenate([[0], np.cumsum(solid)])
+    picks = [0, int(np.flatnonzero(solid)[solid.sum() // 2]) - 40, int(np.flatnonzero(transparent)[5]) - 40,
+             int(np.flatnonzero(alpha)[alpha.sum() // 3]) - 40, bx * bx - 96]
+    kinds = set()
+    for first in picks:
+        first = max(0, min(first, bx * bx - 96))
+        want, _ = oracle.compress("BPTC", img, quality=50, first_block=first, num_blocks=96, rng_mode=1, seed=7,
+                                  wm_base=int(solid_before[first]))
+        want = want.reshape(-1, 16)[first:first + 96]
+        bad = np.flatnonzero((got[first:first + 96] != want).any(1))
+        assert bad.size == 0, (size, first, bad[:8])
+        kinds |= {k for k, m in (("solid", solid), ("transparent", transparent), ("alpha", alpha)) if m[first:first + 96].any()}
+    assert kinds == {"solid", "transparent", "alpha"}
