@@ -3,12 +3,14 @@
 // (ImageLoaderTGA.cpp:36-48 + ImageLoader.cpp:122-149), the KTX writer emits the compressed
 // payload at byte 96 with the "KTXorientation" key (ImageWriterKTX.cpp:69-160).  Beyond the
 // reference: ETC1 payloads can be written to KTX, compressed KTX files can be loaded back,
-// and PNG output needs only zlib.
+// and PNG input / output needs only zlib (no libpng).
 #include "FasTC/ImageFile.h"
 
 #include <zlib.h>
 
+#include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -224,6 +226,115 @@ bool WritePNG(const char *path, FasTC::Image<> &img) {
   return WriteAll(path, out);
 }
 
+// PNG loader with the coverage of the reference's libpng loader (IO/src/ImageLoaderPNG.cpp:58-260):
+// bit depth 8 only ("Only 8-bit images currently supported."), colour types grey, RGB, palette
+// (opaque, like the reference: tRNS is ignored), grey + alpha, RGBA; rows in file order.  Adam7
+// interlacing is rejected (the reference reads rows without interlace handling).
+FasTC::Image<> *LoadPNG(const std::vector<uint8> &d) {
+  static const uint8 sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
+  if (d.size() < 8 || memcmp(d.data(), sig, 8) != 0) {
+    fprintf(stderr, "Incorrect PNG signature\n");
+    return NULL;
+  }
+  auto be32 = [&](size_t at) { return ((uint32)d[at] << 24) | ((uint32)d[at + 1] << 16) | ((uint32)d[at + 2] << 8) | d[at + 3]; };
+  uint32 w = 0, h = 0;
+  int depth = 0, ctype = -1, interlace = 0;
+  std::vector<uint8> idat, plte;
+  for (size_t pos = 8; pos + 12 <= d.size();) {
+    const uint32 len = be32(pos);
+    if (pos + 12 + (size_t)len > d.size()) break;
+    const uint8 *tag = &d[pos + 4], *body = &d[pos + 8];
+    if (!memcmp(tag, "IHDR", 4) && len >= 13) {
+      w = be32(pos + 8); h = be32(pos + 12);
+      depth = body[8]; ctype = body[9]; interlace = body[12];
+    } else if (!memcmp(tag, "PLTE", 4)) {
+      plte.assign(body, body + len);
+    } else if (!memcmp(tag, "IDAT", 4)) {
+      idat.insert(idat.end(), body, body + len);
+    } else if (!memcmp(tag, "IEND", 4)) {
+      break;
+    }
+    pos += 12 + (size_t)len;
+  }
+  if (w == 0 || h == 0 || ctype < 0) {
+    fprintf(stderr, "Could not read PNG header\n");
+    return NULL;
+  }
+  if (depth != 8) {
+    fprintf(stderr, "Only 8-bit images currently supported.\n");
+    return NULL;
+  }
+  int channels = 0;
+  switch (ctype) {
+    case 0: channels = 1; break;
+    case 2: channels = 3; break;
+    case 3: channels = 1; break;
+    case 4: channels = 2; break;
+    case 6: channels = 4; break;
+    default: fprintf(stderr, "PNG color type unsupported\n"); return NULL;
+  }
+  if (interlace != 0) {
+    fprintf(stderr, "Interlaced PNG images are not supported\n");
+    return NULL;
+  }
+  if (ctype == 3 && plte.size() < 3) {
+    fprintf(stderr, "Couldn't find PLTE chunk\n");
+    return NULL;
+  }
+  const size_t stride = (size_t)w * channels;
+  std::vector<uint8> raw((size_t)h * (stride + 1));
+  uLongf rawLen = (uLongf)raw.size();
+  if (idat.empty() || uncompress(raw.data(), &rawLen, idat.data(), (uLong)idat.size()) != Z_OK || rawLen != raw.size()) {
+    fprintf(stderr, "Could not decode PNG image data\n");
+    return NULL;
+  }
+  // undo the per-row filters in place (PNG specification, filter types 0-4)
+  for (uint32 j = 0; j < h; j++) {
+    uint8 *row = &raw[(size_t)j * (stride + 1) + 1];
+    const uint8 *up = j ? row - (stride + 1) : NULL;
+    const int filter = row[-1];
+    for (size_t i = 0; i < stride; i++) {
+      const int a = i >= (size_t)channels ? row[i - channels] : 0, b = up ? up[i] : 0,
+                c = (up && i >= (size_t)channels) ? up[i - channels] : 0;
+      int pred = 0;
+      switch (filter) {
+        case 0: pred = 0; break;
+        case 1: pred = a; break;
+        case 2: pred = b; break;
+        case 3: pred = (a + b) >> 1; break;
+        case 4: {
+          const int pp = a + b - c, pa = abs(pp - a), pb = abs(pp - b), pc = abs(pp - c);
+          pred = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
+          break;
+        }
+        default: fprintf(stderr, "Could not decode PNG image data\n"); return NULL;
+      }
+      row[i] = (uint8)(row[i] + pred);
+    }
+  }
+  std::vector<uint32> px((size_t)w * h);
+  const size_t npal = plte.size() / 3;
+  for (uint32 j = 0; j < h; j++) {
+    const uint8 *row = &raw[(size_t)j * (stride + 1) + 1];
+    for (uint32 i = 0; i < w; i++) {
+      uint32 r, g, b, a = 255;
+      switch (ctype) {
+        case 0: r = g = b = row[i]; break;
+        case 2: r = row[3 * i]; g = row[3 * i + 1]; b = row[3 * i + 2]; break;
+        case 3: {
+          const size_t e = std::min<size_t>(row[i], npal - 1);
+          r = plte[3 * e]; g = plte[3 * e + 1]; b = plte[3 * e + 2];
+          break;
+        }
+        case 4: r = g = b = row[2 * i]; a = row[2 * i + 1]; break;
+        default: r = row[4 * i]; g = row[4 * i + 1]; b = row[4 * i + 2]; a = row[4 * i + 3]; break;
+      }
+      px[(size_t)j * w + i] = r | (g << 8) | (b << 16) | (a << 24);
+    }
+  }
+  return new FasTC::Image<>(w, h, px.data());
+}
+
 }  // namespace
 
 ImageFile::ImageFile(const char *filename) : m_FileFormat(DetectFileFormat(filename)), m_Image(NULL) {
@@ -262,8 +373,9 @@ bool ImageFile::Load() {
   switch (m_FileFormat) {
     case eFileFormat_TGA: m_Image = LoadTGA(d); break;
     case eFileFormat_KTX: m_Image = LoadKTX(d); break;
+    case eFileFormat_PNG: m_Image = LoadPNG(d); break;
     default:
-      fprintf(stderr, "Unable to load image: unsupported input file format (TGA and KTX are).\n");
+      fprintf(stderr, "Unable to load image: unsupported input file format (PNG, TGA and KTX are).\n");
       return false;
   }
   if (!m_Image) fprintf(stderr, "Unable to load image!\n");

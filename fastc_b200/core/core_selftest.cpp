@@ -193,9 +193,18 @@ static int TestGpu(int argc, char **argv) {
   return g_fail ? 1 : 0;
 }
 
+// `convert in out`: ImageFile::Load + ImageFile::Write (no GPU): exercises the loaders / writers.
+static int Convert(const char *in, const char *out) {
+  ImageFile src(in);
+  if (!src.Load()) return 1;
+  ImageFile dst(out, ImageFile::DetectFileFormat(out), *src.GetImage());
+  return dst.Write() ? 0 : 1;
+}
+
 int main(int argc, char **argv) {
   if (argc >= 2 && !strcmp(argv[1], "api")) return TestApi();
+  if (argc >= 4 && !strcmp(argv[1], "convert")) return Convert(argv[2], argv[3]);
   if (argc >= 2 && !strcmp(argv[1], "gpu")) return TestGpu(argc, argv);
-  fprintf(stderr, "usage: core_selftest api | gpu <rgba.raw> <w> <h> <fmt> <quality> <seed> <out-prefix>\n");
+  fprintf(stderr, "usage: core_selftest api | convert <in> <out> | gpu <rgba.raw> <w> <h> <fmt> <quality> <seed> <out-prefix>\n");
   return 2;
 }

@@ -2,7 +2,7 @@
 // reference CLTool/src/tc.cpp:40-346 (`-f -q -n -d -nd -t -j -a -l -v -simd -h`), driving
 // the GPU library through CompressImage.  Additions: `-g N` shards over N GPUs (0 = all),
 // `-s SEED` pins the annealing RNG key.  Differences: PVRTC / *Lib formats are rejected
-// (no GPU encoder), `-l` and `-v` statistics are accepted and ignored, input is TGA / KTX.
+// (no GPU encoder), `-l` and `-v` statistics are accepted and ignored, input is PNG (8-bit, non-interlaced) / TGA / KTX.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>

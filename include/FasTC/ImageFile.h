@@ -1,6 +1,6 @@
 // ImageFile: the file formats either side of the compression path.
 // API mirror of the used part of reference IO/include/FasTC/ImageFile.h: Load() / Write() /
-// GetImage() / DetectFileFormat().  Readers: TGA (uncompressed + RLE true colour, 24/32 bit),
+// GetImage() / DetectFileFormat().  Readers: PNG (8-bit, non-interlaced), TGA (uncompressed + RLE true colour, 24/32 bit),
 // KTX (RGBA8 or a BPTC / DXT1 / DXT5 / ETC1 payload).  Writers: TGA, KTX (compressed
 // payload at byte 96 like reference IO/src/ImageWriterKTX.cpp:69-160, plus ETC1 which the
 // reference cannot write) and PNG (zlib).
