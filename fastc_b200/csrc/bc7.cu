@@ -757,7 +757,6 @@ __device__ __noinline__ void fit_core(int ibits, const uint32_t *pts, int n, con
 
   // ---- k-means over the nb interpolation points until a fixed point (:961-1026, T15)
   float cen[16][4];
-  int cnt[16];
 #pragma unroll 1
   for (int i = 0; i < nb; i++) {
     const float s = __fdiv_rn((float)i, (float)nbm1);
@@ -819,7 +818,6 @@ __device__ __noinline__ void fit_core(int ibits, const uint32_t *pts, int n, con
 #pragma unroll
           for (int k = 0; k < 4; k++) sum[k] = div_small(sum[k], fc, rc);
         }
-        cnt[j] = c;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
           if (!(cen[j][k] == sum[k])) fixed = false;
@@ -831,7 +829,7 @@ __device__ __noinline__ void fit_core(int ibits, const uint32_t *pts, int n, con
   int filled = 0, last = -1;
 #pragma unroll 1
   for (int j = 0; j < nb; j++)
-    if (cnt[j] > 0) { filled++; last = j; }
+    if (s_acc[2][j][tid] > 0) { filled++; last = j; }  // the last pass's counts
   if (filled == 1) {  // one bucket -> CompressSingleColor on its centroid (:1038-1047, fit_finish)
     C.kind = 1;
     C.single = pack_round(cen[last]);
@@ -845,7 +843,7 @@ __device__ __noinline__ void fit_core(int ibits, const uint32_t *pts, int n, con
     const float fb = (float)nbm1;
 #pragma unroll 1
     for (int i = 0; i < nb; i++) {
-      const float fn = (float)cnt[i];
+      const float fn = (float)s_acc[2][i][tid];
       const float a = __fdiv_rn((float)(nbm1 - i), fb), b = __fdiv_rn((float)i, fb);
       asq = __fadd_rn(asq, __fmul_rn(__fmul_rn(fn, a), a));
       bsq = __fadd_rn(bsq, __fmul_rn(__fmul_rn(fn, b), b));
@@ -1177,22 +1175,35 @@ __device__ __forceinline__ void setup_chain(const uint32_t *__restrict__ img, ui
   int twin = twin_slot((selw >> 22) & 1, slot);
   if (twin >= 0 && !decode_chain(selw, twin).active) twin = -1;
 
+  // The block stays in registers (every index below is a compile-time constant); the cluster is
+  // compacted into ONE per-thread array.  Per-thread arrays live in local memory and the kernel's
+  // working set is what its L1 hit rate depends on, so nothing is stored twice: the error pixels
+  // (`pix`) are the points themselves, except for modes 4/5 (n == 16), where they are the block.
   uint32_t blk[16];
   load_block(img, width, blocks_x, first_block + t, blk);
 
   // Cluster of this chain: points in raster order of the subset (m_PointMap).
-  uint32_t pts[16], pix[16];
+  uint32_t smask;  // pixels of the subset
+  if (c.nsub == 1) {
+    smask = 0xFFFFu;
+  } else if (c.nsub == 2) {
+    smask = c.subset ? (uint32_t)c_shape2[c.shape] : (~(uint32_t)c_shape2[c.shape] & 0xFFFFu);
+  } else {
+    const uint32_t m3 = c_shape3[c.shape], lo = m3 & 0x55555555u, hi = (m3 >> 1) & 0x55555555u;
+    const uint32_t sel = c.subset == 0 ? ~(lo | hi) & 0x55555555u : (c.subset == 1 ? lo & ~hi : hi & ~lo);
+    smask = 0;  // one bit per 2-bit field
+#pragma unroll
+    for (int i = 0; i < 16; i++) smask |= ((sel >> (2 * i)) & 1u) << i;
+  }
+  uint32_t pts[16];
   int n = 0;
-  uint32_t mask = 0;
+  const uint32_t mask = smask;
   float sum[4] = {0, 0, 0, 0};
   uint32_t mn = 0xFFFFFFFFu, mx = 0;
-#pragma unroll 1
+#pragma unroll
   for (int i = 0; i < 16; i++) {
-    if (subset_of(i, c.shape, c.nsub) == c.subset) {
-      pix[n] = blk[i];
-      pts[n] = blk[i];
-      n++;
-      mask |= 1u << i;
+    if ((smask >> i) & 1u) {
+      pts[n++] = blk[i];
 #pragma unroll
       for (int k = 0; k < 4; k++) sum[k] = __fadd_rn(sum[k], (float)chan(blk[i], k));  // exact integers
       mn = __vminu4(mn, blk[i]);
@@ -1208,21 +1219,24 @@ __device__ __forceinline__ void setup_chain(const uint32_t *__restrict__ img, ui
   // ---- modes 4/5: CompressCluster alpha variant (Compressor.cpp:632-919), n == 16.
   // Points are rotated and their alpha forced to 255, but avg / bounds / error
   // pixels stay those of the original block (T16).
+  uint32_t pixl[16];
   float alpha_vals[16];
   float amin = FLT_MAX, amax = -FLT_MAX;
   if (A0.rotation) {
-#pragma unroll 1
+#pragma unroll
     for (int i = 0; i < 16; i++) {
       const uint32_t p = blk[i];
       const uint32_t a = c.rot == 0 ? (p >> 24) : chan(p, c.rot - 1);
       uint32_t q = p;
       if (c.rot) q = (p & ~(0xFFu << (8 * (c.rot - 1)))) | ((p >> 24) << (8 * (c.rot - 1)));  // channel <- old alpha
       pts[i] = q | 0xFF000000u;
+      pixl[i] = p;
       alpha_vals[i] = (float)a;
       amin = fminf(amin, (float)a);
       amax = fmaxf(amax, (float)a);
     }
   }
+  const uint32_t *pix = A0.rotation ? pixl : pts;
   // the expensive, mode-independent part runs once for the chain and its twin
   FitCore core;
   fit_core(c0.idx_mode == 0 ? A0.index_bits : A0.alpha_index_bits, pts, n, avg, all_same, s_acc, s_rcp, tid, core);

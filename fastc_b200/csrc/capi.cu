@@ -259,6 +259,12 @@ int run_shard(Shard &s, int format, const uint8_t *rgba_host, uint32_t width, ui
   // BPTC shards are uploaded chunk-wise but encoded per chunk with a running base.
   uint32_t wm_base = s.wm_base;
 
+  // nothing in flight (every submission except the later textures of a batch): restart the slot
+  // rotation, so that the same chunk lands in the same slot call after call and its staging
+  // buffers / BC7 workspace are grown once
+  bool idle = true;
+  for (int i = 0; i < kPipeDepth; i++) idle = idle && !c.slot_busy[i];
+  if (idle) c.next_chunk = 0;
   for (uint32_t k = 0; k < nchunks; k++) {
     const int slot = (int)(c.next_chunk++ % kPipeDepth);
     cudaStream_t st = c.streams[slot];
