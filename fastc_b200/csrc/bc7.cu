@@ -72,6 +72,11 @@ constexpr int kSlots = 16;       // result slots per block
 constexpr int kResWords = 8;     // 32 B per chain result
 // result words: 0 err, 1 p1, 2 p2, 3 p-bit combo, 4-5 colour indices (4 bit each,
 // cluster-local order), 6-7 alpha indices (modes 4/5)
+// Start state of one annealing chain (8 words), written by bc7_setup, read by bc7_anneal.
+//  w0: subset pixel mask [0:15] | mode [16:18] | rot [19:20] | idx_mode [21] | combo [22:23] | n [24:28] | valid [31]
+//  w1/w2: start endpoints (bytes on the grid)   w3: start error   w4: RNG state
+//  w5: alpha error (modes 4/5)   w6: rounded alpha endpoint bytes a1 | a2 << 8 (modes 4/5)
+constexpr int kStateWords = 8;
 constexpr int kTile = 256;       // blocks per watermark tile (= classify CTA)
 
 struct Ws {
@@ -422,7 +427,7 @@ constexpr int kSelWarps = 4;
 
 __global__ void __launch_bounds__(kSelWarps * 32)
 bc7_select(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, uint32_t first_block,
-           uint32_t num_blocks, uint32_t *__restrict__ sel) {
+           uint32_t num_blocks, uint32_t *__restrict__ sel, uint32_t *__restrict__ states) {
   __shared__ uint32_t s_px[kSelWarps][16], s_plo[kSelWarps][16], s_phi[kSelWarps][16];
   __shared__ uint8_t s_w[64];
   if (threadIdx.x < 64) s_w[threadIdx.x] = c_weight[threadIdx.x];
@@ -431,6 +436,10 @@ bc7_select(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
   const bool valid = t < num_blocks;
   uint32_t type = kTypeNormal;
   if (valid) {
+    // every annealing start state of the block begins as "no chain".  This must happen before
+    // bc7_setup runs at all: there a chain also writes the state of its twin (twin_slot), whose
+    // slot is owned by another CTA.
+    if (lane < kSlots) states[((size_t)t * kSlots + lane) * kStateWords] = 0;
     type = sel[t] >> 24;
     if (lane < 16) {
       const uint32_t bi = first_block + t, bx = bi % blocks_x, by = bi / blocks_x;
@@ -945,11 +954,6 @@ __device__ __noinline__ void fit_finish(const Ws &ws, const ModeAttr &A, int mod
 
 constexpr int kChainThreads = 128;
 
-// Start state of one annealing chain (8 words), written by bc7_setup, read by bc7_anneal.
-//  w0: subset pixel mask [0:15] | mode [16:18] | rot [19:20] | idx_mode [21] | combo [22:23] | n [24:28] | valid [31]
-//  w1/w2: start endpoints (bytes on the grid)   w3: start error   w4: RNG state
-//  w5: alpha error (modes 4/5)   w6: rounded alpha endpoint bytes a1 | a2 << 8 (modes 4/5)
-constexpr int kStateWords = 8;
 
 // Sort key of an annealing chain: ((index bits - 2) * 17 + cluster size) * 4 + expected-length level.
 // A chain runs until 50 (-q) consecutive steps bring no new best, so its length is unknown in
@@ -1292,13 +1296,12 @@ bc7_setup(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, u
   const int first = c_group_first[group], count = c_group_count[group];
   const uint32_t t = tile * kChainThreads + tid;
   const uint32_t selw = t < num_blocks ? ws.sel[t] : (uint32_t)kTypeSolid << 24;
-  // pass 1: histogram of the live chains by cluster size; every state word starts as "no chain"
+  // pass 1: histogram of the live chains by cluster size (bc7_select has reset the state words)
   int sizes[4];
 #pragma unroll
   for (int k = 0; k < 4; k++) {
     sizes[k] = 0;
     if (k < count && t < num_blocks) {
-      ws.states[((size_t)t * kSlots + first + k) * kStateWords] = 0;
       const Chain c = decode_chain(selw, first + k);
       // a twin is fitted by its primary chain's lane (see twin_slot)
       const int prim = primary_slot((selw >> 22) & 1, first + k);
@@ -2226,7 +2229,7 @@ cudaError_t launch_bc7(Bc7Workspace &wsp, const void *rgba_dev, uint32_t width, 
     bc7_classify<<<ntiles, kTile, 0, stream>>>(img, width, bx, fb, nb, ws.sel, ws.tile_count);
     bc7_wm_scan<<<1, 1024, 0, stream>>>(ws.tile_count, ntiles, ws.total_solid);
     if (ev) cudaEventRecord(ev[1], stream);
-    bc7_select<<<(nb + kSelWarps - 1) / kSelWarps, kSelWarps * 32, 0, stream>>>(img, width, bx, fb, nb, ws.sel);
+    bc7_select<<<(nb + kSelWarps - 1) / kSelWarps, kSelWarps * 32, 0, stream>>>(img, width, bx, fb, nb, ws.sel, ws.states);
     if (ev) cudaEventRecord(ev[2], stream);
     const uint64_t nthreads = (uint64_t)nb * kSlots;
     cudaMemsetAsync(ws.bins, 0, kBinWords * 4, stream);
