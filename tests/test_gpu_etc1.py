@@ -94,5 +94,9 @@ def test_etc1_config5_size_device_path_roundtrip(gpu, oracle):
     got = d_out.cpu().numpy()
     want, _ = oracle.compress("ETC1", img[:64])
     assert (got[:want.size] == want).all()
+    # block ranges spread over the texture, bit-exact against the oracle run on the range alone
+    for first in (300_000, 524_288 + 777, 1024 * 1024 - 5000):
+        w, _ = oracle.compress("ETC1", img, first_block=first, num_blocks=5000)
+        assert (got[first * 8:(first + 5000) * 8] == w[first * 8:(first + 5000) * 8]).all(), first
     dec = oracle.decode("ETC1", got, 4096, 4096)
     assert oracle.psnr(img, dec) > 30.0
