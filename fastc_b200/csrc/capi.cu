@@ -44,6 +44,8 @@ int fail(const char *fmt, ...) {
 
 constexpr int kMaxDevices = 16;
 constexpr int kPipeDepth = 3;  // staging slots per device for the host path
+constexpr int kStagePieces = 4;               // pinned upload ring (pageable inputs)
+constexpr size_t kStagePieceBytes = 16u << 20;
 
 struct DeviceCtx {
   bool tables_ready = false;
@@ -63,6 +65,19 @@ struct DeviceCtx {
   // one host-path submission (or batch) at a time per device: FasTC's ThreadGroup / WorkerQueue
   // call a CompressionFunc from many threads at once (Core/src/ThreadGroup.cpp:146-188)
   std::mutex host_mu;
+  // Pageable caller memory (what FasTC hands over: new[] / malloc) would make every
+  // cudaMemcpyAsync synchronous and serialise the pipeline, so it is staged through pinned
+  // memory owned by the library: uploads through a ring of kStagePieces pieces (filled by a few
+  // host threads while the previous piece is on the wire), downloads into a pinned buffer per
+  // slot that is copied out when the slot's chunk has finished.
+  void *pin_in[kStagePieces] = {};
+  cudaEvent_t pin_in_ev[kStagePieces] = {};
+  bool pin_in_used[kStagePieces] = {};
+  uint64_t pin_in_next = 0;
+  void *pin_out[kPipeDepth] = {};
+  size_t pin_out_cap[kPipeDepth] = {};
+  uint8_t *pend_dst[kPipeDepth] = {};  // copy-out the slot still owes the caller
+  size_t pend_bytes[kPipeDepth] = {};
   unsigned long long *psnr_sum = nullptr, *psnr_host = nullptr;  // device / pinned accumulators of fastc_gpu_psnr*
   std::mutex mu;
 };
@@ -202,16 +217,95 @@ struct Shard {
 // Host->host for one GPU's slab.  The slab is cut into chunks of whole block
 // rows; chunk k uses staging slot k % kPipeDepth, so its H2D overlaps the
 // kernels of chunk k-1 and the D2H of chunk k-2 (three copy/compute engines).
-// Waits for every chunk still in flight on the device's staging slots and books its kernel time.
-int drain_slots(DeviceCtx &c, double *kernel_ms) {
-  for (int slot = 0; slot < kPipeDepth; slot++) {
-    if (!c.slot_busy[slot]) continue;
-    CU_TRY(cudaStreamSynchronize(c.streams[slot]));
-    float ms = 0;
-    CU_TRY(cudaEventElapsedTime(&ms, c.ev_start[slot], c.ev_stop[slot]));
-    if (kernel_ms) *kernel_ms += ms;
-    c.slot_busy[slot] = false;
+// true: plain pageable host memory (not cudaHostAlloc'ed / cudaHostRegister'ed / managed)
+bool is_pageable(const void *p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();  // older drivers report unregistered memory as an error: clear it
+    return true;
   }
+  return a.type == cudaMemoryTypeUnregistered;
+}
+
+// memcpy split over a few host threads (one thread moves ~10 GB/s; PCIe 5 x16 wants ~50)
+void par_memcpy(void *dst, const void *src, size_t n) {
+  const int nt = (int)std::min<size_t>(8, n >> 20);  // >= 1 MiB per thread
+  if (nt <= 1) {
+    memcpy(dst, src, n);
+    return;
+  }
+  std::vector<std::thread> th;
+  for (int k = 1; k < nt; k++) {
+    const size_t a = n * k / nt, b = n * (k + 1) / nt;
+    th.emplace_back([=] { memcpy((uint8_t *)dst + a, (const uint8_t *)src + a, b - a); });
+  }
+  memcpy(dst, src, n / nt);
+  for (auto &t : th) t.join();
+}
+
+// Host -> device on `st`.  Pinned sources go straight to the copy engine; pageable ones through
+// the pinned ring, piece by piece.
+int upload(DeviceCtx &c, void *dst_dev, const uint8_t *src, size_t bytes, cudaStream_t st) {
+  if (!is_pageable(src)) {
+    CU_TRY(cudaMemcpyAsync(dst_dev, src, bytes, cudaMemcpyHostToDevice, st));
+    return 0;
+  }
+  for (size_t off = 0; off < bytes; off += kStagePieceBytes) {
+    const int i = (int)(c.pin_in_next++ % kStagePieces);
+    const size_t n = std::min(kStagePieceBytes, bytes - off);
+    if (!c.pin_in[i]) {
+      CU_TRY(cudaHostAlloc(&c.pin_in[i], kStagePieceBytes, cudaHostAllocDefault));
+      CU_TRY(cudaEventCreateWithFlags(&c.pin_in_ev[i], cudaEventDisableTiming));
+    }
+    if (c.pin_in_used[i]) CU_TRY(cudaEventSynchronize(c.pin_in_ev[i]));  // its previous upload has left the buffer
+    par_memcpy(c.pin_in[i], src + off, n);
+    CU_TRY(cudaMemcpyAsync((uint8_t *)dst_dev + off, c.pin_in[i], n, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaEventRecord(c.pin_in_ev[i], st));
+    c.pin_in_used[i] = true;
+  }
+  return 0;
+}
+
+// Device -> host on `st` for the chunk in `slot`.  Pageable destinations receive their bytes
+// from the slot's pinned buffer once the chunk has finished (finish_slot).
+int download(DeviceCtx &c, int slot, uint8_t *dst, const void *src_dev, size_t bytes, cudaStream_t st) {
+  if (!is_pageable(dst)) {
+    CU_TRY(cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, st));
+    return 0;
+  }
+  if (c.pin_out_cap[slot] < bytes) {
+    if (c.pin_out[slot]) CU_TRY(cudaFreeHost(c.pin_out[slot]));
+    c.pin_out[slot] = nullptr;
+    c.pin_out_cap[slot] = 0;
+    CU_TRY(cudaHostAlloc(&c.pin_out[slot], bytes, cudaHostAllocDefault));
+    c.pin_out_cap[slot] = bytes;
+  }
+  CU_TRY(cudaMemcpyAsync(c.pin_out[slot], src_dev, bytes, cudaMemcpyDeviceToHost, st));
+  c.pend_dst[slot] = dst;
+  c.pend_bytes[slot] = bytes;
+  return 0;
+}
+
+// Waits for the chunk in `slot`, books its kernel time and hands over a staged download.
+int finish_slot(DeviceCtx &c, int slot, double *kernel_ms) {
+  if (!c.slot_busy[slot]) return 0;
+  CU_TRY(cudaStreamSynchronize(c.streams[slot]));
+  float ms = 0;
+  CU_TRY(cudaEventElapsedTime(&ms, c.ev_start[slot], c.ev_stop[slot]));
+  if (kernel_ms) *kernel_ms += ms;
+  if (c.pend_dst[slot]) {
+    par_memcpy(c.pend_dst[slot], c.pin_out[slot], c.pend_bytes[slot]);
+    c.pend_dst[slot] = nullptr;
+    c.pend_bytes[slot] = 0;
+  }
+  c.slot_busy[slot] = false;
+  return 0;
+}
+
+// Waits for every chunk still in flight on the device's staging slots.
+int drain_slots(DeviceCtx &c, double *kernel_ms) {
+  for (int slot = 0; slot < kPipeDepth; slot++)
+    if (finish_slot(c, slot, kernel_ms)) return 1;
   return 0;
 }
 
@@ -271,23 +365,15 @@ int run_shard(Shard &s, int format, const uint8_t *rgba_host, uint32_t width, ui
     const uint32_t r0 = bounds[k], r1 = bounds[k + 1];
     const size_t in_bytes = (size_t)(r1 - r0) * 4 * width * 4;
     const size_t out_bytes = (size_t)(r1 - r0) * bx * bsz;
-    // slot reuse: wait for the previous occupant (stream order guarantees it,
-    // but the host must not overwrite/free buffers while growing them)
+    // slot reuse: the slot's previous chunk must have finished (its timing is booked and a staged
+    // download handed over) before its buffers are overwritten or regrown
+    if (finish_slot(c, slot, &s.kernel_ms)) return 1;
     if (c.in_cap[slot] < in_bytes || c.out_cap[slot] < out_bytes) {
       CU_TRY(cudaStreamSynchronize(st));
       if (grow(&c.in_buf[slot], &c.in_cap[slot], in_bytes)) return 1;
       if (grow(&c.out_buf[slot], &c.out_cap[slot], out_bytes)) return 1;
     }
-    if (c.slot_busy[slot]) {
-      // collect the timing of the chunk that used this slot before we re-record
-      CU_TRY(cudaEventSynchronize(c.ev_stop[slot]));
-      float ms = 0;
-      CU_TRY(cudaEventElapsedTime(&ms, c.ev_start[slot], c.ev_stop[slot]));
-      s.kernel_ms += ms;
-      c.slot_busy[slot] = false;
-    }
-    CU_TRY(cudaMemcpyAsync(c.in_buf[slot], rgba_host + (size_t)r0 * 4 * width * 4, in_bytes,
-                           cudaMemcpyHostToDevice, st));
+    if (upload(c, c.in_buf[slot], rgba_host + (size_t)r0 * 4 * width * 4, in_bytes, st)) return 1;
     s.h2d += in_bytes;
     // block range of this chunk in chunk-local coordinates (the staged slab is an
     // image of (r1-r0)*4 rows)
@@ -307,8 +393,9 @@ int run_shard(Shard &s, int format, const uint8_t *rgba_host, uint32_t width, ui
     CU_TRY(cudaEventRecord(c.ev_stop[slot], st));
     c.slot_busy[slot] = true;
     wm_base += solid;
-    CU_TRY(cudaMemcpyAsync(out_host + ((size_t)r0 * bx + lo) * bsz, (uint8_t *)c.out_buf[slot] + (size_t)lo * bsz,
-                           (size_t)(hi - lo) * bsz, cudaMemcpyDeviceToHost, st));
+    if (download(c, slot, out_host + ((size_t)r0 * bx + lo) * bsz, (uint8_t *)c.out_buf[slot] + (size_t)lo * bsz,
+                 (size_t)(hi - lo) * bsz, st))
+      return 1;
     s.d2h += (size_t)(hi - lo) * bsz;
   }
   if (drain && drain_slots(c, &s.kernel_ms)) return 1;
@@ -362,6 +449,17 @@ void fastc_gpu_shutdown(void) {
       c.in_buf[i] = c.out_buf[i] = nullptr; c.in_cap[i] = c.out_cap[i] = 0;
     }
     for (int i = 0; i <= kPipeDepth; i++) bc7_free_workspace(c.bc7ws[i]);
+    for (int i = 0; i < kStagePieces; i++) {
+      if (c.pin_in[i]) cudaFreeHost(c.pin_in[i]);
+      if (c.pin_in_ev[i]) cudaEventDestroy(c.pin_in_ev[i]);
+      c.pin_in[i] = nullptr; c.pin_in_ev[i] = nullptr; c.pin_in_used[i] = false;
+    }
+    for (int i = 0; i < kPipeDepth; i++) {
+      if (c.pin_out[i]) cudaFreeHost(c.pin_out[i]);
+      c.pin_out[i] = nullptr; c.pin_out_cap[i] = 0; c.pend_dst[i] = nullptr; c.pend_bytes[i] = 0;
+      c.slot_busy[i] = false;
+    }
+    c.next_chunk = 0; c.pin_in_next = 0;
     if (c.psnr_sum) cudaFree(c.psnr_sum);
     if (c.psnr_host) cudaFreeHost(c.psnr_host);
     c.psnr_sum = c.psnr_host = nullptr;
@@ -586,6 +684,7 @@ int fastc_gpu_decompress(int format, const uint8_t *cmp_host, uint32_t width, ui
   DeviceCtx &c = g_ctx[dev];
   const size_t cmp_bytes = fastc_gpu_compressed_size(format, width, height);
   const size_t out_bytes = (size_t)width * height * 4;
+  std::lock_guard<std::mutex> hl(c.host_mu);  // shares the staging slots with the compress path
   cudaStream_t st = c.streams[0];
   // staging slot 0: the image buffer holds the decoded pixels, the output buffer the blocks
   CU_TRY(cudaStreamSynchronize(st));
@@ -641,6 +740,7 @@ int fastc_gpu_psnr(const uint8_t *a_host, const uint8_t *b_host, uint32_t width,
   if (ensure_ctx(dev)) return 1;
   DeviceCtx &c = g_ctx[dev];
   const size_t bytes = (size_t)width * height * 4;
+  std::lock_guard<std::mutex> hl(c.host_mu);  // shares the staging slots with the compress path
   cudaStream_t st = c.streams[0];
   CU_TRY(cudaStreamSynchronize(st));
   if (grow(&c.in_buf[0], &c.in_cap[0], bytes)) return 1;

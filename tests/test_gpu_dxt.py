@@ -143,3 +143,21 @@ def test_concurrent_ranged_submissions_like_threadgroup(gpu, oracle, fmt):
         t.join()
     assert not errs, errs
     assert _mismatch(out, whole, fmt) == 0
+
+
+@pytest.mark.parametrize("fmt,q", [("DXT5", 0), ("ETC1", 0), ("BPTC", 3)])
+def test_pageable_and_pinned_host_buffers_give_the_same_bytes(gpu, fmt, q):
+    """Pageable caller memory (what FasTC passes) is staged through the library's pinned ring /
+    per-slot pinned download buffers; pinned caller memory goes straight to the copy engines.
+    Same bytes either way, also when only one side is pinned and across several chunks."""
+    import torch
+    img = synth_rgba(1024, 2048, 5, opaque=(fmt == "ETC1"))          # 8 MiB: several DXT / ETC1 chunks
+    pin_in = torch.empty(img.shape, dtype=torch.uint8, pin_memory=True)
+    pin_in.numpy()[...] = img
+    nbytes = (1024 // 4) * (2048 // 4) * BLOCK_BYTES[fmt]
+    pin_out = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    a, _ = gpu.compress(F[fmt], img, quality=q, seed=4)                                   # pageable -> pageable
+    b, _ = gpu.compress(F[fmt], pin_in.numpy(), pin_out.numpy(), quality=q, seed=4)       # pinned -> pinned
+    c, _ = gpu.compress(F[fmt], img, pin_out.numpy().copy() * 0, quality=q, seed=4, chunk_blocks=256 * 7)
+    d, _ = gpu.compress(F[fmt], pin_in.numpy(), np.zeros(nbytes, np.uint8), quality=q, seed=4)  # pinned -> pageable
+    assert (a == b).all() and (a == c).all() and (a == d).all()
