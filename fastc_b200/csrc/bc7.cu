@@ -1464,7 +1464,16 @@ __device__ __forceinline__ uint32_t move_endpoint(uint32_t src, uint32_t dir, in
     if (old_pbit == 0) add = 0;
     else sub = 0;
   }
-  return __vaddus4(__vsubus4(src, sub), add);
+  // Per byte exactly one of sub / add is non-zero, so the two saturating steps commute.  sm_100a has
+  // no byte-wise saturating add (the compiler emulates __vaddus4 / __vsubus4 in ~11 instructions
+  // each), but it has 16x2 min / max: spread the bytes over 16-bit lanes, where the add cannot
+  // carry, clamp at 255, floor the subtraction at 0 with max(t, sub) - sub, and merge.
+  const uint32_t lo = __byte_perm(src, 0u, 0x4240), hi = __byte_perm(src, 0u, 0x4341);
+  const uint32_t alo = __byte_perm(add, 0u, 0x4240), ahi = __byte_perm(add, 0u, 0x4341);
+  const uint32_t slo = __byte_perm(sub, 0u, 0x4240), shi = __byte_perm(sub, 0u, 0x4341);
+  const uint32_t tlo = __viaddmin_u16x2(lo, alo, 0x00FF00FFu), thi = __viaddmin_u16x2(hi, ahi, 0x00FF00FFu);
+  const uint32_t rlo = __vmaxu2(tlo, slo) - slo, rhi = __vmaxu2(thi, shi) - shi;
+  return __byte_perm(rlo, rhi, 0x6240);
 }
 
 // The pixel loops of sa_eval.  UNI: every lane of the warp fits a cluster of nmax pixels (the
