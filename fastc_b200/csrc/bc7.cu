@@ -1026,8 +1026,8 @@ __device__ __forceinline__ int primary_slot(int layout_b, int slot) {  // invers
 __device__ __forceinline__ void setup_variant(const Ws &ws, const Chain &c, const ModeAttr &A, const FitCore &core,
                                               const uint32_t *pts, const uint32_t *pix, int n, uint32_t mask,
                                               int sa_steps, const uint8_t *__restrict__ s_w, const float *__restrict__ s_rcp,
-                                              uint32_t gid, uint32_t rng, uint32_t *res, const float *alpha_vals,
-                                              float amin, float amax) {
+                                              uint32_t (*s_acc)[16][128], int tid, uint32_t gid, uint32_t rng,
+                                              uint32_t *res, const float *alpha_vals, float amin, float amax) {
   FitResult R;
   fit_finish(ws, A, c.mode, c.idx_mode, core, pts, pix, n, sa_steps, s_w, R);  // the one call site
   res[4] = (uint32_t)R.indices; res[5] = (uint32_t)(R.indices >> 32);
@@ -1092,13 +1092,22 @@ __device__ __forceinline__ void setup_variant(const Ws &ws, const Chain &c, cons
     while (!fixed && guard++ < 4096) {
       float av[8];
       fixed = true;
+      // bucket sums / counts are small integers (exact in any order): one pass over the pixels into
+      // the lane's shared accumulators instead of the reference's bucket x pixel scan (:790-806)
+#pragma unroll 1
+      for (int i = 0; i < nba; i++) { s_acc[0][i][tid] = 0; s_acc[2][i][tid] = 0; }
+#pragma unroll 1
+      for (int j = 0; j < 16; j++) {
+        const int b = bucket[j];
+        s_acc[0][b][tid] += (uint32_t)alpha_vals[j];
+        s_acc[2][b][tid] += 1u;
+      }
 #pragma unroll 1
       for (int i = 0; i < nba; i++) {
-        float s = 0.0f, c2 = 0.0f;
-#pragma unroll 1
-        for (int j = 0; j < 16; j++)
-          if (bucket[j] == i) { s = __fadd_rn(s, alpha_vals[j]); c2 = __fadd_rn(c2, 1.0f); }
-        if (c2 > 0.0f) s = div_small(s, c2, s_rcp[(int)c2]);
+        const int cnt = (int)s_acc[2][i][tid];
+        float s = (float)s_acc[0][i][tid];
+        const float c2 = (float)cnt;
+        if (cnt > 0) s = div_small(s, c2, s_rcp[cnt]);
         av[i] = s; npts[i] = c2;
         fixed = fixed && (av[i] == vals[i]);
       }
@@ -1253,7 +1262,7 @@ __device__ __forceinline__ void setup_chain(const uint32_t *__restrict__ img, ui
     const uint32_t gid = t * kSlots + vslot;
     const uint32_t rng = chain_seed(seed, gblock, (uint32_t)c.chain_id);
     uint32_t *res = ws.results + (size_t)gid * kResWords;
-    setup_variant(ws, c, A, core, pts, pix, n, mask, sa_steps, s_w, s_rcp, gid, rng, res, alpha_vals, amin, amax);
+    setup_variant(ws, c, A, core, pts, pix, n, mask, sa_steps, s_w, s_rcp, s_acc, tid, gid, rng, res, alpha_vals, amin, amax);
   }
 }
 
@@ -1944,42 +1953,39 @@ bc7_pack(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, ui
   const bool layout_b = (selw >> 22) & 1;
   unsigned long long best_err = ~0ull;
   int best_mode = -1, best_si = 0, best_first = 0;  // best_first: first slot of the winning candidate
-  const int order[8] = {0, 2, 1, 3, 7, 4, 5, 6};
-  for (int mi = 0; mi < 8; mi++) {
-    const int mode = order[mi];
-    for (int si = 0; si < 2; si++) {
-      // slots of candidate (mode, si)
-      int first = -1, count = 0;
-      if (!layout_b) {
-        if (mode == 0 && si == 1) { first = 0; count = 3; }
-        else if (mode == 2 && si == 1) { first = 3; count = 3; }
-        else if (mode == 1 && si == 0) { first = 6; count = 2; }
-        else if (mode == 3 && si == 0) { first = 8; count = 2; }
-        else if (mode == 7 && si == 0) { first = 10; count = 2; }
-        else if (mode == 6) { first = 12 + si; count = 1; }
-      } else if (si == 0) {
-        if (mode == 4) { first = 0; count = 8; }
-        else if (mode == 5) { first = 8; count = 4; }
-        else if (mode == 6) { first = 12; count = 1; }
-        else if (mode == 7) { first = 13; count = 2; }
-      }
-      if (first < 0) continue;
-      if (!decode_chain(selw, first).active) continue;
-      unsigned long long err;
-      int pick = first;
-      if (mode == 4 || mode == 5) {  // best rotation / index mode, strict < in loop order (:1320-1348)
-        unsigned long long be = ~0ull;
-        for (int k = 0; k < count; k++) {
-          const unsigned long long e = res[(first + k) * kResWords];
-          if (e < be) { be = e; pick = first + k; }
-        }
-        err = be;
-      } else {
-        err = 0;
-        for (int k = 0; k < count; k++) err += res[(first + k) * kResWords];
-      }
-      if (err < best_err) { best_err = err; best_mode = mode; best_si = si; best_first = pick; }
-    }
+  // all sixteen chain errors at once: independent loads, static register indices below (slots
+  // without a live chain hold stale words, which no live candidate reads)
+  uint32_t e[kSlots];
+#pragma unroll
+  for (int k = 0; k < kSlots; k++) e[k] = res[k * kResWords];
+  // candidate (mode, shape slot si): its first chain slot, its error, the slot Pack reads
+  auto consider = [&](int mode, int si, int first, unsigned long long err, int pick) {
+    if (decode_chain(selw, first).active && err < best_err) { best_err = err; best_mode = mode; best_si = si; best_first = pick; }
+  };
+  if (!layout_b) {  // opaque layout, reference order {0, 2, 1, 3, 7, (4, 5: none), 6}
+    consider(0, 1, 0, (unsigned long long)e[0] + e[1] + e[2], 0);
+    consider(2, 1, 3, (unsigned long long)e[3] + e[4] + e[5], 3);
+    consider(1, 0, 6, (unsigned long long)e[6] + e[7], 6);
+    consider(3, 0, 8, (unsigned long long)e[8] + e[9], 8);
+    consider(7, 0, 10, (unsigned long long)e[10] + e[11], 10);
+    consider(6, 0, 12, e[12], 12);
+    consider(6, 1, 13, e[13], 13);
+  } else {          // alpha layout: {7, 4, 5, 6}
+    consider(7, 0, 13, (unsigned long long)e[13] + e[14], 13);
+    // modes 4 / 5: best rotation / index mode, strict < in loop order (:1320-1348)
+    uint32_t be = e[0];
+    int pick = 0;
+#pragma unroll
+    for (int k = 1; k < 8; k++)
+      if (e[k] < be) { be = e[k]; pick = k; }
+    consider(4, 0, 0, be, pick);
+    be = e[8];
+    pick = 8;
+#pragma unroll
+    for (int k = 9; k < 12; k++)
+      if (e[k] < be) { be = e[k]; pick = k; }
+    consider(5, 0, 8, be, pick);
+    consider(6, 0, 12, e[12], 12);
   }
   if (best_mode < 0) {  // unreachable with the default mode mask
     reinterpret_cast<uint4 *>(out)[bi] = make_uint4(0, 0, 0, 0);
