@@ -318,14 +318,23 @@ __global__ void bc7_add_u32(uint32_t *p, const uint32_t *v) { *p += *v; }
 // squared error is |p|^2 + |c|^2 - 2 dp4a(p, c), and the bucket pair comes from one multiply by
 // a per-subset reciprocal; whenever that product lands within 2^-16 of an integer the
 // reference's own divide / multiply sequence decides (RGBAEndpoints.cpp:262-289).
+constexpr int kSelWarps = 4;
+
 struct SubsetBox {
-  uint32_t mn, dlo, dhi, den, base;  // dlo/dhi: extent bytes 0,2 / 1,3 spread over 16-bit halves
+  uint32_t den, base;  // |extent|^2, min . extent
   float inv16, fden;
 };
 
+// interpolation weights of the 3-bit / 2-bit index precisions (bc7tab::kWeight rows 2 / 1; checked
+// against the table in bc7_upload_tables): compile-time constants for the unrolled palette build
+__device__ constexpr uint32_t kSelWeights3[8] = {0, 9, 18, 27, 37, 46, 55, 64};
+__device__ constexpr uint32_t kSelWeights2[4] = {0, 21, 43, 64};
+constexpr int kSelPalRows = 16;  // 2 subsets x 8 buckets, or 3 x 4
+
+// `pal`: the lane's palette column: row (subset * NB + j) = (colour j, colour j + 1) of that subset's
+// bounding-box endpoints, the last row of a subset (colour NB-1 twice).
 template <int NBM1>
-__device__ __forceinline__ uint32_t box_pixel_error(const SubsetBox &b, uint32_t p, uint32_t d,
-                                                    const uint8_t *__restrict__ wtab) {
+__device__ __forceinline__ uint32_t box_pixel_error(const SubsetBox &b, uint32_t p, uint32_t d, const uint2 *pal_sub) {
   const uint32_t num = __dp4a(p, d, 0u) - b.base;  // (p - min) . extent, exact
   const float fnum = (float)num;
   const int v = __float2int_rd(__fmul_rn(fnum, b.inv16));
@@ -340,20 +349,16 @@ __device__ __forceinline__ uint32_t box_pixel_error(const SubsetBox &b, uint32_t
     ja = x1;
     two = x1 + 1 <= x2;
   }
-  const uint32_t wa = wtab[ja], wb = wtab[ja + (two ? 1 : 0)];  // !two: the same bucket twice
-  const uint32_t ca = b.mn + ((((b.dlo * wa + 0x00200020u) >> 6) & 0x00FF00FFu) |
-                              ((((b.dhi * wa + 0x00200020u) >> 6) & 0x00FF00FFu) << 8));
-  const uint32_t cb = b.mn + ((((b.dlo * wb + 0x00200020u) >> 6) & 0x00FF00FFu) |
-                              ((((b.dhi * wb + 0x00200020u) >> 6) & 0x00FF00FFu) << 8));
-  const uint32_t da = __vabsdiffu4(ca, p), db = __vabsdiffu4(cb, p);
-  return min(__dp4a(da, da, 0u), __dp4a(db, db, 0u));
+  const uint2 c = pal_sub[ja * (kSelWarps * 32)];
+  const uint32_t da = __vabsdiffu4(c.x, p), db = __vabsdiffu4(c.y, p);
+  const uint32_t ea = __dp4a(da, da, 0u), eb = __dp4a(db, db, 0u);
+  return two ? min(ea, eb) : ea;
 }
 
 template <int NSUB>
 __device__ __forceinline__ double estimate_shape(const uint32_t *__restrict__ px, const uint32_t *__restrict__ plo,
-                                                 const uint32_t *__restrict__ phi, int shape,
-                                                 const uint8_t *__restrict__ wtab) {
-  constexpr int NBM1 = NSUB == 2 ? 7 : 3;
+                                                 const uint32_t *__restrict__ phi, int shape, uint2 *pal) {
+  constexpr int NB = NSUB == 2 ? 8 : 4, NBM1 = NB - 1;
   // bounding boxes on pixels spread over 16-bit halves (bytes 0,2 / 1,3): unsigned 16x2 min / max
   // is one instruction on sm_100a, byte-wise min / max is not
   uint32_t mnl[NSUB], mnh[NSUB], mxl[NSUB], mxh[NSUB];
@@ -378,15 +383,25 @@ __device__ __forceinline__ double estimate_shape(const uint32_t *__restrict__ px
 #pragma unroll
   for (int s = 0; s < NSUB; s++) {
     // per byte mx >= mn: no borrow (every BC7 partition uses all its subsets)
-    box[s].dlo = mxl[s] - mnl[s];
-    box[s].dhi = mxh[s] - mnh[s];
-    const uint32_t d = box[s].dlo | (box[s].dhi << 8);
+    const uint32_t dlo = mxl[s] - mnl[s], dhi = mxh[s] - mnh[s];
+    const uint32_t d = dlo | (dhi << 8), mn = mnl[s] | (mnh[s] << 8);
     dd[s] = d;
-    box[s].mn = mnl[s] | (mnh[s] << 8);
     box[s].den = __dp4a(d, d, 0u);
-    box[s].base = __dp4a(box[s].mn, d, 0u);
+    box[s].base = __dp4a(mn, d, 0u);
     box[s].fden = (float)box[s].den;
     box[s].inv16 = box[s].den ? __fdiv_rn(65536.0f * (float)NBM1, box[s].fden) : 0.0f;
+    // the subset's palette, once per shape instead of twice per pixel: colour j = min + ((extent *
+    // w_j + 32) >> 6) per channel, two channels per 32-bit multiply (a byte times w <= 64 fits 16 bits)
+    uint32_t cur = mn;  // w_0 = 0
+#pragma unroll
+    for (int j = 1; j <= NBM1; j++) {
+      const uint32_t w = NSUB == 2 ? kSelWeights3[j] : kSelWeights2[j];
+      const uint32_t nxt = mn + ((((dlo * w + 0x00200020u) >> 6) & 0x00FF00FFu) |
+                                 ((((dhi * w + 0x00200020u) >> 6) & 0x00FF00FFu) << 8));
+      pal[(s * NB + j - 1) * (kSelWarps * 32)] = make_uint2(cur, nxt);
+      cur = nxt;
+    }
+    pal[(s * NB + NBM1) * (kSelWarps * 32)] = make_uint2(cur, cur);
   }
   uint32_t tot[NSUB];
 #pragma unroll
@@ -400,7 +415,7 @@ __device__ __forceinline__ double estimate_shape(const uint32_t *__restrict__ px
     for (int q = 1; q < NSUB; q++)
       if (s == q) { b = box[q]; d = dd[q]; }  // selects
     // a point-sized box contributes nothing; its pixels evaluate to 0 anyway (p == min, extent 0)
-    const uint32_t e = box_pixel_error<NBM1>(b, px[i], d, wtab);
+    const uint32_t e = box_pixel_error<NBM1>(b, px[i], d, pal + s * NB * (kSelWarps * 32));
 #pragma unroll
     for (int q = 0; q < NSUB; q++) tot[q] += (s == q) ? e : 0u;
   }
@@ -423,15 +438,13 @@ __device__ __forceinline__ void warp_argmin(double &err, int &idx) {
   }
 }
 
-constexpr int kSelWarps = 4;
-
 __global__ void __launch_bounds__(kSelWarps * 32)
 bc7_select(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, uint32_t first_block,
            uint32_t num_blocks, uint32_t *__restrict__ sel, uint32_t *__restrict__ states) {
   __shared__ uint32_t s_px[kSelWarps][16], s_plo[kSelWarps][16], s_phi[kSelWarps][16];
-  __shared__ uint8_t s_w[64];
-  if (threadIdx.x < 64) s_w[threadIdx.x] = c_weight[threadIdx.x];
+  __shared__ uint2 s_pal[kSelPalRows][kSelWarps * 32];  // one palette column per lane (estimate_shape)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint2 *pal = &s_pal[0][threadIdx.x];
   const uint32_t t = blockIdx.x * kSelWarps + warp;
   const bool valid = t < num_blocks;
   uint32_t type = kTypeNormal;
@@ -463,7 +476,7 @@ bc7_select(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
   double e0 = 0.0, e1 = 0.0;
 #pragma unroll 1
   for (int h = 0; h < 2; h++) {
-    const double e = estimate_shape<2>(px, plo, phi, lane + 32 * h, s_w + 32);  // 8 buckets -> 3-bit weights
+    const double e = estimate_shape<2>(px, plo, phi, lane + 32 * h, pal);  // 8 buckets: 3-bit weights
     if (h == 0) e0 = e; else e1 = e;
   }
   // early-out: first shape (scan order) with estimate < 1e-9 (Compressor.cpp:1706-1710)
@@ -487,7 +500,7 @@ bc7_select(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
   // ---- three-subset shapes (opaque blocks only)
 #pragma unroll 1
   for (int h = 0; h < 2; h++) {
-    const double e = estimate_shape<3>(px, plo, phi, lane + 32 * h, s_w + 16);  // 4 buckets -> 2-bit weights
+    const double e = estimate_shape<3>(px, plo, phi, lane + 32 * h, pal);  // 4 buckets: 2-bit weights
     if (h == 0) e0 = e; else e1 = e;
   }
   const uint32_t y0 = __ballot_sync(0xffffffffu, e0 < 1e-9), y1 = __ballot_sync(0xffffffffu, e1 < 1e-9);
@@ -2182,6 +2195,13 @@ cudaError_t bc7_upload_tables() {
   UP(c_anchor3b, kAnchor3b); UP(c_weight, kWeight); UP(c_opt7, kOpt7Mode5); UP(c_opt6, kOpt6Dxt1);
   UP(c_wm, kWatermark);
 #undef UP
+  {  // bc7_select's compile-time weights must be the table's 3-bit / 2-bit rows
+    static const uint32_t w3[8] = {0, 9, 18, 27, 37, 46, 55, 64}, w2[4] = {0, 21, 43, 64};
+    for (int j = 0; j < 8; j++)
+      if (kWeight[32 + j] != w3[j]) return cudaErrorInvalidValue;
+    for (int j = 0; j < 4; j++)
+      if (kWeight[16 + j] != w2[j]) return cudaErrorInvalidValue;
+  }
   static uint32_t host_single[8 * 2 * 4 * 2 * 256];
   static bool built = false;
   if (!built) { build_single_table(host_single); built = true; }
