@@ -366,16 +366,17 @@ __device__ __forceinline__ double estimate_shape(const uint32_t *__restrict__ px
   for (int s = 0; s < NSUB; s++) { mnl[s] = mnh[s] = 0xFFFFFFFFu; mxl[s] = mxh[s] = 0; }
   const uint32_t m2 = NSUB == 2 ? c_shape2[shape] : 0;
   const uint32_t m3 = NSUB == 3 ? c_shape3[shape] : 0;
-#pragma unroll 2
-  for (int i = 0; i < 16; i++) {
-    const int s = NSUB == 2 ? ((m2 >> i) & 1) : ((m3 >> (2 * i)) & 3);
-    const uint32_t l = plo[i], h = phi[i];
+#pragma unroll 1
+  for (int i = 0; i < 16; i += 2) {  // two pixels per three-input 16x2 min / max
+    const int s0 = NSUB == 2 ? ((m2 >> i) & 1) : ((m3 >> (2 * i)) & 3);
+    const int s1 = NSUB == 2 ? ((m2 >> (i + 1)) & 1) : ((m3 >> (2 * i + 2)) & 3);
+    const uint32_t l0 = plo[i], h0 = phi[i], l1 = plo[i + 1], h1 = phi[i + 1];
 #pragma unroll
     for (int q = 0; q < NSUB; q++) {
-      mnl[q] = __vminu2(mnl[q], s == q ? l : 0xFFFFFFFFu);
-      mnh[q] = __vminu2(mnh[q], s == q ? h : 0xFFFFFFFFu);
-      mxl[q] = __vmaxu2(mxl[q], s == q ? l : 0u);
-      mxh[q] = __vmaxu2(mxh[q], s == q ? h : 0u);
+      mnl[q] = __vimin3_u16x2(mnl[q], s0 == q ? l0 : 0xFFFFFFFFu, s1 == q ? l1 : 0xFFFFFFFFu);
+      mnh[q] = __vimin3_u16x2(mnh[q], s0 == q ? h0 : 0xFFFFFFFFu, s1 == q ? h1 : 0xFFFFFFFFu);
+      mxl[q] = __vimax3_u16x2(mxl[q], s0 == q ? l0 : 0u, s1 == q ? l1 : 0u);
+      mxh[q] = __vimax3_u16x2(mxh[q], s0 == q ? h0 : 0u, s1 == q ? h1 : 0u);
     }
   }
   SubsetBox box[NSUB];
