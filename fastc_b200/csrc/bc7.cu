@@ -149,7 +149,8 @@ __device__ __forceinline__ uint32_t quantize_channel(uint32_t val, uint32_t mask
   return (dl < dh ? lval : hval) & 0xFF;
 }
 // ToPixel for endpoint bytes that are already integers (RGBAEndpoints.cpp:167-177).
-__device__ __forceinline__ uint32_t to_pixel_b(uint32_t p, uint32_t mask, int pbit) {
+// (out of line on purpose: bc7_setup is bound by instruction fetch, see setup_chain)
+__device__ __noinline__ uint32_t to_pixel_b(uint32_t p, uint32_t mask, int pbit) {
   return quantize_channel(p & 0xFF, mask & 0xFF, pbit) | (quantize_channel((p >> 8) & 0xFF, (mask >> 8) & 0xFF, pbit) << 8) |
          (quantize_channel((p >> 16) & 0xFF, (mask >> 16) & 0xFF, pbit) << 16) |
          (quantize_channel(p >> 24, mask >> 24, pbit) << 24);
@@ -526,7 +527,7 @@ struct Chain {
   bool active;
 };
 
-__device__ __forceinline__ Chain decode_chain(uint32_t selw, int slot) {
+__device__ __noinline__ Chain decode_chain(uint32_t selw, int slot) {
   Chain c;
   c.active = false;
   c.rot = 0; c.idx_mode = 0; c.subset = 0; c.shape = 0; c.nsub = 1; c.mode = 0; c.chain_id = 0;
@@ -1202,12 +1203,18 @@ __device__ __forceinline__ void setup_chain(const uint32_t *__restrict__ img, ui
   int twin = twin_slot((selw >> 22) & 1, slot);
   if (twin >= 0 && !decode_chain(selw, twin).active) twin = -1;
 
-  // The block stays in registers (every index below is a compile-time constant); the cluster is
-  // compacted into ONE per-thread array.  Per-thread arrays live in local memory and the kernel's
-  // working set is what its L1 hit rate depends on, so nothing is stored twice: the error pixels
-  // (`pix`) are the points themselves, except for modes 4/5 (n == 16), where they are the block.
-  uint32_t blk[16];
-  load_block(img, width, blocks_x, first_block + t, blk);
+  // The kernel is bound by instruction fetch (5-6 k SASS instructions, the resident warps are in
+  // different phases: "no instruction" is its top stall), so the loops below stay rolled.  Rolled
+  // loops index the block dynamically; to keep it out of local memory it is parked in the lane's
+  // accumulator column, which is free until the k-means starts (fit_core).  Per-thread arrays live
+  // in local memory and their footprint decides the L1 hit rate, so nothing is stored twice: the
+  // error pixels (`pix`) are the points themselves, except for modes 4/5 (n == 16).
+  {
+    uint32_t blk[16];
+    load_block(img, width, blocks_x, first_block + t, blk);
+#pragma unroll
+    for (int i = 0; i < 16; i++) s_acc[0][i][tid] = blk[i];
+  }
 
   // Cluster of this chain: points in raster order of the subset (m_PointMap).
   uint32_t smask;  // pixels of the subset
@@ -1219,7 +1226,7 @@ __device__ __forceinline__ void setup_chain(const uint32_t *__restrict__ img, ui
     const uint32_t m3 = c_shape3[c.shape], lo = m3 & 0x55555555u, hi = (m3 >> 1) & 0x55555555u;
     const uint32_t sel = c.subset == 0 ? ~(lo | hi) & 0x55555555u : (c.subset == 1 ? lo & ~hi : hi & ~lo);
     smask = 0;  // one bit per 2-bit field
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < 16; i++) smask |= ((sel >> (2 * i)) & 1u) << i;
   }
   uint32_t pts[16];
@@ -1227,14 +1234,15 @@ __device__ __forceinline__ void setup_chain(const uint32_t *__restrict__ img, ui
   const uint32_t mask = smask;
   float sum[4] = {0, 0, 0, 0};
   uint32_t mn = 0xFFFFFFFFu, mx = 0;
-#pragma unroll
+#pragma unroll 1
   for (int i = 0; i < 16; i++) {
     if ((smask >> i) & 1u) {
-      pts[n++] = blk[i];
+      const uint32_t p = s_acc[0][i][tid];
+      pts[n++] = p;
 #pragma unroll
-      for (int k = 0; k < 4; k++) sum[k] = __fadd_rn(sum[k], (float)chan(blk[i], k));  // exact integers
-      mn = __vminu4(mn, blk[i]);
-      mx = __vmaxu4(mx, blk[i]);
+      for (int k = 0; k < 4; k++) sum[k] = __fadd_rn(sum[k], (float)chan(p, k));  // exact integers
+      mn = __vminu4(mn, p);
+      mx = __vmaxu4(mx, p);
     }
   }
   float avg[4];
@@ -1250,9 +1258,9 @@ __device__ __forceinline__ void setup_chain(const uint32_t *__restrict__ img, ui
   float alpha_vals[16];
   float amin = FLT_MAX, amax = -FLT_MAX;
   if (A0.rotation) {
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < 16; i++) {
-      const uint32_t p = blk[i];
+      const uint32_t p = s_acc[0][i][tid];
       const uint32_t a = c.rot == 0 ? (p >> 24) : chan(p, c.rot - 1);
       uint32_t q = p;
       if (c.rot) q = (p & ~(0xFFu << (8 * (c.rot - 1)))) | ((p >> 24) << (8 * (c.rot - 1)));  // channel <- old alpha
@@ -1302,7 +1310,7 @@ constexpr int kSlotGroups = 5;
 __constant__ uint8_t c_group_first[kSlotGroups] = {0, 3, 6, 8, 12};
 __constant__ uint8_t c_group_count[kSlotGroups] = {3, 3, 2, 4, 4};  // the last group also owns the dead slot 15
 
-__global__ void __launch_bounds__(kChainThreads)
+__global__ void __launch_bounds__(kChainThreads, 5)
 bc7_setup(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, uint32_t first_block,
           uint32_t num_blocks, Ws ws, int sa_steps, uint64_t seed, uint32_t block_index_base) {
   __shared__ uint8_t s_w[64];

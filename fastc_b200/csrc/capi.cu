@@ -340,12 +340,12 @@ int run_shard(Shard &s, int format, const uint8_t *rgba_host, uint32_t width, ui
   bounds.push_back(row1);
   if (chunk_blocks == 0 && format == FASTC_GPU_BPTC && total_rows >= 64 &&
       (size_t)total_rows * 4 * width * 4 >= ((size_t)96 << 20)) {
-    // BC7 auto: one small head chunk (1/16 of the rows) and the rest.  The big upload then runs
-    // under the head's kernels and the head's download under the big chunk's kernels; only the
-    // head's upload and the tail's download stay exposed, and the persistent annealing kernel
-    // still sees (almost) the whole shard at once.  Only worth it for big uploads (>= 96 MiB, ~2 ms):
-    // every extra submission pays the annealing kernel's ~1.5 ms tail once more.
-    bounds.assign({row0, row0 + total_rows / 16, row1});
+    // BC7 auto, big uploads (>= 96 MiB, ~2 ms on the wire): two halves on two streams.  The second
+    // half's upload and shape selection / fits run under the first half's annealing, the first
+    // half's download under the second's kernels, and each half is still large enough for the
+    // persistent annealing kernel's ~1.5 ms tail not to matter.  Measured at 8192^2
+    // (tools/time_e2e_chunks.py): one chunk 238.9 ms, two halves 236.6 ms, 1/16 + 15/16 250.4 ms.
+    bounds.assign({row0, row0 + total_rows / 2, row1});
   }
   const uint32_t nchunks = (uint32_t)bounds.size() - 1;
   // BC7's watermark chain needs the solid-block count of every earlier chunk;
