@@ -129,7 +129,7 @@ __device__ __forceinline__ uint32_t quant_mask(const ModeAttr &A) {
 }
 
 // QuantizeChannel (RGBAEndpoints.cpp:126-165).  prec = number of mask bits.
-__device__ __forceinline__ uint32_t quantize_channel(uint32_t val, uint32_t mask, int pbit) {
+__device__ __noinline__ uint32_t quantize_channel(uint32_t val, uint32_t mask, int pbit) {
   if (mask == 0xFF) return val;
   if (mask == 0) return 0xFF;
   int prec = __popc(mask);
@@ -575,6 +575,10 @@ __device__ __forceinline__ float div_small(float a, float c, float rc) {
   return __fmaf_rn(r, rc, q);
 }
 
+// IEEE division for the once-per-chain code of bc7_setup, out of line: the inline expansion is ~10
+// instructions per site, and that kernel is bound by instruction fetch (see setup_chain)
+__device__ __noinline__ float div_cold(float a, float b) { return __fdiv_rn(a, b); }
+
 struct F4 { float v[4]; };
 __device__ __forceinline__ float dot4(const float a[4], const float b[4]) {
   float s = __fmul_rn(a[0], b[0]);  // 0 + x == x
@@ -679,7 +683,7 @@ __device__ __noinline__ void fit_core(int ibits, const uint32_t *pts, int n, con
       {
         const float len = length4(dir);
 #pragma unroll
-        for (int k = 0; k < 4; k++) dir[k] = __fdiv_rn(dir[k], len);
+        for (int k = 0; k < 4; k++) dir[k] = div_cold(dir[k], len);
       }
       bool collinear = true;
 #pragma unroll 1
@@ -717,7 +721,7 @@ __device__ __noinline__ void fit_core(int ibits, const uint32_t *pts, int n, con
           for (int i = 0; i < 4; i++)
 #pragma unroll
             for (int j = 0; j <= i; j++, e++) {
-              cov[i][j] = __fdiv_rn(cs[e], 3.0f);
+              cov[i][j] = div_cold(cs[e], 3.0f);
               cov[j][i] = cov[i][j];
             }
         }
@@ -741,12 +745,12 @@ __device__ __noinline__ void fit_core(int ibits, const uint32_t *pts, int n, con
             b[0] = 1.0f; b[1] = 1.0f;
             const float l2 = length4(b);
 #pragma unroll
-            for (int k = 0; k < 4; k++) b[k] = __fdiv_rn(b[k], l2);
+            for (int k = 0; k < 4; k++) b[k] = div_cold(b[k], l2);
             bad = true;
             continue;
           }
 #pragma unroll
-          for (int k = 0; k < 4; k++) nbv[k] = __fdiv_rn(nbv[k], len);
+          for (int k = 0; k < 4; k++) nbv[k] = div_cold(nbv[k], len);
           if (fabs((double)__fsub_rn(1.0f, dot4(b, nbv))) < 1e-8) fixed = true;
 #pragma unroll
           for (int k = 0; k < 4; k++) b[k] = nbv[k];
@@ -783,7 +787,7 @@ __device__ __noinline__ void fit_core(int ibits, const uint32_t *pts, int n, con
   float cen[16][4];
 #pragma unroll 1
   for (int i = 0; i < nb; i++) {
-    const float s = __fdiv_rn((float)i, (float)nbm1);
+    const float s = div_cold((float)i, (float)nbm1);
     const float oms = __fsub_rn(1.0f, s);
 #pragma unroll
     for (int k = 0; k < 4; k++) cen[i][k] = __fadd_rn(__fmul_rn(p1[k], oms), __fmul_rn(p2[k], s));
@@ -868,7 +872,7 @@ __device__ __noinline__ void fit_core(int ibits, const uint32_t *pts, int n, con
 #pragma unroll 1
     for (int i = 0; i < nb; i++) {
       const float fn = (float)s_acc[2][i][tid];
-      const float a = __fdiv_rn((float)(nbm1 - i), fb), b = __fdiv_rn((float)i, fb);
+      const float a = div_cold((float)(nbm1 - i), fb), b = div_cold((float)i, fb);
       asq = __fadd_rn(asq, __fmul_rn(__fmul_rn(fn, a), a));
       bsq = __fadd_rn(bsq, __fmul_rn(__fmul_rn(fn, b), b));
       ab = __fadd_rn(ab, __fmul_rn(__fmul_rn(fn, a), b));
@@ -878,7 +882,7 @@ __device__ __noinline__ void fit_core(int ibits, const uint32_t *pts, int n, con
         bx[k] = __fadd_rn(bx[k], __fmul_rn(__fmul_rn(cen[i][k], b), fn));
       }
     }
-    const float f = __fdiv_rn(1.0f, __fsub_rn(__fmul_rn(asq, bsq), __fmul_rn(ab, ab)));
+    const float f = div_cold(1.0f, __fsub_rn(__fmul_rn(asq, bsq), __fmul_rn(ab, ab)));
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       C.p1[k] = __fmul_rn(__fsub_rn(__fmul_rn(ax[k], bsq), __fmul_rn(bx[k], ab)), f);
@@ -1089,7 +1093,7 @@ __device__ __forceinline__ void setup_variant(const Ws &ws, const Chain &c, cons
     uint8_t bucket[16];
 #pragma unroll 1
     for (int i = 0; i < nba; i++)
-      vals[i] = __fadd_rn(amin, __fmul_rn(__fdiv_rn((float)i, (float)(nba - 1)), __fsub_rn(amax, amin)));
+      vals[i] = __fadd_rn(amin, __fmul_rn(div_cold((float)i, (float)(nba - 1)), __fsub_rn(amax, amin)));
 #pragma unroll 1
     for (int i = 0; i < 16; i++) {
       float md = 255.0f;
@@ -1143,7 +1147,7 @@ __device__ __forceinline__ void setup_variant(const Ws &ws, const Chain &c, cons
     const float fb = (float)(nba - 1);
 #pragma unroll 1
     for (int i = 0; i < nba; i++) {
-      const float a = __fdiv_rn((float)(nba - 1 - i), fb), b = __fdiv_rn((float)i, fb);
+      const float a = div_cold((float)(nba - 1 - i), fb), b = div_cold((float)i, fb);
       const float nn = npts[i], x = vals[i];
       asq = __fadd_rn(asq, __fmul_rn(__fmul_rn(nn, a), a));
       bsq = __fadd_rn(bsq, __fmul_rn(__fmul_rn(nn, b), b));
@@ -1151,7 +1155,7 @@ __device__ __forceinline__ void setup_variant(const Ws &ws, const Chain &c, cons
       ax = __fadd_rn(ax, __fmul_rn(__fmul_rn(x, a), nn));
       bx = __fadd_rn(bx, __fmul_rn(__fmul_rn(x, b), nn));
     }
-    const float f = __fdiv_rn(1.0f, __fsub_rn(__fmul_rn(asq, bsq), __fmul_rn(ab, ab)));
+    const float f = div_cold(1.0f, __fsub_rn(__fmul_rn(asq, bsq), __fmul_rn(ab, ab)));
     a1 = __fmul_rn(f, __fsub_rn(__fmul_rn(ax, bsq), __fmul_rn(bx, ab)));
     a2 = __fmul_rn(f, __fsub_rn(__fmul_rn(bx, asq), __fmul_rn(ax, ab)));
     // std::min(255.0f, std::max(0.0f, a)) -- NaN maps to 0 through std::max's argument order
@@ -1247,7 +1251,7 @@ __device__ __forceinline__ void setup_chain(const uint32_t *__restrict__ img, ui
   }
   float avg[4];
 #pragma unroll
-  for (int k = 0; k < 4; k++) avg[k] = __fdiv_rn(sum[k], (float)n);
+  for (int k = 0; k < 4; k++) avg[k] = div_cold(sum[k], (float)n);
   const bool all_same = mn == mx;
   const uint32_t gblock = block_index_base + first_block + t;
 
