@@ -729,6 +729,7 @@ __device__ __noinline__ void fit_core(int ibits, const uint32_t *pts, int n, con
         float b[4] = {0.5f, 0.5f, 0.5f, 0.5f};
         bool bad = false, fixed = false;
         int it = 0;
+#pragma unroll 1
         while (!fixed && ++it < 5) {
           float nbv[4];
 #pragma unroll
