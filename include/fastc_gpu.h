@@ -29,6 +29,15 @@
  * that the caller must free.  There is NO CPU fallback: if no CUDA device is
  * usable the call fails.
  *
+ * Threads: every entry point may be called from any thread.  Host-pointer
+ * submissions to one device are serialised inside the library (the reference's
+ * ThreadGroup / WorkerQueue call a CompressionFunc from up to 256 threads at
+ * once on disjoint block ranges, Core/src/ThreadGroup.cpp:146-188).
+ *
+ * Host buffers may be pageable (new[] / malloc: staged through pinned memory
+ * owned by the library) or pinned (cudaHostAlloc / cudaHostRegister: used
+ * directly by the copy engines, ~2.5x faster end to end for DXT / ETC1).
+ *
  * Pixel layout: row-major RGBA8, R in the lowest byte, pitch = width*4
  * (RGBAEndpoints.h:64-72, Pixel.cpp:165-179).  Block i (raster order over
  * width/4 x height/4 blocks) is written at out + i*block_bytes, exactly like
@@ -140,7 +149,7 @@ int fastc_gpu_bc7_counters(uint64_t *qe_calls, uint64_t *pixel_bucket_evals);
  * setup(+sort), anneal, pack, total}, synchronising on its events. */
 int fastc_gpu_bc7_stage_ms(int enable, double *ms6);
 
-/* Diagnostics: after a BPTC fastc_gpu_compress_device call of nblocks (<= 2^19)
+/* Diagnostics: after a BPTC fastc_gpu_compress_device call of nblocks (<= 2^22)
  * blocks on this device, copies the per-block selection word and the per-chain
  * fit results (nblocks x 16 slots x 8 words) out of the scratch. */
 int fastc_gpu_debug_bc7_dump(uint32_t nblocks, uint32_t *sel_out, uint32_t *results_out);
