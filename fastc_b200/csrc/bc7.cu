@@ -321,36 +321,39 @@ __global__ void bc7_add_u32(uint32_t *p, const uint32_t *v) { *p += *v; }
 // reference's own divide / multiply sequence decides (RGBAEndpoints.cpp:262-289).
 constexpr int kSelWarps = 4;
 
-struct SubsetBox {
-  uint32_t den, base;  // |extent|^2, min . extent
-  float inv16, fden;
-};
 
 // interpolation weights of the 3-bit / 2-bit index precisions (bc7tab::kWeight rows 2 / 1; checked
 // against the table in bc7_upload_tables): compile-time constants for the unrolled palette build
 __device__ constexpr uint32_t kSelWeights3[8] = {0, 9, 18, 27, 37, 46, 55, 64};
 __device__ constexpr uint32_t kSelWeights2[4] = {0, 21, 43, 64};
-constexpr int kSelPalRows = 16;  // 2 subsets x 8 buckets, or 3 x 4
+constexpr int kSelPalRows = 22;  // 16 palette rows (2 subsets x 8 buckets, or 3 x 4) + 2 rows of box scalars per subset
+constexpr int kSelBoxRow = 16;   // row 16 + 2 s: (|extent|^2, min . extent), row 17 + 2 s: (reciprocal bits, extent bytes)
 
-// `pal`: the lane's palette column: row (subset * NB + j) = (colour j, colour j + 1) of that subset's
-// bounding-box endpoints, the last row of a subset (colour NB-1 twice).
-template <int NBM1>
-__device__ __forceinline__ uint32_t box_pixel_error(const SubsetBox &b, uint32_t p, uint32_t d, const uint2 *pal_sub) {
-  const uint32_t num = __dp4a(p, d, 0u) - b.base;  // (p - min) . extent, exact
+// `pal`: the lane's column of shared memory.  Row (subset * NB + j) = (colour j, colour j + 1) of that
+// subset's bounding-box endpoints (the last row of a subset: colour NB-1 twice); rows kSelBoxRow.. hold
+// the subset's scalars.  The kernel is bound by the ALU pipe: fetching the subset's operands with two
+// 64-bit shared loads instead of selecting them from registers takes 5-10 ALU instructions off every pixel.
+template <int NB>
+__device__ __forceinline__ uint32_t box_pixel_error(const uint2 *pal, int s, uint32_t p) {
+  constexpr int NBM1 = NB - 1, STRIDE = kSelWarps * 32;
+  const uint2 b0 = pal[(kSelBoxRow + 2 * s) * STRIDE], b1 = pal[(kSelBoxRow + 2 * s + 1) * STRIDE];
+  const uint32_t den = b0.x, base = b0.y, d = b1.y;
+  const float inv16 = __uint_as_float(b1.x);
+  const uint32_t num = __dp4a(p, d, 0u) - base;  // (p - min) . extent, exact
   const float fnum = (float)num;
-  const int v = __float2int_rd(__fmul_rn(fnum, b.inv16));
+  const int v = __float2int_rd(__fmul_rn(fnum, inv16));
   int ja = min(v >> 16, NBM1);
   bool two = ja < NBM1;
-  if (num == 0 || num == b.den) {
+  if (num == 0 || num == den) {
     two = false;  // pct is exactly 0 or 1: floor == ceil
     ja = num ? NBM1 : 0;
   } else if ((((uint32_t)v + 1u) & 0xFFFFu) <= 1u) {
-    const float t = __fmul_rn(__fdiv_rn(fnum, b.fden), (float)NBM1);
+    const float t = __fmul_rn(__fdiv_rn(fnum, (float)den), (float)NBM1);
     const int x1 = min(max(0, (int)floorf(t)), NBM1), x2 = min((int)ceilf(t), NBM1);
     ja = x1;
     two = x1 + 1 <= x2;
   }
-  const uint2 c = pal_sub[ja * (kSelWarps * 32)];
+  const uint2 c = pal[(s * NB + ja) * STRIDE];
   const uint32_t da = __vabsdiffu4(c.x, p), db = __vabsdiffu4(c.y, p);
   const uint32_t ea = __dp4a(da, da, 0u), eb = __dp4a(db, db, 0u);
   return two ? min(ea, eb) : ea;
@@ -380,18 +383,17 @@ __device__ __forceinline__ double estimate_shape(const uint32_t *__restrict__ px
       mxh[q] = __vimax3_u16x2(mxh[q], s0 == q ? h0 : 0u, s1 == q ? h1 : 0u);
     }
   }
-  SubsetBox box[NSUB];
-  uint32_t dd[NSUB];
+  uint32_t dens[NSUB];
 #pragma unroll
   for (int s = 0; s < NSUB; s++) {
     // per byte mx >= mn: no borrow (every BC7 partition uses all its subsets)
     const uint32_t dlo = mxl[s] - mnl[s], dhi = mxh[s] - mnh[s];
     const uint32_t d = dlo | (dhi << 8), mn = mnl[s] | (mnh[s] << 8);
-    dd[s] = d;
-    box[s].den = __dp4a(d, d, 0u);
-    box[s].base = __dp4a(mn, d, 0u);
-    box[s].fden = (float)box[s].den;
-    box[s].inv16 = box[s].den ? __fdiv_rn(65536.0f * (float)NBM1, box[s].fden) : 0.0f;
+    const uint32_t den = __dp4a(d, d, 0u);
+    dens[s] = den;
+    const float inv16 = den ? __fdiv_rn(65536.0f * (float)NBM1, (float)den) : 0.0f;
+    pal[(kSelBoxRow + 2 * s) * (kSelWarps * 32)] = make_uint2(den, __dp4a(mn, d, 0u));
+    pal[(kSelBoxRow + 2 * s + 1) * (kSelWarps * 32)] = make_uint2(__float_as_uint(inv16), d);
     // the subset's palette, once per shape instead of twice per pixel: colour j = min + ((extent *
     // w_j + 32) >> 6) per channel, two channels per 32-bit multiply (a byte times w <= 64 fits 16 bits)
     uint32_t cur = mn;  // w_0 = 0
@@ -411,20 +413,15 @@ __device__ __forceinline__ double estimate_shape(const uint32_t *__restrict__ px
 #pragma unroll 2
   for (int i = 0; i < 16; i++) {
     const int s = NSUB == 2 ? ((m2 >> i) & 1) : ((m3 >> (2 * i)) & 3);
-    SubsetBox b = box[0];
-    uint32_t d = dd[0];
-#pragma unroll
-    for (int q = 1; q < NSUB; q++)
-      if (s == q) { b = box[q]; d = dd[q]; }  // selects
     // a point-sized box contributes nothing; its pixels evaluate to 0 anyway (p == min, extent 0)
-    const uint32_t e = box_pixel_error<NBM1>(b, px[i], d, pal + s * NB * (kSelWarps * 32));
+    const uint32_t e = box_pixel_error<NB>(pal, s, px[i]);
 #pragma unroll
     for (int q = 0; q < NSUB; q++) tot[q] += (s == q) ? e : 0u;
   }
   double err = 0.0;
 #pragma unroll
   for (int s = 0; s < NSUB; s++) {
-    const double e = box[s].den == 0 ? 0.0 : __dadd_rn(0.0001, (double)tot[s]);
+    const double e = dens[s] == 0 ? 0.0 : __dadd_rn(0.0001, (double)tot[s]);
     err = __dadd_rn(err, e);
   }
   return err;
