@@ -548,11 +548,23 @@ int fastc_gpu_compress(int format, const uint8_t *rgba_host, uint32_t width, uin
   // process-global counter, Compressor.cpp:135-140,1457).  Counting on the host keeps a
   // sub-range / sharded submission bit-identical to the same bytes of a full submission.
   if (format == FASTC_GPU_BPTC) {
-    uint32_t run = host_count_solid(rgba_host, width, 0, first_block);
+    // the blocks before the submission and every shard but the last, counted concurrently (the
+    // scan is memory-bound: one host thread per slab instead of one slab after the other)
+    std::vector<uint32_t> counts(num_gpus, 0);
+    uint32_t before = 0;
+    {
+      std::vector<std::thread> th;
+      for (int g = 0; g + 1 < num_gpus; g++)
+        th.emplace_back([&, g] {
+          counts[g] = host_count_solid(rgba_host, width, shards[g].first_block, shards[g].first_block + shards[g].num_blocks);
+        });
+      before = host_count_solid(rgba_host, width, 0, first_block);
+      for (auto &t : th) t.join();
+    }
+    uint32_t run = before;
     for (int g = 0; g < num_gpus; g++) {
       shards[g].wm_base = run;
-      if (g + 1 < num_gpus)
-        run += host_count_solid(rgba_host, width, shards[g].first_block, shards[g].first_block + shards[g].num_blocks);
+      run += counts[g];
     }
   }
   if (num_gpus == 1) cudaGetDevice(&shards[0].dev);  // one GPU: the caller's current device
