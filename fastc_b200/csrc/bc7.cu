@@ -326,6 +326,7 @@ constexpr int kSelWarps = 4;
 // against the table in bc7_upload_tables): compile-time constants for the unrolled palette build
 __device__ constexpr uint32_t kSelWeights3[8] = {0, 9, 18, 27, 37, 46, 55, 64};
 __device__ constexpr uint32_t kSelWeights2[4] = {0, 21, 43, 64};
+__device__ constexpr uint32_t kWeights4[16] = {0, 4, 9, 13, 17, 21, 26, 30, 34, 38, 43, 47, 51, 55, 60, 64};
 constexpr int kSelPalRows = 22;  // 16 palette rows (2 subsets x 8 buckets, or 3 x 4) + 2 rows of box scalars per subset
 constexpr int kSelBoxRow = 16;   // row 16 + 2 s: (|extent|^2, min . extent), row 17 + 2 s: (reciprocal bits, extent bytes)
 
@@ -1564,6 +1565,24 @@ __device__ __forceinline__ void sa_pixels(uint32_t (*s_pix)[kPixStride], const u
 #undef SA_PIXEL
 }
 
+// The palette of a warp whose lanes all use the same index precision (the usual case: the CTAs have
+// a home precision class): unrolled with the weights as immediates; colour 0 and colour NB-1 are
+// the endpoints themselves (weights 0 and 64), so only the NB - 2 inner colours are interpolated.
+template <int NB>
+__device__ __forceinline__ void sa_palette_uniform(uint2 (*s_pal)[kSaThreads], int tid, uint32_t q1, uint32_t q2,
+                                                   uint32_t blo, uint32_t dlo, uint32_t bhi, uint32_t dhi) {
+  uint32_t cur = q1;
+#pragma unroll
+  for (int j = 1; j <= NB - 2; j++) {
+    const uint32_t w = NB == 4 ? kSelWeights2[j] : (NB == 8 ? kSelWeights3[j] : kWeights4[j]);
+    const uint32_t nxt = (((blo + dlo * w) >> 6) & 0x00FF00FFu) | (((bhi + dhi * w) << 2) & 0xFF00FF00u);
+    s_pal[j - 1][tid] = make_uint2(cur, nxt);
+    cur = nxt;
+  }
+  s_pal[NB - 2][tid] = make_uint2(cur, q2);
+  s_pal[NB - 1][tid] = make_uint2(q2, q2);
+}
+
 // Evaluate one cluster against quantised endpoints q1/q2: returns the total error and the
 // chosen bucket of every pixel (4 bits each, cluster-local order) in idx_lo / idx_hi.
 // nmax / nbmax: the warp's largest cluster size / bucket count - 1 (warp-uniform loop bounds).
@@ -1572,7 +1591,7 @@ __device__ __forceinline__ void sa_pixels(uint32_t (*s_pix)[kPixStride], const u
 // candidate buckets of a pixel (floor and ceil of its projection) come from one 64-bit load.
 __device__ __forceinline__ uint32_t sa_eval(uint32_t (*s_pix)[kPixStride], uint2 (*s_pal)[kSaThreads],
                                             const uint8_t *__restrict__ s_w, int tid, const SaConst &K, int nmax,
-                                            int nbmax, bool uniform, uint32_t q1, uint32_t q2, uint32_t &idx_lo,
+                                            int nbmax, int uflags, uint32_t q1, uint32_t q2, uint32_t &idx_lo,
                                             uint32_t &idx_hi) {
   const uint32_t d11 = __dp4a(q1, q1, 0u), d12 = __dp4a(q1, q2, 0u), d22 = __dp4a(q2, q2, 0u);
   const int den = (int)d22 - 2 * (int)d12 + (int)d11;       // |e2 - e1|^2
@@ -1583,14 +1602,20 @@ __device__ __forceinline__ uint32_t sa_eval(uint32_t (*s_pix)[kPixStride], uint2
     const uint32_t e1lo = q1 & 0x00FF00FFu, e1hi = (q1 >> 8) & 0x00FF00FFu;
     const uint32_t dlo = (q2 & 0x00FF00FFu) - e1lo, dhi = ((q2 >> 8) & 0x00FF00FFu) - e1hi;
     const uint32_t blo = e1lo * 64u + 0x00200020u, bhi = e1hi * 64u + 0x00200020u;
-    const uint8_t *wt = s_w + K.woff + 1;
-    uint32_t cur = q1;  // colour 0 (weight 0) is endpoint 1 itself
+    if (uflags & 2) {  // every lane of the warp has nbm1 == nbmax
+      if (nbmax == 3) sa_palette_uniform<4>(s_pal, tid, q1, q2, blo, dlo, bhi, dhi);
+      else if (nbmax == 7) sa_palette_uniform<8>(s_pal, tid, q1, q2, blo, dlo, bhi, dhi);
+      else sa_palette_uniform<16>(s_pal, tid, q1, q2, blo, dlo, bhi, dhi);
+    } else {
+      const uint8_t *wt = s_w + K.woff + 1;
+      uint32_t cur = q1;  // colour 0 (weight 0) is endpoint 1 itself
 #pragma unroll 4
-    for (int j = 0; j <= nbmax; j++) {  // rows past this lane's bucket count are never read by it
-      const uint32_t w = wt[j];
-      const uint32_t nxt = (((blo + dlo * w) >> 6) & 0x00FF00FFu) | (((bhi + dhi * w) << 2) & 0xFF00FF00u);
-      s_pal[j][tid] = make_uint2(cur, nxt);
-      cur = nxt;
+      for (int j = 0; j <= nbmax; j++) {  // rows past this lane's bucket count are never read by it
+        const uint32_t w = wt[j];
+        const uint32_t nxt = (((blo + dlo * w) >> 6) & 0x00FF00FFu) | (((bhi + dhi * w) << 2) & 0xFF00FF00u);
+        s_pal[j][tid] = make_uint2(cur, nxt);
+        cur = nxt;
+      }
     }
   }
   const float fden = (float)den, fnb = (float)K.nbm1;
@@ -1604,7 +1629,7 @@ __device__ __forceinline__ uint32_t sa_eval(uint32_t (*s_pix)[kPixStride], uint2
   const int n = K.n, nbm1 = K.nbm1;
   const uint2 *pal = &s_pal[0][tid];
   uint32_t total = 0, slow = 0, word[2];
-  if (uniform) sa_pixels<true>(s_pix, pal, tid, n, nbm1, nmax, q1p, q2p, cq, inv16, total, slow, word);
+  if (uflags & 1) sa_pixels<true>(s_pix, pal, tid, n, nbm1, nmax, q1p, q2p, cq, inv16, total, slow, word);
   else sa_pixels<false>(s_pix, pal, tid, n, nbm1, nmax, q1p, q2p, cq, inv16, total, slow, word);
   // pixel i sits at bit nmax - 1 - i of `slow`; drop the flags of pixels past the lane's cluster
   slow &= 0xFFFFFFFFu << (nmax - n);
@@ -1725,8 +1750,8 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
   uint32_t gid = 0, cur1 = 0, cur2 = 0, best1 = 0, best2 = 0, cur_err = 0, best_err = 0, rng = 0;
   uint32_t best_lo = 0, best_hi = 0;
   int cur_combo = 0, best_combo = 0, energy = 0, rotation = 0;
-  bool improved = false, uniform = false;
-  int nmax = 0, nbmax = 0;
+  bool improved = false;
+  int nmax = 0, nbmax = 0, uflags = 0;
 #ifdef FASTC_GPU_COUNTERS
   uint32_t ncalls = 0, npbe = 0;
 #endif
@@ -1811,7 +1836,8 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
       // chain with the queue dry leaves them larger than needed, which is harmless)
       nmax = __reduce_max_sync(full, have ? K.n : 0);
       nbmax = __reduce_max_sync(full, have ? K.nbm1 : 0);
-      uniform = __all_sync(full, !have || K.n == nmax);
+      // bit 0: every lane's cluster has nmax pixels, bit 1: every lane has nbmax + 1 buckets
+      uflags = (__all_sync(full, !have || K.n == nmax) ? 1 : 0) | (__all_sync(full, !have || K.nbm1 == nbmax) ? 2 : 0);
     }
     if (!__any_sync(full, have)) break;
     if (!have) continue;
@@ -1835,7 +1861,7 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
       // modes without p-bits evaluate with a zero p-bit (reference quirk, see fit_cluster): their combo is 0
       const uint32_t q1 = sa_quantize(s_q, K, n1, (ncombo >> K.sh0) & 1), q2 = sa_quantize(s_q, K, n2, ncombo & 1);
       uint32_t ilo, ihi;
-      const uint32_t err = sa_eval(s_pix, s_pal, s_w, tid, K, nmax, nbmax, uniform, q1, q2, ilo, ihi);
+      const uint32_t err = sa_eval(s_pix, s_pal, s_w, tid, K, nmax, nbmax, uflags, q1, q2, ilo, ihi);
 #ifdef FASTC_GPU_COUNTERS
       ncalls++; npbe += K.n;
 #endif
@@ -2212,6 +2238,9 @@ cudaError_t bc7_upload_tables() {
       if (kWeight[32 + j] != w3[j]) return cudaErrorInvalidValue;
     for (int j = 0; j < 4; j++)
       if (kWeight[16 + j] != w2[j]) return cudaErrorInvalidValue;
+    static const uint32_t w4[16] = {0, 4, 9, 13, 17, 21, 26, 30, 34, 38, 43, 47, 51, 55, 60, 64};
+    for (int j = 0; j < 16; j++)
+      if (kWeight[48 + j] != w4[j]) return cudaErrorInvalidValue;
   }
   static uint32_t host_single[8 * 2 * 4 * 2 * 256];
   static bool built = false;
