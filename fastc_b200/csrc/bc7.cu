@@ -1562,8 +1562,30 @@ __device__ __forceinline__ void sa_pixels(uint32_t (*s_pix)[kPixStride], const u
     const int cnt = i1 - i0;
     word[half] = cnt > 0 ? acc >> (4 * (8 - cnt)) : 0u;
   }
-#undef SA_PIXEL
 }
+
+// The same for a warp whose lanes all fit 16-pixel clusters (mode 6 and the mode 4/5 fits: two
+// thirds of all annealing steps): no loop, no validity tests, no partial index words.
+__device__ __forceinline__ void sa_pixels16(uint32_t (*s_pix)[kPixStride], const uint2 *pal, int tid, int nbm1,
+                                            uint32_t q1p, uint32_t q2p, uint32_t cq, float inv16, uint32_t &total,
+                                            uint32_t &slow, uint32_t (&word)[2]) {
+#pragma unroll
+  for (int half = 0; half < 2; half++) {
+    uint32_t acc = 0;
+#pragma unroll
+    for (int g = 0; g < 2; g++) {
+      const int i = 8 * half + 4 * g;
+      bool f0, f1, f2, f3;
+      SA_PIXEL(s_pix[i][tid], true, f0)
+      SA_PIXEL(s_pix[i + 1][tid], true, f1)
+      SA_PIXEL(s_pix[i + 2][tid], true, f2)
+      SA_PIXEL(s_pix[i + 3][tid], true, f3)
+      slow = (slow << 4) | (f0 ? 8u : 0u) | (f1 ? 4u : 0u) | (f2 ? 2u : 0u) | (f3 ? 1u : 0u);
+    }
+    word[half] = acc;
+  }
+}
+#undef SA_PIXEL
 
 // The palette of a warp whose lanes all use the same index precision (the usual case: the CTAs have
 // a home precision class): unrolled with the weights as immediates; colour 0 and colour NB-1 are
@@ -1629,7 +1651,8 @@ __device__ __forceinline__ uint32_t sa_eval(uint32_t (*s_pix)[kPixStride], uint2
   const int n = K.n, nbm1 = K.nbm1;
   const uint2 *pal = &s_pal[0][tid];
   uint32_t total = 0, slow = 0, word[2];
-  if (uflags & 1) sa_pixels<true>(s_pix, pal, tid, n, nbm1, nmax, q1p, q2p, cq, inv16, total, slow, word);
+  if ((uflags & 1) && nmax == 16) sa_pixels16(s_pix, pal, tid, nbm1, q1p, q2p, cq, inv16, total, slow, word);
+  else if (uflags & 1) sa_pixels<true>(s_pix, pal, tid, n, nbm1, nmax, q1p, q2p, cq, inv16, total, slow, word);
   else sa_pixels<false>(s_pix, pal, tid, n, nbm1, nmax, q1p, q2p, cq, inv16, total, slow, word);
   // pixel i sits at bit nmax - 1 - i of `slow`; drop the flags of pixels past the lane's cluster
   slow &= 0xFFFFFFFFu << (nmax - n);
