@@ -47,8 +47,8 @@ LANE_OPS_PER_BLOCK = 1.2e6
 ALU_PEAK_LANE_OPS = 148 * 128 * 1.965e9
 ALGO_BYTES_PER_BLOCK = 64 + 16  # read one 4x4 RGBA block, write one 128-bit BC7 block (5 B/px)
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE bc7_anneal launch over the whole 8192^2 texture
-# (ncu, profiles/r01_v13_dram_8192.csv): the sorted start states, the pixels of every chain, the results
-ANNEAL_DRAM_BYTES_8192 = 7_587_076_608 + 1_576_985_856
+# (ncu, profiles/r01_v14_dram_8192.csv): the sorted start states, the pixels of every chain, the results
+ANNEAL_DRAM_BYTES_8192 = 7_862_972_416 + 1_578_225_920
 
 
 _REAL_STDOUT = None
@@ -301,14 +301,16 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "frac": achieved_gbs / hbm_peak,
         # measured for the full texture; a rank's slab moves its share of it
         "traffic": (ANNEAL_DRAM_BYTES_8192 * nblk / ((WIDTH // 4) * (HEIGHT // 4))) if WIDTH == 8192 else None,
-        "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_v13_dram_8192.csv)",
+        "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_v14_dram_8192.csv)",
         "algorithmic_bytes": nblk * ALGO_BYTES_PER_BLOCK, "kernel": "bc7_anneal",
         "kernel_ms": k_ms, "kernel_share_of_step": share, "peak_source": peak_src,
         "note": "BC7 is ALU-issue bound, not HBM bound (SURVEY 8d): see alu_issue",
         "alu_issue": {"achieved_lane_ops_per_s": lane_ops, "peak_lane_ops_per_s": ALU_PEAK_LANE_OPS,
                       "frac": lane_ops / ALU_PEAK_LANE_OPS,
-                      "model": "1.2e6 lane-ops per block at -q 50 (SURVEY 8d op model) / bc7_anneal time; "
-                               "peak = 148 SM x 128 lanes x 1.965 GHz"},
+                      "model": "1.2e6 lane-ops per block at -q 50 (SURVEY 8d op model of the REFERENCE's instruction "
+                               "mix) / bc7_anneal time; peak = 148 SM x 128 lanes x 1.965 GHz.  The GPU formulation needs "
+                               "fewer instructions than the model, so this overstates utilisation: the measured figure is "
+                               "ncu's issue-slot utilisation in profiles/ (86.6 % with 28.3 of 32 lanes active)"},
         "stages_ms": {k: sum(s[k] for s in stage_tot) / len(stage_tot) for k in stage_tot[0]},
     }
 
