@@ -1409,7 +1409,7 @@ __global__ void bc7_bin_offsets(uint32_t *bins, uint32_t grid_ctas) {
 }
 
 // Counting-sort scatter.  Ranks are taken in shared memory and each CTA reserves one range per
-// key with a single global atomic (51 hot counters would otherwise serialise ~10 chains/block).
+// key with a single global atomic (a few hot counters would otherwise serialise ~10 chains/block).
 __global__ void __launch_bounds__(256) bc7_scatter(Ws ws, uint32_t num_blocks) {
   __shared__ uint32_t s_cnt[kSortKeys], s_base[kSortKeys];
   for (int k = threadIdx.x; k < kSortKeys; k += 256) s_cnt[k] = 0;
