@@ -133,3 +133,35 @@ def test_small_division_exact():
             r = Fraction(float(rn(a - q * c)))          # the FMA's exact product, rounded once
             assert r == a - q * c                       # ... and that remainder is exactly representable
             assert rn(q + r * rc) == rn(Fraction(a, c)), (a, c)
+
+
+def test_fast_projection_guard_band():
+    """bc7_anneal / bc7_select pick a pixel's two candidate buckets from v = floor(float(num) * inv16),
+    inv16 = RN(65536 * nbm1 / den), a 16.16 fixed-point bucket coordinate, and only trust it when v is
+    not within one unit of a multiple of 65536 (otherwise the reference's own float sequence is replayed).
+    Check, in float32 emulation, that every UNFLAGGED v gives the reference's candidates
+    (RGBAEndpoints.cpp:262-289): j1 = clamp(floor(t)), j2 = min(ceil(t), nbm1), t = RN(RN(num / den) * nbm1)."""
+    f = np.float32
+    rng = np.random.default_rng(42)
+    for nbm1 in (3, 7, 15):
+        den = np.concatenate([rng.integers(1, 260101, 400000), rng.integers(1, 2000, 200000)]).astype(np.int64)
+        num = (rng.random(den.size) * 1.2 - 0.1) * den            # mostly inside [0, den], some outside
+        num = np.rint(num).astype(np.int64)
+        # adversarial: projections that land next to a bucket boundary
+        k = rng.integers(0, nbm1 + 1, den.size)
+        near = (k * den) // nbm1 + rng.integers(-1, 2, den.size)
+        num = np.where(rng.random(den.size) < 0.5, near, num)
+        fden, fnum = den.astype(f), num.astype(f)
+        inv16 = (f(65536.0) * f(nbm1)) / fden                      # __fdiv_rn(__fmul_rn(65536, nbm1), fden)
+        v = np.floor((fnum * inv16).astype(f)).astype(np.int64)
+        flagged = ((v + 1) & 0xFFFE) == 0
+        t = ((fnum / fden).astype(f) * f(nbm1)).astype(f)
+        j1 = np.clip(np.floor(t).astype(np.int64), 0, nbm1)
+        j2 = np.minimum(np.ceil(t).astype(np.int64), nbm1)
+        ref_two = (j1 + 1) <= j2
+        ja = np.clip(v >> 16, 0, nbm1)
+        gpu_two = (v >= 0) & (ja < nbm1)                           # the last palette row repeats its colour
+        ok = ~flagged
+        assert ok.mean() > 0.5
+        assert (ja[ok] == j1[ok]).all(), nbm1
+        assert (gpu_two[ok] == ref_two[ok]).all(), nbm1
