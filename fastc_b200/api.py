@@ -53,7 +53,7 @@ class SCompressionSettings:
     bUsePVRTexLib: bool = False
     bUseNVTT: bool = False
     logStream: object = None
-    # extensions (not in the reference): GPU count and RNG seed
+    # extensions (not in the reference): GPU count (0 = all visible) and RNG seed
     iNumGPUs: int = 1
     seed: int = 0
 
@@ -62,6 +62,17 @@ class _Timing(C.Structure):
     _fields_ = [("kernel_ms", C.c_double), ("total_ms", C.c_double),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("kernel_launches", C.c_uint32)]
+
+
+class _Options(C.Structure):
+    """fastc_gpu_options (include/fastc_gpu.h): BPTCC::CompressionSettings' m_BlockModes /
+    m_ErrorMetric and rg_etc1's quality level."""
+    _fields_ = [("struct_size", C.c_uint32), ("bptc_block_modes", C.c_uint32),
+                ("bptc_error_metric", C.c_int32), ("etc1_quality", C.c_int32)]
+
+
+def _options(block_modes: int = 0xFF, error_metric: int = 0, etc1_quality: int = 0):
+    return _Options(C.sizeof(_Options), block_modes, error_metric, etc1_quality)
 
 
 class _Job(C.Structure):
@@ -76,6 +87,7 @@ class GpuLibrary:
         "fastc_gpu_device_count", "fastc_gpu_init", "fastc_gpu_shutdown", "fastc_gpu_block_bytes",
         "fastc_gpu_compressed_size", "fastc_gpu_compress", "fastc_gpu_compress_batch",
         "fastc_gpu_compress_device", "fastc_gpu_count_solid_device", "fastc_gpu_bc7_counters",
+        "fastc_gpu_compress_opt", "fastc_gpu_compress_batch_opt", "fastc_gpu_compress_device_opt",
         "fastc_gpu_debug_bc7_dump", "fastc_gpu_bc7_stage_ms",
         "fastc_gpu_decompress", "fastc_gpu_decompress_device", "fastc_gpu_psnr", "fastc_gpu_psnr_device",
         "fastc_gpu_last_error",
@@ -99,6 +111,10 @@ class GpuLibrary:
         L.fastc_gpu_compress_batch.argtypes = [i, C.POINTER(_Job), u32, i, u64, i, C.POINTER(_Timing)]
         L.fastc_gpu_compress_device.argtypes = [i, vp, u32, u32, u32, u32, vp, i, u64, u32, u32, vp,
                                                 C.POINTER(u32)]
+        po = C.POINTER(_Options)
+        L.fastc_gpu_compress_opt.argtypes = L.fastc_gpu_compress.argtypes + [po]
+        L.fastc_gpu_compress_batch_opt.argtypes = L.fastc_gpu_compress_batch.argtypes + [po]
+        L.fastc_gpu_compress_device_opt.argtypes = L.fastc_gpu_compress_device.argtypes + [po]
         L.fastc_gpu_count_solid_device.argtypes = [vp, u32, u32, u32, u32, vp, C.POINTER(u32)]
         L.fastc_gpu_bc7_counters.argtypes = [C.POINTER(u64), C.POINTER(u64)]
         L.fastc_gpu_debug_bc7_dump.argtypes = [u32, vp, vp]
@@ -117,63 +133,81 @@ class GpuLibrary:
             raise FastcGpuError(self.error())
 
     # ---- host -> host -------------------------------------------------------
+    @staticmethod
+    def _check_image(rgba) -> tuple[int, int]:
+        if (not isinstance(rgba, np.ndarray) or rgba.dtype != np.uint8 or rgba.ndim != 3 or rgba.shape[2] != 4
+                or not rgba.flags.c_contiguous):
+            raise FastcGpuError("rgba must be a C-contiguous (H, W, 4) uint8 array")
+        return rgba.shape[0], rgba.shape[1]
+
+    @staticmethod
+    def _check_output(out, size: int):
+        if not isinstance(out, np.ndarray) or out.dtype != np.uint8 or not out.flags.c_contiguous:
+            raise FastcGpuError("the output must be a C-contiguous uint8 array")
+        if out.nbytes < size:
+            # reference: "Not enough space for compressed data!" (TexComp.cpp:493-496)
+            raise FastcGpuError("Not enough space for compressed data!")
+
     def compress(self, fmt: int, rgba: np.ndarray, out: np.ndarray | None = None, *, quality: int = 50,
                  seed: int = 0, first_block: int = 0, num_blocks: int = 0, chunk_blocks: int = 0,
-                 num_gpus: int = 1):
+                 num_gpus: int = 1, block_modes: int = 0xFF, error_metric: int = 0, etc1_quality: int = 0):
         """rgba: (H, W, 4) uint8, C-contiguous (pinned or pageable host memory).
         Returns (out bytes, timing dict)."""
-        if rgba.dtype != np.uint8 or rgba.ndim != 3 or rgba.shape[2] != 4 or not rgba.flags.c_contiguous:
-            raise FastcGpuError("rgba must be a C-contiguous (H, W, 4) uint8 array")
-        h, w = rgba.shape[:2]
+        h, w = self._check_image(rgba)
         size = int(self.cdll.fastc_gpu_compressed_size(int(fmt), w, h))
         if out is None:
             out = np.zeros(size, dtype=np.uint8)
-        elif out.nbytes < size:
-            # reference: "Not enough space for compressed data!" (TexComp.cpp:493-496)
-            raise FastcGpuError("Not enough space for compressed data!")
+        else:
+            self._check_output(out, size)
         tm = _Timing()
-        self.check(self.cdll.fastc_gpu_compress(int(fmt), rgba.ctypes.data, w, h, first_block, num_blocks,
-                                                out.ctypes.data, quality, seed, chunk_blocks, num_gpus,
-                                                C.byref(tm)))
+        opt = _options(block_modes, error_metric, etc1_quality)
+        self.check(self.cdll.fastc_gpu_compress_opt(int(fmt), rgba.ctypes.data, w, h, first_block, num_blocks,
+                                                    out.ctypes.data, quality, seed, chunk_blocks, num_gpus,
+                                                    C.byref(tm), C.byref(opt)))
         return out, {"kernel_ms": tm.kernel_ms, "total_ms": tm.total_ms, "h2d_bytes": tm.h2d_bytes,
                      "d2h_bytes": tm.d2h_bytes, "kernel_launches": tm.kernel_launches}
 
     def compress_batch(self, fmt: int, images: list[np.ndarray], *, quality: int = 50, seed: int = 0,
-                       num_gpus: int = 1, outs: list[np.ndarray] | None = None):
+                       num_gpus: int = 1, outs: list[np.ndarray] | None = None, block_modes: int = 0xFF,
+                       error_metric: int = 0, etc1_quality: int = 0):
         """One submission for a list of textures (fastc_gpu_compress_batch).  `outs`: optional
         preallocated output arrays (e.g. pinned memory), one per texture."""
         jobs = (_Job * len(images))()
         given, outs = outs, []
+        if given is not None and len(given) != len(images):
+            raise FastcGpuError("one output array per texture")
         for k, im in enumerate(images):
-            h, w = im.shape[:2]
+            h, w = self._check_image(im)
             size = int(self.cdll.fastc_gpu_compressed_size(int(fmt), w, h))
             if given is not None:
                 o = given[k]
-                if o.nbytes < size:
-                    raise FastcGpuError("Not enough space for compressed data!")
+                self._check_output(o, size)
             else:
                 o = np.zeros(size, dtype=np.uint8)
             outs.append(o)
             jobs[k] = _Job(im.ctypes.data, o.ctypes.data, w, h)
         tm = _Timing()
-        self.check(self.cdll.fastc_gpu_compress_batch(int(fmt), jobs, len(images), quality, seed, num_gpus,
-                                                      C.byref(tm)))
+        opt = _options(block_modes, error_metric, etc1_quality)
+        self.check(self.cdll.fastc_gpu_compress_batch_opt(int(fmt), jobs, len(images), quality, seed, num_gpus,
+                                                          C.byref(tm), C.byref(opt)))
         return outs, {"kernel_ms": tm.kernel_ms, "total_ms": tm.total_ms, "h2d_bytes": tm.h2d_bytes,
                       "d2h_bytes": tm.d2h_bytes, "kernel_launches": tm.kernel_launches}
 
     # ---- device -> device (torch tensors are only the memory/stream plumbing) --
     def compress_device(self, fmt: int, rgba_dev, out_dev, *, width: int, height: int, quality: int = 50,
                         seed: int = 0, first_block: int = 0, num_blocks: int = 0, wm_base: int = 0,
-                        block_index_base: int = 0, stream: int | None = None) -> int:
+                        block_index_base: int = 0, stream: int | None = None, block_modes: int = 0xFF,
+                        error_metric: int = 0, etc1_quality: int = 0) -> int:
         """rgba_dev / out_dev: CUDA torch uint8 tensors on the current device.
         Asynchronous on `stream` (raw cudaStream_t; default torch's current)."""
         import torch
         if stream is None:
             stream = torch.cuda.current_stream().cuda_stream
         n = C.c_uint32(0)
-        self.check(self.cdll.fastc_gpu_compress_device(int(fmt), rgba_dev.data_ptr(), width, height, first_block,
-                                                       num_blocks, out_dev.data_ptr(), quality, seed, wm_base,
-                                                       block_index_base, stream, C.byref(n)))
+        opt = _options(block_modes, error_metric, etc1_quality)
+        self.check(self.cdll.fastc_gpu_compress_device_opt(int(fmt), rgba_dev.data_ptr(), width, height, first_block,
+                                                           num_blocks, out_dev.data_ptr(), quality, seed, wm_base,
+                                                           block_index_base, stream, C.byref(n), C.byref(opt)))
         return n.value
 
     def count_solid_device(self, rgba_dev, *, width: int, height: int, first_block: int = 0,
@@ -284,7 +318,7 @@ def CompressImageData(data: np.ndarray, width: int, height: int, cmpData: np.nda
     try:
         for _ in range(n):
             _, tm = lib().compress(fmt, img, cmpData, quality=max(0, settings.iQuality), seed=settings.seed,
-                                   chunk_blocks=max(0, settings.iJobSize), num_gpus=max(1, settings.iNumGPUs))
+                                   chunk_blocks=max(0, settings.iJobSize), num_gpus=max(0, settings.iNumGPUs))
             total += tm["total_ms"]
     except FastcGpuError as e:
         _report_error(str(e))

@@ -17,6 +17,7 @@
 
 #include "FasTC/BlockCompressors.h"
 #include "FasTC/Image.h"
+#include "FasTC/ImageFile.h"
 #include "FasTC/Pixel.h"
 #include "fastc_gpu.h"
 
@@ -40,7 +41,7 @@ int GpuFormat(ECompressionFormat f) {
 }
 
 // One CompressionFunc call: the job's raster block range on the current device.
-void RunJob(const CompressionJob &cj, int quality, unsigned long long seed) {
+void RunJob(const CompressionJob &cj, int quality, unsigned long long seed, const fastc_gpu_options *opt = NULL) {
   const int fmt = GpuFormat(cj.Format());
   if (fmt < 0) {
     ReportError("Could not find adequate compression function for specified settings");
@@ -48,8 +49,8 @@ void RunJob(const CompressionJob &cj, int quality, unsigned long long seed) {
   }
   const uint32 n = cj.NumBlocks();
   if (n == 0) return;
-  if (fastc_gpu_compress(fmt, cj.InBuf(), cj.Width(), cj.Height(), cj.FirstBlock(), n, cj.OutBuf(), quality, seed, 0,
-                         1, NULL) != 0)
+  if (fastc_gpu_compress_opt(fmt, cj.InBuf(), cj.Width(), cj.Height(), cj.FirstBlock(), n, cj.OutBuf(), quality, seed, 0,
+                             1, NULL, opt) != 0)
     ReportError(fastc_gpu_last_error());
 }
 
@@ -63,7 +64,12 @@ void Compress(const CompressionJob &cj, CompressionSettings settings) {
     ReportError("BPTC shape-selection callbacks cannot run on the GPU path");
     return;
   }
-  RunJob(cj, (int)settings.m_NumSimulatedAnnealingSteps, 0);
+  // m_BlockModes restricts the mode search, m_ErrorMetric weights the channel errors
+  // (reference Compressor.cpp:1848-1857, :205-208)
+  fastc_gpu_options opt = FASTC_GPU_OPTIONS_INIT;
+  opt.bptc_block_modes = settings.m_BlockModes;
+  opt.bptc_error_metric = (int)settings.m_ErrorMetric;
+  RunJob(cj, (int)settings.m_NumSimulatedAnnealingSteps, 0, &opt);
 }
 void Decompress(const FasTC::DecompressionJob &dj) {
   if (fastc_gpu_decompress(FASTC_GPU_BPTC, dj.InBuf(), dj.Width(), dj.Height(), dj.OutBuf(), NULL) != 0)
@@ -216,6 +222,15 @@ CompressedImage *CompressImage(FasTC::Image<PixelType> *img, const SCompressionS
   return new CompressedImage(width, height, settings.format, cmpData.data());
 }
 template CompressedImage *CompressImage(FasTC::Image<FasTC::Pixel> *, const SCompressionSettings &settings);
+
+// Declared by the reference (Core/include/FasTC/TexComp.h:93) and never defined there; here it is
+// the PSNR `tc` prints: the compressed image decoded on the GPU against the file's pixels.
+double ComputePSNR(const CompressedImage &ci, const ImageFile &file) {
+  FasTC::Image<> *img = file.GetImage();
+  if (!img) return -1.0;
+  CompressedImage copy(ci);
+  return img->ComputePSNR(&copy);
+}
 
 void YieldThread() { sched_yield(); }
 

@@ -440,7 +440,10 @@ __device__ __forceinline__ void warp_argmin(double &err, int &idx) {
 
 __global__ void __launch_bounds__(kSelWarps * 32)
 bc7_select(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, uint32_t first_block,
-           uint32_t num_blocks, uint32_t *__restrict__ sel, uint32_t *__restrict__ states) {
+           uint32_t num_blocks, uint32_t *__restrict__ sel, uint32_t *__restrict__ states, uint32_t block_modes) {
+  // block_modes: BPTCC::CompressionSettings::m_BlockModes, ANDed into the selection's mode set
+  // (Compressor.cpp:1857); solid / transparent blocks never reach it (:1822-1846)
+  const uint32_t mode_keep = ~(0xFFu << 12) | ((block_modes & 0xFFu) << 12);
   __shared__ uint32_t s_px[kSelWarps][16], s_plo[kSelWarps][16], s_phi[kSelWarps][16];
   __shared__ uint2 s_pal[kSelPalRows][kSelWarps * 32];  // one palette column per lane (estimate_shape)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -485,7 +488,7 @@ bc7_select(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
   if (z0 | z1) {
     const int s = z0 ? (__ffs(z0) - 1) : (32 + __ffs(z1) - 1);
     word = (uint32_t)s | (0x8Au << 12) | (1u << 20);  // modes {1,3,7}, one shape
-    if (lane == 0) sel[t] = word;
+    if (lane == 0) sel[t] = word & mode_keep;
     return;
   }
   double be = e0;
@@ -494,7 +497,7 @@ bc7_select(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
   warp_argmin(be, bi2);
   if (!opaque) {
     word = (uint32_t)bi2 | (0xF0u << 12) | (1u << 20) | (1u << 22);  // modes {4,5,6,7}, layout B
-    if (lane == 0) sel[t] = word;
+    if (lane == 0) sel[t] = word & mode_keep;
     return;
   }
   // ---- three-subset shapes (opaque blocks only)
@@ -507,7 +510,7 @@ bc7_select(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
   if (y0 | y1) {
     const int s = y0 ? (__ffs(y0) - 1) : (32 + __ffs(y1) - 1);
     word = (uint32_t)bi2 | ((uint32_t)s << 6) | (0x05u << 12) | (2u << 20);  // modes {0,2}
-    if (lane == 0) sel[t] = word;
+    if (lane == 0) sel[t] = word & mode_keep;
     return;
   }
   double be3 = e0;
@@ -515,7 +518,7 @@ bc7_select(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
   if (e1 < be3) { be3 = e1; bi3 = lane + 32; }
   warp_argmin(be3, bi3);
   word = (uint32_t)bi2 | ((uint32_t)bi3 << 6) | (0xCFu << 12) | (2u << 20);  // all but modes 4,5
-  if (lane == 0) sel[t] = word;
+  if (lane == 0) sel[t] = word & mode_keep;
 }
 
 // ------------------------------------------------------------------ chains
@@ -2287,73 +2290,122 @@ void bc7_free_workspace(Bc7Workspace &ws) {
 // Blocks per internal chunk: bounds the scratch (512 B of chain results per block).
 constexpr uint32_t kChunkBlocks = 1u << 22;
 
+uint32_t bc7_max_submission() { return kChunkBlocks; }
+
+// One submission of <= kChunkBlocks blocks, in two halves so that a caller can learn the
+// submission's solid-block count (and those of earlier submissions on other streams / GPUs)
+// before the watermark base is needed:
+//   bc7_front  classify + scan, shape selection, fits, annealing; the solid count is copied to
+//              wsp.host_count and `count_ready` (if given) recorded right after the scan
+//   bc7_back   sets the watermark base and packs
+cudaError_t bc7_front(Bc7Workspace &wsp, const void *rgba_dev, uint32_t width, uint32_t first_block,
+                      uint32_t num_blocks, const EncodeParams &prm, uint32_t block_index_base, cudaStream_t stream,
+                      cudaEvent_t count_ready, uint32_t *launches) {
+  if (num_blocks == 0 || num_blocks > kChunkBlocks) return cudaErrorInvalidValue;
+  cudaError_t e = ensure_ws(wsp, ws_bytes(num_blocks) + 256);
+  if (e != cudaSuccess) return e;
+  const uint32_t *img = static_cast<const uint32_t *>(rgba_dev);
+  const uint32_t bx = width / 4, nb = num_blocks, fb = first_block;
+  Ws ws = carve(wsp.base, nb);
+  ws.wm_running = wsp.wm_running;
+  ws.counters = wsp.counters;
+#ifdef FASTC_GPU_COUNTERS
+  cudaMemsetAsync(wsp.counters, 0, 16, stream);
+#endif
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const uint32_t sa_grid = (uint32_t)sms * kSaCtasPerSm;  // persistent lanes: a multiple of the SM count
+  const uint32_t ntiles = (nb + kTile - 1) / kTile;
+  uint32_t n = 0;
+  cudaEvent_t *ev = nullptr;
+  if (wsp.timing && wsp.timed_chunks < Bc7Workspace::kMaxTimedChunks) {
+    ev = wsp.ev[wsp.timed_chunks++];
+    for (int k = 0; k < 5; k++)
+      if (!ev[k] && (e = cudaEventCreate(&ev[k])) != cudaSuccess) return e;
+    if (!wsp.ev_mid[wsp.timed_chunks - 1] && (e = cudaEventCreate(&wsp.ev_mid[wsp.timed_chunks - 1])) != cudaSuccess) return e;
+    cudaEventRecord(ev[0], stream);
+  }
+  wsp.cur_ev = ev;
+  bc7_classify<<<ntiles, kTile, 0, stream>>>(img, width, bx, fb, nb, ws.sel, ws.tile_count);
+  bc7_wm_scan<<<1, 1024, 0, stream>>>(ws.tile_count, ntiles, ws.total_solid);
+  n += 2;
+  if (count_ready) {
+    if ((e = cudaMemcpyAsync(wsp.host_count, ws.total_solid, 4, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
+    if ((e = cudaEventRecord(count_ready, stream)) != cudaSuccess) return e;
+  }
+  if (ev) cudaEventRecord(ev[1], stream);
+  bc7_select<<<(nb + kSelWarps - 1) / kSelWarps, kSelWarps * 32, 0, stream>>>(img, width, bx, fb, nb, ws.sel, ws.states,
+                                                                            prm.block_modes);
+  if (ev) cudaEventRecord(ev[2], stream);
+  const uint64_t nthreads = (uint64_t)nb * kSlots;
+  cudaMemsetAsync(ws.bins, 0, kBinWords * 4, stream);
+  bc7_setup<<<((nb + kChainThreads - 1) / kChainThreads) * kSlotGroups, kChainThreads, 0, stream>>>(
+      img, width, bx, fb, nb, ws, prm.quality, prm.seed, block_index_base);
+  n += 2;
+  if (prm.quality > 0) {
+    bc7_bin_offsets<<<1, 1, 0, stream>>>(ws.bins, sa_grid);
+    bc7_scatter<<<(uint32_t)((nthreads + 255) / 256), 256, 0, stream>>>(ws, nb);
+    if (ev) cudaEventRecord(wsp.ev_mid[wsp.timed_chunks - 1], stream);
+#ifdef FASTC_GPU_TAILSTATS
+    bc7_tail_reset<<<1, 1, 0, stream>>>();
+#endif
+    bc7_anneal<<<sa_grid, kSaThreads, 0, stream>>>(img, width, bx, fb, ws, prm.quality);
+#ifdef FASTC_GPU_TAILSTATS
+    bc7_tail_report<<<1, 1, 0, stream>>>();
+#endif
+    n += 3;
+  } else if (ev) {
+    cudaEventRecord(wsp.ev_mid[wsp.timed_chunks - 1], stream);
+  }
+  if (ev) cudaEventRecord(ev[3], stream);
+  if (launches) *launches += n;
+  return cudaGetLastError();
+}
+
+// wm_base_dev: device word holding the base (chained submissions of launch_bc7), or NULL: `wm_base`.
+cudaError_t bc7_back(Bc7Workspace &wsp, const void *rgba_dev, uint32_t width, uint32_t first_block,
+                     uint32_t num_blocks, void *out_dev, uint32_t wm_base, bool base_on_device, cudaStream_t stream,
+                     uint32_t *launches) {
+  if (num_blocks == 0 || !wsp.base) return cudaErrorInvalidValue;
+  const uint32_t *img = static_cast<const uint32_t *>(rgba_dev);
+  Ws ws = carve(wsp.base, num_blocks);
+  ws.wm_running = wsp.wm_running;
+  ws.counters = wsp.counters;
+  uint32_t n = 0;
+  if (!base_on_device) {
+    bc7_set_u32<<<1, 1, 0, stream>>>(wsp.wm_running, wm_base);
+    n++;
+  }
+  bc7_pack<<<(num_blocks + 127) / 128, 128, 0, stream>>>(img, width, width / 4, first_block, num_blocks, ws,
+                                                         static_cast<uint8_t *>(out_dev));
+  n++;
+  if (wsp.cur_ev) cudaEventRecord(wsp.cur_ev[4], stream);
+  wsp.cur_ev = nullptr;
+  if (launches) *launches += n;
+  return cudaGetLastError();
+}
+
 cudaError_t launch_bc7(Bc7Workspace &wsp, const void *rgba_dev, uint32_t width, uint32_t height,
-                       uint32_t first_block, uint32_t num_blocks, void *out_dev, int quality, uint64_t seed,
+                       uint32_t first_block, uint32_t num_blocks, void *out_dev, const EncodeParams &prm,
                        uint32_t wm_base, uint32_t block_index_base, cudaStream_t stream, uint32_t *launches) {
   (void)height;
   if (num_blocks == 0) return cudaSuccess;
   const uint32_t chunk = num_blocks < kChunkBlocks ? num_blocks : kChunkBlocks;
   cudaError_t e = ensure_ws(wsp, ws_bytes(chunk) + 256);
   if (e != cudaSuccess) return e;
-  const uint32_t *img = static_cast<const uint32_t *>(rgba_dev);
-  const uint32_t bx = width / 4;
   // The running watermark base lives on the device, so chunks chain without a host sync.
   uint32_t n = 0;
-  Ws ws = carve(wsp.base, chunk);
-  ws.wm_running = wsp.wm_running;
-  ws.counters = wsp.counters;
-#ifdef FASTC_GPU_COUNTERS
-  cudaMemsetAsync(wsp.counters, 0, 16, stream);
-#endif
   bc7_set_u32<<<1, 1, 0, stream>>>(wsp.wm_running, wm_base);
   n++;
   wsp.timed_chunks = 0;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const uint32_t sa_grid = (uint32_t)sms * kSaCtasPerSm;  // persistent lanes: a multiple of the SM count
   for (uint32_t off = 0; off < num_blocks; off += chunk) {
     const uint32_t nb = num_blocks - off < chunk ? num_blocks - off : chunk;
     const uint32_t fb = first_block + off;
-    const uint32_t ntiles = (nb + kTile - 1) / kTile;
-    cudaEvent_t *ev = nullptr;
-    if (wsp.timing && wsp.timed_chunks < Bc7Workspace::kMaxTimedChunks) {
-      ev = wsp.ev[wsp.timed_chunks++];
-      for (int k = 0; k < 5; k++)
-        if (!ev[k] && (e = cudaEventCreate(&ev[k])) != cudaSuccess) return e;
-      if (!wsp.ev_mid[wsp.timed_chunks - 1] && (e = cudaEventCreate(&wsp.ev_mid[wsp.timed_chunks - 1])) != cudaSuccess) return e;
-      cudaEventRecord(ev[0], stream);
-    }
-    bc7_classify<<<ntiles, kTile, 0, stream>>>(img, width, bx, fb, nb, ws.sel, ws.tile_count);
-    bc7_wm_scan<<<1, 1024, 0, stream>>>(ws.tile_count, ntiles, ws.total_solid);
-    if (ev) cudaEventRecord(ev[1], stream);
-    bc7_select<<<(nb + kSelWarps - 1) / kSelWarps, kSelWarps * 32, 0, stream>>>(img, width, bx, fb, nb, ws.sel, ws.states);
-    if (ev) cudaEventRecord(ev[2], stream);
-    const uint64_t nthreads = (uint64_t)nb * kSlots;
-    cudaMemsetAsync(ws.bins, 0, kBinWords * 4, stream);
-    bc7_setup<<<((nb + kChainThreads - 1) / kChainThreads) * kSlotGroups, kChainThreads, 0, stream>>>(
-        img, width, bx, fb, nb, ws, quality, seed, block_index_base);
-    n++;
-    if (quality > 0) {
-      bc7_bin_offsets<<<1, 1, 0, stream>>>(ws.bins, sa_grid);
-      bc7_scatter<<<(uint32_t)((nthreads + 255) / 256), 256, 0, stream>>>(ws, nb);
-      if (ev) cudaEventRecord(wsp.ev_mid[wsp.timed_chunks - 1], stream);
-#ifdef FASTC_GPU_TAILSTATS
-      bc7_tail_reset<<<1, 1, 0, stream>>>();
-#endif
-      bc7_anneal<<<sa_grid, kSaThreads, 0, stream>>>(img, width, bx, fb, ws, quality);
-#ifdef FASTC_GPU_TAILSTATS
-      bc7_tail_report<<<1, 1, 0, stream>>>();
-#endif
-      n += 3;
-    } else if (ev) {
-      cudaEventRecord(wsp.ev_mid[wsp.timed_chunks - 1], stream);
-    }
-    if (ev) cudaEventRecord(ev[3], stream);
-    bc7_pack<<<(nb + 127) / 128, 128, 0, stream>>>(img, width, bx, fb, nb, ws, static_cast<uint8_t *>(out_dev));
-    if (ev) cudaEventRecord(ev[4], stream);
-    n += 4;
+    if ((e = bc7_front(wsp, rgba_dev, width, fb, nb, prm, block_index_base, stream, nullptr, &n)) != cudaSuccess) return e;
+    if ((e = bc7_back(wsp, rgba_dev, width, fb, nb, out_dev, 0, true, stream, &n)) != cudaSuccess) return e;
     if (off + chunk < num_blocks) {
+      Ws ws = carve(wsp.base, nb);
       bc7_add_u32<<<1, 1, 0, stream>>>(wsp.wm_running, ws.total_solid);
       n++;
     }

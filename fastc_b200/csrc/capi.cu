@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -79,6 +80,18 @@ struct DeviceCtx {
   uint8_t *pend_dst[kPipeDepth] = {};  // copy-out the slot still owes the caller
   size_t pend_bytes[kPipeDepth] = {};
   unsigned long long *psnr_sum = nullptr, *psnr_host = nullptr;  // device / pinned accumulators of fastc_gpu_psnr*
+  // BC7 host path: the chunk in a slot is packed once the watermark base is known (complete_piece)
+  cudaEvent_t ev_count[kPipeDepth] = {};
+  struct Pending {
+    bool active = false;
+    int piece = 0;                 // index in the submission's WmChain
+    uint32_t lo = 0, nblk = 0, height = 0;
+    uint8_t *dst = nullptr;        // caller memory of the chunk's first encoded block
+  } pending[kPipeDepth];
+  // The device API's BC7 scratch (bc7ws[kPipeDepth]) is shared by every caller stream of the device:
+  // each use waits for the previous one (api_done) before it touches the scratch
+  cudaEvent_t api_done = nullptr;
+  bool api_used = false;
   std::mutex mu;
 };
 
@@ -115,6 +128,7 @@ int ensure_ctx(int dev) {
     CU_TRY(cudaStreamCreateWithFlags(&c.streams[i], cudaStreamNonBlocking));
     CU_TRY(cudaEventCreate(&c.ev_start[i]));
     CU_TRY(cudaEventCreate(&c.ev_stop[i]));
+    CU_TRY(cudaEventCreateWithFlags(&c.ev_count[i], cudaEventDisableTiming));
   }
   c.ready = true;
   return 0;
@@ -140,11 +154,11 @@ int check_dims(int format, uint32_t width, uint32_t height) {
   return 0;
 }
 
-// Enqueue every kernel needed to encode [first_block, first_block+num_blocks)
-// on `stream` of the current device.
-int enqueue(int dev, int ws_slot, int format, const void *rgba_dev, uint32_t width, uint32_t height,
-            uint32_t first_block, uint32_t num_blocks, void *out_dev, int quality, uint64_t seed,
-            uint32_t wm_base, uint32_t block_index_base, cudaStream_t stream, uint32_t *launches) {
+// Device API: enqueue every kernel needed to encode [first_block, first_block+num_blocks) on
+// `stream` of the current device.
+int enqueue(int dev, int format, const void *rgba_dev, uint32_t width, uint32_t height, uint32_t first_block,
+            uint32_t num_blocks, void *out_dev, const EncodeParams &prm, uint32_t wm_base, uint32_t block_index_base,
+            cudaStream_t stream, uint32_t *launches) {
   uint32_t n = 0;
   switch (format) {
     case FASTC_GPU_DXT1:
@@ -153,14 +167,19 @@ int enqueue(int dev, int ws_slot, int format, const void *rgba_dev, uint32_t wid
       n = num_blocks ? 1 : 0;
       break;
     case FASTC_GPU_ETC1:
-      CU_TRY(launch_etc1(rgba_dev, width, first_block, num_blocks, out_dev, stream));
+      CU_TRY(launch_etc1(rgba_dev, width, first_block, num_blocks, out_dev, prm.etc1_quality, stream));
       n = num_blocks ? 1 : 0;
       break;
     case FASTC_GPU_BPTC: {
       DeviceCtx &c = g_ctx[dev];
       std::lock_guard<std::mutex> lk(c.mu);
-      CU_TRY(launch_bc7(c.bc7ws[ws_slot], rgba_dev, width, height, first_block, num_blocks, out_dev, quality, seed,
-                        wm_base, block_index_base, stream, &n));
+      // one scratch for every caller stream of the device: order this use after the previous one
+      if (!c.api_done) CU_TRY(cudaEventCreateWithFlags(&c.api_done, cudaEventDisableTiming));
+      if (c.api_used) CU_TRY(cudaStreamWaitEvent(stream, c.api_done, 0));
+      CU_TRY(launch_bc7(c.bc7ws[kPipeDepth], rgba_dev, width, height, first_block, num_blocks, out_dev, prm, wm_base,
+                        block_index_base, stream, &n));
+      CU_TRY(cudaEventRecord(c.api_done, stream));
+      c.api_used = true;
       break;
     }
   }
@@ -168,51 +187,160 @@ int enqueue(int dev, int ws_slot, int format, const void *rgba_dev, uint32_t wid
   return 0;
 }
 
-// Solid-colour blocks in the raster range [lo, hi) of a host image (64 B compare per
-// block, split over a few host threads).  Solid-ness depends on the input only, so
-// the BC7 watermark order (Compressor.cpp:135-140,1457) can be fixed before encoding.
-uint32_t host_count_solid(const uint8_t *rgba_host, uint32_t width, uint32_t lo, uint32_t hi) {
-  if (hi <= lo) return 0;
-  const uint32_t bx = width / 4;
-  const uint32_t *img = reinterpret_cast<const uint32_t *>(rgba_host);
-  auto count = [&](uint32_t a, uint32_t b) {
-    uint32_t cnt = 0;
-    for (uint32_t bi = a; bi < b; bi++) {
-      const uint32_t *p = img + (size_t)(bi / bx) * 4 * width + (size_t)(bi % bx) * 4;
-      const uint32_t v = p[0];
-      bool same = true;
-      for (int j = 0; j < 4 && same; j++)
-        for (int i = 0; i < 4; i++)
-          if (p[(size_t)j * width + i] != v) { same = false; break; }
-      cnt += same;
-    }
-    return cnt;
-  };
-  const uint32_t n = hi - lo;
-  const int nt = (int)std::min<uint32_t>(8, std::max<uint32_t>(1, n >> 16));
-  if (nt == 1) return count(lo, hi);
-  std::vector<uint32_t> part(nt, 0);
-  std::vector<std::thread> th;
-  for (int k = 0; k < nt; k++)
-    th.emplace_back([&, k] {
-      part[k] = count(lo + (uint32_t)((uint64_t)n * k / nt), lo + (uint32_t)((uint64_t)n * (k + 1) / nt));
-    });
-  for (auto &t : th) t.join();
-  uint32_t total = 0;
-  for (uint32_t c : part) total += c;
-  return total;
+// Solid-colour blocks of block row `row`, columns [c0, c1) of a host image (64 B compare per block).
+uint32_t host_count_solid_row(const uint32_t *img, uint32_t width, uint32_t row, uint32_t c0, uint32_t c1) {
+  uint32_t cnt = 0;
+  const uint32_t *base = img + (size_t)row * 4 * width;
+  for (uint32_t b = c0; b < c1; b++) {
+    const uint32_t *p = base + (size_t)b * 4;
+    const uint32_t v = p[0];
+    bool same = true;
+    for (int j = 0; j < 4 && same; j++)
+      for (int i = 0; i < 4; i++)
+        if (p[(size_t)j * width + i] != v) { same = false; break; }
+    cnt += same;
+  }
+  return cnt;
 }
+
+// BC7 watermark order (Compressor.cpp:135-140,1457): the word a solid block carries is the number
+// of solid blocks before it in raster order over the WHOLE image, so a sub-range submission
+// (first_block > 0: one CompressionFunc call of a ThreadGroup-style split) needs the solid count of
+// the blocks before it, which never reach the GPU.  Those are counted on the host, once: the
+// per-block-row cumulative counts of the last image are kept, so T ranged calls on one image scan
+// it once in total instead of O(T^2 / 2) times.  The entry is keyed by (pointer, size) and checked
+// against a fingerprint of sampled pixels of the scanned rows; the watermark is a signature in
+// otherwise unused index bits and never changes a decoded pixel.
+struct PrefixCache {
+  std::mutex mu;
+  const uint8_t *ptr = nullptr;
+  uint32_t width = 0, height = 0;
+  std::vector<uint32_t> cum;  // cum[r] = solid blocks in block rows [0, r); rows scanned = cum.size() - 1
+  uint64_t fingerprint = 0;
+} g_prefix;
+
+uint64_t sample_fingerprint(const uint32_t *img, uint32_t width, uint32_t rows_scanned) {
+  const uint64_t npix = (uint64_t)rows_scanned * 4 * width;
+  uint64_t h = 0x9E3779B97F4A7C15ull ^ npix, x = 0x2545F4914F6CDD1Dull;
+  for (int k = 0; k < 2048 && npix; k++) {
+    x ^= x << 13; x ^= x >> 7; x ^= x << 17;  // xorshift64
+    h = (h ^ img[x % npix]) * 0x100000001B3ull;
+  }
+  return h;
+}
+
+uint32_t host_prefix_solid(const uint8_t *rgba_host, uint32_t width, uint32_t height, uint32_t first_block) {
+  if (first_block == 0) return 0;
+  const uint32_t bx = width / 4, row = first_block / bx, rem = first_block % bx;
+  const uint32_t *img = reinterpret_cast<const uint32_t *>(rgba_host);
+  std::lock_guard<std::mutex> lk(g_prefix.mu);
+  PrefixCache &pc = g_prefix;
+  const bool hit = pc.ptr == rgba_host && pc.width == width && pc.height == height && !pc.cum.empty() &&
+                   sample_fingerprint(img, width, (uint32_t)pc.cum.size() - 1) == pc.fingerprint;
+  if (!hit) {
+    pc.ptr = rgba_host; pc.width = width; pc.height = height;
+    pc.cum.assign(1, 0u);
+  }
+  const uint32_t done = (uint32_t)pc.cum.size() - 1;
+  if (row > done) {  // extend the scan to the rows before `row` (memory-bound: a few host threads)
+    const uint32_t n = row - done;
+    std::vector<uint32_t> cnt(n);
+    const int nt = (int)std::min<uint32_t>(8, std::max<uint32_t>(1, (uint32_t)(((uint64_t)n * bx) >> 16)));
+    auto work = [&](int k) {
+      for (uint32_t r = (uint32_t)((uint64_t)n * k / nt); r < (uint32_t)((uint64_t)n * (k + 1) / nt); r++)
+        cnt[r] = host_count_solid_row(img, width, done + r, 0, bx);
+    };
+    std::vector<std::thread> th;
+    for (int k = 1; k < nt; k++) th.emplace_back(work, k);
+    work(0);
+    for (auto &t : th) t.join();
+    for (uint32_t r = 0; r < n; r++) pc.cum.push_back(pc.cum.back() + cnt[r]);
+  }
+  if (!hit || row > done) pc.fingerprint = sample_fingerprint(img, width, (uint32_t)pc.cum.size() - 1);
+  return pc.cum[row] + (rem ? host_count_solid_row(img, width, row, 0, rem) : 0u);
+}
+
+// Watermark bases of one host submission.  Its pieces (the pipeline chunks of every GPU's slab,
+// numbered in raster order) are encoded concurrently; piece p packs with
+//   base(p) = blocks before the submission + solid blocks of pieces 0 .. p-1,
+// each count coming from the piece's own classification pass on its GPU (no host scan of the
+// pixels, no GPU waits for another: only the pack, the last and cheapest kernel, needs the base).
+struct WmChain {
+  std::mutex mu;
+  std::condition_variable cv;
+  uint32_t before = 0;
+  std::vector<uint32_t> counts;
+  std::vector<char> known;
+  bool failed = false;
+  void resize(size_t n) { counts.assign(n, 0); known.assign(n, 0); }
+  size_t size() const { return counts.size(); }
+  void publish(int p, uint32_t n) {
+    { std::lock_guard<std::mutex> lk(mu); counts[p] = n; known[p] = 1; }
+    cv.notify_all();
+  }
+  void fail_all() {
+    { std::lock_guard<std::mutex> lk(mu); failed = true; }
+    cv.notify_all();
+  }
+  bool base_of(int p, uint32_t *base) {  // false: a piece it depends on failed
+    std::unique_lock<std::mutex> lk(mu);
+    cv.wait(lk, [&] {
+      if (failed) return true;
+      for (int i = 0; i < p; i++) if (!known[i]) return false;
+      return true;
+    });
+    if (failed) return false;
+    uint32_t b = before;
+    for (int i = 0; i < p; i++) b += counts[i];
+    *base = b;
+    return true;
+  }
+};
 
 struct Shard {
   int dev;
   uint32_t first_block, num_blocks;  // within the image
-  uint32_t wm_base = 0;
+  int piece0 = 0;                    // first piece of the slab in the submission's WmChain
+  std::vector<uint32_t> bounds;      // chunk k covers block rows [bounds[k], bounds[k + 1])
   double kernel_ms = 0;
   uint32_t launches = 0;
   uint64_t h2d = 0, d2h = 0;
   int rc = 0;
   char err[512] = "";
 };
+
+// The pipeline chunks of a slab, in whole block rows.
+void plan_chunks(Shard &s, int format, uint32_t width, uint32_t chunk_blocks) {
+  s.bounds.clear();
+  if (s.num_blocks == 0) return;
+  const uint32_t bx = width / 4;
+  const uint32_t row0 = s.first_block / bx;
+  const uint32_t row1 = (s.first_block + s.num_blocks + bx - 1) / bx;
+  const uint32_t total_rows = row1 - row0;
+  uint32_t rows_per_chunk;
+  if (chunk_blocks == 0 && format == FASTC_GPU_BPTC) {
+    // BC7 is compute-bound (copies are ~1% of the time): no chunking unless asked for
+    rows_per_chunk = total_rows;
+  } else if (chunk_blocks == 0) {
+    // auto: ~4 Mi pixels per chunk keeps the copy engines busy without making the pipeline too coarse
+    rows_per_chunk = (1u << 18) / bx;
+  } else {
+    rows_per_chunk = chunk_blocks / bx;
+  }
+  if (format == FASTC_GPU_BPTC) rows_per_chunk = std::min(rows_per_chunk, bc7_max_submission() / bx);  // scratch bound
+  rows_per_chunk = std::max<uint32_t>(1, rows_per_chunk);
+  for (uint32_t r = row0; r < row1; r += rows_per_chunk) s.bounds.push_back(r);
+  s.bounds.push_back(row1);
+  if (chunk_blocks == 0 && format == FASTC_GPU_BPTC && s.bounds.size() == 2 && total_rows >= 64 &&
+      (size_t)total_rows * 4 * width * 4 >= ((size_t)96 << 20)) {
+    // BC7 auto, big uploads (>= 96 MiB, ~2 ms on the wire): two halves on two streams.  The second
+    // half's upload and shape selection / fits run under the first half's annealing, the first
+    // half's download under the second's kernels, and each half is still large enough for the
+    // persistent annealing kernel's ~1.5 ms tail not to matter.  Measured at 8192^2
+    // (tools/time_e2e_chunks.py): one chunk 238.9 ms, two halves 236.6 ms, 1/16 + 15/16 250.4 ms.
+    s.bounds.assign({row0, row0 + total_rows / 2, row1});
+  }
+}
 
 // Host->host for one GPU's slab.  The slab is cut into chunks of whole block
 // rows; chunk k uses staging slot k % kPipeDepth, so its H2D overlaps the
@@ -286,6 +414,27 @@ int download(DeviceCtx &c, int slot, uint8_t *dst, const void *src_dev, size_t b
   return 0;
 }
 
+// BC7: packs the chunk waiting in `slot` -- publishes its solid count if a later piece needs it,
+// waits for the counts of the pieces before it, then enqueues the pack and the download.
+int complete_piece(DeviceCtx &c, int slot, uint32_t width, WmChain &chain, Shard &s) {
+  DeviceCtx::Pending &p = c.pending[slot];
+  if (!p.active) return 0;
+  p.active = false;
+  cudaStream_t st = c.streams[slot];
+  if ((size_t)p.piece + 1 < chain.size()) {
+    CU_TRY(cudaEventSynchronize(c.ev_count[slot]));  // recorded right after the chunk's classification
+    chain.publish(p.piece, *c.bc7ws[slot].host_count);
+  }
+  uint32_t base = 0;
+  if (!chain.base_of(p.piece, &base)) return fail("an earlier part of the submission failed");
+  CU_TRY(bc7_back(c.bc7ws[slot], c.in_buf[slot], width, p.lo, p.nblk, c.out_buf[slot], base, false, st, &s.launches));
+  CU_TRY(cudaEventRecord(c.ev_stop[slot], st));
+  const size_t bytes = (size_t)p.nblk * 16;
+  if (download(c, slot, p.dst, (uint8_t *)c.out_buf[slot] + (size_t)p.lo * 16, bytes, st)) return 1;
+  s.d2h += bytes;
+  return 0;
+}
+
 // Waits for the chunk in `slot`, books its kernel time and hands over a staged download.
 int finish_slot(DeviceCtx &c, int slot, double *kernel_ms) {
   if (!c.slot_busy[slot]) return 0;
@@ -309,49 +458,31 @@ int drain_slots(DeviceCtx &c, double *kernel_ms) {
   return 0;
 }
 
+// Error path: nothing of a failed submission may linger in the slots (a later submission would
+// otherwise copy stale bytes into this caller's, possibly freed, buffer).
+void abort_slots(DeviceCtx &c) {
+  for (int slot = 0; slot < kPipeDepth; slot++) {
+    if (c.streams[slot]) cudaStreamSynchronize(c.streams[slot]);
+    c.slot_busy[slot] = false;
+    c.pending[slot].active = false;
+    c.pend_dst[slot] = nullptr;
+    c.pend_bytes[slot] = 0;
+  }
+  cudaGetLastError();
+}
+
 // drain = false leaves the last chunks in flight (batch submissions: the caller drains once at
 // the end, so consecutive textures overlap).
-int run_shard(Shard &s, int format, const uint8_t *rgba_host, uint32_t width, uint32_t height,
-              uint8_t *out_host, int quality, uint64_t seed, uint32_t chunk_blocks, bool drain = true) {
-  if (ensure_ctx(s.dev)) return 1;
+int run_shard_impl(Shard &s, int format, const uint8_t *rgba_host, uint32_t width, uint32_t height,
+                   uint8_t *out_host, const EncodeParams &prm, WmChain &chain, bool drain) {
+  (void)height;
   DeviceCtx &c = g_ctx[s.dev];
   const uint32_t bx = width / 4;
   const uint32_t bsz = fastc_gpu_block_bytes(format);
-  // Work in whole block rows: rows [row0, row1) cover the shard's block range.
-  const uint32_t row0 = s.first_block / bx;
-  const uint32_t row1 = (s.first_block + s.num_blocks + bx - 1) / bx;
-  uint32_t rows_per_chunk;
-  if (chunk_blocks == 0 && format == FASTC_GPU_BPTC) {
-    // BC7 is compute-bound (copies are ~1% of the time) and its watermark chain is kept
-    // on the device inside one submission: no host-side chunking unless asked for.
-    rows_per_chunk = row1 - row0;
-  } else if (chunk_blocks == 0) {
-    // auto: ~4 Mi pixels per chunk keeps the copy engines busy without making the
-    // pipeline too coarse.
-    rows_per_chunk = std::max<uint32_t>(1, (1u << 18) / bx);
-  } else {
-    rows_per_chunk = std::max<uint32_t>(1, chunk_blocks / bx);
-  }
-  const uint32_t total_rows = row1 - row0;
-  rows_per_chunk = std::max<uint32_t>(1, rows_per_chunk);
-  // chunk k covers block rows [bounds[k], bounds[k + 1])
-  std::vector<uint32_t> bounds;
-  for (uint32_t r = row0; r < row1; r += rows_per_chunk) bounds.push_back(r);
-  bounds.push_back(row1);
-  if (chunk_blocks == 0 && format == FASTC_GPU_BPTC && total_rows >= 64 &&
-      (size_t)total_rows * 4 * width * 4 >= ((size_t)96 << 20)) {
-    // BC7 auto, big uploads (>= 96 MiB, ~2 ms on the wire): two halves on two streams.  The second
-    // half's upload and shape selection / fits run under the first half's annealing, the first
-    // half's download under the second's kernels, and each half is still large enough for the
-    // persistent annealing kernel's ~1.5 ms tail not to matter.  Measured at 8192^2
-    // (tools/time_e2e_chunks.py): one chunk 238.9 ms, two halves 236.6 ms, 1/16 + 15/16 250.4 ms.
-    bounds.assign({row0, row0 + total_rows / 2, row1});
-  }
-  const uint32_t nchunks = (uint32_t)bounds.size() - 1;
-  // BC7's watermark chain needs the solid-block count of every earlier chunk;
-  // bc7 tracks that itself when the whole shard is submitted as one range, so
-  // BPTC shards are uploaded chunk-wise but encoded per chunk with a running base.
-  uint32_t wm_base = s.wm_base;
+  const uint32_t nchunks = s.bounds.empty() ? 0 : (uint32_t)s.bounds.size() - 1;
+  if (nchunks == 0) return 0;
+  const uint32_t row0 = s.bounds.front(), row1 = s.bounds.back();
+  const bool bc7 = format == FASTC_GPU_BPTC;
 
   // nothing in flight (every submission except the later textures of a batch): restart the slot
   // rotation, so that the same chunk lands in the same slot call after call and its staging
@@ -359,14 +490,21 @@ int run_shard(Shard &s, int format, const uint8_t *rgba_host, uint32_t width, ui
   bool idle = true;
   for (int i = 0; i < kPipeDepth; i++) idle = idle && !c.slot_busy[i];
   if (idle) c.next_chunk = 0;
+  int slots[kPipeDepth];  // slots of the chunks whose pack is still owed, oldest first
+  int nowed = 0;
   for (uint32_t k = 0; k < nchunks; k++) {
     const int slot = (int)(c.next_chunk++ % kPipeDepth);
     cudaStream_t st = c.streams[slot];
-    const uint32_t r0 = bounds[k], r1 = bounds[k + 1];
+    const uint32_t r0 = s.bounds[k], r1 = s.bounds[k + 1];
     const size_t in_bytes = (size_t)(r1 - r0) * 4 * width * 4;
     const size_t out_bytes = (size_t)(r1 - r0) * bx * bsz;
-    // slot reuse: the slot's previous chunk must have finished (its timing is booked and a staged
-    // download handed over) before its buffers are overwritten or regrown
+    // slot reuse: the slot's previous chunk must be packed and finished (its timing booked, a
+    // staged download handed over) before its buffers are overwritten or regrown
+    if (nowed == kPipeDepth) {  // the oldest owed pack sits in this very slot
+      if (complete_piece(c, slots[0], width, chain, s)) return 1;
+      for (int i = 1; i < nowed; i++) slots[i - 1] = slots[i];
+      nowed--;
+    }
     if (finish_slot(c, slot, &s.kernel_ms)) return 1;
     if (c.in_cap[slot] < in_bytes || c.out_cap[slot] < out_bytes) {
       CU_TRY(cudaStreamSynchronize(st));
@@ -380,33 +518,73 @@ int run_shard(Shard &s, int format, const uint8_t *rgba_host, uint32_t width, ui
     uint32_t lo = (k == 0) ? s.first_block - row0 * bx : 0;
     uint32_t hi = (r1 - r0) * bx;
     if (r1 == row1) hi = s.first_block + s.num_blocks - r0 * bx;
-    uint32_t solid = 0;
-    if (format == FASTC_GPU_BPTC && nchunks > 1) {
-      // need this chunk's solid count before the next chunk can be packed
-      if (fastc_gpu_count_solid_device(c.in_buf[slot], width, (r1 - r0) * 4, lo, hi - lo, st, &solid)) return 1;
-      s.launches += 1;
-    }
+    uint8_t *dst = out_host + ((size_t)r0 * bx + lo) * bsz;
     CU_TRY(cudaEventRecord(c.ev_start[slot], st));
-    if (enqueue(s.dev, slot, format, c.in_buf[slot], width, (r1 - r0) * 4, lo, hi - lo, c.out_buf[slot], quality,
-                seed, wm_base, r0 * bx, st, &s.launches))
-      return 1;
-    CU_TRY(cudaEventRecord(c.ev_stop[slot], st));
     c.slot_busy[slot] = true;
-    wm_base += solid;
-    if (download(c, slot, out_host + ((size_t)r0 * bx + lo) * bsz, (uint8_t *)c.out_buf[slot] + (size_t)lo * bsz,
-                 (size_t)(hi - lo) * bsz, st))
-      return 1;
-    s.d2h += (size_t)(hi - lo) * bsz;
+    if (bc7) {
+      // everything but the pack; the chunk's solid count travels to the host right after its
+      // classification when a later piece of the submission needs it
+      const int piece = s.piece0 + (int)k;
+      const bool later = (size_t)piece + 1 < chain.size();
+      CU_TRY(bc7_front(c.bc7ws[slot], c.in_buf[slot], width, lo, hi - lo, prm, r0 * bx, st,
+                       later ? c.ev_count[slot] : nullptr, &s.launches));
+      DeviceCtx::Pending &p = c.pending[slot];
+      p.active = true; p.piece = piece; p.lo = lo; p.nblk = hi - lo; p.height = (r1 - r0) * 4; p.dst = dst;
+      slots[nowed++] = slot;
+      CU_TRY(cudaEventRecord(c.ev_stop[slot], st));  // (re-recorded after the pack)
+    } else {
+      EncodeParams none = prm;
+      if (enqueue(s.dev, format, c.in_buf[slot], width, (r1 - r0) * 4, lo, hi - lo, c.out_buf[slot], none, 0, 0, st,
+                  &s.launches))
+        return 1;
+      CU_TRY(cudaEventRecord(c.ev_stop[slot], st));
+      if (download(c, slot, dst, (uint8_t *)c.out_buf[slot] + (size_t)lo * bsz, (size_t)(hi - lo) * bsz, st)) return 1;
+      s.d2h += (size_t)(hi - lo) * bsz;
+    }
   }
+  for (int i = 0; i < nowed; i++)
+    if (complete_piece(c, slots[i], width, chain, s)) return 1;
   if (drain && drain_slots(c, &s.kernel_ms)) return 1;
   return 0;
 }
 
+int run_shard(Shard &s, int format, const uint8_t *rgba_host, uint32_t width, uint32_t height, uint8_t *out_host,
+              const EncodeParams &prm, WmChain &chain, bool drain = true) {
+  if (ensure_ctx(s.dev)) {
+    chain.fail_all();
+    return 1;
+  }
+  const int rc = run_shard_impl(s, format, rgba_host, width, height, out_host, prm, chain, drain);
+  if (rc) {
+    chain.fail_all();  // pieces of other GPUs that wait for this slab's counts give up
+    abort_slots(g_ctx[s.dev]);
+  }
+  return rc;
+}
+
 int run_shard_locked(Shard &s, int format, const uint8_t *rgba_host, uint32_t width, uint32_t height,
-                     uint8_t *out_host, int quality, uint64_t seed, uint32_t chunk_blocks) {
-  if (s.dev < 0 || s.dev >= kMaxDevices) return fail("bad device %d", s.dev);
+                     uint8_t *out_host, const EncodeParams &prm, WmChain &chain) {
+  if (s.dev < 0 || s.dev >= kMaxDevices) {
+    chain.fail_all();
+    return fail("bad device %d", s.dev);
+  }
   std::lock_guard<std::mutex> lk(g_ctx[s.dev].host_mu);
-  return run_shard(s, format, rgba_host, width, height, out_host, quality, seed, chunk_blocks);
+  return run_shard(s, format, rgba_host, width, height, out_host, prm, chain);
+}
+
+// Block range checks shared by the entry points (no 32-bit wrap).
+int check_range(uint32_t width, uint32_t height, uint32_t first_block, uint32_t *num_blocks) {
+  const uint32_t total = (width / 4) * (height / 4);
+  if (first_block > total) return fail("first_block %u beyond the image's %u blocks", first_block, total);
+  if (*num_blocks == 0) *num_blocks = total - first_block;
+  if (*num_blocks > total - first_block) return fail("block range exceeds the image");
+  return 0;
+}
+
+int current_device(int *dev) {
+  CU_TRY(cudaGetDevice(dev));
+  if (*dev < 0 || *dev >= kMaxDevices) return fail("device index %d not supported (at most %d devices)", *dev, kMaxDevices);
+  return 0;
 }
 
 }  // namespace
@@ -476,65 +654,75 @@ uint64_t fastc_gpu_compressed_size(int format, uint32_t width, uint32_t height) 
   return (uint64_t)((width + 3) / 4) * ((height + 3) / 4) * fastc_gpu_block_bytes(format);
 }
 
-int fastc_gpu_compress_device(int format, const void *rgba_dev, uint32_t width, uint32_t height,
-                              uint32_t first_block, uint32_t num_blocks, void *out_dev, int quality,
-                              uint64_t seed, uint32_t wm_base, uint32_t block_index_base, void *cuda_stream,
-                              uint32_t *launches_out) {
+namespace {
+
+// The settings one submission runs with: the per-call arguments plus the thread's BPTC options.
+EncodeParams make_params(int quality, uint64_t seed, const fastc_gpu_options *opt) {
+  EncodeParams prm;
+  prm.quality = quality;
+  prm.seed = seed;
+  if (opt) {
+    prm.block_modes = opt->bptc_block_modes & 0xFFu;
+    prm.error_metric = opt->bptc_error_metric;
+    prm.etc1_quality = opt->etc1_quality;
+  }
+  return prm;
+}
+
+int check_options(const fastc_gpu_options *opt) {
+  if (!opt) return 0;
+  if (opt->struct_size != sizeof(fastc_gpu_options)) return fail("fastc_gpu_options::struct_size does not match this library");
+  if (opt->bptc_error_metric != 0 && opt->bptc_error_metric != 1) return fail("unknown BPTC error metric %d", opt->bptc_error_metric);
+  if (opt->etc1_quality < 0 || opt->etc1_quality > 2) return fail("unknown ETC1 quality %d", opt->etc1_quality);
+  if ((opt->bptc_block_modes & 0xFFu) == 0) return fail("BPTC block-mode mask selects no mode");
+  return 0;
+}
+
+int compress_device_impl(int format, const void *rgba_dev, uint32_t width, uint32_t height, uint32_t first_block,
+                         uint32_t num_blocks, void *out_dev, int quality, uint64_t seed, uint32_t wm_base,
+                         uint32_t block_index_base, void *cuda_stream, uint32_t *launches_out,
+                         const fastc_gpu_options *opt) {
   if (check_dims(format, width, height)) return 1;
-  const uint32_t total = (width / 4) * (height / 4);
-  if (first_block > total) return fail("first_block %u beyond the image's %u blocks", first_block, total);
-  if (num_blocks == 0) num_blocks = total - first_block;
-  if (first_block + num_blocks > total) return fail("block range exceeds the image");
+  if (check_range(width, height, first_block, &num_blocks)) return 1;
   if (!rgba_dev || !out_dev) return fail("null device pointer");
   if (quality < 0) return fail("quality must be >= 0");
+  if (check_options(opt)) return 1;
   int dev = 0;
-  CU_TRY(cudaGetDevice(&dev));
-  if (dev >= kMaxDevices) return fail("device index %d not supported", dev);
+  if (current_device(&dev)) return 1;
   if (ensure_tables(dev)) return 1;
   uint32_t n = 0;
-  if (enqueue(dev, kPipeDepth, format, rgba_dev, width, height, first_block, num_blocks, out_dev, quality, seed, wm_base,
-              block_index_base, static_cast<cudaStream_t>(cuda_stream), &n))
+  if (enqueue(dev, format, rgba_dev, width, height, first_block, num_blocks, out_dev, make_params(quality, seed, opt),
+              wm_base, block_index_base, static_cast<cudaStream_t>(cuda_stream), &n))
     return 1;
   if (launches_out) *launches_out = n;
   return 0;
 }
 
-int fastc_gpu_count_solid_device(const void *rgba_dev, uint32_t width, uint32_t height, uint32_t first_block,
-                                 uint32_t num_blocks, void *cuda_stream, uint32_t *count_out) {
-  if (check_dims(FASTC_GPU_BPTC, width, height)) return 1;
-  int dev = 0;
-  CU_TRY(cudaGetDevice(&dev));
-  if (ensure_tables(dev)) return 1;
-  DeviceCtx &c = g_ctx[dev];
-  std::lock_guard<std::mutex> lk(c.mu);
-  CU_TRY(bc7_count_solid(c.bc7ws[kPipeDepth], rgba_dev, width, first_block, num_blocks, static_cast<cudaStream_t>(cuda_stream),
-                         count_out));
-  return 0;
-}
-
-int fastc_gpu_compress(int format, const uint8_t *rgba_host, uint32_t width, uint32_t height,
-                       uint32_t first_block, uint32_t num_blocks, uint8_t *out_host, int quality, uint64_t seed,
-                       uint32_t chunk_blocks, int num_gpus, fastc_gpu_timing *timing) {
+int compress_impl(int format, const uint8_t *rgba_host, uint32_t width, uint32_t height, uint32_t first_block,
+                  uint32_t num_blocks, uint8_t *out_host, int quality, uint64_t seed, uint32_t chunk_blocks,
+                  int num_gpus, fastc_gpu_timing *timing, const fastc_gpu_options *opt) {
   auto t0 = std::chrono::steady_clock::now();
   if (check_dims(format, width, height)) return 1;
   if (!rgba_host || !out_host) return fail("null host pointer");
   if (quality < 0) return fail("quality must be >= 0");
-  const uint32_t bx = width / 4, total = bx * (height / 4);
-  if (first_block > total) return fail("first_block %u beyond the image's %u blocks", first_block, total);
-  if (num_blocks == 0) num_blocks = total - first_block;
-  if (first_block + num_blocks > total) return fail("block range exceeds the image");
+  if (check_options(opt)) return 1;
+  const uint32_t bx = width / 4;
+  if (check_range(width, height, first_block, &num_blocks)) return 1;
   int ndev = device_count();
   if (ndev <= 0) return fail("no CUDA device available (there is no CPU fallback)");
-  if (num_gpus <= 0) num_gpus = g_num_init > 0 ? g_num_init : 1;
+  if (num_gpus <= 0) num_gpus = ndev;  // "all visible" (SCompressionSettings::iNumGPUs == 0, tc -g 0)
   num_gpus = std::min(num_gpus, ndev);
   int prev = 0;
   cudaGetDevice(&prev);
+  const EncodeParams prm = make_params(quality, seed, opt);
 
   // Contiguous block-row slabs, one per GPU.
   const uint32_t row0 = first_block / bx, row1 = (first_block + num_blocks + bx - 1) / bx;
   const uint32_t rows = row1 - row0;
   num_gpus = std::max(1, std::min<int>(num_gpus, rows));
   std::vector<Shard> shards(num_gpus);
+  WmChain chain;
+  int npieces = 0;
   for (int g = 0; g < num_gpus; g++) {
     uint32_t a = row0 + (uint32_t)((uint64_t)rows * g / num_gpus);
     uint32_t b = row0 + (uint32_t)((uint64_t)rows * (g + 1) / num_gpus);
@@ -542,42 +730,26 @@ int fastc_gpu_compress(int format, const uint8_t *rgba_host, uint32_t width, uin
     shards[g].dev = g;
     shards[g].first_block = lo;
     shards[g].num_blocks = hi > lo ? hi - lo : 0;
+    plan_chunks(shards[g], format, width, chunk_blocks);
+    shards[g].piece0 = npieces;
+    npieces += shards[g].bounds.empty() ? 0 : (int)shards[g].bounds.size() - 1;
   }
-  // BC7 watermark order: the word index of a solid block is the number of solid blocks
-  // before it in raster order over the WHOLE image (the reference's single-threaded
-  // process-global counter, Compressor.cpp:135-140,1457).  Counting on the host keeps a
-  // sub-range / sharded submission bit-identical to the same bytes of a full submission.
-  if (format == FASTC_GPU_BPTC) {
-    // the blocks before the submission and every shard but the last, counted concurrently (the
-    // scan is memory-bound: one host thread per slab instead of one slab after the other)
-    std::vector<uint32_t> counts(num_gpus, 0);
-    uint32_t before = 0;
-    {
-      std::vector<std::thread> th;
-      for (int g = 0; g + 1 < num_gpus; g++)
-        th.emplace_back([&, g] {
-          counts[g] = host_count_solid(rgba_host, width, shards[g].first_block, shards[g].first_block + shards[g].num_blocks);
-        });
-      before = host_count_solid(rgba_host, width, 0, first_block);
-      for (auto &t : th) t.join();
-    }
-    uint32_t run = before;
-    for (int g = 0; g < num_gpus; g++) {
-      shards[g].wm_base = run;
-      run += counts[g];
-    }
-  }
-  if (num_gpus == 1) cudaGetDevice(&shards[0].dev);  // one GPU: the caller's current device
-
+  chain.resize((size_t)npieces);
+  // BC7 watermark order: the word index of a solid block is the number of solid blocks before it
+  // in raster order over the WHOLE image (the reference's single-threaded process-global counter,
+  // Compressor.cpp:135-140,1457).  The counts of the submission's own pieces come from the GPUs
+  // (WmChain); only the blocks before a sub-range submission are counted on the host (cached).
+  if (format == FASTC_GPU_BPTC) chain.before = host_prefix_solid(rgba_host, width, height, first_block);
   if (num_gpus == 1) {
-    shards[0].rc = run_shard_locked(shards[0], format, rgba_host, width, height, out_host, quality, seed, chunk_blocks);
+    cudaGetDevice(&shards[0].dev);  // one GPU: the caller's current device
+    shards[0].rc = run_shard_locked(shards[0], format, rgba_host, width, height, out_host, prm, chain);
     if (shards[0].rc) snprintf(shards[0].err, sizeof(shards[0].err), "%s", tl_error);
   } else {
     std::vector<std::thread> th;
     for (int g = 0; g < num_gpus; g++)
       th.emplace_back([&, g] {
         if (shards[g].num_blocks == 0) return;
-        shards[g].rc = run_shard_locked(shards[g], format, rgba_host, width, height, out_host, quality, seed, chunk_blocks);
+        shards[g].rc = run_shard_locked(shards[g], format, rgba_host, width, height, out_host, prm, chain);
         if (shards[g].rc) snprintf(shards[g].err, sizeof(shards[g].err), "%s", tl_error);
       });
     for (auto &t : th) t.join();
@@ -596,13 +768,15 @@ int fastc_gpu_compress(int format, const uint8_t *rgba_host, uint32_t width, uin
   return 0;
 }
 
-int fastc_gpu_compress_batch(int format, const fastc_gpu_job *jobs, uint32_t num_jobs, int quality, uint64_t seed,
-                             int num_gpus, fastc_gpu_timing *timing) {
+int compress_batch_impl(int format, const fastc_gpu_job *jobs, uint32_t num_jobs, int quality, uint64_t seed,
+                        int num_gpus, fastc_gpu_timing *timing, const fastc_gpu_options *opt) {
   auto t0 = std::chrono::steady_clock::now();
   if (!jobs && num_jobs) return fail("null job list");
+  if (quality < 0) return fail("quality must be >= 0");
+  if (check_options(opt)) return 1;
   int ndev = device_count();
   if (ndev <= 0) return fail("no CUDA device available (there is no CPU fallback)");
-  if (num_gpus <= 0) num_gpus = g_num_init > 0 ? g_num_init : 1;
+  if (num_gpus <= 0) num_gpus = ndev;
   num_gpus = std::max(1, std::min(num_gpus, ndev));
   for (uint32_t j = 0; j < num_jobs; j++) {
     if (check_dims(format, jobs[j].width, jobs[j].height)) return 1;
@@ -617,19 +791,23 @@ int fastc_gpu_compress_batch(int format, const fastc_gpu_job *jobs, uint32_t num
   std::vector<int> rcs(num_gpus, 0);
   std::vector<std::string> errs(num_gpus);
   auto worker = [&](int g) {
-    int last_dev = -1, dev = g;
+    int dev = g;
     if (num_gpus == 1) cudaGetDevice(&dev);
     if (dev < 0 || dev >= kMaxDevices) { rcs[g] = 1; errs[g] = "bad device"; return; }
     std::lock_guard<std::mutex> lk(g_ctx[dev].host_mu);
+    bool any = false;
     for (uint32_t j = g; j < num_jobs; j += num_gpus) {
       Shard s;
       s.dev = dev;
       s.first_block = 0;
       s.num_blocks = (jobs[j].width / 4) * (jobs[j].height / 4);
+      plan_chunks(s, format, jobs[j].width, 0);
+      WmChain chain;
+      chain.resize(s.bounds.size() - 1);
+      EncodeParams prm = make_params(quality, seed + ((uint64_t)j << 40), opt);
       // no drain between textures: the staging slots keep rotating across jobs
-      if (run_shard(s, format, jobs[j].rgba_host, jobs[j].width, jobs[j].height, jobs[j].out_host, quality,
-                    seed + ((uint64_t)j << 40), 0, /*drain=*/false)) {
-        drain_slots(g_ctx[s.dev], nullptr);
+      if (run_shard(s, format, jobs[j].rgba_host, jobs[j].width, jobs[j].height, jobs[j].out_host, prm, chain,
+                    /*drain=*/false)) {
         rcs[g] = 1;
         errs[g] = tl_error;
         return;
@@ -638,11 +816,12 @@ int fastc_gpu_compress_batch(int format, const fastc_gpu_job *jobs, uint32_t num
       per[g].kernel_launches += s.launches;
       per[g].h2d_bytes += s.h2d;
       per[g].d2h_bytes += s.d2h;
-      last_dev = s.dev;
+      any = true;
     }
-    if (last_dev >= 0) {
+    if (any) {
       double ms = 0;
-      if (drain_slots(g_ctx[last_dev], &ms)) {
+      if (drain_slots(g_ctx[dev], &ms)) {
+        abort_slots(g_ctx[dev]);
         rcs[g] = 1;
         errs[g] = tl_error;
         return;
@@ -671,13 +850,75 @@ int fastc_gpu_compress_batch(int format, const fastc_gpu_job *jobs, uint32_t num
   return 0;
 }
 
+}  // namespace
+
+int fastc_gpu_compress_device(int format, const void *rgba_dev, uint32_t width, uint32_t height,
+                              uint32_t first_block, uint32_t num_blocks, void *out_dev, int quality,
+                              uint64_t seed, uint32_t wm_base, uint32_t block_index_base, void *cuda_stream,
+                              uint32_t *launches_out) {
+  return compress_device_impl(format, rgba_dev, width, height, first_block, num_blocks, out_dev, quality, seed, wm_base,
+                              block_index_base, cuda_stream, launches_out, nullptr);
+}
+
+int fastc_gpu_compress_device_opt(int format, const void *rgba_dev, uint32_t width, uint32_t height,
+                                  uint32_t first_block, uint32_t num_blocks, void *out_dev, int quality,
+                                  uint64_t seed, uint32_t wm_base, uint32_t block_index_base, void *cuda_stream,
+                                  uint32_t *launches_out, const fastc_gpu_options *options) {
+  return compress_device_impl(format, rgba_dev, width, height, first_block, num_blocks, out_dev, quality, seed, wm_base,
+                              block_index_base, cuda_stream, launches_out, options);
+}
+
+int fastc_gpu_count_solid_device(const void *rgba_dev, uint32_t width, uint32_t height, uint32_t first_block,
+                                 uint32_t num_blocks, void *cuda_stream, uint32_t *count_out) {
+  if (check_dims(FASTC_GPU_BPTC, width, height)) return 1;
+  if (!rgba_dev || !count_out) return fail("null pointer");
+  if (check_range(width, height, first_block, &num_blocks)) return 1;
+  int dev = 0;
+  if (current_device(&dev)) return 1;
+  if (ensure_tables(dev)) return 1;
+  DeviceCtx &c = g_ctx[dev];
+  std::lock_guard<std::mutex> lk(c.mu);
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  // shares the device API's scratch with fastc_gpu_compress_device (see enqueue)
+  if (!c.api_done) CU_TRY(cudaEventCreateWithFlags(&c.api_done, cudaEventDisableTiming));
+  if (c.api_used) CU_TRY(cudaStreamWaitEvent(st, c.api_done, 0));
+  CU_TRY(bc7_count_solid(c.bc7ws[kPipeDepth], rgba_dev, width, first_block, num_blocks, st, count_out));
+  CU_TRY(cudaEventRecord(c.api_done, st));
+  c.api_used = true;
+  return 0;
+}
+
+int fastc_gpu_compress(int format, const uint8_t *rgba_host, uint32_t width, uint32_t height,
+                       uint32_t first_block, uint32_t num_blocks, uint8_t *out_host, int quality, uint64_t seed,
+                       uint32_t chunk_blocks, int num_gpus, fastc_gpu_timing *timing) {
+  return compress_impl(format, rgba_host, width, height, first_block, num_blocks, out_host, quality, seed, chunk_blocks,
+                       num_gpus, timing, nullptr);
+}
+
+int fastc_gpu_compress_opt(int format, const uint8_t *rgba_host, uint32_t width, uint32_t height,
+                           uint32_t first_block, uint32_t num_blocks, uint8_t *out_host, int quality, uint64_t seed,
+                           uint32_t chunk_blocks, int num_gpus, fastc_gpu_timing *timing,
+                           const fastc_gpu_options *options) {
+  return compress_impl(format, rgba_host, width, height, first_block, num_blocks, out_host, quality, seed, chunk_blocks,
+                       num_gpus, timing, options);
+}
+
+int fastc_gpu_compress_batch(int format, const fastc_gpu_job *jobs, uint32_t num_jobs, int quality, uint64_t seed,
+                             int num_gpus, fastc_gpu_timing *timing) {
+  return compress_batch_impl(format, jobs, num_jobs, quality, seed, num_gpus, timing, nullptr);
+}
+
+int fastc_gpu_compress_batch_opt(int format, const fastc_gpu_job *jobs, uint32_t num_jobs, int quality, uint64_t seed,
+                                 int num_gpus, fastc_gpu_timing *timing, const fastc_gpu_options *options) {
+  return compress_batch_impl(format, jobs, num_jobs, quality, seed, num_gpus, timing, options);
+}
+
 int fastc_gpu_decompress_device(int format, const void *cmp_dev, uint32_t width, uint32_t height, void *rgba_out_dev,
                                 void *cuda_stream) {
   if (check_dims(format, width, height)) return 1;
   if (!cmp_dev || !rgba_out_dev) return fail("null device pointer");
   int dev = 0;
-  CU_TRY(cudaGetDevice(&dev));
-  if (dev >= kMaxDevices) return fail("device index %d not supported", dev);
+  if (current_device(&dev)) return 1;
   if (ensure_tables(dev)) return 1;
   CU_TRY(launch_decode(format, cmp_dev, width, 0, (width / 4) * (height / 4), rgba_out_dev,
                        static_cast<cudaStream_t>(cuda_stream)));
@@ -690,8 +931,7 @@ int fastc_gpu_decompress(int format, const uint8_t *cmp_host, uint32_t width, ui
   if (check_dims(format, width, height)) return 1;
   if (!cmp_host || !rgba_out_host) return fail("null host pointer");
   int dev = 0;
-  CU_TRY(cudaGetDevice(&dev));
-  if (dev >= kMaxDevices) return fail("device index %d not supported", dev);
+  if (current_device(&dev)) return 1;
   if (ensure_ctx(dev)) return 1;
   DeviceCtx &c = g_ctx[dev];
   const size_t cmp_bytes = fastc_gpu_compressed_size(format, width, height);
@@ -726,8 +966,7 @@ int fastc_gpu_psnr_device(const void *a_dev, const void *b_dev, uint32_t width, 
   if (!a_dev || !b_dev || !psnr_out) return fail("null pointer");
   if (width == 0 || height == 0) return fail("empty image");
   int dev = 0;
-  CU_TRY(cudaGetDevice(&dev));
-  if (dev >= kMaxDevices) return fail("device index %d not supported", dev);
+  if (current_device(&dev)) return 1;
   DeviceCtx &c = g_ctx[dev];
   std::lock_guard<std::mutex> lk(c.mu);
   if (!c.psnr_sum) {
@@ -747,8 +986,7 @@ int fastc_gpu_psnr(const uint8_t *a_host, const uint8_t *b_host, uint32_t width,
   if (!a_host || !b_host || !psnr_out) return fail("null pointer");
   if (width == 0 || height == 0) return fail("empty image");
   int dev = 0;
-  CU_TRY(cudaGetDevice(&dev));
-  if (dev >= kMaxDevices) return fail("device index %d not supported", dev);
+  if (current_device(&dev)) return 1;
   if (ensure_ctx(dev)) return 1;
   DeviceCtx &c = g_ctx[dev];
   const size_t bytes = (size_t)width * height * 4;
@@ -765,7 +1003,7 @@ int fastc_gpu_psnr(const uint8_t *a_host, const uint8_t *b_host, uint32_t width,
 
 int fastc_gpu_bc7_counters(uint64_t *qe_calls, uint64_t *pixel_bucket_evals) {
   int dev = 0;
-  CU_TRY(cudaGetDevice(&dev));
+  if (current_device(&dev)) return 1;
   DeviceCtx &c = g_ctx[dev];
   std::lock_guard<std::mutex> lk(c.mu);
   CU_TRY(bc7_read_counters(c.bc7ws[kPipeDepth], qe_calls, pixel_bucket_evals));
@@ -774,7 +1012,7 @@ int fastc_gpu_bc7_counters(uint64_t *qe_calls, uint64_t *pixel_bucket_evals) {
 
 int fastc_gpu_bc7_stage_ms(int enable, double *ms6) {
   int dev = 0;
-  CU_TRY(cudaGetDevice(&dev));
+  if (current_device(&dev)) return 1;
   DeviceCtx &c = g_ctx[dev];
   std::lock_guard<std::mutex> lk(c.mu);
   CU_TRY(bc7_stage_timing(c.bc7ws[kPipeDepth], enable, ms6));
@@ -783,7 +1021,7 @@ int fastc_gpu_bc7_stage_ms(int enable, double *ms6) {
 
 int fastc_gpu_debug_bc7_dump(uint32_t nblocks, uint32_t *sel_out, uint32_t *results_out) {
   int dev = 0;
-  CU_TRY(cudaGetDevice(&dev));
+  if (current_device(&dev)) return 1;
   DeviceCtx &c = g_ctx[dev];
   std::lock_guard<std::mutex> lk(c.mu);
   CU_TRY(bc7_debug_dump(c.bc7ws[kPipeDepth], nblocks, sel_out, results_out));

@@ -370,8 +370,9 @@ cudaError_t etc1_upload_tables() {
 }
 
 cudaError_t launch_etc1(const void *rgba_dev, uint32_t width, uint32_t first_block, uint32_t num_blocks,
-                        void *out_dev, cudaStream_t stream) {
+                        void *out_dev, int quality, cudaStream_t stream) {
   if (num_blocks == 0) return cudaSuccess;
+  if (quality != 0) return cudaErrorNotSupported;  // medium / high: see etc1_quality
   const uint32_t grid = (num_blocks + kEtcBlocksPerCta - 1) / kEtcBlocksPerCta;
   etc1_encode_kernel<<<grid, kEtcThreads, 0, stream>>>(static_cast<const uint32_t *>(rgba_dev), width, width / 4,
                                                        first_block, num_blocks, static_cast<uint2 *>(out_dev));

@@ -16,7 +16,7 @@ cudaError_t launch_dxt(bool dxt5, const void *rgba_dev, uint32_t width, uint32_t
                        uint32_t num_blocks, void *out_dev, cudaStream_t stream);
 
 cudaError_t launch_etc1(const void *rgba_dev, uint32_t width, uint32_t first_block, uint32_t num_blocks,
-                        void *out_dev, cudaStream_t stream);
+                        void *out_dev, int quality, cudaStream_t stream);
 
 // Decoders + PSNR (decode.cu).  format: include/fastc_gpu.h numbering.
 cudaError_t launch_decode(int format, const void *cmp_dev, uint32_t width, uint32_t first_block, uint32_t num_blocks,
@@ -33,22 +33,43 @@ struct Bc7Workspace {
   size_t bytes = 0;
   uint32_t *host_count = nullptr;  // pinned, 1 word (count_solid result)
   uint32_t *wm_running = nullptr;  // device: watermark base of the chunk being packed
-  unsigned long long *counters = nullptr;
+  unsigned long long *counters = nullptr;  // device: [0] QuantizedError calls, [1] pixel-bucket evaluations
   // optional per-stage timing (CUDA events on the launching stream)
   bool timing = false;
   int timed_chunks = 0;
   static constexpr int kMaxTimedChunks = 64;
   cudaEvent_t ev[kMaxTimedChunks][5] = {};
-  cudaEvent_t ev_mid[kMaxTimedChunks] = {};  // between setup(+sort) and anneal  // device: [0] QuantizedError calls, [1] pixel-bucket evaluations
+  cudaEvent_t ev_mid[kMaxTimedChunks] = {};  // between setup(+sort) and anneal
+  cudaEvent_t *cur_ev = nullptr;             // the timed chunk bc7_back closes
 };
 void bc7_free_workspace(Bc7Workspace &ws);
 
 // block_index_base: raster index (in the full texture) of the buffer's block 0;
 // keys the per-chain RNG streams so sharded / chunked runs are bit-identical to
 // a single submission.  wm_base: solid blocks preceding first_block.
+// Encoder settings as the kernels see them: BPTCC::CompressionSettings (reference
+// BPTCEncoder/include/FasTC/BPTCCompressor.h:123-158) and rg_etc1's quality (ETCEncoder/src/rg_etc1.h:24-29)
+struct EncodeParams {
+  int quality = 50;            // m_NumSimulatedAnnealingSteps
+  uint64_t seed = 0;           // keys the per-chain RNG streams
+  uint32_t block_modes = 0xFF; // m_BlockModes
+  int error_metric = 0;        // m_ErrorMetric: 0 uniform, 1 non-uniform
+  int etc1_quality = 0;        // rg_etc1::etc1_quality: 0 cLowQuality (what FasTC uses), 1 medium, 2 high
+};
 cudaError_t launch_bc7(Bc7Workspace &ws, const void *rgba_dev, uint32_t width, uint32_t height,
-                       uint32_t first_block, uint32_t num_blocks, void *out_dev, int quality, uint64_t seed,
+                       uint32_t first_block, uint32_t num_blocks, void *out_dev, const EncodeParams &prm,
                        uint32_t wm_base, uint32_t block_index_base, cudaStream_t stream, uint32_t *launches);
+// The same in two halves for one submission of <= bc7_max_submission() blocks (the host path chains
+// watermark bases across streams and GPUs between the two): front = everything but the pack, with
+// the submission's solid-block count copied to ws.host_count and `count_ready` recorded right after
+// the classification; back = set the watermark base (unless it already sits in ws.wm_running) and pack.
+uint32_t bc7_max_submission();
+cudaError_t bc7_front(Bc7Workspace &ws, const void *rgba_dev, uint32_t width, uint32_t first_block,
+                      uint32_t num_blocks, const EncodeParams &prm, uint32_t block_index_base, cudaStream_t stream,
+                      cudaEvent_t count_ready, uint32_t *launches);
+cudaError_t bc7_back(Bc7Workspace &ws, const void *rgba_dev, uint32_t width, uint32_t first_block,
+                     uint32_t num_blocks, void *out_dev, uint32_t wm_base, bool base_on_device, cudaStream_t stream,
+                     uint32_t *launches);
 
 cudaError_t bc7_count_solid(Bc7Workspace &ws, const void *rgba_dev, uint32_t width, uint32_t first_block,
                             uint32_t num_blocks, cudaStream_t stream, uint32_t *count_out);

@@ -19,7 +19,9 @@ typedef void (*CompressionFunc)(const FasTC::CompressionJob &);
 namespace BPTCC {
 struct CompressionSettings {
   // reference BPTCCompressor.h:123-158.  m_ShapeSelectionFn is a host callback and cannot run
-  // on the device: it must stay NULL.  m_BlockModes / m_ErrorMetric keep their defaults.
+  // on the device: it must stay NULL (a call with it set is rejected).  m_BlockModes (bit m = mode
+  // m allowed) and m_ErrorMetric (0 = eErrorMetric_Uniform, 1 = eErrorMetric_Nonuniform) are
+  // honoured like the reference's (Compressor.cpp:1857, :205-208).
   void *m_ShapeSelectionFn;
   const void *m_ShapeSelectionUserData;
   uint32 m_BlockModes;

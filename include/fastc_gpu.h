@@ -32,7 +32,10 @@
  * Threads: every entry point may be called from any thread.  Host-pointer
  * submissions to one device are serialised inside the library (the reference's
  * ThreadGroup / WorkerQueue call a CompressionFunc from up to 256 threads at
- * once on disjoint block ranges, Core/src/ThreadGroup.cpp:146-188).
+ * once on disjoint block ranges, Core/src/ThreadGroup.cpp:146-188).  The
+ * device-pointer BPTC entry points of one device share one scratch area: calls
+ * on different streams are ordered one after the other on the device (each
+ * waits, on its stream, for the previous call's kernels), never corrupted.
  *
  * Host buffers may be pageable (new[] / malloc: staged through pinned memory
  * owned by the library) or pinned (cudaHostAlloc / cudaHostRegister: used
@@ -74,6 +77,20 @@ typedef struct fastc_gpu_timing {
   uint32_t kernel_launches; /* number of our kernels launched by the call */
 } fastc_gpu_timing;
 
+/* Encoder settings beyond (format, quality): what the reference passes per call as
+ * BPTCC::CompressionSettings (BPTCEncoder/include/FasTC/BPTCCompressor.h:123-158; applied at
+ * BPTCEncoder/src/Compressor.cpp:1848-1857) and rg_etc1's quality level
+ * (ETCEncoder/src/rg_etc1.h:24-29; FasTC itself always passes cLowQuality,
+ * ETCEncoder/src/Compressor.cpp:36-37).  Taken by the *_opt variants of the compress entry
+ * points; a NULL pointer means the defaults below, which is what the plain entry points use. */
+typedef struct fastc_gpu_options {
+  uint32_t struct_size;       /* = sizeof(fastc_gpu_options) */
+  uint32_t bptc_block_modes;  /* m_BlockModes: bit m set = BC7 mode m may be used (default 0xFF)     */
+  int32_t bptc_error_metric;  /* m_ErrorMetric: 0 = eErrorMetric_Uniform (default), 1 = _Nonuniform  */
+  int32_t etc1_quality;       /* 0 = cLowQuality (default), 1 = cMediumQuality, 2 = cHighQuality     */
+} fastc_gpu_options;
+#define FASTC_GPU_OPTIONS_INIT { (uint32_t)sizeof(fastc_gpu_options), 0xFFu, 0, 0 }
+
 /* Number of visible CUDA devices (<0 on error). Creates nothing. */
 int fastc_gpu_device_count(void);
 
@@ -89,8 +106,8 @@ uint64_t fastc_gpu_compressed_size(int format, uint32_t width, uint32_t height);
  * image (num_blocks == 0 means "to the end").  quality = SA steps (BPTC only;
  * SCompressionSettings::iQuality), seed keys the per-block RNG streams,
  * chunk_blocks = blocks per pipeline chunk (SCompressionSettings::iJobSize;
- * 0 = auto), num_gpus = devices to shard block rows over (<=0: all
- * initialised).  timing may be NULL. */
+ * 0 = auto), num_gpus = devices to shard block rows over (<= 0: all visible
+ * devices).  timing may be NULL. */
 int fastc_gpu_compress(int format, const uint8_t *rgba_host, uint32_t width, uint32_t height,
                        uint32_t first_block, uint32_t num_blocks, uint8_t *out_host,
                        int quality, uint64_t seed, uint32_t chunk_blocks, int num_gpus,
@@ -100,6 +117,17 @@ int fastc_gpu_compress(int format, const uint8_t *rgba_host, uint32_t width, uin
  * to the GPUs. */
 int fastc_gpu_compress_batch(int format, const fastc_gpu_job *jobs, uint32_t num_jobs,
                              int quality, uint64_t seed, int num_gpus, fastc_gpu_timing *timing);
+
+/* The same three with explicit encoder settings (BPTCC::Compress(job, settings),
+ * BPTCEncoder/src/Compressor.cpp:1473; rg_etc1::pack_etc1_block(..., pack_params),
+ * ETCEncoder/src/rg_etc1.cpp:2192). */
+int fastc_gpu_compress_opt(int format, const uint8_t *rgba_host, uint32_t width, uint32_t height,
+                           uint32_t first_block, uint32_t num_blocks, uint8_t *out_host,
+                           int quality, uint64_t seed, uint32_t chunk_blocks, int num_gpus,
+                           fastc_gpu_timing *timing, const fastc_gpu_options *options);
+int fastc_gpu_compress_batch_opt(int format, const fastc_gpu_job *jobs, uint32_t num_jobs,
+                                 int quality, uint64_t seed, int num_gpus, fastc_gpu_timing *timing,
+                                 const fastc_gpu_options *options);
 
 /* Device -> device on the CURRENT device, asynchronous on `cuda_stream`
  * (a cudaStream_t passed as void*; NULL = legacy default stream).
@@ -115,6 +143,12 @@ int fastc_gpu_compress_device(int format, const void *rgba_dev, uint32_t width, 
                               uint32_t first_block, uint32_t num_blocks, void *out_dev,
                               int quality, uint64_t seed, uint32_t wm_base, uint32_t block_index_base,
                               void *cuda_stream, uint32_t *launches_out);
+
+int fastc_gpu_compress_device_opt(int format, const void *rgba_dev, uint32_t width, uint32_t height,
+                                  uint32_t first_block, uint32_t num_blocks, void *out_dev,
+                                  int quality, uint64_t seed, uint32_t wm_base, uint32_t block_index_base,
+                                  void *cuda_stream, uint32_t *launches_out,
+                                  const fastc_gpu_options *options);
 
 /* Counts solid-colour blocks in the range (needed to chain wm_base across
  * shards).  Synchronous with respect to `cuda_stream`. */

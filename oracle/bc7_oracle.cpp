@@ -101,7 +101,15 @@ struct Ctx {
   uint32_t block;     // global raster block index (rng_mode 1 key)
   uint32_t local;     // current chain's state (rng_mode 1)
   uint64_t qe_calls = 0, pbe = 0;
+  uint32_t block_modes = 0xFF;  // CompressionSettings::m_BlockModes (BPTCCompressor.h:148)
+  int error_metric = 0;         // CompressionSettings::m_ErrorMetric: 0 uniform, 1 non-uniform
 };
+
+// kErrorMetrics (Compressor.cpp:205-208)
+inline const float *error_weights(int metric) {
+  static const float kW[2][4] = {{1.0f, 1.0f, 1.0f, 1.0f}, {sqrtf(0.3f), sqrtf(0.56f), sqrtf(0.11f), 1.0f}};
+  return kW[metric ? 1 : 0];
+}
 
 // ---------------------------------------------------------------------------
 // QuantizeChannel / ToPixel (RGBAEndpoints.cpp:126-177)
@@ -386,7 +394,18 @@ struct Mode {
   int rotation() const { return A.has_rotation ? rot : 0; }
   int index_bits() const { return idx_mode == 0 ? A.index_bits : A.alpha_index_bits; }
   int alpha_index_bits() const { return idx_mode == 0 ? A.alpha_index_bits : A.index_bits; }
-  V4 metric() const { return splat(1.0f); }  // eErrorMetric_Uniform under any rotation
+  V4 metric() const {  // GetErrorMetric (CompressionMode.h:196-205): the weights follow the rotation
+    const float *w = error_weights(cx.error_metric);
+    V4 m;
+    m[0] = w[0]; m[1] = w[1]; m[2] = w[2]; m[3] = w[3];
+    switch (rotation()) {
+      case 1: m[0] = w[3]; m[3] = w[0]; break;
+      case 2: m[1] = w[3]; m[3] = w[1]; break;
+      case 3: m[2] = w[3]; m[3] = w[2]; break;
+      default: break;
+    }
+    return m;
+  }
   uint32_t qmask() const {                   // GetQuantizationMask (CompressionMode.h:212-232)
     const int32_t seed = (int32_t)0x80000000;
     const uint32_t cbits = A.color_bits - 1, abits = A.alpha_bits - 1;
@@ -485,7 +504,7 @@ struct Mode {
       }
       float error = 0.0f;
       for (int i = 0; i < 4; i++) {
-        const float e = (float)dist[i] * 1.0f;
+        const float e = (float)dist[i] * error_weights(cx.error_metric)[i];  // un-rotated (Compressor.cpp:334)
         error += e * e;
       }
       if (error < best_error) {
@@ -730,7 +749,7 @@ struct Mode {
     double alpha_error = DBL_MAX;
     const int abits = alpha_index_bits();
     const uint32_t(*interp)[2] = kInterp[abits - 1];
-    const float weight = 1.0f;
+    const float weight = metric()[3];  // GetErrorMetric().A() (Compressor.cpp:712)
     const int nbuckets = 1 << abits;
     if (a1 == a2) {
       const uint8_t a1be = (uint8_t)a1, a2be = (uint8_t)a2;
@@ -975,7 +994,10 @@ double estimate_error(Ctx &cx, const Cluster &c, int nbuckets) {
   const V4 d = sub(c.mx, c.mn);
   if (dot(d, d) == 0) return 0.0;
   double e = 0.0001;
-  e += quantized_error(cx, c, c.mn, c.mx, nbuckets, 0xFFFFFFFFu, splat(1.0f), nullptr, nullptr);
+  const float *w = error_weights(cx.error_metric);
+  V4 met;
+  met[0] = w[0]; met[1] = w[1]; met[2] = w[2]; met[3] = w[3];
+  e += quantized_error(cx, c, c.mn, c.mx, nbuckets, 0xFFFFFFFFu, met, nullptr, nullptr);
   return e;
 }
 
@@ -1110,7 +1132,8 @@ bool compress_block(Ctx &cx, const uint32_t block[16], uint8_t *out, uint32_t wm
     s.write(1u << 6, 7);
     return false;
   }
-  const Selection sel = box_selection(cx, block);
+  Selection sel = box_selection(cx, block);
+  sel.modes &= cx.block_modes;  // Compressor.cpp:1857
   compress_clusters(cx, sel, block, out);
   return false;
 }
@@ -1120,9 +1143,11 @@ bool compress_block(Ctx &cx, const uint32_t block[16], uint8_t *out, uint32_t wm
 
 static void run_bc7(const uint8_t *rgba, uint32_t width, uint32_t first_block, uint32_t num_blocks, uint8_t *out,
                     int quality, int rng_mode, uint32_t *lcg_state, uint64_t seed, uint32_t wm_base,
-                    uint32_t block_index_base) {
+                    uint32_t block_index_base, uint32_t block_modes = 0xFF, int error_metric = 0) {
   const uint32_t bw = width / 4;
   Ctx cx;
+  cx.block_modes = block_modes;
+  cx.error_metric = error_metric;
   cx.sa_steps = quality;
   cx.rng_mode = rng_mode;
   cx.global = lcg_state;
@@ -1158,6 +1183,17 @@ extern "C" void fastc_oracle_bc7_keyed(const uint8_t *rgba, uint32_t width, uint
   (void)height;
   uint32_t dummy = 0;
   run_bc7(rgba, width, first_block, num_blocks, out, quality, 1, &dummy, seed, wm_base, block_index_base);
+}
+
+// With the reference's per-call CompressionSettings (BPTCC::Compress(job, settings), Compressor.cpp:1473):
+// m_BlockModes and m_ErrorMetric.
+extern "C" void fastc_oracle_bc7_settings(const uint8_t *rgba, uint32_t width, uint32_t height, uint32_t first_block,
+                                          uint32_t num_blocks, uint8_t *out, int quality, int rng_mode,
+                                          uint32_t *lcg_state, uint64_t seed, uint32_t wm_base,
+                                          uint32_t block_index_base, uint32_t block_modes, int error_metric) {
+  (void)height;
+  run_bc7(rgba, width, first_block, num_blocks, out, quality, rng_mode, lcg_state, seed, wm_base, block_index_base,
+          block_modes, error_metric);
 }
 
 // Work counters of the last fastc_oracle_bc7 call (SURVEY.md §8d op model).

@@ -34,6 +34,14 @@ void fastc_oracle_bc7_keyed(const uint8_t *rgba, uint32_t width, uint32_t height
                             uint32_t first_block, uint32_t num_blocks, uint8_t *out,
                             int quality, uint64_t seed, uint32_t wm_base, uint32_t block_index_base);
 
+// The same with the reference's per-call BPTCC::CompressionSettings: m_BlockModes (bit m = mode m
+// allowed) and m_ErrorMetric (0 uniform, 1 non-uniform).
+void fastc_oracle_bc7_settings(const uint8_t *rgba, uint32_t width, uint32_t height,
+                               uint32_t first_block, uint32_t num_blocks, uint8_t *out,
+                               int quality, int rng_mode, uint32_t *lcg_state, uint64_t seed,
+                               uint32_t wm_base, uint32_t block_index_base, uint32_t block_modes,
+                               int error_metric);
+
 // Decoders + the reference's PSNR definition (Base/src/Image.cpp:205-255).
 void fastc_oracle_decode(int format, const uint8_t *cmp, uint32_t width, uint32_t height,
                          uint8_t *rgba_out);

@@ -27,6 +27,8 @@
 #include <fcntl.h>
 
 #include "FasTC/TexComp.h"
+#include "FasTC/BPTCCompressor.h"
+#include "FasTC/CompressionJob.h"
 #include "FasTC/CompressedImage.h"
 #include "FasTC/CompressionFormat.h"
 #include "FasTC/Image.h"
@@ -103,6 +105,20 @@ double fastc_ref_psnr(const uint8_t *a, const uint8_t *b, uint32_t width,
   delete[] pa;
   delete[] pb;
   return ia.ComputePSNR(&ib);
+}
+
+// BPTCC::Compress(job, settings) over the whole image (BPTCEncoder/src/Compressor.cpp:1473): the
+// reference's per-format operator entry with non-default CompressionSettings -- m_BlockModes and
+// m_ErrorMetric are not reachable through CompressImageData.
+int fastc_ref_bptc_compress_settings(const uint8_t *rgba, uint32_t width, uint32_t height, uint8_t *out,
+                                     int quality, uint32_t block_modes, int error_metric) {
+  BPTCC::CompressionSettings s;
+  s.m_NumSimulatedAnnealingSteps = (uint32_t)quality;
+  s.m_BlockModes = block_modes;
+  s.m_ErrorMetric = error_metric ? BPTCC::eErrorMetric_Nonuniform : BPTCC::eErrorMetric_Uniform;
+  FasTC::CompressionJob cj(FasTC::eCompressionFormat_BPTC, rgba, out, width, height);
+  BPTCC::Compress(cj, s);
+  return 0;
 }
 
 uint32_t fastc_ref_compressed_size(int format, uint32_t width, uint32_t height) {

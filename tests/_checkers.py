@@ -43,6 +43,10 @@ class Oracle:
             L.fastc_oracle_bc7.argtypes = [_u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _u8p,
                                            C.c_int, C.c_int, C.POINTER(C.c_uint32), C.c_uint64, C.c_uint32]
             L.fastc_oracle_bc7.restype = None
+        L.fastc_oracle_bc7_settings.argtypes = [_u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _u8p,
+                                                C.c_int, C.c_int, C.POINTER(C.c_uint32), C.c_uint64, C.c_uint32,
+                                                C.c_uint32, C.c_uint32, C.c_int]
+        L.fastc_oracle_bc7_settings.restype = None
         if hasattr(L, "fastc_oracle_decode"):
             L.fastc_oracle_decode.argtypes = [C.c_int, _u8p, C.c_uint32, C.c_uint32, _u8p]
             L.fastc_oracle_decode.restype = None
@@ -51,7 +55,8 @@ class Oracle:
 
     def compress(self, fmt: str, img: np.ndarray, *, quality: int = 50, first_block: int = 0,
                  num_blocks: int | None = None, rng_mode: int = 1, lcg_state: int = 1,
-                 seed: int = 0, wm_base: int = 0):
+                 seed: int = 0, wm_base: int = 0, block_index_base: int = 0, block_modes: int = 0xFF,
+                 error_metric: int = 0):
         """Returns (bytes array for the WHOLE image (untouched blocks zero), final lcg state)."""
         img = np.ascontiguousarray(img, dtype=np.uint8)
         h, w = img.shape[:2]
@@ -65,8 +70,9 @@ class Oracle:
         elif fmt == "ETC1":
             self.lib.fastc_oracle_etc1(_p(img), w, h, first_block, num_blocks, _p(out))
         else:
-            self.lib.fastc_oracle_bc7(_p(img), w, h, first_block, num_blocks, _p(out), quality, rng_mode,
-                                      C.byref(st), seed, wm_base)
+            self.lib.fastc_oracle_bc7_settings(_p(img), w, h, first_block, num_blocks, _p(out), quality, rng_mode,
+                                               C.byref(st), seed, wm_base, block_index_base, block_modes,
+                                               error_metric)
         return out, st.value
 
     def decode(self, fmt: str, cmp: np.ndarray, w: int, h: int) -> np.ndarray:
@@ -99,6 +105,9 @@ class Reference:
         L.fastc_ref_set_state.argtypes = [C.c_uint32, C.c_uint32]
         L.fastc_ref_set_state.restype = None
         L.fastc_ref_get_seed.restype = C.c_uint32
+        L.fastc_ref_bptc_compress_settings.argtypes = [_u8p, C.c_uint32, C.c_uint32, _u8p, C.c_int, C.c_uint32,
+                                                       C.c_int]
+        L.fastc_ref_bptc_compress_settings.restype = C.c_int
 
     @staticmethod
     def available() -> bool:
@@ -124,6 +133,17 @@ class Reference:
         if rc != 0:
             raise RuntimeError("reference CompressImageData failed")
         return out, ms.value
+
+    def compress_bptc_settings(self, img: np.ndarray, *, quality: int = 0, block_modes: int = 0xFF,
+                               error_metric: int = 0, seed: int = 1, wm_count: int = 0) -> np.ndarray:
+        """BPTCC::Compress(job, settings) with m_BlockModes / m_ErrorMetric (single thread)."""
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        h, w = img.shape[:2]
+        out = np.zeros(nblocks(w, h) * 16, dtype=np.uint8)
+        self.set_state(seed, wm_count)
+        if self.lib.fastc_ref_bptc_compress_settings(_p(img), w, h, _p(out), quality, block_modes, error_metric) != 0:
+            raise RuntimeError("reference BPTCC::Compress failed")
+        return out
 
     def decode(self, fmt: str, cmp: np.ndarray, w: int, h: int) -> np.ndarray:
         cmp = np.ascontiguousarray(cmp, dtype=np.uint8)

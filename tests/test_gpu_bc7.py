@@ -200,3 +200,103 @@ def test_bc7_q50_at_config_sizes_matches_oracle_on_sampled_ranges(gpu, oracle, s
         assert bad.size == 0, (size, first, bad[:8])
         kinds |= {k for k, m in (("solid", solid), ("transparent", transparent), ("alpha", alpha)) if m[first:first + 96].any()}
     assert kinds == {"solid", "transparent", "alpha"}
+
+
+# ---- BPTCC::CompressionSettings beyond the annealing steps (reference BPTCCompressor.h:123-158)
+@pytest.mark.parametrize("mask", [0x40, 0x0F, 0xF0, 0xA5, 0x12, 0x81])
+def test_bc7_block_modes_q0_matches_oracle(gpu, oracle, mask):
+    """m_BlockModes is ANDed into the selection's mode set (Compressor.cpp:1857): bit-exact at -q 0
+    for several masks (the oracle is pinned to the reference's BPTCC::Compress(job, settings) in
+    tests/test_oracle_vs_ref.py); every block's mode obeys the mask."""
+    img = synth_rgba(128, 128, 4)
+    got, _ = gpu.compress(F.BPTC, img, quality=0, block_modes=mask)
+    want, _ = oracle.compress("BPTC", img, quality=0, block_modes=mask)
+    bad = _bad(got, want)
+    assert len(bad) == 0, f"mask {mask:#x}: {len(bad)} blocks differ, first {bad[:8]}"
+    blocks = img.reshape(32, 4, 32, 4, 4).transpose(0, 2, 1, 3, 4).reshape(-1, 16, 4)
+    normal = ~(blocks == blocks[:, :1]).all((1, 2)) & ~(blocks[..., 3] == 0).all(1) & got.reshape(-1, 16).any(1)
+    b0 = got.reshape(-1, 16)[normal, 0].astype(np.int64)
+    modes = np.log2(b0 & -b0).astype(int)
+    assert ((mask >> modes) & 1).all()
+
+
+def test_bc7_block_modes_annealing_matches_oracle(gpu, oracle):
+    img = synth_rgba(128, 128, 6, noise_mask=63)
+    for mask, q in ((0x4A, 3), (0xF0, 8), (0x85, 5)):
+        got, _ = gpu.compress(F.BPTC, img, quality=q, seed=3, block_modes=mask)
+        want, _ = oracle.compress("BPTC", img, quality=q, rng_mode=1, seed=3, block_modes=mask)
+        bad = _bad(got, want)
+        assert len(bad) == 0, f"mask {mask:#x} q {q}: {len(bad)} blocks differ, first {bad[:8]}"
+
+
+def test_bc7_options_are_validated(gpu):
+    from fastc_b200 import FastcGpuError
+    img = synth_rgba(16, 16, 1)
+    with pytest.raises(FastcGpuError):
+        gpu.compress(F.BPTC, img, quality=0, block_modes=0)
+    with pytest.raises(FastcGpuError):
+        gpu.compress(F.BPTC, img, quality=0, error_metric=7)
+
+
+def test_bc7_chunked_watermark_chain_and_many_ranges(gpu, oracle):
+    """The watermark base of every pipeline chunk comes from the GPU's own classification of the
+    earlier chunks (no host scan); T ThreadGroup-style ranged calls share one cached host prefix
+    scan.  Both must reproduce the single-submission bytes, solid blocks (watermark words) included."""
+    img = synth_rgba(512, 512, 1)
+    blocks = img.reshape(128, 4, 128, 4, 4).transpose(0, 2, 1, 3, 4).reshape(-1, 16, 4)
+    assert (blocks == blocks[:, :1]).all((1, 2)).sum() > 300  # plenty of watermark words
+    full, _ = gpu.compress(F.BPTC, img, quality=1, seed=5)
+    for chunk in (128, 128 * 7, 128 * 50):
+        got, tm = gpu.compress(F.BPTC, img, quality=1, seed=5, chunk_blocks=chunk)
+        assert (got == full).all(), chunk
+    out = np.zeros_like(full)
+    edges = [0, 777, 4096, 4097, 9000, 12345, 16384]
+    for a, b in reversed(list(zip(edges[:-1], edges[1:]))):   # out of order on purpose
+        gpu.compress(F.BPTC, img, out, quality=1, seed=5, first_block=a, num_blocks=b - a)
+    assert (out == full).all()
+    # the cached prefix must not survive a different image in the same buffer
+    img2 = synth_rgba(512, 512, 2)
+    img[...] = img2
+    full2, _ = gpu.compress(F.BPTC, img, quality=1, seed=5)
+    out2 = np.zeros_like(full2)
+    gpu.compress(F.BPTC, img, out2, quality=1, seed=5, first_block=8000, num_blocks=3000)
+    assert (out2[8000 * 16:11000 * 16] == full2[8000 * 16:11000 * 16]).all()
+
+
+def test_bc7_device_api_concurrent_streams_share_the_scratch_safely(gpu):
+    """Two BPTC device calls (and a solid count) on different streams of one device: the library
+    orders them on the device, results equal the serial ones."""
+    import torch
+    a = torch.from_numpy(synth_rgba(512, 512, 1)).cuda()
+    b = torch.from_numpy(synth_rgba(512, 512, 2, noise_mask=63)).cuda()
+    outs = [torch.zeros(128 * 128 * 16, dtype=torch.uint8, device="cuda") for _ in range(4)]
+    gpu.compress_device(F.BPTC, a, outs[0], width=512, height=512, quality=6, seed=1)
+    gpu.compress_device(F.BPTC, b, outs[1], width=512, height=512, quality=6, seed=1)
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(3):
+        gpu.compress_device(F.BPTC, a, outs[2], width=512, height=512, quality=6, seed=1, stream=s1.cuda_stream)
+        gpu.compress_device(F.BPTC, b, outs[3], width=512, height=512, quality=6, seed=1, stream=s2.cuda_stream)
+        n = gpu.count_solid_device(a, width=512, height=512, stream=s1.cuda_stream)
+    torch.cuda.synchronize()
+    assert n == gpu.count_solid_device(a, width=512, height=512)
+    assert (outs[2] == outs[0]).all() and (outs[3] == outs[1]).all()
+
+
+def test_all_visible_gpus_host_path_equals_single_gpu(gpu, oracle):
+    """num_gpus = 0 means every visible device (SCompressionSettings::iNumGPUs == 0, tc -g 0); on a
+    one-GPU box this is the one-GPU path, on the 8-GPU box the in-process sharder with the
+    GPU-side watermark chain.  Must equal num_gpus = 1 byte for byte, pinned or pageable."""
+    import torch
+    img = synth_rgba(1024, 1024, 1)
+    one, _ = gpu.compress(F.BPTC, img, quality=2, seed=9, num_gpus=1)
+    allg, tm = gpu.compress(F.BPTC, img, quality=2, seed=9, num_gpus=0)
+    assert (one == allg).all()
+    pin_in = torch.from_numpy(img).pin_memory().numpy()
+    pin_out = torch.empty(one.size, dtype=torch.uint8).pin_memory().numpy()
+    gpu.compress(F.BPTC, pin_in, pin_out, quality=2, seed=9, num_gpus=0)
+    assert (pin_out == one).all()
+    # ranged + sharded: rows split over the GPUs, first block inside a row
+    out = np.zeros_like(one)
+    gpu.compress(F.BPTC, img, out, quality=2, seed=9, num_gpus=0, first_block=1000, num_blocks=50000)
+    assert (out[1000 * 16:51000 * 16] == one[1000 * 16:51000 * 16]).all() and not out[:16000].any()
