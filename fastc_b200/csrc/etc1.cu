@@ -1,7 +1,10 @@
 // ETC1 block encoder for sm_100a.
 //
-// Behavioural contract: bit-identical to rg_etc1 v1.04 driven the way the
-// reference drives it (cLowQuality, no dithering):
+// Behavioural contract: bit-identical to rg_etc1 v1.04, no dithering, at the quality the
+// reference drives it with (cLowQuality, template argument Q = 0) and at the library's other two
+// levels (Q = 1 cMediumQuality: 3^3 lattice scan; Q = 2 cHighQuality: 9^3 scan with the
+// exhaustive per-pixel selector search of evaluate_solution, rg_etc1.cpp:1674-1765, plus the
+// constrained solid-colour trial of one-colour sub-blocks, :2035-2147):
 //   reference/ETCEncoder/src/Compressor.cpp:26-54       block loop
 //   reference/ETCEncoder/src/rg_etc1.cpp:2192-2451      pack_etc1_block
 //   reference/ETCEncoder/src/rg_etc1.cpp:1483-1672      etc1_optimizer::compute / init
@@ -24,6 +27,7 @@
 //     packed bytes (exact integers).
 // A CTA of 128 threads stages its 32 blocks (2 KiB) through shared memory with
 // 16 B coalesced row loads; stores are 8 B per block, contiguous per warp.
+#include <initializer_list>
 #include <vector>
 
 #include "common.cuh"
@@ -178,6 +182,228 @@ __device__ __forceinline__ bool optimize(const uint32_t (&px)[8], bool color4, b
   return true;
 }
 
+// evaluate_solution (rg_etc1.cpp:1674-1765): every selector of every intensity table for every
+// pixel, first strict minimum in ascending selector / table order.
+__device__ __forceinline__ void evaluate_full(const uint32_t (&px)[8], const uint32_t (&p2)[8], uint32_t color,
+                                              bool color4, Sol &trial) {
+  const uint32_t base = scale_color(color, color4);
+  const int b0 = base & 0xFF, b1 = (base >> 8) & 0xFF, b2 = (base >> 16) & 0xFF;
+  trial.err = 0xFFFFFFFFu;
+  trial.color = color;
+  trial.inten = 0;
+  trial.sel = 0;
+#pragma unroll 1
+  for (int it = 0; it < 8; it++) {
+    uint32_t bc[4], bc2[4];
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+      const int yd = c_inten[it][s];
+      const uint32_t r = clamp255(b0 + yd), g = clamp255(b1 + yd), b = clamp255(b2 + yd);
+      bc[s] = r | (g << 8) | (b << 16);
+      bc2[s] = __dp4a(bc[s], bc[s], 0u);
+    }
+    uint32_t total = 0, sel = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      // distances relative to |p|^2 (added once below): the comparison order is unchanged
+      uint32_t be = bc2[0] - 2u * __dp4a(px[i], bc[0], 0u) + p2[i], bs = 0;
+#pragma unroll
+      for (uint32_t s2 = 1; s2 < 4; s2++) {
+        const uint32_t e = bc2[s2] - 2u * __dp4a(px[i], bc[s2], 0u) + p2[i];
+        if (e < be) { be = e; bs = s2; }
+      }
+      total += be;
+      sel |= bs << (2 * i);
+    }
+    // (the reference's running "total >= trial error" break only skips work: a table that triggers
+    // it is never accepted)
+    if (total < trial.err) {
+      trial.err = total;
+      trial.inten = it;
+      trial.sel = sel;
+    }
+  }
+}
+
+// etc1_optimizer at cMediumQuality / cHighQuality: init once, then compute() over one or two sets
+// of scan deltas (rg_etc1.cpp:1483-1625, :2283-2340); the running best survives between the calls.
+template <int Q>
+struct Optimizer {
+  uint32_t px[8], p2[8], luma2[8];
+  uint32_t lmin, lmax, base5;
+  float avg[3];
+  int m[3], limit;
+  bool color4, constrain, valid;
+  Sol best;
+
+  __device__ __forceinline__ void init(const uint32_t (&sub)[8], bool c4, bool cons, uint32_t b5) {
+    color4 = c4; constrain = cons; base5 = b5;
+    limit = c4 ? 15 : 31;
+    uint32_t sr = 0, sg = 0, sb = 0;
+    lmin = 0xFFFFFFFFu; lmax = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      px[i] = sub[i];
+      const uint32_t r = px[i] & 0xFF, g = (px[i] >> 8) & 0xFF, b = px[i] >> 16;
+      sr += r; sg += g; sb += b;
+      const uint32_t l = r + g + b;
+      lmin = min(lmin, l);
+      lmax = max(lmax, l);
+      luma2[i] = 2 * l;
+      p2[i] = __dp4a(px[i], px[i], 0u);
+    }
+    const float flimit = (float)limit;
+    avg[0] = __fmul_rn((float)sr, 0.125f); avg[1] = __fmul_rn((float)sg, 0.125f); avg[2] = __fmul_rn((float)sb, 0.125f);
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+      m[k] = min(max(__float2int_rz(__fadd_rn(__fdiv_rn(__fmul_rn(avg[k], flimit), 255.0f), 0.5f)), 0), limit);
+    best.err = 0xFFFFFFFFu; best.color = 0; best.sel = 0; best.inten = 0;
+    valid = false;
+  }
+
+  __device__ __forceinline__ bool allowed(int r, int g, int b) const {
+    if (!constrain) return true;
+    const int dr = r - (int)(base5 & 0xFF), dg = g - (int)((base5 >> 8) & 0xFF), db = b - (int)(base5 >> 16);
+    return min(dr, min(dg, db)) >= -4 && max(dr, max(dg, db)) <= 3;
+  }
+
+  // evaluate_solution(_fast) + "better than the running best?"
+  __device__ __forceinline__ bool try_point(int r, int g, int b) {
+    if (!allowed(r, g, b)) return false;
+    const uint32_t col = (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16);
+    Sol t;
+    if (Q == 2) evaluate_full(px, p2, col, color4, t);
+    else evaluate(px, p2, luma2, lmin, lmax, col, color4, t);
+    if (t.err < best.err) { best = t; valid = true; return true; }
+    return false;
+  }
+
+  // deltas: see pack_deltas
+  __device__ __forceinline__ void compute(uint64_t deltas, int ndeltas) {
+    const float flimit = (float)limit;
+#pragma unroll 1
+    for (int zi = 0; zi < ndeltas; zi++) {
+      const int zd = (int)((deltas >> (5 * zi)) & 31) - 8, mbb = m[2] + zd;
+      if (mbb < 0) continue;
+      if (mbb > limit) break;
+#pragma unroll 1
+      for (int yi = 0; yi < ndeltas; yi++) {
+        const int yd = (int)((deltas >> (5 * yi)) & 31) - 8, mbg = m[1] + yd;
+        if (mbg < 0) continue;
+        if (mbg > limit) break;
+#pragma unroll 1
+        for (int xi = 0; xi < ndeltas; xi++) {
+          const int xd = (int)((deltas >> (5 * xi)) & 31) - 8, mbr = m[0] + xd;
+          if (mbr < 0) continue;
+          if (mbr > limit) break;
+          if (!try_point(mbr, mbg, mbb)) continue;
+          const int max_trials = ((xd | yd | zd) == 0) ? 4 : 2;
+#pragma unroll 1
+          for (int trial = 0; trial < max_trials; trial++) {
+            const uint32_t base = scale_color(best.color, color4);
+            int cnt[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+              const uint32_t s = (best.sel >> (2 * i)) & 3;
+#pragma unroll
+              for (int q = 0; q < 4; q++) cnt[q] += (s == (uint32_t)q);
+            }
+            int ds[3] = {0, 0, 0};
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+              const int ydl = c_inten[best.inten][s];
+#pragma unroll
+              for (int k = 0; k < 3; k++) {
+                const int bk = (base >> (8 * k)) & 0xFF;
+                ds[k] += cnt[s] * (clamp255(bk + ydl) - bk);
+              }
+            }
+            if (!ds[0] && !ds[1] && !ds[2]) break;
+            int n1[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+              const float ad = __fdiv_rn((float)ds[k], 8.0f);
+              const float f = __fadd_rn(__fdiv_rn(__fmul_rn(__fsub_rn(avg[k], ad), flimit), 255.0f), 0.5f);
+              n1[k] = min(max(__float2int_rz(f), 0), limit);  // x86 cvttss2si, then clamp<int>
+            }
+            if (n1[0] == mbr && n1[1] == mbg && n1[2] == mbb) break;
+            const uint32_t ncol = (uint32_t)n1[0] | ((uint32_t)n1[1] << 8) | ((uint32_t)n1[2] << 16);
+            if (ncol == best.color) break;
+            if (n1[0] == m[0] && n1[1] == m[1] && n1[2] == m[2]) break;
+            if (!try_point(n1[0], n1[1], n1[2])) break;
+          }
+        }
+      }
+    }
+  }
+};
+
+// scan deltas packed five bits each (value + 8), in the reference's array order (rg_etc1.cpp:2283-2334)
+constexpr uint64_t pack_deltas(std::initializer_list<int> d) {
+  uint64_t v = 0;
+  int k = 0;
+  for (int x : d) v |= (uint64_t)(x + 8) << (5 * k++);
+  return v;
+}
+constexpr uint64_t kScan1 = pack_deltas({-1, 0, 1});
+constexpr uint64_t kScan4 = pack_deltas({-4, -3, -2, -1, 0, 1, 2, 3, 4});
+constexpr uint64_t kScan23 = pack_deltas({-3, -2, 2, 3});
+constexpr uint64_t kScan55 = pack_deltas({-5, 5});
+constexpr uint64_t kScan58 = pack_deltas({-8, -7, -6, -5, 5, 6, 7, 8});
+
+// pack_etc1_block_solid_color_constrained (rg_etc1.cpp:2035-2147) for an 8-pixel sub-block of one
+// colour: best exact-table configuration of the given mode, optionally within the differential
+// range of sub-block 0's base colour.  Returns false when no configuration is admissible.
+__device__ __noinline__ bool solid_constrained(uint32_t pixel, bool use_diff, bool have_base, uint32_t base5, Sol &res) {
+  const int col[3] = {(int)(pixel & 0xFF), (int)((pixel >> 8) & 0xFF), (int)((pixel >> 16) & 0xFF)};
+  const int b5[3] = {(int)(base5 & 0xFF), (int)((base5 >> 8) & 0xFF), (int)(base5 >> 16)};
+  const int next_comp[4] = {1, 2, 0, 1};
+  uint32_t best_error = 0xFFFFFFFFu, best_x = 0, best_c1 = 0, best_c2 = 0;
+  int best_i = 0;
+  bool perfect = false;
+  for (int i = 0; i < 3 && !perfect; i++) {
+    const int c1 = col[next_comp[i]], c2 = col[next_comp[i + 1]];
+    for (int delta = -1; delta <= 1 && !perfect; delta++) {
+      const int cpd = clamp255(col[i] + delta);
+      const int d0 = cpd - col[i];
+      for (uint32_t k = g_cfg_off[cpd]; k < g_cfg_off[cpd + 1]; k++) {
+        const uint32_t x = g_cfg[k];
+        const bool diff = x & 1;
+        if (diff != use_diff) continue;
+        const bool lim = diff && have_base;
+        if (lim) {
+          const int d = (int)((x >> 8) & 255) - b5[i];
+          if (d < -4 || d > 3) continue;
+        }
+        const uint32_t p1 = g_inverse[(x & 0xFF) * 256 + c1], p2 = g_inverse[(x & 0xFF) * 256 + c2];
+        if (lim) {
+          const int d1 = (int)(p1 & 0xFF) - b5[next_comp[i]], d2 = (int)(p2 & 0xFF) - b5[next_comp[i + 1]];
+          if (d1 < -4 || d1 > 3 || d2 < -4 || d2 > 3) continue;
+        }
+        const uint32_t err = (uint32_t)(d0 * d0) + (p1 >> 8) * (p1 >> 8) + (p2 >> 8) * (p2 >> 8);
+        if (err < best_error) {
+          best_error = err; best_x = x; best_c1 = p1 & 0xFF; best_c2 = p2 & 0xFF; best_i = i;
+          if (!err) { perfect = true; break; }
+        }
+      }
+    }
+  }
+  if (best_error == 0xFFFFFFFFu) return false;
+  res.err = best_error * 8u;
+  res.inten = (int)((best_x >> 1) & 7);
+  res.sel = ((best_x >> 4) & 3) * 0x5555u;
+  uint32_t c[3] = {0, 0, 0};
+  const uint32_t vals[3] = {(best_x >> 8) & 255, best_c1, best_c2};
+  const int where[3] = {best_i, next_comp[best_i], next_comp[best_i + 1]};
+#pragma unroll
+  for (int k = 0; k < 3; k++)
+#pragma unroll
+    for (int w = 0; w < 3; w++)
+      if (where[k] == w) c[w] = vals[k];
+  res.color = c[0] | (c[1] << 8) | (c[2] << 16);
+  return true;
+}
+
 // pack_etc1_block_solid_color (rg_etc1.cpp:1951-2033)
 __device__ uint2 pack_solid(uint32_t pixel) {
   const int col[3] = {(int)(pixel & 0xFF), (int)((pixel >> 8) & 0xFF), (int)((pixel >> 16) & 0xFF)};
@@ -223,7 +449,8 @@ __device__ uint2 pack_solid(uint32_t pixel) {
 constexpr int kEtcThreads = 128;
 constexpr int kEtcBlocksPerCta = kEtcThreads / 4;
 
-__global__ void __launch_bounds__(kEtcThreads, 6)
+template <int Q>
+__global__ void __launch_bounds__(kEtcThreads, Q == 0 ? 6 : 4)
 etc1_encode_kernel(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, uint32_t first_block,
                    uint32_t num_blocks, uint2 *__restrict__ out) {
   __shared__ uint32_t s_px[kEtcBlocksPerCta][17];  // +1 word: quads of a warp hit distinct banks
@@ -267,7 +494,31 @@ etc1_encode_kernel(const uint32_t *__restrict__ img, uint32_t width, uint32_t bl
       sub[i] = (flip ? a : b) & 0x00FFFFFFu;
     }
     if (ok) {
-      ok = optimize(sub, color4, !color4 && sb == 1, res[0].color, res[sb]);
+      if (Q == 0) {
+        ok = optimize(sub, color4, !color4 && sb == 1, res[0].color, res[sb]);
+      } else {
+        // a one-colour sub-block also tries the exact solid-colour tables (rg_etc1.cpp:2259-2269)
+        Sol solid_res;
+        bool have_solid = false;
+        if (sb == 1 || color4) {
+          bool same = true;
+#pragma unroll
+          for (int i = 1; i < 8; i++) same = same && sub[i] == sub[0];
+          if (same) have_solid = solid_constrained(sub[0], !color4, sb == 1 && !color4, res[0].color, solid_res);
+        }
+        Optimizer<Q> o;
+        o.init(sub, color4, !color4 && sb == 1, res[0].color);
+        o.compute(Q == 2 ? kScan4 : kScan1, Q == 2 ? 9 : 3);
+        ok = o.valid;
+        if (ok) {
+          if (o.best.err > 3000u) {  // refinement_error_thresh0 / 1 (:2312-2340)
+            if (Q == 1) o.compute(kScan23, 4);
+            else if (o.best.err > 6000u) o.compute(kScan58, 8);
+            else o.compute(kScan55, 2);
+          }
+          res[sb] = (have_solid && solid_res.err < o.best.err) ? solid_res : o.best;
+        }
+      }
       if (ok) total += res[sb].err;
     }
   }
@@ -372,10 +623,13 @@ cudaError_t etc1_upload_tables() {
 cudaError_t launch_etc1(const void *rgba_dev, uint32_t width, uint32_t first_block, uint32_t num_blocks,
                         void *out_dev, int quality, cudaStream_t stream) {
   if (num_blocks == 0) return cudaSuccess;
-  if (quality != 0) return cudaErrorNotSupported;  // medium / high: see etc1_quality
   const uint32_t grid = (num_blocks + kEtcBlocksPerCta - 1) / kEtcBlocksPerCta;
-  etc1_encode_kernel<<<grid, kEtcThreads, 0, stream>>>(static_cast<const uint32_t *>(rgba_dev), width, width / 4,
-                                                       first_block, num_blocks, static_cast<uint2 *>(out_dev));
+  const uint32_t *img = static_cast<const uint32_t *>(rgba_dev);
+  uint2 *out = static_cast<uint2 *>(out_dev);
+  if (quality == 0) etc1_encode_kernel<0><<<grid, kEtcThreads, 0, stream>>>(img, width, width / 4, first_block, num_blocks, out);
+  else if (quality == 1) etc1_encode_kernel<1><<<grid, kEtcThreads, 0, stream>>>(img, width, width / 4, first_block, num_blocks, out);
+  else if (quality == 2) etc1_encode_kernel<2><<<grid, kEtcThreads, 0, stream>>>(img, width, width / 4, first_block, num_blocks, out);
+  else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
 

@@ -133,10 +133,12 @@ struct Solution {
   bool valid = false;
 };
 
-// etc1_optimizer for one 8-pixel subblock (rg_etc1.cpp:1346-1885), low quality:
-// one lattice point + at most two refinement trials.
+// etc1_optimizer for one 8-pixel subblock (rg_etc1.cpp:1346-1885).  quality 0 (cLowQuality, what
+// FasTC passes): one lattice point + at most two refinement trials, fast evaluation; 1 (cMedium):
+// a 3^3 scan, fast evaluation; 2 (cHigh): a 9^3 scan, exhaustive per-pixel selector search.
 struct Optimizer {
   const uint8_t (*px)[4];  // 8 source pixels
+  int quality = 0;
   bool color4;
   bool constrain;
   int base5[3];
@@ -172,12 +174,50 @@ struct Optimizer {
     else { out[0] = (r >> 2) | (r << 3); out[1] = (g >> 2) | (g << 3); out[2] = (b >> 2) | (b << 3); }
   }
 
-  // evaluate_solution_fast (rg_etc1.cpp:1767-1885)
-  bool evaluate(int r, int g, int b) {
-    if (constrain) {
-      const int dr = r - base5[0], dg = g - base5[1], db = b - base5[2];
-      if (std::min(dr, std::min(dg, db)) < -4 || std::max(dr, std::max(dg, db)) > 3) return false;
+  bool violates_base5(int r, int g, int b) const {
+    if (!constrain) return false;
+    const int dr = r - base5[0], dg = g - base5[1], db = b - base5[2];
+    return std::min(dr, std::min(dg, db)) < -4 || std::max(dr, std::max(dg, db)) > 3;
+  }
+
+  // evaluate_solution (rg_etc1.cpp:1674-1765): every selector of every intensity table per pixel
+  bool evaluate_full(int r, int g, int b) {
+    if (violates_base5(r, g, b)) return false;
+    int base[3];
+    scaled(r, g, b, base);
+    Solution trial;
+    uint8_t tmp[8];
+    for (int it = 0; it < 8; it++) {
+      int bc[4][3];
+      for (int s = 0; s < 4; s++)
+        for (int k = 0; k < 3; k++) bc[s][k] = clampi(base[k] + kInten[it][s], 0, 255);
+      uint64_t total = 0;
+      for (int c = 0; c < 8; c++) {
+        uint32_t be = 0xFFFFFFFFu;
+        int bs = 0;
+        for (int sidx = 0; sidx < 4; sidx++) {
+          const uint32_t e = (uint32_t)(sq(px[c][0] - bc[sidx][0]) + sq(px[c][1] - bc[sidx][1]) + sq(px[c][2] - bc[sidx][2]));
+          if (e < be) { be = e; bs = sidx; }
+        }
+        tmp[c] = (uint8_t)bs;
+        total += be;
+        if (total >= trial.error) break;
+      }
+      if (total < trial.error) {
+        trial.error = total;
+        trial.inten = it;
+        memcpy(trial.sel, tmp, 8);
+        trial.valid = true;
+      }
     }
+    trial.r = r; trial.g = g; trial.b = b;
+    if (trial.error < best.error) { best = trial; return true; }
+    return false;
+  }
+
+  // evaluate_solution_fast (rg_etc1.cpp:1767-1885)
+  bool evaluate_fast(int r, int g, int b) {
+    if (violates_base5(r, g, b)) return false;
     int base[3];
     scaled(r, g, b, base);
     Solution trial;
@@ -230,37 +270,103 @@ struct Optimizer {
     return false;
   }
 
-  // etc1_optimizer::compute (rg_etc1.cpp:1483-1625) with scan delta {0}
-  bool compute() {
-    if (evaluate(br, bg, bb)) {
-      for (int trial = 0; trial < 2; trial++) {
-        int base[3];
-        scaled(best.r, best.g, best.b, base);
-        int ds[3] = {0, 0, 0};
-        for (int i = 0; i < 8; i++) {
-          const int yd = kInten[best.inten][best.sel[i]];
-          for (int k = 0; k < 3; k++) ds[k] += clampi(base[k] + yd, 0, 255) - base[k];
+  bool evaluate(int r, int g, int b) { return quality == 2 ? evaluate_full(r, g, b) : evaluate_fast(r, g, b); }
+
+  // etc1_optimizer::compute (rg_etc1.cpp:1483-1625) over the lattice points centre + deltas^3
+  bool compute(const int *deltas, int ndeltas) {
+    for (int zi = 0; zi < ndeltas; zi++) {
+      const int zd = deltas[zi], mbb = bb + zd;
+      if (mbb < 0) continue; else if (mbb > limit) break;
+      for (int yi = 0; yi < ndeltas; yi++) {
+        const int yd = deltas[yi], mbg = bg + yd;
+        if (mbg < 0) continue; else if (mbg > limit) break;
+        for (int xi = 0; xi < ndeltas; xi++) {
+          const int xd = deltas[xi], mbr = br + xd;
+          if (mbr < 0) continue; else if (mbr > limit) break;
+          if (!evaluate(mbr, mbg, mbb)) continue;
+          const int max_trials = quality == 0 ? 2 : (((xd | yd | zd) == 0) ? 4 : 2);
+          for (int trial = 0; trial < max_trials; trial++) {
+            int base[3];
+            scaled(best.r, best.g, best.b, base);
+            int ds[3] = {0, 0, 0};
+            for (int i = 0; i < 8; i++) {
+              const int ydl = kInten[best.inten][best.sel[i]];
+              for (int k = 0; k < 3; k++) ds[k] += clampi(base[k] + ydl, 0, 255) - base[k];
+            }
+            if (!ds[0] && !ds[1] && !ds[2]) break;
+            int n1[3];
+            for (int k = 0; k < 3; k++) {
+              const float ad = (float)ds[k] / 8.0f;
+              const float f = (avg[k] - ad) * limit / 255.0f + .5f;
+              // static_cast<uint>(float) on x86-64: cvttss2si (64-bit) then truncation to 32 bits,
+              // reinterpreted as int by clamp<int>
+              n1[k] = clampi((int)(uint32_t)(int64_t)f, 0, limit);
+            }
+            if (n1[0] == mbr && n1[1] == mbg && n1[2] == mbb) break;
+            if (n1[0] == best.r && n1[1] == best.g && n1[2] == best.b) break;
+            if (n1[0] == br && n1[1] == bg && n1[2] == bb) break;
+            if (!evaluate(n1[0], n1[1], n1[2])) break;
+          }
         }
-        if (!ds[0] && !ds[1] && !ds[2]) break;
-        int n1[3];
-        for (int k = 0; k < 3; k++) {
-          const float ad = (float)ds[k] / 8.0f;
-          const float f = (avg[k] - ad) * limit / 255.0f + .5f;
-          // static_cast<uint>(float) on x86-64: cvttss2si (64-bit) then truncation to 32 bits,
-          // reinterpreted as int by clamp<int>
-          n1[k] = clampi((int)(uint32_t)(int64_t)f, 0, limit);
-        }
-        if (n1[0] == br && n1[1] == bg && n1[2] == bb) break;  // both "mbr == br1" and "m_br == br1" (scan delta 0)
-        if (n1[0] == best.r && n1[1] == best.g && n1[2] == best.b) break;
-        if (!evaluate(n1[0], n1[1], n1[2])) break;
       }
     }
     return best.valid;
   }
 };
 
+// pack_etc1_block_solid_color_constrained (rg_etc1.cpp:2035-2147) for an 8-pixel subblock of one
+// colour: the best exact-table configuration in the given mode (diff or not), optionally within
+// the differential range of subblock 0's base colour.  false: no admissible configuration.
+bool solid_constrained(Solution &res, const uint8_t *color, bool use_diff, const int *base5) {
+  const SolidTables &T = solid_tables();
+  static const int next_comp[4] = {1, 2, 0, 1};
+  uint32_t best_error = 0xFFFFFFFFu, best_i = 0;
+  int best_x = 0, best_c1 = 0, best_c2 = 0;
+  bool perfect = false;
+  for (int i = 0; i < 3 && !perfect; i++) {
+    const int c1 = color[next_comp[i]], c2 = color[next_comp[i + 1]];
+    for (int delta = -1; delta <= 1 && !perfect; delta++) {
+      const int cpd = clampi(color[i] + delta, 0, 255);
+      for (uint16_t x : T.config[cpd]) {
+        const int diff = x & 1;
+        if ((int)use_diff != diff) continue;
+        if (diff && base5) {
+          const int d = ((x >> 8) & 255) - base5[i];
+          if (d < -4 || d > 3) continue;
+        }
+        const uint16_t p1 = T.inverse[x & 0xFF][c1], p2 = T.inverse[x & 0xFF][c2];
+        if (diff && base5) {
+          const int d1 = (p1 & 0xFF) - base5[next_comp[i]], d2 = (p2 & 0xFF) - base5[next_comp[i + 1]];
+          if (d1 < -4 || d1 > 3 || d2 < -4 || d2 > 3) continue;
+        }
+        const uint32_t err = (uint32_t)(sq(cpd - color[i]) + sq(p1 >> 8) + sq(p2 >> 8));
+        if (err < best_error) {
+          best_error = err;
+          best_x = x;
+          best_c1 = p1 & 0xFF;
+          best_c2 = p2 & 0xFF;
+          best_i = (uint32_t)i;
+          if (!best_error) { perfect = true; break; }
+        }
+      }
+    }
+  }
+  if (best_error == 0xFFFFFFFFu) return false;
+  res = Solution();
+  res.error = (uint64_t)(uint32_t)(best_error * 8u);
+  res.inten = (best_x >> 1) & 7;
+  memset(res.sel, (best_x >> 4) & 3, 8);
+  int c[3];
+  c[best_i] = (best_x >> 8) & 255;
+  c[next_comp[best_i]] = best_c1;
+  c[next_comp[best_i + 1]] = best_c2;
+  res.r = c[0]; res.g = c[1]; res.b = c[2];
+  res.valid = true;
+  return true;
+}
+
 // pack_etc1_block (rg_etc1.cpp:2192-2451)
-void pack_block(uint8_t *out, const uint8_t px[16][4]) {
+void pack_block(uint8_t *out, const uint8_t px[16][4], int quality) {
   uint32_t first;
   memcpy(&first, px[0], 4);
   bool solid = true;
@@ -269,7 +375,7 @@ void pack_block(uint8_t *out, const uint8_t px[16][4]) {
     memcpy(&v, px[i], 4);
     solid = solid && v == first;
   }
-  if (solid) { pack_solid(out, px[0]); return; }
+  if (solid) { pack_solid(out, px[0]); return; }  // (same at every quality)
 
   uint64_t best_error = ~0ull;
   int best_flip = 0, best_c4 = 0;
@@ -284,13 +390,35 @@ void pack_block(uint8_t *out, const uint8_t px[16][4]) {
         if (flip) memcpy(sub, px[sb * 8], 32);
         else
           for (int i = 0; i < 8; i++) memcpy(sub[i], px[sb * 2 + (i >> 2) + 4 * (i & 3)], 4);
+        // medium / high: a one-colour subblock also tries the exact solid-colour tables (:2259-2269)
+        Solution solid_res;
+        bool have_solid = false;
+        if (quality >= 1 && (sb || c4)) {
+          bool same = true;
+          for (int i = 1; i < 8; i++) same = same && memcmp(sub[i], sub[0], 4) == 0;
+          if (same) {
+            const int b5[3] = {res[0].r, res[0].g, res[0].b};
+            have_solid = solid_constrained(solid_res, sub[0], !c4, (sb && !c4) ? b5 : nullptr);
+          }
+        }
         Optimizer o;
         o.px = sub;
+        o.quality = quality;
         o.color4 = c4 != 0;
         o.constrain = !c4 && sb;
         if (o.constrain) { o.base5[0] = res[0].r; o.base5[1] = res[0].g; o.base5[2] = res[0].b; }
         o.init();
-        if (!o.compute()) break;
+        static const int d0[] = {0}, d1[] = {-1, 0, 1}, d4[] = {-4, -3, -2, -1, 0, 1, 2, 3, 4};
+        static const int d23[] = {-3, -2, 2, 3}, d55[] = {-5, 5}, d58[] = {-8, -7, -6, -5, 5, 6, 7, 8};
+        if (!(quality == 2 ? o.compute(d4, 9) : (quality == 1 ? o.compute(d1, 3) : o.compute(d0, 1)))) break;
+        if (quality >= 1) {
+          if (o.best.error > 3000) {  // refinement_error_thresh0 / 1 (:2312-2340)
+            if (quality == 1) o.compute(d23, 4);
+            else if (o.best.error > 6000) o.compute(d58, 8);
+            else o.compute(d55, 2);
+          }
+          if (have_solid && solid_res.error < o.best.error) o.best = solid_res;
+        }
         res[sb] = o.best;
         trial += res[sb].error;
         if (trial >= best_error) break;
@@ -335,16 +463,29 @@ void pack_block(uint8_t *out, const uint8_t px[16][4]) {
 }  // namespace
 
 // ETCC::Compress_RG's block loop (ETCEncoder/src/Compressor.cpp:26-54)
-extern "C" void fastc_oracle_etc1(const uint8_t *rgba, uint32_t width, uint32_t height, uint32_t first_block,
-                                  uint32_t num_blocks, uint8_t *out) {
-  (void)height;
+static void run_etc1(const uint8_t *rgba, uint32_t width, uint32_t first_block, uint32_t num_blocks, uint8_t *out,
+                     int quality) {
   const uint32_t bw = width / 4;
   for (uint32_t n = 0; n < num_blocks; n++) {
     const uint32_t bi = first_block + n, bx = bi % bw, by = bi / bw;
     uint8_t px[16][4];
     for (int j = 0; j < 4; j++) memcpy(px[4 * j], rgba + ((size_t)(by * 4 + j) * width + bx * 4) * 4, 16);
-    pack_block(out + (size_t)bi * 8, px);
+    pack_block(out + (size_t)bi * 8, px, quality);
   }
+}
+
+extern "C" void fastc_oracle_etc1(const uint8_t *rgba, uint32_t width, uint32_t height, uint32_t first_block,
+                                  uint32_t num_blocks, uint8_t *out) {
+  (void)height;
+  run_etc1(rgba, width, first_block, num_blocks, out, 0);
+}
+
+// rg_etc1::pack_etc1_block with etc1_pack_params::m_quality = 0 cLowQuality / 1 cMediumQuality /
+// 2 cHighQuality (dithering off).
+extern "C" void fastc_oracle_etc1_quality(const uint8_t *rgba, uint32_t width, uint32_t height, uint32_t first_block,
+                                          uint32_t num_blocks, uint8_t *out, int quality) {
+  (void)height;
+  run_etc1(rgba, width, first_block, num_blocks, out, quality);
 }
 
 // Derived solid-colour tables, for tests/test_tables.py: writes the config list of `color`

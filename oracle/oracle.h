@@ -20,6 +20,10 @@ void fastc_oracle_dxt(int dxt5, const uint8_t *rgba, uint32_t width, uint32_t he
 void fastc_oracle_etc1(const uint8_t *rgba, uint32_t width, uint32_t height,
                        uint32_t first_block, uint32_t num_blocks, uint8_t *out);
 
+// quality: rg_etc1::etc1_quality (0 low -- what FasTC passes --, 1 medium, 2 high)
+void fastc_oracle_etc1_quality(const uint8_t *rgba, uint32_t width, uint32_t height,
+                               uint32_t first_block, uint32_t num_blocks, uint8_t *out, int quality);
+
 // rng_mode 0: the reference's single global LCG, *lcg_state is read and updated
 //             (pins the restatement against oracle/_ref at q>0, -t 1);
 // rng_mode 1: per-chain keyed streams derived from (seed, block index, chain id)

@@ -27,6 +27,7 @@
 #include <fcntl.h>
 
 #include "FasTC/TexComp.h"
+#include "rg_etc1.h"
 #include "FasTC/BPTCCompressor.h"
 #include "FasTC/CompressionJob.h"
 #include "FasTC/CompressedImage.h"
@@ -118,6 +119,25 @@ int fastc_ref_bptc_compress_settings(const uint8_t *rgba, uint32_t width, uint32
   s.m_ErrorMetric = error_metric ? BPTCC::eErrorMetric_Nonuniform : BPTCC::eErrorMetric_Uniform;
   FasTC::CompressionJob cj(FasTC::eCompressionFormat_BPTC, rgba, out, width, height);
   BPTCC::Compress(cj, s);
+  return 0;
+}
+
+// rg_etc1::pack_etc1_block over the whole image at a given quality (FasTC's ETCC::Compress_RG,
+// ETCEncoder/src/Compressor.cpp:26-54, hard-codes cLowQuality; this is its block loop with the
+// library's other two levels).
+int fastc_ref_etc1_compress_quality(const uint8_t *rgba, uint32_t width, uint32_t height, uint8_t *out, int quality) {
+  rg_etc1::etc1_pack_params params;
+  params.m_quality = quality == 0 ? rg_etc1::cLowQuality : (quality == 1 ? rg_etc1::cMediumQuality : rg_etc1::cHighQuality);
+  params.m_dithering = false;
+  rg_etc1::pack_etc1_block_init();
+  const uint32_t *in = reinterpret_cast<const uint32_t *>(rgba);
+  for (uint32_t j = 0; j < height; j += 4)
+    for (uint32_t i = 0; i < width; i += 4) {
+      uint32_t pixels[16];
+      for (int r = 0; r < 4; r++) memcpy(pixels + 4 * r, in + (size_t)(j + r) * width + i, 16);
+      rg_etc1::pack_etc1_block(out, pixels, params);
+      out += 8;
+    }
   return 0;
 }
 

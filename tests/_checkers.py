@@ -43,6 +43,8 @@ class Oracle:
             L.fastc_oracle_bc7.argtypes = [_u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _u8p,
                                            C.c_int, C.c_int, C.POINTER(C.c_uint32), C.c_uint64, C.c_uint32]
             L.fastc_oracle_bc7.restype = None
+        L.fastc_oracle_etc1_quality.argtypes = [_u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _u8p, C.c_int]
+        L.fastc_oracle_etc1_quality.restype = None
         L.fastc_oracle_bc7_settings.argtypes = [_u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _u8p,
                                                 C.c_int, C.c_int, C.POINTER(C.c_uint32), C.c_uint64, C.c_uint32,
                                                 C.c_uint32, C.c_uint32, C.c_int]
@@ -56,7 +58,7 @@ class Oracle:
     def compress(self, fmt: str, img: np.ndarray, *, quality: int = 50, first_block: int = 0,
                  num_blocks: int | None = None, rng_mode: int = 1, lcg_state: int = 1,
                  seed: int = 0, wm_base: int = 0, block_index_base: int = 0, block_modes: int = 0xFF,
-                 error_metric: int = 0):
+                 error_metric: int = 0, etc1_quality: int = 0):
         """Returns (bytes array for the WHOLE image (untouched blocks zero), final lcg state)."""
         img = np.ascontiguousarray(img, dtype=np.uint8)
         h, w = img.shape[:2]
@@ -68,7 +70,7 @@ class Oracle:
         if fmt in ("DXT1", "DXT5"):
             self.lib.fastc_oracle_dxt(int(fmt == "DXT5"), _p(img), w, h, first_block, num_blocks, _p(out))
         elif fmt == "ETC1":
-            self.lib.fastc_oracle_etc1(_p(img), w, h, first_block, num_blocks, _p(out))
+            self.lib.fastc_oracle_etc1_quality(_p(img), w, h, first_block, num_blocks, _p(out), etc1_quality)
         else:
             self.lib.fastc_oracle_bc7_settings(_p(img), w, h, first_block, num_blocks, _p(out), quality, rng_mode,
                                                C.byref(st), seed, wm_base, block_index_base, block_modes,
@@ -108,6 +110,8 @@ class Reference:
         L.fastc_ref_bptc_compress_settings.argtypes = [_u8p, C.c_uint32, C.c_uint32, _u8p, C.c_int, C.c_uint32,
                                                        C.c_int]
         L.fastc_ref_bptc_compress_settings.restype = C.c_int
+        L.fastc_ref_etc1_compress_quality.argtypes = [_u8p, C.c_uint32, C.c_uint32, _u8p, C.c_int]
+        L.fastc_ref_etc1_compress_quality.restype = C.c_int
 
     @staticmethod
     def available() -> bool:
@@ -133,6 +137,14 @@ class Reference:
         if rc != 0:
             raise RuntimeError("reference CompressImageData failed")
         return out, ms.value
+
+    def compress_etc1_quality(self, img: np.ndarray, quality: int) -> np.ndarray:
+        """rg_etc1::pack_etc1_block over the image at cLow / cMedium / cHigh quality (0 / 1 / 2)."""
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        h, w = img.shape[:2]
+        out = np.zeros(nblocks(w, h) * 8, dtype=np.uint8)
+        self.lib.fastc_ref_etc1_compress_quality(_p(img), w, h, _p(out), quality)
+        return out
 
     def compress_bptc_settings(self, img: np.ndarray, *, quality: int = 0, block_modes: int = 0xFF,
                                error_metric: int = 0, seed: int = 1, wm_count: int = 0) -> np.ndarray:

@@ -100,3 +100,38 @@ def test_etc1_config5_size_device_path_roundtrip(gpu, oracle):
         assert (got[first * 8:(first + 5000) * 8] == w[first * 8:(first + 5000) * 8]).all(), first
     dec = oracle.decode("ETC1", got, 4096, 4096)
     assert oracle.psnr(img, dec) > 30.0
+
+
+@pytest.mark.parametrize("quality", [1, 2])
+def test_etc1_medium_high_quality_match_oracle(gpu, oracle, quality):
+    """rg_etc1's cMediumQuality / cHighQuality (BASELINE configs[4] names the high one; FasTC itself
+    hard-codes cLowQuality): bit-exact against the oracle, which tests/test_oracle_vs_ref.py pins to
+    rg_etc1::pack_etc1_block at the same quality."""
+    rng = np.random.default_rng(23)
+    smooth = synth_rgba(128, 64 if quality == 2 else 128, 3, opaque=True)
+    noise = rng.integers(0, 256, (32, 128, 4), dtype=np.uint8)
+    base = rng.integers(0, 256, (8, 32, 1, 1, 4))
+    low = (base + rng.integers(-6, 7, (8, 32, 4, 4, 4))).clip(0, 255).astype(np.uint8)
+    low = low.transpose(0, 2, 1, 3, 4).reshape(32, 128, 4)
+    half = rng.integers(0, 256, (32, 128, 4), dtype=np.uint8)
+    cols = rng.integers(0, 256, (8, 32, 4), dtype=np.uint8)
+    for by in range(8):
+        for bx in range(32):
+            ys, xs = [(slice(0, 2), slice(0, 4)), (slice(2, 4), slice(0, 4)), (slice(0, 4), slice(0, 2)),
+                      (slice(0, 4), slice(2, 4))][(by * 32 + bx) % 4]
+            blk = half[by * 4:by * 4 + 4, bx * 4:bx * 4 + 4]
+            blk[ys, xs] = cols[by, bx]
+            if (by + bx) % 3 == 0:
+                blk[...] = cols[by, bx]
+                blk[ys, xs] = (cols[by, bx].astype(int) + rng.integers(-9, 10, 4)).clip(0, 255)
+    solid = np.repeat(np.repeat(rng.integers(0, 256, (2, 32, 4), dtype=np.uint8), 4, 0), 4, 1)
+    img = np.ascontiguousarray(np.concatenate([smooth, noise, low, half, solid], 0))
+    img[..., 3] = 255
+    got, _ = gpu.compress(F.ETC1, img, etc1_quality=quality)
+    want, _ = oracle.compress("ETC1", img, etc1_quality=quality)
+    bad = np.flatnonzero((got.reshape(-1, 8) != want.reshape(-1, 8)).any(1))
+    assert bad.size == 0, (quality, bad[:10])
+    # higher quality never decodes worse than the reference's cLowQuality
+    lowq, _ = gpu.compress(F.ETC1, img)
+    assert oracle.psnr(img, oracle.decode("ETC1", got, 128, img.shape[0])) >= \
+        oracle.psnr(img, oracle.decode("ETC1", lowq, 128, img.shape[0]))

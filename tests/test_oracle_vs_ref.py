@@ -182,3 +182,35 @@ def test_bc7_oracle_nonuniform_metric_equals_reference(oracle, reference, mask, 
     assert keep.mean() > 0.5
     assert (a.reshape(-1, 16)[keep] == b.reshape(-1, 16)[keep]).all()
     assert st == reference.get_seed()
+
+
+@pytest.mark.parametrize("quality", [0, 1, 2])
+def test_etc1_oracle_quality_levels_equal_reference(oracle, reference, quality):
+    """rg_etc1's three quality levels (FasTC only ever passes cLowQuality; BASELINE configs[4] names
+    the high one): the oracle against rg_etc1::pack_etc1_block itself."""
+    rng = np.random.default_rng(17)
+    h = 64 if quality == 2 else 128
+    smooth = synth_rgba(128, h, 3, opaque=True)
+    noise = rng.integers(0, 256, (32, 128, 4), dtype=np.uint8)
+    base = rng.integers(0, 256, (8, 32, 1, 1, 4))
+    low = (base + rng.integers(-6, 7, (8, 32, 4, 4, 4))).clip(0, 255).astype(np.uint8)
+    low = low.transpose(0, 2, 1, 3, 4).reshape(32, 128, 4)
+    # half-solid blocks: one 2x4 / 4x2 subblock of a single colour (the constrained solid path)
+    half = rng.integers(0, 256, (32, 128, 4), dtype=np.uint8)
+    cols = rng.integers(0, 256, (8, 32, 4), dtype=np.uint8)
+    for by in range(8):
+        for bx in range(32):
+            k = (by * 32 + bx) % 4
+            ys, xs = [(slice(0, 2), slice(0, 4)), (slice(2, 4), slice(0, 4)), (slice(0, 4), slice(0, 2)),
+                      (slice(0, 4), slice(2, 4))][k]
+            blk = half[by * 4:by * 4 + 4, bx * 4:bx * 4 + 4]
+            blk[ys, xs] = cols[by, bx]
+            if (by + bx) % 3 == 0:   # both halves solid, close colours
+                blk[...] = cols[by, bx]
+                blk[ys, xs] = (cols[by, bx].astype(int) + rng.integers(-9, 10, 4)).clip(0, 255)
+    img = np.ascontiguousarray(np.concatenate([smooth, noise, low, half], 0))
+    img[..., 3] = 255
+    a, _ = oracle.compress("ETC1", img, etc1_quality=quality)
+    b = reference.compress_etc1_quality(img, quality)
+    bad = np.flatnonzero((a.reshape(-1, 8) != b.reshape(-1, 8)).any(1))
+    assert bad.size == 0, (quality, bad[:10])
