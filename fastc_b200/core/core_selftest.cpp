@@ -201,10 +201,24 @@ static int Convert(const char *in, const char *out) {
   return dst.Write() ? 0 : 1;
 }
 
+// `writektx fmt w h payload.bin out.ktx`: a compressed payload wrapped by the KTX writer (no GPU).
+static int WriteKtx(const char *fmt, const char *w, const char *h, const char *payload, const char *out) {
+  const uint32 width = (uint32)atoi(w), height = (uint32)atoi(h);
+  const FasTC::ECompressionFormat f = ParseFormat(fmt);
+  std::vector<uint8> data(CompressedImage::GetCompressedSize(width, height, f));
+  FILE *fp = fopen(payload, "rb");
+  if (!fp || fread(data.data(), 1, data.size(), fp) != data.size()) return 2;
+  fclose(fp);
+  CompressedImage ci(width, height, f, data.data());
+  ImageFile dst(out, eFileFormat_KTX, ci);
+  return dst.Write() ? 0 : 1;
+}
+
 int main(int argc, char **argv) {
+  if (argc >= 7 && !strcmp(argv[1], "writektx")) return WriteKtx(argv[2], argv[3], argv[4], argv[5], argv[6]);
   if (argc >= 2 && !strcmp(argv[1], "api")) return TestApi();
   if (argc >= 4 && !strcmp(argv[1], "convert")) return Convert(argv[2], argv[3]);
   if (argc >= 2 && !strcmp(argv[1], "gpu")) return TestGpu(argc, argv);
-  fprintf(stderr, "usage: core_selftest api | convert <in> <out> | gpu <rgba.raw> <w> <h> <fmt> <quality> <seed> <out-prefix>\n");
+  fprintf(stderr, "usage: core_selftest api | convert <in> <out> | writektx <fmt> <w> <h> <payload> <out.ktx> | gpu <rgba.raw> <w> <h> <fmt> <quality> <seed> <out-prefix>\n");
   return 2;
 }

@@ -27,6 +27,7 @@
 #include <fcntl.h>
 
 #include "FasTC/TexComp.h"
+#include "FasTC/ImageFile.h"
 #include "rg_etc1.h"
 #include "FasTC/BPTCCompressor.h"
 #include "FasTC/CompressionJob.h"
@@ -139,6 +140,15 @@ int fastc_ref_etc1_compress_quality(const uint8_t *rgba, uint32_t width, uint32_
       out += 8;
     }
   return 0;
+}
+
+// The reference's own KTX writer (IO/src/ImageWriterKTX.cpp:69-160) through ImageFile::Write.
+// NOTE the writer keeps the payload size in function-local statics, so one process must use one
+// image size per format family (BPTC / DXT5, DXT1, RGBA).
+int fastc_ref_write_ktx(int format, const uint8_t *cmp, uint32_t width, uint32_t height, const char *path) {
+  CompressedImage ci(width, height, to_format(format), cmp);
+  ImageFile f(path, eFileFormat_KTX, ci);
+  return f.Write() ? 0 : 1;
 }
 
 uint32_t fastc_ref_compressed_size(int format, uint32_t width, uint32_t height) {

@@ -138,6 +138,13 @@ class Reference:
             raise RuntimeError("reference CompressImageData failed")
         return out, ms.value
 
+    def write_ktx(self, fmt: str, cmp: np.ndarray, w: int, h: int, path) -> None:
+        """The reference's ImageWriterKTX through ImageFile::Write."""
+        cmp = np.ascontiguousarray(cmp, dtype=np.uint8)
+        self.lib.fastc_ref_write_ktx.argtypes = [C.c_int, _u8p, C.c_uint32, C.c_uint32, C.c_char_p]
+        if self.lib.fastc_ref_write_ktx(FMT[fmt], _p(cmp), w, h, str(path).encode()) != 0:
+            raise RuntimeError("reference KTX write failed")
+
     def compress_etc1_quality(self, img: np.ndarray, quality: int) -> np.ndarray:
         """rg_etc1::pack_etc1_block over the image at cLow / cMedium / cHigh quality (0 / 1 / 2)."""
         img = np.ascontiguousarray(img, dtype=np.uint8)

@@ -223,3 +223,24 @@ def test_png_write_then_load_roundtrip(tmp_path):
     except ImportError:
         return
     assert (np.asarray(PILImage.open(tmp_path / "b.png").convert("RGBA")) == img).all()
+
+
+@pytest.mark.parametrize("fmt", ["BPTC", "DXT1", "DXT5"])
+def test_ktx_file_is_byte_identical_to_the_reference_writer(tmp_path, fmt):
+    """a whole .ktx written by our ImageFile (what `tc -d out.ktx` calls) equals, byte
+    for byte, the file the reference's ImageWriterKTX (IO/src/ImageWriterKTX.cpp:69-160) writes for
+    the same payload: identifier, endianness, GL enums, dimensions, the KTXorientation key/value block
+    with its padding, imageSize and the payload.  CPU only."""
+    from _checkers import Reference, BLOCK_BYTES
+    if not Reference.available():
+        pytest.skip("oracle/_ref/libfastc_ref.so not built")
+    w, h = 64, 32  # one size per process: the reference writer caches imageSize in a static
+    payload = np.random.default_rng(3).integers(0, 256, (w // 4) * (h // 4) * BLOCK_BYTES[fmt], dtype=np.uint8)
+    (tmp_path / "p.bin").write_bytes(payload.tobytes())
+    r = subprocess.run([str(SELFTEST), "writektx", fmt, str(w), str(h), str(tmp_path / "p.bin"), str(tmp_path / "ours.ktx")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    Reference().write_ktx(fmt, payload, w, h, tmp_path / "ref.ktx")
+    ours, ref = (tmp_path / "ours.ktx").read_bytes(), (tmp_path / "ref.ktx").read_bytes()
+    assert len(ours) == 96 + payload.size
+    assert ours == ref
