@@ -992,7 +992,24 @@ __device__ __forceinline__ int sort_key(int ibits, int n, uint32_t err) {
   const uint32_t e = err / (uint32_t)max(n, 1);
   const int lvl = e < 4096u ? (e < 128u ? 0 : 1)
                             : (e < 16384u ? (e < 8192u ? 2 : 3) : (e < 32768u ? 4 : (e < 49152u ? 5 : (e < 65536u ? 6 : 7))));
+#ifdef FASTC_SORT_SIZE_MAJOR
   return ((ibits - 2) * 17 + n) * kLenLevels + lvl;
+#else
+  // level-major: EVERY expected-long chain of a precision class is dequeued before any expected-short
+  // one (size-major order left the long chains of the small clusters for the end of the queue: the
+  // persistent kernel's tail); within a level the clusters still come sorted by size, so the lanes
+  // of a warp keep fitting clusters of (nearly) one size
+  return ((ibits - 2) * kLenLevels + lvl) * 17 + n;
+#endif
+}
+__device__ __forceinline__ void sort_key_parts(int k, int &cls, int &lvl, int &n) {
+#ifdef FASTC_SORT_SIZE_MAJOR
+  const int base = k / kLenLevels;
+  lvl = k % kLenLevels; cls = base / 17; n = base % 17;
+#else
+  const int base = k / 17;
+  n = k % 17; cls = base / kLenLevels; lvl = base % kLenLevels;
+#endif
 }
 // mean steps of a chain of each level (same measurement), for the work estimate of bc7_bin_offsets
 __constant__ float c_level_steps[kLenLevels] = {57.0f, 170.0f, 245.0f, 297.0f, 372.0f, 437.0f, 500.0f, 586.0f};
@@ -1379,9 +1396,9 @@ __global__ void bc7_bin_offsets(uint32_t *bins, uint32_t grid_ctas) {
   uint32_t off = 0;
   float work[3] = {0.0f, 0.0f, 0.0f};
   for (int k = kSortKeys - 1; k >= 0; k--) {
-    const int base = k / kLenLevels, lvl = k % kLenLevels;
-    const int cls = base / 17, n = base % 17;
-    if (n == 16 && lvl == kLenLevels - 1) bins[kBinFetch + cls] = off;  // the class's region starts with its largest clusters
+    int cls, lvl, n;
+    sort_key_parts(k, cls, lvl, n);
+    if (n == 16 && lvl == kLenLevels - 1) bins[kBinFetch + cls] = off;  // the class's region starts with its top key
     bins[kBinOffset + k] = off;
     off += bins[kBinCount + k];
     bins[kBinCursor + k] = 0;
@@ -1517,7 +1534,7 @@ __device__ __forceinline__ uint32_t move_endpoint(uint32_t src, uint32_t dir, in
 // usual case, the work list is sorted by cluster size), so no pixel needs a validity test.
 template <bool UNI>
 __device__ __forceinline__ void sa_pixels(uint32_t (*s_pix)[kPixStride], const uint2 *pal, int tid, int n, int nbm1,
-                                          int nmax, uint32_t q1p, uint32_t q2p, uint32_t cq, float inv16,
+                                          int nmax, uint32_t q1p, uint32_t q2p, uint32_t cq, float inv16, uint32_t k256,
                                           uint32_t &total, uint32_t &slow, uint32_t (&word)[2]) {
   const int n1 = n - 1, n2 = n - 2, n3 = n - 3;  // pixel i + k of a group of four is valid iff i < n - k
   // One pixel: adds its error unless it is flagged or past the lane's cluster, shifts the chosen
@@ -1525,22 +1542,28 @@ __device__ __forceinline__ void sa_pixels(uint32_t (*s_pix)[kPixStride], const u
 #define SA_PIXEL(PX, VALID, FLAG)                                                                          \
   {                                                                                                        \
     const uint32_t px_ = (PX);                                                                             \
-    const int num_ = (int)(__dp4a(px_, q2p, 0u) - __dp4a(px_, q1p, cq));                                   \
-    const int v_ = __float2int_rd(__fmul_rn((float)num_, inv16)); /* 16.16 fixed point bucket coordinate */ \
+    /* num + 0x4B400000: the bit pattern of the float 12582912 + num (|num| < 2^22), so the int -> float   \
+       conversion is one exact FADD on the FMA pipe instead of an I2F on the (binding) ALU pipe */        \
+    const int nb_ = (int)(__dp4a(px_, q2p, 0x4B400000u) - __dp4a(px_, q1p, cq));                           \
+    const float fn_ = __fsub_rn(__int_as_float(nb_), 12582912.0f);                                         \
+    /* vp = floor(num * inv16) + 1: the 16.16 fixed point bucket coordinate, plus one */                   \
+    const int vp_ = __float2int_rd(__fmaf_rn(fn_, inv16, 1.0f));                                           \
     /* flagged: within 2^-16 of a bucket boundary (or past the cluster: those flags are masked off later) */ \
-    const bool ok_ = (VALID) && ((((uint32_t)v_ + 1u) & 0xFFFEu) != 0u);                                   \
+    const bool ok_ = (VALID) && (((uint32_t)vp_ & 0xFFFEu) != 0u);                                         \
     FLAG = !ok_;                                                                                           \
-    const int ja_ = __vimin_s32_relu(v_ >> 16, nbm1); /* floor, clamped */                                 \
+    const int ja_ = __vimin_s32_relu(vp_ >> 16, nbm1); /* floor, clamped (differs from it only when flagged) */ \
     const uint2 c_ = pal[ja_ * kSaThreads];                                                                \
     const uint32_t da_ = __vabsdiffu4(c_.x, px_), db_ = __vabsdiffu4(c_.y, px_);                           \
-    const uint32_t ea_ = __dp4a(da_, da_, 0u), eb_ = __dp4a(db_, db_, 0u);                                 \
+    /* keys = error << 8 | bucket: one min picks the error and the bucket (the lower bucket wins ties,     \
+       like the reference's strict <), the sum of <= 16 keys carries sum(error) << 8 | sum(bucket) with    \
+       no carry between the fields (errors < 2^18, buckets <= 15) */                                       \
+    uint32_t ka_ = __dp4a(da_, da_, 0u) * k256 + (uint32_t)ja_;                                            \
+    const uint32_t kb_ = __dp4a(db_, db_, 0u) * k256 + (uint32_t)ja_;                                      \
     /* a projection before endpoint 1 only tests bucket 0; past endpoint 2 both colours are bucket nbm1 */ \
-    uint32_t e_, pick_;                                                                                    \
-    asm("{\n\t.reg .pred p, q;\n\tsetp.ge.s32 q, %4, 0;\n\tsetp.lt.and.u32 p, %3, %2, q;\n\t"              \
-        "selp.u32 %0, %3, %2, p;\n\tmov.u32 %1, %5;\n\t@p add.u32 %1, %1, 1;\n\t}"                           \
-        : "=r"(e_), "=&r"(pick_) : "r"(ea_), "r"(eb_), "r"(v_), "r"(ja_));                                 \
-    if (ok_) total += e_;                                                                                  \
-    acc = __funnelshift_r(acc, pick_, 4);                                                                  \
+    if (vp_ >= 1) ka_ = __viaddmin_u32(kb_, 1u, ka_);                                                      \
+    if (!(VALID)) ka_ = 0u;                                                                                \
+    total += ka_; /* flagged pixels included: the exact replay takes their provisional key back */         \
+    acc = __funnelshift_r(acc, ka_, 4);                                                                    \
   }
 #pragma unroll
   for (int half = 0; half < 2; half++) {
@@ -1570,8 +1593,8 @@ __device__ __forceinline__ void sa_pixels(uint32_t (*s_pix)[kPixStride], const u
 // The same for a warp whose lanes all fit 16-pixel clusters (mode 6 and the mode 4/5 fits: two
 // thirds of all annealing steps): no loop, no validity tests, no partial index words.
 __device__ __forceinline__ void sa_pixels16(uint32_t (*s_pix)[kPixStride], const uint2 *pal, int tid, int nbm1,
-                                            uint32_t q1p, uint32_t q2p, uint32_t cq, float inv16, uint32_t &total,
-                                            uint32_t &slow, uint32_t (&word)[2]) {
+                                            uint32_t q1p, uint32_t q2p, uint32_t cq, float inv16, uint32_t k256,
+                                            uint32_t &total, uint32_t &slow, uint32_t (&word)[2]) {
 #pragma unroll
   for (int half = 0; half < 2; half++) {
     uint32_t acc = 0;
@@ -1599,8 +1622,10 @@ __device__ __forceinline__ void sa_palette_uniform(uint2 (*s_pal)[kSaThreads], i
   uint32_t cur = q1;
 #pragma unroll
   for (int j = 1; j <= NB - 2; j++) {
-    const uint32_t w = NB == 4 ? kSelWeights2[j] : (NB == 8 ? kSelWeights3[j] : kWeights4[j]);
-    const uint32_t nxt = (((blo + dlo * w) >> 6) & 0x00FF00FFu) | (((bhi + dhi * w) << 2) & 0xFF00FF00u);
+    const uint32_t w4 = 4u * (NB == 4 ? kSelWeights2[j] : (NB == 8 ? kSelWeights3[j] : kWeights4[j]));
+    // the interpolated byte of each channel sits in byte 1 / 3 of its 16-bit lane (see sa_eval): two
+    // multiply-adds and one byte permute per colour
+    const uint32_t nxt = __byte_perm(blo + dlo * w4, bhi + dhi * w4, 0x7351);
     s_pal[j - 1][tid] = make_uint2(cur, nxt);
     cur = nxt;
   }
@@ -1616,28 +1641,31 @@ __device__ __forceinline__ void sa_palette_uniform(uint2 (*s_pal)[kSaThreads], i
 // candidate buckets of a pixel (floor and ceil of its projection) come from one 64-bit load.
 __device__ __forceinline__ uint32_t sa_eval(uint32_t (*s_pix)[kPixStride], uint2 (*s_pal)[kSaThreads],
                                             const uint8_t *__restrict__ s_w, int tid, const SaConst &K, int nmax,
-                                            int nbmax, int uflags, uint32_t q1, uint32_t q2, uint32_t &idx_lo,
-                                            uint32_t &idx_hi) {
+                                            int nbmax, int uflags, uint32_t q1, uint32_t q2, uint32_t k256,
+                                            uint32_t &idx_lo, uint32_t &idx_hi) {
   const uint32_t d11 = __dp4a(q1, q1, 0u), d12 = __dp4a(q1, q2, 0u), d22 = __dp4a(q2, q2, 0u);
   const int den = (int)d22 - 2 * (int)d12 + (int)d11;       // |e2 - e1|^2
   {
     // ((64 - w) * e1 + w * e2 + 32) >> 6 per channel == (64 * e1 + 32 + w * (e2 - e1)) >> 6, channels
-    // 0,2 and 1,3 in 16-bit halves; the packed difference may borrow across halves, the sum is
-    // exact modulo 2^32 and the true value has no carries
+    // 0,2 and 1,3 in 16-bit lanes; the packed difference may borrow across lanes, the sum is
+    // exact modulo 2^32 and the true value has no carries.  Everything is scaled by 4 (the largest
+    // value, 4 * (64 * 255 + 32), still fits 16 bits) so that the >> 6 becomes "take byte 1 of the
+    // lane": one byte permute packs the four channels.
     const uint32_t e1lo = q1 & 0x00FF00FFu, e1hi = (q1 >> 8) & 0x00FF00FFu;
     const uint32_t dlo = (q2 & 0x00FF00FFu) - e1lo, dhi = ((q2 >> 8) & 0x00FF00FFu) - e1hi;
-    const uint32_t blo = e1lo * 64u + 0x00200020u, bhi = e1hi * 64u + 0x00200020u;
+    const uint32_t blo = e1lo * k256 + 0x00800080u, bhi = e1hi * k256 + 0x00800080u;
     if (uflags & 2) {  // every lane of the warp has nbm1 == nbmax
       if (nbmax == 3) sa_palette_uniform<4>(s_pal, tid, q1, q2, blo, dlo, bhi, dhi);
       else if (nbmax == 7) sa_palette_uniform<8>(s_pal, tid, q1, q2, blo, dlo, bhi, dhi);
       else sa_palette_uniform<16>(s_pal, tid, q1, q2, blo, dlo, bhi, dhi);
     } else {
       const uint8_t *wt = s_w + K.woff + 1;
+      const uint32_t dlo4 = dlo * 4u, dhi4 = dhi * 4u;
       uint32_t cur = q1;  // colour 0 (weight 0) is endpoint 1 itself
 #pragma unroll 4
       for (int j = 0; j <= nbmax; j++) {  // rows past this lane's bucket count are never read by it
         const uint32_t w = wt[j];
-        const uint32_t nxt = (((blo + dlo * w) >> 6) & 0x00FF00FFu) | (((bhi + dhi * w) << 2) & 0xFF00FF00u);
+        const uint32_t nxt = __byte_perm(blo + dlo4 * w, bhi + dhi4 * w, 0x7351);
         s_pal[j][tid] = make_uint2(cur, nxt);
         cur = nxt;
       }
@@ -1654,9 +1682,10 @@ __device__ __forceinline__ uint32_t sa_eval(uint32_t (*s_pix)[kPixStride], uint2
   const int n = K.n, nbm1 = K.nbm1;
   const uint2 *pal = &s_pal[0][tid];
   uint32_t total = 0, slow = 0, word[2];
-  if ((uflags & 1) && nmax == 16) sa_pixels16(s_pix, pal, tid, nbm1, q1p, q2p, cq, inv16, total, slow, word);
-  else if (uflags & 1) sa_pixels<true>(s_pix, pal, tid, n, nbm1, nmax, q1p, q2p, cq, inv16, total, slow, word);
-  else sa_pixels<false>(s_pix, pal, tid, n, nbm1, nmax, q1p, q2p, cq, inv16, total, slow, word);
+  // `total` sums the pixels' keys (error << 8 | bucket, see SA_PIXEL)
+  if ((uflags & 1) && nmax == 16) sa_pixels16(s_pix, pal, tid, nbm1, q1p, q2p, cq, inv16, k256, total, slow, word);
+  else if (uflags & 1) sa_pixels<true>(s_pix, pal, tid, n, nbm1, nmax, q1p, q2p, cq, inv16, k256, total, slow, word);
+  else sa_pixels<false>(s_pix, pal, tid, n, nbm1, nmax, q1p, q2p, cq, inv16, k256, total, slow, word);
   // pixel i sits at bit nmax - 1 - i of `slow`; drop the flags of pixels past the lane's cluster
   slow &= 0xFFFFFFFFu << (nmax - n);
   // Flagged pixels: too close to a bucket boundary for the fast product.  Nearly all of them sit
@@ -1670,11 +1699,21 @@ __device__ __forceinline__ uint32_t sa_eval(uint32_t (*s_pix)[kPixStride], uint2
     slow &= slow - 1u;
     const int i = nmax - 1 - bit;
     const uint32_t px = s_pix[i][tid];
+    const int num = (int)(__dp4a(px, q2p, 0u) - __dp4a(px, q1p, cq));
+    const int vp = __float2int_rd(__fmaf_rn((float)num, inv16, 1.0f));
+    {  // take the main loop's provisional key of this pixel back
+      const int jp = __vimin_s32_relu(vp >> 16, nbm1);
+      const uint2 c = pal[jp * kSaThreads];
+      const uint32_t da = __vabsdiffu4(c.x, px), db = __vabsdiffu4(c.y, px);
+      uint32_t ka = __dp4a(da, da, 0u) * 256u + (uint32_t)jp;
+      const uint32_t kb = __dp4a(db, db, 0u) * 256u + (uint32_t)jp;
+      if (vp >= 1) ka = __viaddmin_u32(kb, 1u, ka);
+      total -= ka;
+    }
     int ja = 0;
     bool two = false;
     if (den != 0) {
-      const int num = (int)(__dp4a(px, q2p, 0u) - __dp4a(px, q1p, cq));
-      const int k = (__float2int_rd(__fmul_rn((float)num, inv16)) + 0x8000) >> 16;
+      const int k = (vp - 1 + 0x8000) >> 16;
       if (num * nbm1 == k * den) {
         ja = __vimin_s32_relu(k, nbm1);
       } else {
@@ -1688,8 +1727,8 @@ __device__ __forceinline__ uint32_t sa_eval(uint32_t (*s_pix)[kPixStride], uint2
     const uint32_t da = __vabsdiffu4(c.x, px), db = __vabsdiffu4(c.y, px);
     const uint32_t ea = __dp4a(da, da, 0u), eb = __dp4a(db, db, 0u);
     const bool up = two && eb < ea;
-    total += up ? eb : ea;
     const uint32_t pick = (uint32_t)ja + (up ? 1u : 0u);
+    total += ((up ? eb : ea) << 8) | pick;
     const int sh = 4 * (i & 7);
     const uint32_t clr = ~(0xFu << sh), ins = pick << sh;
     if (i < 8) word[0] = (word[0] & clr) | ins;
@@ -1697,7 +1736,7 @@ __device__ __forceinline__ uint32_t sa_eval(uint32_t (*s_pix)[kPixStride], uint2
   }
   idx_lo = word[0];
   idx_hi = word[1];
-  return total;
+  return total >> 8;
 }
 
 #ifdef FASTC_GPU_TAILSTATS
@@ -1720,6 +1759,26 @@ __global__ void bc7_tail_report() {
   printf("  last chain to finish: %llu steps, ran %llu us; longest chain: %llu steps, ran %llu us\n",
          ((g_tail[9] >> 14) & 0x3FFull) * 4ull, (g_tail[9] & 0xFFFull) * 16ull, g_tail[10] >> 32, g_tail[10] & 0xFFFFFFFFull);
   printf("  last chain: class %llu\n", (g_tail[9] >> 12) & 3ull);
+}
+#endif
+
+#ifdef FASTC_GPU_CHAINSTATS
+// debug build: chain length (annealing steps) against the start error per pixel, the predictor the
+// work list is ordered by.  Row = floor(log2(error per pixel + 1)).
+__device__ unsigned long long g_cs_count[32], g_cs_steps[32];
+__device__ unsigned int g_cs_max[32], g_cs_hist[32][16];
+__global__ void bc7_chainstats_reset() {
+  const int t = threadIdx.x;
+  if (t < 32) { g_cs_count[t] = 0; g_cs_steps[t] = 0; g_cs_max[t] = 0; for (int k = 0; k < 16; k++) g_cs_hist[t][k] = 0; }
+}
+__global__ void bc7_chainstats_report() {
+  printf("chainstats: log2(err/px+1) | chains | mean steps | max steps | histogram of log2(steps)\n");
+  for (int r = 0; r < 32; r++) {
+    if (!g_cs_count[r]) continue;
+    printf("cs %2d %10llu %8.1f %6u |", r, g_cs_count[r], (double)g_cs_steps[r] / (double)g_cs_count[r], g_cs_max[r]);
+    for (int k = 0; k < 13; k++) printf(" %u", g_cs_hist[r][k]);
+    printf("\n");
+  }
 }
 #endif
 
@@ -1767,6 +1826,9 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
   uint32_t dbg_steps = 0;
   unsigned long long dbg_start = 0;
 #endif
+  // 256 from a place the compiler cannot see through: `x * k256 + y` stays an IMAD (FMA pipe, which
+  // has headroom) instead of a shift / LEA on the ALU pipe, the one that binds this kernel
+  const uint32_t k256 = ws.bins[kBinWords - 1] + 256u;
   const float f_tm1 = (float)(sa_steps - 1);
   const float c_x = __fmul_rn(0.1f, f_tm1);  // fast Metropolis exponent: 0.1 * diff / (energy / (steps - 1))
   const int home = blockIdx.x >= ws.bins[kBinHome + 0] ? 0 : (blockIdx.x >= ws.bins[kBinHome + 1] ? 1 : 2);
@@ -1780,6 +1842,10 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
   int nmax = 0, nbmax = 0, uflags = 0;
 #ifdef FASTC_GPU_COUNTERS
   uint32_t ncalls = 0, npbe = 0;
+#endif
+#ifdef FASTC_GPU_CHAINSTATS
+  uint32_t cs_steps = 0;
+  int cs_row = 0;
 #endif
 
   for (;;) {
@@ -1838,6 +1904,10 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
           energy = 0;
           improved = false;
           have = true;
+#ifdef FASTC_GPU_CHAINSTATS
+          cs_steps = 0;
+          cs_row = 31 - __clz((s0.w / max((w0 >> 24) & 31u, 1u)) + 1u);
+#endif
 #ifdef FASTC_GPU_TAILSTATS
           dbg_steps = 0;
           dbg_start = gtime();
@@ -1887,7 +1957,7 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
       // modes without p-bits evaluate with a zero p-bit (reference quirk, see fit_cluster): their combo is 0
       const uint32_t q1 = sa_quantize(s_q, K, n1, (ncombo >> K.sh0) & 1), q2 = sa_quantize(s_q, K, n2, ncombo & 1);
       uint32_t ilo, ihi;
-      const uint32_t err = sa_eval(s_pix, s_pal, s_w, tid, K, nmax, nbmax, uflags, q1, q2, ilo, ihi);
+      const uint32_t err = sa_eval(s_pix, s_pal, s_w, tid, K, nmax, nbmax, uflags, q1, q2, k256, ilo, ihi);
 #ifdef FASTC_GPU_COUNTERS
       ncalls++; npbe += K.n;
 #endif
@@ -1934,6 +2004,15 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
                                      (cls_ << 12) | (unsigned long long)min(dur_us / 16ull, 4095ull);
       atomicMax(&g_tail[9], rec);
       atomicMax(&g_tail[10], ((unsigned long long)dbg_steps << 32) | (unsigned long long)(uint32_t)dur_us);
+    }
+#endif
+#ifdef FASTC_GPU_CHAINSTATS
+    cs_steps++;
+    if (done) {
+      atomicAdd(&g_cs_count[cs_row], 1ull);
+      atomicAdd(&g_cs_steps[cs_row], (unsigned long long)cs_steps);
+      atomicMax(&g_cs_max[cs_row], cs_steps);
+      atomicAdd(&g_cs_hist[cs_row][min(31 - __clz(cs_steps), 15)], 1u);
     }
 #endif
     if (done) {
@@ -2350,7 +2429,13 @@ cudaError_t bc7_front(Bc7Workspace &wsp, const void *rgba_dev, uint32_t width, u
 #ifdef FASTC_GPU_TAILSTATS
     bc7_tail_reset<<<1, 1, 0, stream>>>();
 #endif
+#ifdef FASTC_GPU_CHAINSTATS
+    bc7_chainstats_reset<<<1, 32, 0, stream>>>();
+#endif
     bc7_anneal<<<sa_grid, kSaThreads, 0, stream>>>(img, width, bx, fb, ws, prm.quality);
+#ifdef FASTC_GPU_CHAINSTATS
+    bc7_chainstats_report<<<1, 1, 0, stream>>>();
+#endif
 #ifdef FASTC_GPU_TAILSTATS
     bc7_tail_report<<<1, 1, 0, stream>>>();
 #endif

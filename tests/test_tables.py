@@ -139,6 +139,8 @@ def test_fast_projection_guard_band():
     """bc7_anneal / bc7_select pick a pixel's two candidate buckets from v = floor(float(num) * inv16),
     inv16 = RN(65536 * nbm1 / den), a 16.16 fixed-point bucket coordinate, and only trust it when v is
     not within one unit of a multiple of 65536 (otherwise the reference's own float sequence is replayed).
+    bc7_anneal computes vp = floor(fma(float(num), inv16, 1)) = v + 1 in one rounding and tests vp instead
+    (flag: vp mod 65536 in {0, 1}; bucket: vp >> 16; "not before endpoint 1": vp >= 1): checked too.
     Check, in float32 emulation, that every UNFLAGGED v gives the reference's candidates
     (RGBAEndpoints.cpp:262-289): j1 = clamp(floor(t)), j2 = min(ceil(t), nbm1), t = RN(RN(num / den) * nbm1)."""
     f = np.float32
@@ -165,3 +167,13 @@ def test_fast_projection_guard_band():
         assert ok.mean() > 0.5
         assert (ja[ok] == j1[ok]).all(), nbm1
         assert (gpu_two[ok] == ref_two[ok]).all(), nbm1
+        # the fused form: one rounding of the exact product plus one
+        exact = fnum.astype(np.float64) * inv16.astype(np.float64) + 1.0   # exact in float64 (24 x 24 bit product)
+        vp = np.floor(exact.astype(f)).astype(np.int64)
+        flagged_p = (vp & 0xFFFE) == 0
+        jp = np.clip(vp >> 16, 0, nbm1)
+        two_p = (vp >= 1) & (jp < nbm1)
+        okp = ~flagged_p
+        assert okp.mean() > 0.5
+        assert (jp[okp] == j1[okp]).all(), nbm1
+        assert (two_p[okp] == ref_two[okp]).all(), nbm1

@@ -32,7 +32,7 @@ def main():
         for rep in range(args.repeat):
             for lib in args.libs:
                 shutil.copy2(lib, LIB)
-                r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--no-cpu-baseline", "--size", str(args.size),
+                r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--no-cpu-baseline", "--no-other-configs", "--size", str(args.size),
                                     "--steps", str(args.steps)], capture_output=True, text=True)
                 if r.returncode != 0:
                     print(f"{lib}: bench failed\n{r.stderr[-400:]}")
