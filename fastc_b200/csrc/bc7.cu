@@ -1741,6 +1741,7 @@ __device__ __forceinline__ uint32_t sa_eval(uint32_t (*s_pix)[kPixStride], uint2
 
 #ifdef FASTC_GPU_TAILSTATS
 // debug build: when did the queues run dry, when did the lanes / CTAs end (ns, globaltimer)
+__device__ unsigned long long g_wid_steps[64];  // annealing steps executed by the lanes of hardware warp slot %warpid
 __device__ unsigned long long g_tail[12];  // 0 start(min) 1 first dry(min) 2 last dry(max) 3 end(max) 4 - 5 CTAs 6..8 class c first seen dry
 __device__ __forceinline__ unsigned long long gtime() {
   unsigned long long t;
@@ -1750,6 +1751,7 @@ __device__ __forceinline__ unsigned long long gtime() {
 __global__ void bc7_tail_reset() {
   g_tail[0] = g_tail[1] = g_tail[6] = g_tail[7] = g_tail[8] = ~0ull;
   g_tail[2] = g_tail[3] = g_tail[4] = g_tail[5] = g_tail[9] = g_tail[10] = 0;
+  for (int k = 0; k < 64; k++) g_wid_steps[k] = 0;
 }
 __global__ void bc7_tail_report() {
   const double t0 = (double)g_tail[0];
@@ -1759,6 +1761,11 @@ __global__ void bc7_tail_report() {
   printf("  last chain to finish: %llu steps, ran %llu us; longest chain: %llu steps, ran %llu us\n",
          ((g_tail[9] >> 14) & 0x3FFull) * 4ull, (g_tail[9] & 0xFFFull) * 16ull, g_tail[10] >> 32, g_tail[10] & 0xFFFFFFFFull);
   printf("  last chain: class %llu\n", (g_tail[9] >> 12) & 3ull);
+  // the SM's schedulers do not share issue slots evenly among their eight resident warps: this is
+  // what decides how long one (serial) chain takes, see DESIGN.md
+  printf("  lane-steps by hardware warp slot (%%warpid):");
+  for (int k = 0; k < 64; k++) printf(" %llu", g_wid_steps[k] >> 10);
+  printf(" (x1024)\n");
 }
 #endif
 
@@ -1823,7 +1830,7 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
   uint32_t drymask = 0;
 #ifdef FASTC_GPU_TAILSTATS
   if (threadIdx.x == 0) atomicMin(&g_tail[0], gtime());
-  uint32_t dbg_steps = 0;
+  uint32_t dbg_steps = 0, dbg_total = 0;
   unsigned long long dbg_start = 0;
 #endif
   // 256 from a place the compiler cannot see through: `x * k256 + y` stays an IMAD (FMA pipe, which
@@ -1995,6 +2002,7 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
     }
 #ifdef FASTC_GPU_TAILSTATS
     dbg_steps++;
+    dbg_total++;
     if (done) {
       const unsigned long long t = gtime();
       const unsigned long long dur_us = (t - dbg_start) / 1000ull;
@@ -2043,6 +2051,11 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
   atomicAdd(&ws.counters[1], (unsigned long long)npbe);
 #endif
 #ifdef FASTC_GPU_TAILSTATS
+  {
+    uint32_t warp_slot;
+    asm volatile("mov.u32 %0, %%warpid;" : "=r"(warp_slot));
+    atomicAdd(&g_wid_steps[warp_slot & 63], (unsigned long long)dbg_total);
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned long long t = gtime();
