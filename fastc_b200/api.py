@@ -68,11 +68,13 @@ class _Options(C.Structure):
     """fastc_gpu_options (include/fastc_gpu.h): BPTCC::CompressionSettings' m_BlockModes /
     m_ErrorMetric and rg_etc1's quality level."""
     _fields_ = [("struct_size", C.c_uint32), ("bptc_block_modes", C.c_uint32),
-                ("bptc_error_metric", C.c_int32), ("etc1_quality", C.c_int32)]
+                ("bptc_error_metric", C.c_int32), ("etc1_quality", C.c_int32),
+                ("bptc_block_stats", C.c_void_p)]
 
 
-def _options(block_modes: int = 0xFF, error_metric: int = 0, etc1_quality: int = 0):
-    return _Options(C.sizeof(_Options), block_modes, error_metric, etc1_quality)
+def _options(block_modes: int = 0xFF, error_metric: int = 0, etc1_quality: int = 0, block_stats=None):
+    return _Options(C.sizeof(_Options), block_modes, error_metric, etc1_quality,
+                    block_stats.ctypes.data if block_stats is not None else None)
 
 
 class _Job(C.Structure):
@@ -150,17 +152,22 @@ class GpuLibrary:
 
     def compress(self, fmt: int, rgba: np.ndarray, out: np.ndarray | None = None, *, quality: int = 50,
                  seed: int = 0, first_block: int = 0, num_blocks: int = 0, chunk_blocks: int = 0,
-                 num_gpus: int = 1, block_modes: int = 0xFF, error_metric: int = 0, etc1_quality: int = 0):
+                 num_gpus: int = 1, block_modes: int = 0xFF, error_metric: int = 0, etc1_quality: int = 0,
+                 block_stats: np.ndarray | None = None):
         """rgba: (H, W, 4) uint8, C-contiguous (pinned or pageable host memory).
-        Returns (out bytes, timing dict)."""
+        block_stats (BPTC): optional (blocks, 10) float64 array receiving per block the mode, the path and
+        the error of each mode tried (fastc_gpu_bptc_block_stat).  Returns (out bytes, timing dict)."""
         h, w = self._check_image(rgba)
+        if block_stats is not None and (block_stats.dtype != np.float64 or not block_stats.flags.c_contiguous
+                                        or block_stats.shape != ((w // 4) * (h // 4), 10)):
+            raise FastcGpuError("block_stats must be a C-contiguous (blocks, 10) float64 array")
         size = int(self.cdll.fastc_gpu_compressed_size(int(fmt), w, h))
         if out is None:
             out = np.zeros(size, dtype=np.uint8)
         else:
             self._check_output(out, size)
         tm = _Timing()
-        opt = _options(block_modes, error_metric, etc1_quality)
+        opt = _options(block_modes, error_metric, etc1_quality, block_stats)
         self.check(self.cdll.fastc_gpu_compress_opt(int(fmt), rgba.ctypes.data, w, h, first_block, num_blocks,
                                                     out.ctypes.data, quality, seed, chunk_blocks, num_gpus,
                                                     C.byref(tm), C.byref(opt)))

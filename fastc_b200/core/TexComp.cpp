@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstring>
 #include <ctime>
+#include <ostream>
 #include <sched.h>
 #include <vector>
 
@@ -143,6 +144,25 @@ bool ValidateRequest(const SCompressionSettings &settings, uint32 width, uint32 
 }
 }  // namespace
 
+namespace {
+// The per-block lines of the reference's BPTCC::CompressWithStats log ("<block>: <stat> -- <value>",
+// BPTCEncoder/src/Compressor.cpp:106-131, :1947-1951, :1982-1992): path, mode, and per mode the
+// estimate and the error.  The GPU selection kernel keeps no per-mode estimates: they are logged as -1,
+// the value the reference logs for "not computed".
+void WriteBlockStats(std::ostream &os, const std::vector<fastc_gpu_bptc_block_stat> &stats) {
+  static const char *kModeName[8] = {"Zero", "One", "Two", "Three", "Four", "Five", "Six", "Seven"};
+  for (size_t i = 0; i < stats.size(); i++) {
+    const fastc_gpu_bptc_block_stat &b = stats[i];
+    os << i << ": BlockStat_Path -- " << (int)b.path << std::endl;
+    os << i << ": BlockStat_Mode -- " << (int)b.mode << std::endl;
+    for (int m = 0; m < 8; m++) {
+      os << i << ": BlockStat_Mode" << kModeName[m] << "Estimate -- " << -1.0 << std::endl;
+      os << i << ": BlockStat_Mode" << kModeName[m] << "Error -- " << b.mode_error[m] << std::endl;
+    }
+  }
+}
+}  // namespace
+
 bool CompressImageData(const unsigned char *data, const unsigned int width, const unsigned int height,
                        unsigned char *cmpData, const unsigned int cmpDataSz, const SCompressionSettings &settings) {
   if (!ValidateRequest(settings, width, height, cmpDataSz, true)) return false;
@@ -155,16 +175,23 @@ bool CompressImageData(const unsigned char *data, const unsigned int width, cons
   // "blocks handed out at a time" as the pipeline chunk size.
   const int reps = settings.iNumCompressions > 0 ? settings.iNumCompressions : 0;
   double total_ms = 0.0;
+  // logStream + BPTC: the reference switches to its statistics-gathering encoder
+  // (ChooseFuncFromSettings, TexComp.cpp:110-155); here the pack kernel fills per-block records
+  const bool wantStats = settings.logStream != NULL && settings.format == FasTC::eCompressionFormat_BPTC;
+  std::vector<fastc_gpu_bptc_block_stat> stats(wantStats ? (size_t)(width / 4) * (height / 4) : 0);
+  fastc_gpu_options opt = FASTC_GPU_OPTIONS_INIT;
+  opt.bptc_block_stats = wantStats ? stats.data() : NULL;
   for (int i = 0; i < reps; i++) {
     fastc_gpu_timing tm;
-    if (fastc_gpu_compress(GpuFormat(settings.format), data, width, height, 0, 0, cmpData, settings.iQuality,
-                           settings.uSeed, settings.iJobSize > 0 ? (uint32)settings.iJobSize : 0, settings.iNumGPUs,
-                           &tm) != 0) {
+    if (fastc_gpu_compress_opt(GpuFormat(settings.format), data, width, height, 0, 0, cmpData, settings.iQuality,
+                               settings.uSeed, settings.iJobSize > 0 ? (uint32)settings.iJobSize : 0,
+                               settings.iNumGPUs, &tm, &opt) != 0) {
       ReportError(fastc_gpu_last_error());
       return false;
     }
     total_ms += tm.total_ms;
   }
+  if (wantStats && reps) WriteBlockStats(*settings.logStream, stats);
   fprintf(stdout, "Compression time: %0.3f ms\n", reps ? total_ms / reps : 0.0);
   return true;
 }

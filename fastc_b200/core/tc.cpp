@@ -5,6 +5,7 @@
 // (no GPU encoder), `-l` and `-v` statistics are accepted and ignored, input is PNG (8-bit, non-interlaced) / TGA / KTX.
 #include <algorithm>
 #include <cstdio>
+#include <fstream>
 #include <cstdlib>
 #include <cstring>
 
@@ -19,7 +20,7 @@ static void PrintUsage() {
   fprintf(stderr, "\t-v\t\tVerbose mode (accepted; image statistics are not computed)\n");
   fprintf(stderr, "\t-f <fmt>\tFormat to use. Either \"BPTC\", \"ETC1\", \"DXT1\" or \"DXT5\".\n");
   fprintf(stderr, "\t\t\tDefault: BPTC\n");
-  fprintf(stderr, "\t-l\t\tSave an output log (accepted; the GPU path records no per-block log).\n");
+  fprintf(stderr, "\t-l\t\tSave an output log (<basename>.log: BPTC per-block path / mode / errors).\n");
   fprintf(stderr, "\t-d <file>\tSpecify decompressed output (default: basename-<fmt>.png); .ktx stores the compressed payload\n");
   fprintf(stderr, "\t-nd\t\tSuppress decompressed output\n");
   fprintf(stderr, "\t-q <quality>\tSet compression quality level. Default: 50\n");
@@ -52,7 +53,7 @@ int main(int argc, char **argv) {
     exit(1);
   }
   char decompressedOutput[256] = "";
-  bool bDecompress = true, bUseSIMD = false, bUseAtomics = false, bFormatOk = true;
+  bool bDecompress = true, bUseSIMD = false, bUseAtomics = false, bFormatOk = true, bSaveLog = false;
   int numJobs = 0, quality = 50, numThreads = 1, numCompressions = 1, numGPUs = 1;
   unsigned long long seed = 0;
   FasTC::ECompressionFormat format = FasTC::eCompressionFormat_BPTC;
@@ -97,7 +98,8 @@ int main(int argc, char **argv) {
       if (fileArg == argc) { PrintUsage(); exit(1); }
       snprintf(decompressedOutput, sizeof(decompressedOutput), "%s", argv[fileArg++]);
     } else if (!strcmp(a, "-nd")) { fileArg++; bDecompress = false; }
-    else if (!strcmp(a, "-l") || !strcmp(a, "-v")) fileArg++;
+    else if (!strcmp(a, "-l")) { bSaveLog = true; fileArg++; }
+    else if (!strcmp(a, "-v")) fileArg++;
     else if (!strcmp(a, "-simd")) { fileArg++; bUseSIMD = true; }
     else if (!strcmp(a, "-a")) { fileArg++; bUseAtomics = true; }
     else known = false;
@@ -129,6 +131,14 @@ int main(int argc, char **argv) {
   settings.iJobSize = numJobs;
   settings.iNumGPUs = numGPUs;
   settings.uSeed = seed;
+  // -l: "<basename>.log" like the reference (CLTool/src/tc.cpp:268-291)
+  std::ofstream logFile;
+  if (bSaveLog) {
+    char logname[300];
+    snprintf(logname, sizeof(logname), "%s.log", basename);
+    logFile.open(logname);
+    settings.logStream = &logFile;
+  }
 
   CompressedImage *ci = CompressImage(&img, settings);
   if (NULL == ci) return 1;

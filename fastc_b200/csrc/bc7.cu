@@ -28,7 +28,9 @@
 // The unit of parallelism for the expensive part is the *chain* (one subset of
 // one candidate mode/shape/rotation): ~14 independent serial chains per block.
 #include <cfloat>
+#include <cmath>
 #include <cstdio>
+#include <type_traits>
 
 #include "bc7_tables.cuh"
 #include "common.cuh"
@@ -45,6 +47,10 @@ __constant__ uint8_t c_weight[64];  // [index_bits-1][16] weight of endpoint 2 (
 __constant__ uint8_t c_opt7[512];   // [v][2]
 __constant__ uint8_t c_opt6[1536];  // [v][2][3]
 __constant__ uint32_t c_wm[9];
+
+// kErrorMetrics[eErrorMetric_Nonuniform] (Compressor.cpp:205-208): sqrtf(0.3f), sqrtf(0.56f), sqrtf(0.11f), 1
+// (computed on the host like the reference's static initialiser, uploaded by bc7_upload_tables)
+__constant__ float c_nu_weights[4];
 
 // Per-mode attributes (BC7 spec; reference kModeAttributes Compressor.cpp:170-203).
 struct ModeAttr {
@@ -66,7 +72,7 @@ __device__ uint32_t g_single[8 * 2 * 4 * 2 * 256];
 // ------------------------------------------------------------------ layout of the scratch
 // sel word per block
 //  [0:5] best 2-subset shape  [6:11] best 3-subset shape  [12:19] mode mask
-//  [20:21] number of shapes   [22] layout B (alpha path)   [24:25] type
+//  [20:21] number of shapes   [22] layout B (alpha path)   [23] a shape estimate was ~0 (early-out)   [24:25] type
 enum { kTypeNormal = 0, kTypeSolid = 1, kTypeTransparent = 2 };
 constexpr int kSlots = 16;       // result slots per block
 constexpr int kResWords = 8;     // 32 B per chain result
@@ -77,6 +83,7 @@ constexpr int kResWords = 8;     // 32 B per chain result
 //  w1/w2: start endpoints (bytes on the grid)   w3: start error   w4: RNG state
 //  w5: alpha error (modes 4/5)   w6: rounded alpha endpoint bytes a1 | a2 << 8 (modes 4/5)
 constexpr int kStateWords = 8;
+constexpr int kStatDoubles = 10; // per-block statistics record: mode, path, error of modes 0..7 (-1: not tried)
 constexpr int kTile = 256;       // blocks per watermark tile (= classify CTA)
 
 struct Ws {
@@ -88,6 +95,8 @@ struct Ws {
   uint4 *sorted;        // [nblocks*kSlots][2] the live chains' start states, sorted by descending
                         // (index precision, cluster size); word 7 = the chain's id (block * kSlots + slot)
   uint32_t *bins;       // histogram / offsets / cursors (see bc7_bin_offsets)
+  double *stats;        // [nblocks][kStatDoubles] per-block statistics (mode, path, error of every mode tried), or NULL
+  double *err64;        // [nblocks][kSlots] non-uniform metric only: the chains' errors as doubles (else NULL)
   const uint32_t *wm_running;    // watermark base of this chunk (device side, chunks chain without a host sync)
   unsigned long long *counters;  // qe calls, pbe
 };
@@ -237,6 +246,30 @@ __device__ __forceinline__ int qe_pixel(const QeEndpoints &q, uint32_t pt, uint3
   return e;
 }
 
+// The same under a non-uniform metric (m_ErrorMetric = eErrorMetric_Nonuniform): the error of a
+// pixel against one interpolated colour is the float  sum_k (float(|p_k - c_k|) * w_k)^2, summed
+// in channel order exactly like the reference (RGBAEndpoints.cpp:291-296, VectorBase::Dot); the
+// totals are float sums in pixel order.  Kernels take the metric as a template flag (NU); the
+// uniform instantiations keep the all-integer fast paths.
+__device__ __forceinline__ float nu_error(uint32_t colour, uint32_t px, const float w[4]) {
+  const uint32_t d = __vabsdiffu4(colour, px);
+  const float e0 = __fmul_rn((float)(d & 0xFF), w[0]), e1 = __fmul_rn((float)((d >> 8) & 0xFF), w[1]);
+  const float e2 = __fmul_rn((float)((d >> 16) & 0xFF), w[2]), e3 = __fmul_rn((float)(d >> 24), w[3]);
+  float s = __fmul_rn(e0, e0);
+  s = __fadd_rn(s, __fmul_rn(e1, e1));
+  s = __fadd_rn(s, __fmul_rn(e2, e2));
+  s = __fadd_rn(s, __fmul_rn(e3, e3));
+  return s;
+}
+// metric of a chain: the weights follow the rotation (CompressionMode::GetErrorMetric, CompressionMode.h:196-205)
+__device__ __forceinline__ void nu_metric(int rot, float w[4]) {
+#pragma unroll
+  for (int k = 0; k < 4; k++) w[k] = c_nu_weights[k];
+  if (rot == 1) { w[0] = c_nu_weights[3]; w[3] = c_nu_weights[0]; }
+  else if (rot == 2) { w[1] = c_nu_weights[3]; w[3] = c_nu_weights[1]; }
+  else if (rot == 3) { w[2] = c_nu_weights[3]; w[3] = c_nu_weights[2]; }
+}
+
 // ------------------------------------------------------------------ classify + watermark scan
 __device__ __forceinline__ uint32_t classify_block(const uint32_t px[16]) {
   bool solid = true, transparent = true;
@@ -334,8 +367,8 @@ constexpr int kSelBoxRow = 16;   // row 16 + 2 s: (|extent|^2, min . extent), ro
 // subset's bounding-box endpoints (the last row of a subset: colour NB-1 twice); rows kSelBoxRow.. hold
 // the subset's scalars.  The kernel is bound by the ALU pipe: fetching the subset's operands with two
 // 64-bit shared loads instead of selecting them from registers takes 5-10 ALU instructions off every pixel.
-template <int NB>
-__device__ __forceinline__ uint32_t box_pixel_error(const uint2 *pal, int s, uint32_t p) {
+template <int NB, bool NU = false>
+__device__ __forceinline__ typename std::conditional<NU, float, uint32_t>::type box_pixel_error(const uint2 *pal, int s, uint32_t p) {
   constexpr int NBM1 = NB - 1, STRIDE = kSelWarps * 32;
   const uint2 b0 = pal[(kSelBoxRow + 2 * s) * STRIDE], b1 = pal[(kSelBoxRow + 2 * s + 1) * STRIDE];
   const uint32_t den = b0.x, base = b0.y, d = b1.y;
@@ -355,12 +388,19 @@ __device__ __forceinline__ uint32_t box_pixel_error(const uint2 *pal, int s, uin
     two = x1 + 1 <= x2;
   }
   const uint2 c = pal[(s * NB + ja) * STRIDE];
-  const uint32_t da = __vabsdiffu4(c.x, p), db = __vabsdiffu4(c.y, p);
-  const uint32_t ea = __dp4a(da, da, 0u), eb = __dp4a(db, db, 0u);
-  return two ? min(ea, eb) : ea;
+  if constexpr (NU) {
+    float w[4];
+    nu_metric(0, w);
+    const float ea = nu_error(c.x, p, w), eb = nu_error(c.y, p, w);
+    return (two && eb < ea) ? eb : ea;
+  } else {
+    const uint32_t da = __vabsdiffu4(c.x, p), db = __vabsdiffu4(c.y, p);
+    const uint32_t ea = __dp4a(da, da, 0u), eb = __dp4a(db, db, 0u);
+    return two ? min(ea, eb) : ea;
+  }
 }
 
-template <int NSUB>
+template <int NSUB, bool NU = false>
 __device__ __forceinline__ double estimate_shape(const uint32_t *__restrict__ px, const uint32_t *__restrict__ plo,
                                                  const uint32_t *__restrict__ phi, int shape, uint2 *pal) {
   constexpr int NB = NSUB == 2 ? 8 : 4, NBM1 = NB - 1;
@@ -408,16 +448,20 @@ __device__ __forceinline__ double estimate_shape(const uint32_t *__restrict__ px
     }
     pal[(s * NB + NBM1) * (kSelWarps * 32)] = make_uint2(cur, cur);
   }
-  uint32_t tot[NSUB];
+  typename std::conditional<NU, float, uint32_t>::type tot[NSUB];
 #pragma unroll
   for (int s = 0; s < NSUB; s++) tot[s] = 0;
 #pragma unroll 2
   for (int i = 0; i < 16; i++) {
     const int s = NSUB == 2 ? ((m2 >> i) & 1) : ((m3 >> (2 * i)) & 3);
     // a point-sized box contributes nothing; its pixels evaluate to 0 anyway (p == min, extent 0)
-    const uint32_t e = box_pixel_error<NB>(pal, s, px[i]);
+    const auto e = box_pixel_error<NB, NU>(pal, s, px[i]);
+    // (NU: float sums in the subset's pixel order; adding 0 to the other subsets' sums is exact)
 #pragma unroll
-    for (int q = 0; q < NSUB; q++) tot[q] += (s == q) ? e : 0u;
+    for (int q = 0; q < NSUB; q++) {
+      if constexpr (NU) tot[q] = __fadd_rn(tot[q], (s == q) ? e : 0.0f);
+      else tot[q] += (s == q) ? e : 0u;
+    }
   }
   double err = 0.0;
 #pragma unroll
@@ -438,6 +482,7 @@ __device__ __forceinline__ void warp_argmin(double &err, int &idx) {
   }
 }
 
+template <bool NU>
 __global__ void __launch_bounds__(kSelWarps * 32)
 bc7_select(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, uint32_t first_block,
            uint32_t num_blocks, uint32_t *__restrict__ sel, uint32_t *__restrict__ states, uint32_t block_modes) {
@@ -479,7 +524,7 @@ bc7_select(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
   double e0 = 0.0, e1 = 0.0;
 #pragma unroll 1
   for (int h = 0; h < 2; h++) {
-    const double e = estimate_shape<2>(px, plo, phi, lane + 32 * h, pal);  // 8 buckets: 3-bit weights
+    const double e = estimate_shape<2, NU>(px, plo, phi, lane + 32 * h, pal);  // 8 buckets: 3-bit weights
     if (h == 0) e0 = e; else e1 = e;
   }
   // early-out: first shape (scan order) with estimate < 1e-9 (Compressor.cpp:1706-1710)
@@ -487,7 +532,7 @@ bc7_select(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
   uint32_t word;
   if (z0 | z1) {
     const int s = z0 ? (__ffs(z0) - 1) : (32 + __ffs(z1) - 1);
-    word = (uint32_t)s | (0x8Au << 12) | (1u << 20);  // modes {1,3,7}, one shape
+    word = (uint32_t)s | (0x8Au << 12) | (1u << 20) | (1u << 23);  // modes {1,3,7}, one shape; bit 23: early-out
     if (lane == 0) sel[t] = word & mode_keep;
     return;
   }
@@ -503,13 +548,13 @@ bc7_select(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
   // ---- three-subset shapes (opaque blocks only)
 #pragma unroll 1
   for (int h = 0; h < 2; h++) {
-    const double e = estimate_shape<3>(px, plo, phi, lane + 32 * h, pal);  // 4 buckets: 2-bit weights
+    const double e = estimate_shape<3, NU>(px, plo, phi, lane + 32 * h, pal);  // 4 buckets: 2-bit weights
     if (h == 0) e0 = e; else e1 = e;
   }
   const uint32_t y0 = __ballot_sync(0xffffffffu, e0 < 1e-9), y1 = __ballot_sync(0xffffffffu, e1 < 1e-9);
   if (y0 | y1) {
     const int s = y0 ? (__ffs(y0) - 1) : (32 + __ffs(y1) - 1);
-    word = (uint32_t)bi2 | ((uint32_t)s << 6) | (0x05u << 12) | (2u << 20);  // modes {0,2}
+    word = (uint32_t)bi2 | ((uint32_t)s << 6) | (0x05u << 12) | (2u << 20) | (1u << 23);  // modes {0,2}
     if (lane == 0) sel[t] = word & mode_keep;
     return;
   }
@@ -609,6 +654,27 @@ __device__ __forceinline__ uint32_t single_color(int mode, int idx_mode, int npb
   return best_err;
 }
 
+// The same under the non-uniform metric (Compressor.cpp:334-338): the combo's error is the float
+// sum_c (float(dist_c) * w_c)^2 with the UN-rotated weights; returns its bit pattern.
+__device__ __forceinline__ uint32_t single_color_nu(int mode, int idx_mode, int npbit, uint32_t pixel, uint32_t &p1,
+                                                    uint32_t &p2, int &best_combo) {
+  float best_err = FLT_MAX;
+  for (int pbi = 0; pbi < npbit; pbi++) {
+    uint32_t v1 = 0, v2 = 0;
+    float err = 0.0f;
+#pragma unroll
+    for (int ci = 0; ci < 4; ci++) {
+      const uint32_t e = g_single[((((mode * 2 + idx_mode) * 4 + pbi) * 2 + (ci == 3)) << 8) + chan(pixel, ci)];
+      v1 |= (e & 0xFF) << (8 * ci);
+      v2 |= ((e >> 8) & 0xFF) << (8 * ci);
+      const float d = __fmul_rn((float)(e >> 16), c_nu_weights[ci]);
+      err = __fadd_rn(err, __fmul_rn(d, d));
+    }
+    if (err < best_err) { best_err = err; best_combo = pbi; p1 = v1; p2 = v2; }
+  }
+  return __float_as_uint(best_err);
+}
+
 #ifdef FASTC_GPU_COUNTERS
 #define COUNT_QE(ws, ncalls, npbe) do { atomicAdd(&(ws).counters[0], (unsigned long long)(ncalls)); atomicAdd(&(ws).counters[1], (unsigned long long)(npbe)); } while (0)
 #else
@@ -631,12 +697,64 @@ __device__ __forceinline__ uint32_t qe_cluster(const uint32_t *pts, const uint32
   return total;
 }
 
+// QuantizedError under the non-uniform metric `w` (already rotated for the chain): float error per
+// candidate bucket, first strict minimum of the (at most two) candidates, float total in pixel
+// order (RGBAEndpoints.cpp:254-306).  Returns the total's bit pattern (non-negative floats order
+// like their bit patterns, so the callers' comparisons stay integer compares).
+__device__ __forceinline__ float qe_bucket_error_nu(const QeEndpoints &q, const int pb[4], int wgt, const float w[4]) {
+  float err = 0.0f;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int ip = q.e1[k] + ((q.d[k] * wgt + 32) >> 6);
+    const float e = __fmul_rn((float)abs(pb[k] - ip), w[k]);
+    err = __fadd_rn(err, __fmul_rn(e, e));
+  }
+  return err;
+}
+__device__ __forceinline__ uint32_t qe_cluster_nu(const uint32_t *pts, const uint32_t *pix, int n, uint32_t q1, uint32_t q2,
+                                                  int nbm1, const uint8_t *__restrict__ wtab, const float w[4],
+                                                  unsigned long long *indices) {
+  QeEndpoints q;
+  qe_prepare(q, q1, q2);
+  float total = 0.0f;
+  unsigned long long idx = 0;
+  for (int i = 0; i < n; i++) {
+    int pb[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) pb[k] = chan(pix[i], k);
+    int b = 0;
+    float e;
+    if (q.den == 0) {
+      e = qe_bucket_error_nu(q, pb, 0, w);
+    } else {
+      int num = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) num += (chan(pts[i], k) - q.e1[k]) * q.d[k];
+      const float t = __fmul_rn(__fdiv_rn((float)num, (float)q.den), (float)nbm1);
+      int j1 = (int)floorf(t), j2 = (int)ceilf(t);
+      j1 = min(max(0, j1), nbm1);
+      j2 = min(j2, nbm1);
+      e = qe_bucket_error_nu(q, pb, wtab[j1], w);
+      b = j1;
+      if (j1 + 1 <= j2) {
+        const float e2 = qe_bucket_error_nu(q, pb, wtab[j1 + 1], w);
+        if (e2 < e) { e = e2; b = j1 + 1; }
+      }
+    }
+    total = __fadd_rn(total, e);
+    idx |= (unsigned long long)b << (4 * i);
+  }
+  if (indices) *indices = idx;
+  return __float_as_uint(total);
+}
+
 // The fit of one chain: CompressCluster (Compressor.cpp:921-1094) followed by
 // OptimizeEndpointsForCluster (:538-630).  pts/pix are this thread's private
 // copies of the cluster (n points).  avg/mn/mx are the cluster statistics the
 // reference would see (for the rotated mode-4/5 fit these are the STALE ones of
 // the un-rotated block, T16).  Returns the total error.
 struct FitResult {
+  double err64;  // non-uniform metric: the chain's error as the reference's double
   uint32_t err, p1, p2;
   int combo;
   unsigned long long indices;
@@ -894,10 +1012,12 @@ __device__ __noinline__ void fit_core(int ibits, const uint32_t *pts, int n, con
   C.kind = 2;
 }
 
-__device__ __noinline__ void fit_finish(const Ws &ws, const ModeAttr &A, int mode, int idx_mode, const FitCore &C,
+template <bool NU>
+__device__ __noinline__ void fit_finish(const Ws &ws, const ModeAttr &A, int mode, int idx_mode, int rot, const FitCore &C,
                                         const uint32_t *pts, const uint32_t *pix, int n, int sa_steps,
                                         const uint8_t *__restrict__ s_w, FitResult &R) {
   R.need_sa = false;
+  R.err64 = 0.0;
   const int ibits = idx_mode == 0 ? A.index_bits : A.alpha_index_bits;
   const int nbm1 = (1 << ibits) - 1;
   const uint8_t *wtab = s_w + 16 * (ibits - 1);
@@ -906,7 +1026,13 @@ __device__ __noinline__ void fit_finish(const Ws &ws, const ModeAttr &A, int mod
   if (C.kind != 2) {  // CompressSingleColor (:252-353) on point 0 / on the only bucket's centroid
     int combo = 0;
     uint32_t q1 = 0, q2 = 0;
-    const uint32_t e = single_color(mode, idx_mode, npbit, C.single, q1, q2, combo);
+    uint32_t e;
+    if constexpr (NU) {
+      e = single_color_nu(mode, idx_mode, npbit, C.single, q1, q2, combo);
+      R.err64 = (double)n * (double)__uint_as_float(e);  // cluster.GetNumPoints() * CompressSingleColor(...)
+    } else {
+      e = single_color(mode, idx_mode, npbit, C.single, q1, q2, combo);
+    }
     R.err = (uint32_t)n * e;
     R.p1 = q1; R.p2 = q2; R.combo = combo;
     R.indices = 0x1111111111111111ull;
@@ -958,8 +1084,17 @@ __device__ __noinline__ void fit_finish(const Ws &ws, const ModeAttr &A, int mod
   // one evaluation serves both outcomes: its error starts the annealing chain, its indices are
   // the result when there is no annealing (same quirky quantisation either way)
   unsigned long long indices;
-  const uint32_t cur_err = qe_cluster(pts, pix, n, to_pixel_b(c1, qm, has_pbit ? pb0 : 0),
-                                      to_pixel_b(c2, qm, has_pbit ? pb1 : 0), nbm1, wtab, &indices);
+  uint32_t cur_err;
+  if constexpr (NU) {
+    float w[4];
+    nu_metric(A.rotation ? rot : 0, w);
+    cur_err = qe_cluster_nu(pts, pix, n, to_pixel_b(c1, qm, has_pbit ? pb0 : 0), to_pixel_b(c2, qm, has_pbit ? pb1 : 0),
+                            nbm1, wtab, w, &indices);
+    R.err64 = (double)__uint_as_float(cur_err);
+  } else {
+    cur_err = qe_cluster(pts, pix, n, to_pixel_b(c1, qm, has_pbit ? pb0 : 0), to_pixel_b(c2, qm, has_pbit ? pb1 : 0), nbm1,
+                         wtab, &indices);
+  }
   COUNT_QE(ws, 1, 0);
   if (sa_steps > 0 && cur_err > 0) {  // hand over to bc7_anneal
     R.need_sa = true;
@@ -1023,6 +1158,10 @@ constexpr int kBinEnd = 1540;     // [3] end of class c's region
 constexpr int kBinHome = 1544;    // [3] first CTA whose home class is c or lower
 constexpr int kBinWords = 2048;
 
+// (under the non-uniform metric R.err is a float's bit pattern: the length predictor takes its value)
+__device__ __forceinline__ uint32_t sort_error(const Ws &ws, uint32_t err) {
+  return ws.err64 ? (uint32_t)__uint_as_float(err) : err;
+}
 __device__ __forceinline__ void write_state(const Ws &ws, uint32_t gid, uint32_t mask, const Chain &c, int n,
                                             const FitResult &R, uint32_t rng, uint32_t alpha_err, uint32_t abytes) {
   uint32_t *st = ws.states + (size_t)gid * kStateWords;
@@ -1034,7 +1173,7 @@ __device__ __forceinline__ void write_state(const Ws &ws, uint32_t gid, uint32_t
   const int ibits = c.idx_mode == 0 ? c_modes[c.mode].index_bits : c_modes[c.mode].alpha_index_bits;
   {
     // one atomic per distinct key among the lanes that arrive here together
-    const int key = sort_key(ibits, n, R.err);
+    const int key = sort_key(ibits, n, sort_error(ws, R.err));
     const unsigned act = __activemask();
     const unsigned peers = __match_any_sync(act, key);
     if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&ws.bins[kBinCount + key], (uint32_t)__popc(peers));
@@ -1061,13 +1200,14 @@ __device__ __forceinline__ int primary_slot(int layout_b, int slot) {  // invers
 
 // Per-mode tail of one chain: ClampEndpointsToGrid + first evaluation (fit_finish), the scalar alpha fit
 // of modes 4/5, and the result / annealing start state.
+template <bool NU>
 __device__ __forceinline__ void setup_variant(const Ws &ws, const Chain &c, const ModeAttr &A, const FitCore &core,
                                               const uint32_t *pts, const uint32_t *pix, int n, uint32_t mask,
                                               int sa_steps, const uint8_t *__restrict__ s_w, const float *__restrict__ s_rcp,
                                               uint32_t (*s_acc)[16][128], int tid, uint32_t gid, uint32_t rng,
                                               uint32_t *res, const float *alpha_vals, float amin, float amax) {
   FitResult R;
-  fit_finish(ws, A, c.mode, c.idx_mode, core, pts, pix, n, sa_steps, s_w, R);  // the one call site
+  fit_finish<NU>(ws, A, c.mode, c.idx_mode, c.rot, core, pts, pix, n, sa_steps, s_w, R);  // the one call site
   res[4] = (uint32_t)R.indices; res[5] = (uint32_t)(R.indices >> 32);
   if (!A.rotation) {
     if (R.need_sa) {
@@ -1076,6 +1216,7 @@ __device__ __forceinline__ void setup_variant(const Ws &ws, const Chain &c, cons
     }
     res[0] = R.err; res[1] = R.p1; res[2] = R.p2; res[3] = (uint32_t)R.combo;
     res[4] = (uint32_t)R.indices; res[5] = (uint32_t)(R.indices >> 32);
+    if constexpr (NU) ws.err64[gid] = R.err64;
     return;
   }
 
@@ -1084,6 +1225,15 @@ __device__ __forceinline__ void setup_variant(const Ws &ws, const Chain &c, cons
   const uint8_t *wa = s_w + 16 * (abits - 1);
   float a1 = amin, a2 = amax;
   uint32_t alpha_err = 0;
+  // non-uniform metric: the alpha error is the double sum of the floats (weight * |difference|)^2,
+  // weight = the rotated metric's alpha entry (Compressor.cpp:712, :756-760, :905-915)
+  double alpha_err64 = 0.0;
+  float wgt_a = 1.0f;
+  if constexpr (NU) {
+    float w[4];
+    nu_metric(c.rot, w);
+    wgt_a = w[3];
+  }
   unsigned long long aidx = 0;
   if (a1 == a2) {
     const int a1be = (int)a1;
@@ -1105,6 +1255,10 @@ __device__ __forceinline__ void setup_variant(const Ws &ws, const Chain &c, cons
       const int ip = (((int)a1 * w0 + (int)a2 * w1 + 32) >> 6) & 0xFF;
       const int d = a1be > ip ? a1be - ip : ip - a1be;
       alpha_err = 16u * (uint32_t)(d * d);
+      if constexpr (NU) {
+        const float px = __fmul_rn(wgt_a, (float)d);
+        alpha_err64 = (double)__fmul_rn(16.0f, __fmul_rn(px, px));
+      }
     }
   } else {
     // scalar k-means over the alpha interpolation points (:770-842)
@@ -1196,12 +1350,17 @@ __device__ __forceinline__ void setup_variant(const Ws &ws, const Chain &c, cons
         if (e < me) { me = e; bb = j; }
       }
       alpha_err += (uint32_t)me;
+      if constexpr (NU) {
+        const float px = __fmul_rn(wgt_a, __fsqrt_rn((float)me));  // |difference| (exact: a perfect square < 2^16)
+        alpha_err64 = __dadd_rn(alpha_err64, (double)__fmul_rn(px, px));
+      }
       aidx |= (unsigned long long)bb << (4 * i);
     }
   }
   // endpoints handed to Pack: rgb from the fit, alpha = the float a1/a2 (Pack rounds them)
   res[6] = (uint32_t)aidx; res[7] = (uint32_t)(aidx >> 32);
   if (R.need_sa) {
+    if constexpr (NU) ws.err64[gid] = alpha_err64;  // bc7_anneal adds the colour fit's error
     write_state(ws, gid, 0xFFFFu, c, 16, R, rng, alpha_err, round_byte(a1) | (round_byte(a2) << 8));
     return;
   }
@@ -1209,11 +1368,13 @@ __device__ __forceinline__ void setup_variant(const Ws &ws, const Chain &c, cons
   const uint32_t e2 = (R.p2 & 0x00FFFFFFu) | (round_byte(a2) << 24);
   res[0] = R.err + alpha_err; res[1] = e1; res[2] = e2; res[3] = 0;
   res[4] = (uint32_t)R.indices; res[5] = (uint32_t)(R.indices >> 32);
+  if constexpr (NU) ws.err64[gid] = __dadd_rn(R.err64, alpha_err64);
 }
 
 // One endpoint-fit chain: cluster statistics, CompressCluster's start (fit_cluster), and for
 // modes 4/5 the scalar alpha fit.  Writes either the finished result or the start state of the
 // annealing chain.
+template <bool NU>
 __device__ __forceinline__ void setup_chain(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x,
                                             uint32_t first_block, const Ws &ws, int sa_steps, uint64_t seed,
                                             uint32_t block_index_base, uint32_t t, int slot,
@@ -1307,7 +1468,7 @@ __device__ __forceinline__ void setup_chain(const uint32_t *__restrict__ img, ui
     const uint32_t gid = t * kSlots + vslot;
     const uint32_t rng = chain_seed(seed, gblock, (uint32_t)c.chain_id);
     uint32_t *res = ws.results + (size_t)gid * kResWords;
-    setup_variant(ws, c, A, core, pts, pix, n, mask, sa_steps, s_w, s_rcp, s_acc, tid, gid, rng, res, alpha_vals, amin, amax);
+    setup_variant<NU>(ws, c, A, core, pts, pix, n, mask, sa_steps, s_w, s_rcp, s_acc, tid, gid, rng, res, alpha_vals, amin, amax);
   }
 }
 
@@ -1333,6 +1494,7 @@ constexpr int kSlotGroups = 5;
 __constant__ uint8_t c_group_first[kSlotGroups] = {0, 3, 6, 8, 12};
 __constant__ uint8_t c_group_count[kSlotGroups] = {3, 3, 2, 4, 4};  // the last group also owns the dead slot 15
 
+template <bool NU>
 __global__ void __launch_bounds__(kChainThreads, 5)
 bc7_setup(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, uint32_t first_block,
           uint32_t num_blocks, Ws ws, int sa_steps, uint64_t seed, uint32_t block_index_base) {
@@ -1380,8 +1542,8 @@ bc7_setup(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, u
   // pass 2: one chain per lane and trip
   for (uint32_t e = tid; e < total; e += kChainThreads) {
     const uint32_t entry = s_list[e];
-    setup_chain(img, width, blocks_x, first_block, ws, sa_steps, seed, block_index_base,
-                tile * kChainThreads + (entry >> 4), (int)(entry & 15), s_w, s_rcp, s_acc, tid);
+    setup_chain<NU>(img, width, blocks_x, first_block, ws, sa_steps, seed, block_index_base,
+                    tile * kChainThreads + (entry >> 4), (int)(entry & 15), s_w, s_rcp, s_acc, tid);
   }
 }
 
@@ -1444,7 +1606,7 @@ __global__ void __launch_bounds__(256) bc7_scatter(Ws ws, uint32_t num_blocks) {
     if (w0 >> 31) {
       const int mode = (w0 >> 16) & 7, idx_mode = (w0 >> 21) & 1;
       const int ibits = idx_mode == 0 ? c_modes[mode].index_bits : c_modes[mode].alpha_index_bits;
-      key = sort_key(ibits, (w0 >> 24) & 31, st0.w);
+      key = sort_key(ibits, (w0 >> 24) & 31, sort_error(ws, st0.w));
       rank = atomicAdd(&s_cnt[key], 1u);
     }
   }
@@ -1639,9 +1801,10 @@ __device__ __forceinline__ void sa_palette_uniform(uint2 (*s_pal)[kSaThreads], i
 // The palette is stored as PAIRS: row j of the lane's column holds (colour j, colour j + 1), the
 // last row (colour nbm1, colour nbm1) -- the weight table is padded with 64 -- so the two
 // candidate buckets of a pixel (floor and ceil of its projection) come from one 64-bit load.
+template <bool NU>
 __device__ __forceinline__ uint32_t sa_eval(uint32_t (*s_pix)[kPixStride], uint2 (*s_pal)[kSaThreads],
                                             const uint8_t *__restrict__ s_w, int tid, const SaConst &K, int nmax,
-                                            int nbmax, int uflags, uint32_t q1, uint32_t q2, uint32_t k256,
+                                            int nbmax, int uflags, uint32_t q1, uint32_t q2, uint32_t k256, int rot,
                                             uint32_t &idx_lo, uint32_t &idx_hi) {
   const uint32_t d11 = __dp4a(q1, q1, 0u), d12 = __dp4a(q1, q2, 0u), d22 = __dp4a(q2, q2, 0u);
   const int den = (int)d22 - 2 * (int)d12 + (int)d11;       // |e2 - e1|^2
@@ -1681,6 +1844,50 @@ __device__ __forceinline__ uint32_t sa_eval(uint32_t (*s_pix)[kPixStride], uint2
   const uint32_t cq = (uint32_t)((int)d12 - (int)d11 - K.calpha * ((int)(q2 >> 24) - (int)(q1 >> 24)));
   const int n = K.n, nbm1 = K.nbm1;
   const uint2 *pal = &s_pal[0][tid];
+  if constexpr (NU) {
+    // Non-uniform metric: float errors, summed in pixel order (the sum is not associative), so every
+    // pixel is finished -- exact replay included -- before the next one is added.  Returns the
+    // total's bit pattern.  (A niche setting: no warp-uniform fast paths here.)
+    float w[4];
+    nu_metric(rot, w);
+    float total = 0.0f;
+    uint32_t word[2] = {0u, 0u};
+#pragma unroll 1
+    for (int i = 0; i < n; i++) {
+      const uint32_t px = s_pix[i][tid];
+      const int num = (int)(__dp4a(px, q2p, 0u) - __dp4a(px, q1p, cq));
+      const int vp = __float2int_rd(__fmaf_rn((float)num, inv16, 1.0f));
+      int ja = __vimin_s32_relu(vp >> 16, nbm1);
+      bool two = vp >= 1;
+      if (((uint32_t)vp & 0xFFFEu) == 0u) {  // within 2^-16 of a bucket boundary: the reference's own sequence
+        ja = 0;
+        two = false;
+        if (den != 0) {
+          const int k = (vp - 1 + 0x8000) >> 16;
+          if (num * nbm1 == k * den) {
+            ja = __vimin_s32_relu(k, nbm1);
+          } else {
+            const float t = __fmul_rn(__fdiv_rn((float)num, fden), fnb);
+            const int x1 = min(max(0, (int)floorf(t)), nbm1), x2 = min((int)ceilf(t), nbm1);
+            ja = x1;
+            two = x1 + 1 <= x2;
+          }
+        }
+      }
+      const uint2 c = pal[ja * kSaThreads];
+      float e = nu_error(c.x, px, w);
+      uint32_t pick = (uint32_t)ja;
+      if (two) {
+        const float eb = nu_error(c.y, px, w);
+        if (eb < e) { e = eb; pick = (uint32_t)ja + 1u; }  // (the last row repeats its colour: never taken there)
+      }
+      total = __fadd_rn(total, e);
+      word[i >> 3] |= pick << (4 * (i & 7));
+    }
+    idx_lo = word[0];
+    idx_hi = word[1];
+    return __float_as_uint(total);
+  }
   uint32_t total = 0, slow = 0, word[2];
   // `total` sums the pixels' keys (error << 8 | bucket, see SA_PIXEL)
   if ((uflags & 1) && nmax == 16) sa_pixels16(s_pix, pal, tid, nbm1, q1p, q2p, cq, inv16, k256, total, slow, word);
@@ -1789,6 +1996,7 @@ __global__ void bc7_chainstats_report() {
 }
 #endif
 
+template <bool NU>
 __global__ void __launch_bounds__(kSaThreads, kSaCtasPerSm)
 bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, uint32_t first_block, Ws ws,
            int sa_steps) {
@@ -1964,7 +2172,8 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
       // modes without p-bits evaluate with a zero p-bit (reference quirk, see fit_cluster): their combo is 0
       const uint32_t q1 = sa_quantize(s_q, K, n1, (ncombo >> K.sh0) & 1), q2 = sa_quantize(s_q, K, n2, ncombo & 1);
       uint32_t ilo, ihi;
-      const uint32_t err = sa_eval(s_pix, s_pal, s_w, tid, K, nmax, nbmax, uflags, q1, q2, k256, ilo, ihi);
+      const uint32_t err = sa_eval<NU>(s_pix, s_pal, s_w, tid, K, nmax, nbmax, uflags, q1, q2, k256,
+                                       rotation ? (K.qins ? (K.qsh >> 3) + 1 : 0) : 0, ilo, ihi);
 #ifdef FASTC_GPU_COUNTERS
       ncalls++; npbe += K.n;
 #endif
@@ -1978,6 +2187,10 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
         const float fr = __fsub_rn(__uint_as_float((127u << 23) | m), 1.0f);
         if (energy == 0) {
           accept = false;  // temp == 0: exp(-inf) = 0, exp(NaN) = NaN -> never accepted
+        } else if (NU) {  // the errors are floats (bit patterns): the reference's double expression
+          const float temp = __fdiv_rn((float)energy, f_tm1);
+          const double x = ((double)0.1f * ((double)__uint_as_float(cur_err) - (double)__uint_as_float(err))) / (double)temp;
+          accept = (double)fr < exp(x);
         } else {
           const float diff = (float)((int)cur_err - (int)err);  // exact (|.| < 2^24)
           // exp(0.1 * diff / temp), temp = energy / (steps - 1), through fast reciprocal / exponential
@@ -2036,6 +2249,10 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
         o2 = (o2 & 0x00FFFFFFu) | (((abytes >> 8) & 0xFF) << 24);
       }
       *reinterpret_cast<uint4 *>(res) = make_uint4(best_err + alpha_err, o1, o2, (uint32_t)best_combo);
+      if constexpr (NU) {  // the chain's error as the reference's double: colour fit (+ the alpha fit's, parked by bc7_setup)
+        const double e = (double)__uint_as_float(best_err);
+        ws.err64[gid] = rotation ? __dadd_rn(e, ws.err64[gid]) : e;
+      }
       if (improved) {
         // nibbles past the cluster size come from the warp's longer loops: clear them
         const int n = K.n;
@@ -2080,6 +2297,7 @@ struct BitWriter {
   }
 };
 
+template <bool NU>
 __global__ void __launch_bounds__(128)
 bc7_pack(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, uint32_t first_block,
          uint32_t num_blocks, Ws ws, uint8_t *__restrict__ out) {
@@ -2108,10 +2326,20 @@ bc7_pack(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, ui
     s.write(0xaaaaaaabu, 31);
     s.write(c_wm[before % 9], 31);
     reinterpret_cast<uint4 *>(out)[bi] = make_uint4(s.w[0], s.w[1], s.w[2], s.w[3]);
+    if (ws.stats) {  // the statistics variant's records (Compressor.cpp:2012-2019): mode 5, path 0
+      double *st = ws.stats + (size_t)t * kStatDoubles;
+      st[0] = 5.0; st[1] = 0.0;
+      for (int m = 0; m < 8; m++) st[2 + m] = -1.0;
+    }
     return;
   }
   if (type == kTypeTransparent) {  // WriteTransparentBlock (:1416-1421)
     reinterpret_cast<uint4 *>(out)[bi] = make_uint4(1u << 6, 0, 0, 0);
+    if (ws.stats) {  // (:2036-2043): mode 6, path 1
+      double *st = ws.stats + (size_t)t * kStatDoubles;
+      st[0] = 6.0; st[1] = 1.0;
+      for (int m = 0; m < 8; m++) st[2 + m] = -1.0;
+    }
     return;
   }
 
@@ -2119,29 +2347,42 @@ bc7_pack(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, ui
   // shape slots ascending, strict <.
   const uint32_t *res = ws.results + (size_t)t * kSlots * kResWords;
   const bool layout_b = (selw >> 22) & 1;
-  unsigned long long best_err = ~0ull;
+  // errors: exact integers under the uniform metric; the reference's doubles under the non-uniform
+  // one (sums over the subsets in subset order)
+  using Err = typename std::conditional<NU, double, unsigned long long>::type;
+  Err best_err = NU ? (Err)DBL_MAX : (Err)~0ull;
   int best_mode = -1, best_si = 0, best_first = 0;  // best_first: first slot of the winning candidate
   // all sixteen chain errors at once: independent loads, static register indices below (slots
   // without a live chain hold stale words, which no live candidate reads)
-  uint32_t e[kSlots];
+  Err e[kSlots];
 #pragma unroll
-  for (int k = 0; k < kSlots; k++) e[k] = res[k * kResWords];
+  for (int k = 0; k < kSlots; k++) {
+    if constexpr (NU) e[k] = ws.err64[(size_t)t * kSlots + k];
+    else e[k] = res[k * kResWords];
+  }
   // candidate (mode, shape slot si): its first chain slot, its error, the slot Pack reads
-  auto consider = [&](int mode, int si, int first, unsigned long long err, int pick) {
-    if (decode_chain(selw, first).active && err < best_err) { best_err = err; best_mode = mode; best_si = si; best_first = pick; }
+  double mode_err[8] = {-1.0, -1.0, -1.0, -1.0, -1.0, -1.0, -1.0, -1.0};  // statistics: errors[mode] (Compressor.cpp:1797-1798)
+  auto consider = [&](int mode, int si, int first, Err err, int pick) {
+    if (!decode_chain(selw, first).active) return;
+    if (ws.stats) {
+#pragma unroll
+      for (int m = 0; m < 8; m++)
+        if (m == mode && (mode_err[m] < 0.0 || (double)err < mode_err[m])) mode_err[m] = (double)err;
+    }
+    if (err < best_err) { best_err = err; best_mode = mode; best_si = si; best_first = pick; }
   };
   if (!layout_b) {  // opaque layout, reference order {0, 2, 1, 3, 7, (4, 5: none), 6}
-    consider(0, 1, 0, (unsigned long long)e[0] + e[1] + e[2], 0);
-    consider(2, 1, 3, (unsigned long long)e[3] + e[4] + e[5], 3);
-    consider(1, 0, 6, (unsigned long long)e[6] + e[7], 6);
-    consider(3, 0, 8, (unsigned long long)e[8] + e[9], 8);
-    consider(7, 0, 10, (unsigned long long)e[10] + e[11], 10);
+    consider(0, 1, 0, e[0] + e[1] + e[2], 0);
+    consider(2, 1, 3, e[3] + e[4] + e[5], 3);
+    consider(1, 0, 6, e[6] + e[7], 6);
+    consider(3, 0, 8, e[8] + e[9], 8);
+    consider(7, 0, 10, e[10] + e[11], 10);
     consider(6, 0, 12, e[12], 12);
     consider(6, 1, 13, e[13], 13);
   } else {          // alpha layout: {7, 4, 5, 6}
-    consider(7, 0, 13, (unsigned long long)e[13] + e[14], 13);
+    consider(7, 0, 13, e[13] + e[14], 13);
     // modes 4 / 5: best rotation / index mode, strict < in loop order (:1320-1348)
-    uint32_t be = e[0];
+    Err be = e[0];
     int pick = 0;
 #pragma unroll
     for (int k = 1; k < 8; k++)
@@ -2154,6 +2395,13 @@ bc7_pack(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, ui
       if (e[k] < be) { be = e[k]; pick = k; }
     consider(5, 0, 8, be, pick);
     consider(6, 0, 12, e[12], 12);
+  }
+  if (ws.stats) {  // path 2: a shape estimate hit zero (early-out), 3: full search (Compressor.cpp:2110, :2164, :2172)
+    double *st = ws.stats + (size_t)t * kStatDoubles;
+    st[0] = (double)best_mode;
+    st[1] = ((selw >> 23) & 1) ? 2.0 : 3.0;
+#pragma unroll
+    for (int m = 0; m < 8; m++) st[2 + m] = mode_err[m];
   }
   if (best_mode < 0) {  // unreachable with the default mode mask
     reinterpret_cast<uint4 *>(out)[bi] = make_uint4(0, 0, 0, 0);
@@ -2288,7 +2536,7 @@ void build_single_table(uint32_t *tab) {
         }
 }
 
-size_t ws_bytes(uint32_t nblocks) {
+size_t ws_bytes(uint32_t nblocks, bool nu) {
   const size_t ntiles = (nblocks + kTile - 1) / kTile;
   size_t b = 0;
   b += ((size_t)nblocks * 4 + 255) & ~(size_t)255;               // sel
@@ -2298,10 +2546,11 @@ size_t ws_bytes(uint32_t nblocks) {
   b += (size_t)nblocks * kSlots * 8 * 4;                         // states
   b += (size_t)nblocks * kSlots * kStateWords * 4;               // sorted states
   b += kBinWords * 4;                                            // bins
+  if (nu) b += (size_t)nblocks * kSlots * 8;                     // chain errors as doubles (non-uniform metric)
   return b;
 }
 
-Ws carve(void *base, uint32_t nblocks) {
+Ws carve(void *base, uint32_t nblocks, bool nu) {
   const size_t ntiles = (nblocks + kTile - 1) / kTile;
   uint8_t *p = static_cast<uint8_t *>(base);
   Ws w;
@@ -2313,7 +2562,9 @@ Ws carve(void *base, uint32_t nblocks) {
   w.results = reinterpret_cast<uint32_t *>(p); p += (size_t)nblocks * kSlots * kResWords * 4;
   w.states = reinterpret_cast<uint32_t *>(p); p += (size_t)nblocks * kSlots * 8 * 4;
   w.sorted = reinterpret_cast<uint4 *>(p); p += (size_t)nblocks * kSlots * kStateWords * 4;
-  w.bins = reinterpret_cast<uint32_t *>(p);
+  w.bins = reinterpret_cast<uint32_t *>(p); p += kBinWords * 4;
+  w.err64 = nu ? reinterpret_cast<double *>(p) : nullptr;
+  w.stats = nullptr;
   return w;
 }
 
@@ -2360,6 +2611,10 @@ cudaError_t bc7_upload_tables() {
     for (int j = 0; j < 16; j++)
       if (kWeight[48 + j] != w4[j]) return cudaErrorInvalidValue;
   }
+  {  // kErrorMetrics[eErrorMetric_Nonuniform] (Compressor.cpp:205-208), rounded like the reference's initialiser
+    const float w[4] = {sqrtf(0.3f), sqrtf(0.56f), sqrtf(0.11f), 1.0f};
+    if ((e = cudaMemcpyToSymbol(c_nu_weights, w, sizeof(w))) != cudaSuccess) return e;
+  }
   static uint32_t host_single[8 * 2 * 4 * 2 * 256];
   static bool built = false;
   if (!built) { build_single_table(host_single); built = true; }
@@ -2383,6 +2638,7 @@ void bc7_free_workspace(Bc7Workspace &ws) {
 constexpr uint32_t kChunkBlocks = 1u << 22;
 
 uint32_t bc7_max_submission() { return kChunkBlocks; }
+uint32_t bc7_stat_doubles() { return kStatDoubles; }
 
 // One submission of <= kChunkBlocks blocks, in two halves so that a caller can learn the
 // submission's solid-block count (and those of earlier submissions on other streams / GPUs)
@@ -2394,11 +2650,13 @@ cudaError_t bc7_front(Bc7Workspace &wsp, const void *rgba_dev, uint32_t width, u
                       uint32_t num_blocks, const EncodeParams &prm, uint32_t block_index_base, cudaStream_t stream,
                       cudaEvent_t count_ready, uint32_t *launches) {
   if (num_blocks == 0 || num_blocks > kChunkBlocks) return cudaErrorInvalidValue;
-  cudaError_t e = ensure_ws(wsp, ws_bytes(num_blocks) + 256);
+  const bool nu = prm.error_metric != 0;
+  wsp.nu = nu;
+  cudaError_t e = ensure_ws(wsp, ws_bytes(num_blocks, nu) + 256);
   if (e != cudaSuccess) return e;
   const uint32_t *img = static_cast<const uint32_t *>(rgba_dev);
   const uint32_t bx = width / 4, nb = num_blocks, fb = first_block;
-  Ws ws = carve(wsp.base, nb);
+  Ws ws = carve(wsp.base, nb, nu);
   ws.wm_running = wsp.wm_running;
   ws.counters = wsp.counters;
 #ifdef FASTC_GPU_COUNTERS
@@ -2427,13 +2685,21 @@ cudaError_t bc7_front(Bc7Workspace &wsp, const void *rgba_dev, uint32_t width, u
     if ((e = cudaEventRecord(count_ready, stream)) != cudaSuccess) return e;
   }
   if (ev) cudaEventRecord(ev[1], stream);
-  bc7_select<<<(nb + kSelWarps - 1) / kSelWarps, kSelWarps * 32, 0, stream>>>(img, width, bx, fb, nb, ws.sel, ws.states,
-                                                                            prm.block_modes);
+  if (nu)
+    bc7_select<true><<<(nb + kSelWarps - 1) / kSelWarps, kSelWarps * 32, 0, stream>>>(img, width, bx, fb, nb, ws.sel, ws.states,
+                                                                                    prm.block_modes);
+  else
+    bc7_select<false><<<(nb + kSelWarps - 1) / kSelWarps, kSelWarps * 32, 0, stream>>>(img, width, bx, fb, nb, ws.sel, ws.states,
+                                                                                     prm.block_modes);
   if (ev) cudaEventRecord(ev[2], stream);
   const uint64_t nthreads = (uint64_t)nb * kSlots;
   cudaMemsetAsync(ws.bins, 0, kBinWords * 4, stream);
-  bc7_setup<<<((nb + kChainThreads - 1) / kChainThreads) * kSlotGroups, kChainThreads, 0, stream>>>(
-      img, width, bx, fb, nb, ws, prm.quality, prm.seed, block_index_base);
+  if (nu)
+    bc7_setup<true><<<((nb + kChainThreads - 1) / kChainThreads) * kSlotGroups, kChainThreads, 0, stream>>>(
+        img, width, bx, fb, nb, ws, prm.quality, prm.seed, block_index_base);
+  else
+    bc7_setup<false><<<((nb + kChainThreads - 1) / kChainThreads) * kSlotGroups, kChainThreads, 0, stream>>>(
+        img, width, bx, fb, nb, ws, prm.quality, prm.seed, block_index_base);
   n += 2;
   if (prm.quality > 0) {
     bc7_bin_offsets<<<1, 1, 0, stream>>>(ws.bins, sa_grid);
@@ -2445,7 +2711,8 @@ cudaError_t bc7_front(Bc7Workspace &wsp, const void *rgba_dev, uint32_t width, u
 #ifdef FASTC_GPU_CHAINSTATS
     bc7_chainstats_reset<<<1, 32, 0, stream>>>();
 #endif
-    bc7_anneal<<<sa_grid, kSaThreads, 0, stream>>>(img, width, bx, fb, ws, prm.quality);
+    if (nu) bc7_anneal<true><<<sa_grid, kSaThreads, 0, stream>>>(img, width, bx, fb, ws, prm.quality);
+    else bc7_anneal<false><<<sa_grid, kSaThreads, 0, stream>>>(img, width, bx, fb, ws, prm.quality);
 #ifdef FASTC_GPU_CHAINSTATS
     bc7_chainstats_report<<<1, 1, 0, stream>>>();
 #endif
@@ -2464,19 +2731,24 @@ cudaError_t bc7_front(Bc7Workspace &wsp, const void *rgba_dev, uint32_t width, u
 // wm_base_dev: device word holding the base (chained submissions of launch_bc7), or NULL: `wm_base`.
 cudaError_t bc7_back(Bc7Workspace &wsp, const void *rgba_dev, uint32_t width, uint32_t first_block,
                      uint32_t num_blocks, void *out_dev, uint32_t wm_base, bool base_on_device, cudaStream_t stream,
-                     uint32_t *launches) {
+                     uint32_t *launches, double *stats_dev) {
   if (num_blocks == 0 || !wsp.base) return cudaErrorInvalidValue;
   const uint32_t *img = static_cast<const uint32_t *>(rgba_dev);
-  Ws ws = carve(wsp.base, num_blocks);
+  Ws ws = carve(wsp.base, num_blocks, wsp.nu);
   ws.wm_running = wsp.wm_running;
   ws.counters = wsp.counters;
+  ws.stats = stats_dev;
   uint32_t n = 0;
   if (!base_on_device) {
     bc7_set_u32<<<1, 1, 0, stream>>>(wsp.wm_running, wm_base);
     n++;
   }
-  bc7_pack<<<(num_blocks + 127) / 128, 128, 0, stream>>>(img, width, width / 4, first_block, num_blocks, ws,
-                                                         static_cast<uint8_t *>(out_dev));
+  if (wsp.nu)
+    bc7_pack<true><<<(num_blocks + 127) / 128, 128, 0, stream>>>(img, width, width / 4, first_block, num_blocks, ws,
+                                                                 static_cast<uint8_t *>(out_dev));
+  else
+    bc7_pack<false><<<(num_blocks + 127) / 128, 128, 0, stream>>>(img, width, width / 4, first_block, num_blocks, ws,
+                                                                  static_cast<uint8_t *>(out_dev));
   n++;
   if (wsp.cur_ev) cudaEventRecord(wsp.cur_ev[4], stream);
   wsp.cur_ev = nullptr;
@@ -2490,7 +2762,7 @@ cudaError_t launch_bc7(Bc7Workspace &wsp, const void *rgba_dev, uint32_t width, 
   (void)height;
   if (num_blocks == 0) return cudaSuccess;
   const uint32_t chunk = num_blocks < kChunkBlocks ? num_blocks : kChunkBlocks;
-  cudaError_t e = ensure_ws(wsp, ws_bytes(chunk) + 256);
+  cudaError_t e = ensure_ws(wsp, ws_bytes(chunk, prm.error_metric != 0) + 256);
   if (e != cudaSuccess) return e;
   // The running watermark base lives on the device, so chunks chain without a host sync.
   uint32_t n = 0;
@@ -2501,9 +2773,9 @@ cudaError_t launch_bc7(Bc7Workspace &wsp, const void *rgba_dev, uint32_t width, 
     const uint32_t nb = num_blocks - off < chunk ? num_blocks - off : chunk;
     const uint32_t fb = first_block + off;
     if ((e = bc7_front(wsp, rgba_dev, width, fb, nb, prm, block_index_base, stream, nullptr, &n)) != cudaSuccess) return e;
-    if ((e = bc7_back(wsp, rgba_dev, width, fb, nb, out_dev, 0, true, stream, &n)) != cudaSuccess) return e;
+    if ((e = bc7_back(wsp, rgba_dev, width, fb, nb, out_dev, 0, true, stream, &n, nullptr)) != cudaSuccess) return e;
     if (off + chunk < num_blocks) {
-      Ws ws = carve(wsp.base, nb);
+      Ws ws = carve(wsp.base, nb, wsp.nu);
       bc7_add_u32<<<1, 1, 0, stream>>>(wsp.wm_running, ws.total_solid);
       n++;
     }
@@ -2534,7 +2806,7 @@ cudaError_t bc7_count_solid(Bc7Workspace &wsp, const void *rgba_dev, uint32_t wi
 
 cudaError_t bc7_debug_dump(Bc7Workspace &wsp, uint32_t nblocks, uint32_t *sel_out, uint32_t *results_out) {
   if (!wsp.base) return cudaErrorInvalidValue;
-  Ws ws = carve(wsp.base, nblocks);
+  Ws ws = carve(wsp.base, nblocks, wsp.nu);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) return e;
   e = cudaMemcpy(sel_out, ws.sel, (size_t)nblocks * 4, cudaMemcpyDeviceToHost);

@@ -11,6 +11,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <deque>
 #include <chrono>
 #include <condition_variable>
 #include <cstdarg>
@@ -80,6 +82,8 @@ struct DeviceCtx {
   uint8_t *pend_dst[kPipeDepth] = {};  // copy-out the slot still owes the caller
   size_t pend_bytes[kPipeDepth] = {};
   unsigned long long *psnr_sum = nullptr, *psnr_host = nullptr;  // device / pinned accumulators of fastc_gpu_psnr*
+  void *stats_buf[kPipeDepth] = {};  // BPTC per-block statistics of the chunk in the slot (only when asked for)
+  size_t stats_cap[kPipeDepth] = {};
   // BC7 host path: the chunk in a slot is packed once the watermark base is known (complete_piece)
   cudaEvent_t ev_count[kPipeDepth] = {};
   struct Pending {
@@ -87,6 +91,7 @@ struct DeviceCtx {
     int piece = 0;                 // index in the submission's WmChain
     uint32_t lo = 0, nblk = 0, height = 0;
     uint8_t *dst = nullptr;        // caller memory of the chunk's first encoded block
+    fastc_gpu_bptc_block_stat *stats = nullptr;  // caller's record of the chunk's first encoded block (or NULL)
   } pending[kPipeDepth];
   // The device API's BC7 scratch (bc7ws[kPipeDepth]) is shared by every caller stream of the device:
   // each use waits for the previous one (api_done) before it touches the scratch
@@ -332,12 +337,13 @@ void plan_chunks(Shard &s, int format, uint32_t width, uint32_t chunk_blocks) {
   for (uint32_t r = row0; r < row1; r += rows_per_chunk) s.bounds.push_back(r);
   s.bounds.push_back(row1);
   if (chunk_blocks == 0 && format == FASTC_GPU_BPTC && s.bounds.size() == 2 && total_rows >= 64 &&
-      (size_t)total_rows * 4 * width * 4 >= ((size_t)96 << 20)) {
-    // BC7 auto, big uploads (>= 96 MiB, ~2 ms on the wire): two halves on two streams.  The second
-    // half's upload and shape selection / fits run under the first half's annealing, the first
-    // half's download under the second's kernels, and each half is still large enough for the
-    // persistent annealing kernel's ~1.5 ms tail not to matter.  Measured at 8192^2
-    // (tools/time_e2e_chunks.py): one chunk 238.9 ms, two halves 236.6 ms, 1/16 + 15/16 250.4 ms.
+      (size_t)total_rows * 4 * width * 4 >= ((size_t)192 << 20)) {
+    // BC7 auto, very big uploads (>= 192 MiB, ~4 ms on the wire): two halves on two streams.  The
+    // second half's upload and shape selection / fits run under the first half's annealing, the
+    // first half's download under the second's kernels.  Each half pays the persistent annealing
+    // kernel's tail once more, so this only wins when the copies are long: measured
+    // (tools/time_e2e_chunks.py, profiles/r02_e2e_chunks.log) 8192^2 (256 MiB): one chunk 211.9 ms,
+    // two halves 210.0 ms; 8192 x 4096 (128 MiB, the slab of one of two GPUs): 106.6 vs 115.6 ms.
     s.bounds.assign({row0, row0 + total_rows / 2, row1});
   }
 }
@@ -355,21 +361,83 @@ bool is_pageable(const void *p) {
   return a.type == cudaMemoryTypeUnregistered;
 }
 
-// memcpy split over a few host threads (one thread moves ~10 GB/s; PCIe 5 x16 wants ~50)
-void par_memcpy(void *dst, const void *src, size_t n) {
-  const int nt = (int)std::min<size_t>(8, n >> 20);  // >= 1 MiB per thread
-  if (nt <= 1) {
-    memcpy(dst, src, n);
-    return;
+// memcpy split over a few host threads (one thread moves ~10 GB/s; PCIe 5 x16 wants ~50).  The
+// threads are a process-wide pool created on first use (spawning threads per 16 MiB piece cost as
+// much as the copy itself); the caller works too, so the pool can be shared by the per-GPU host
+// threads of one submission without deadlock.
+class CopyPool {
+ public:
+  static CopyPool &get() {
+    static CopyPool *pool = new CopyPool();  // leaked on purpose: its threads may outlive static destructors
+    return *pool;
   }
-  std::vector<std::thread> th;
-  for (int k = 1; k < nt; k++) {
-    const size_t a = n * k / nt, b = n * (k + 1) / nt;
-    th.emplace_back([=] { memcpy((uint8_t *)dst + a, (const uint8_t *)src + a, b - a); });
+  void copy(void *dst, const void *src, size_t n) {
+    const size_t kPart = (size_t)1 << 20;
+    if (n < 2 * kPart || workers_ == 0) {
+      memcpy(dst, src, n);
+      return;
+    }
+    const int parts = (int)std::min<size_t>((size_t)workers_ + 1, n / kPart);
+    std::atomic<int> left(parts);
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      for (int k = 1; k < parts; k++) {
+        const size_t a = n * k / parts, b = n * (k + 1) / parts;
+        tasks_.push_back(Task{(uint8_t *)dst + a, (const uint8_t *)src + a, b - a, &left});
+      }
+    }
+    cv_.notify_all();
+    memcpy(dst, src, n / parts);
+    left.fetch_sub(1, std::memory_order_acq_rel);
+    Task t;
+    while (left.load(std::memory_order_acquire) > 0) {
+      if (pop(t)) run(t);  // help: the tasks queued may be this call's own
+      else std::this_thread::yield();
+    }
   }
-  memcpy(dst, src, n / nt);
-  for (auto &t : th) t.join();
-}
+
+ private:
+  struct Task {
+    uint8_t *dst;
+    const uint8_t *src;
+    size_t n;
+    std::atomic<int> *left;
+  };
+  CopyPool() {
+    const unsigned hc = std::thread::hardware_concurrency();
+    workers_ = (int)std::min<unsigned>(12, hc > 2 ? hc - 2 : 0);
+    for (int k = 0; k < workers_; k++) std::thread([this] { loop(); }).detach();
+  }
+  static void run(const Task &t) {
+    memcpy(t.dst, t.src, t.n);
+    t.left->fetch_sub(1, std::memory_order_acq_rel);
+  }
+  bool pop(Task &t) {
+    std::lock_guard<std::mutex> lk(mu_);
+    if (tasks_.empty()) return false;
+    t = tasks_.front();
+    tasks_.pop_front();
+    return true;
+  }
+  void loop() {
+    for (;;) {
+      Task t;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [this] { return !tasks_.empty(); });
+        t = tasks_.front();
+        tasks_.pop_front();
+      }
+      run(t);
+    }
+  }
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::deque<Task> tasks_;
+  int workers_ = 0;
+};
+
+void par_memcpy(void *dst, const void *src, size_t n) { CopyPool::get().copy(dst, src, n); }
 
 // Host -> device on `st`.  Pinned sources go straight to the copy engine; pageable ones through
 // the pinned ring, piece by piece.
@@ -427,8 +495,17 @@ int complete_piece(DeviceCtx &c, int slot, uint32_t width, WmChain &chain, Shard
   }
   uint32_t base = 0;
   if (!chain.base_of(p.piece, &base)) return fail("an earlier part of the submission failed");
-  CU_TRY(bc7_back(c.bc7ws[slot], c.in_buf[slot], width, p.lo, p.nblk, c.out_buf[slot], base, false, st, &s.launches));
+  double *stats_dev = nullptr;
+  if (p.stats) {
+    static_assert(sizeof(fastc_gpu_bptc_block_stat) == 10 * sizeof(double), "record layout");
+    if (grow(&c.stats_buf[slot], &c.stats_cap[slot], (size_t)p.nblk * sizeof(fastc_gpu_bptc_block_stat))) return 1;
+    stats_dev = static_cast<double *>(c.stats_buf[slot]);
+  }
+  CU_TRY(bc7_back(c.bc7ws[slot], c.in_buf[slot], width, p.lo, p.nblk, c.out_buf[slot], base, false, st, &s.launches,
+                  stats_dev));
   CU_TRY(cudaEventRecord(c.ev_stop[slot], st));
+  if (p.stats)  // (an analysis path: a plain copy into the caller's memory, pinned or not)
+    CU_TRY(cudaMemcpyAsync(p.stats, stats_dev, (size_t)p.nblk * sizeof(fastc_gpu_bptc_block_stat), cudaMemcpyDeviceToHost, st));
   const size_t bytes = (size_t)p.nblk * 16;
   if (download(c, slot, p.dst, (uint8_t *)c.out_buf[slot] + (size_t)p.lo * 16, bytes, st)) return 1;
   s.d2h += bytes;
@@ -474,7 +551,8 @@ void abort_slots(DeviceCtx &c) {
 // drain = false leaves the last chunks in flight (batch submissions: the caller drains once at
 // the end, so consecutive textures overlap).
 int run_shard_impl(Shard &s, int format, const uint8_t *rgba_host, uint32_t width, uint32_t height,
-                   uint8_t *out_host, const EncodeParams &prm, WmChain &chain, bool drain) {
+                   uint8_t *out_host, const EncodeParams &prm, WmChain &chain, bool drain,
+                   fastc_gpu_bptc_block_stat *stats) {
   (void)height;
   DeviceCtx &c = g_ctx[s.dev];
   const uint32_t bx = width / 4;
@@ -530,6 +608,7 @@ int run_shard_impl(Shard &s, int format, const uint8_t *rgba_host, uint32_t widt
                        later ? c.ev_count[slot] : nullptr, &s.launches));
       DeviceCtx::Pending &p = c.pending[slot];
       p.active = true; p.piece = piece; p.lo = lo; p.nblk = hi - lo; p.height = (r1 - r0) * 4; p.dst = dst;
+      p.stats = stats ? stats + ((size_t)r0 * bx + lo) : nullptr;
       slots[nowed++] = slot;
       CU_TRY(cudaEventRecord(c.ev_stop[slot], st));  // (re-recorded after the pack)
     } else {
@@ -549,12 +628,12 @@ int run_shard_impl(Shard &s, int format, const uint8_t *rgba_host, uint32_t widt
 }
 
 int run_shard(Shard &s, int format, const uint8_t *rgba_host, uint32_t width, uint32_t height, uint8_t *out_host,
-              const EncodeParams &prm, WmChain &chain, bool drain = true) {
+              const EncodeParams &prm, WmChain &chain, bool drain = true, fastc_gpu_bptc_block_stat *stats = nullptr) {
   if (ensure_ctx(s.dev)) {
     chain.fail_all();
     return 1;
   }
-  const int rc = run_shard_impl(s, format, rgba_host, width, height, out_host, prm, chain, drain);
+  const int rc = run_shard_impl(s, format, rgba_host, width, height, out_host, prm, chain, drain, stats);
   if (rc) {
     chain.fail_all();  // pieces of other GPUs that wait for this slab's counts give up
     abort_slots(g_ctx[s.dev]);
@@ -563,13 +642,13 @@ int run_shard(Shard &s, int format, const uint8_t *rgba_host, uint32_t width, ui
 }
 
 int run_shard_locked(Shard &s, int format, const uint8_t *rgba_host, uint32_t width, uint32_t height,
-                     uint8_t *out_host, const EncodeParams &prm, WmChain &chain) {
+                     uint8_t *out_host, const EncodeParams &prm, WmChain &chain, fastc_gpu_bptc_block_stat *stats) {
   if (s.dev < 0 || s.dev >= kMaxDevices) {
     chain.fail_all();
     return fail("bad device %d", s.dev);
   }
   std::lock_guard<std::mutex> lk(g_ctx[s.dev].host_mu);
-  return run_shard(s, format, rgba_host, width, height, out_host, prm, chain);
+  return run_shard(s, format, rgba_host, width, height, out_host, prm, chain, true, stats);
 }
 
 // Block range checks shared by the entry points (no 32-bit wrap).
@@ -623,6 +702,8 @@ void fastc_gpu_shutdown(void) {
       if (c.ev_stop[i]) cudaEventDestroy(c.ev_stop[i]);
       if (c.in_buf[i]) cudaFree(c.in_buf[i]);
       if (c.out_buf[i]) cudaFree(c.out_buf[i]);
+      if (c.stats_buf[i]) cudaFree(c.stats_buf[i]);
+      c.stats_buf[i] = nullptr; c.stats_cap[i] = 0;
       c.streams[i] = nullptr; c.ev_start[i] = c.ev_stop[i] = nullptr;
       c.in_buf[i] = c.out_buf[i] = nullptr; c.in_cap[i] = c.out_cap[i] = 0;
     }
@@ -715,6 +796,7 @@ int compress_impl(int format, const uint8_t *rgba_host, uint32_t width, uint32_t
   int prev = 0;
   cudaGetDevice(&prev);
   const EncodeParams prm = make_params(quality, seed, opt);
+  fastc_gpu_bptc_block_stat *stats = (opt && format == FASTC_GPU_BPTC) ? opt->bptc_block_stats : nullptr;
 
   // Contiguous block-row slabs, one per GPU.
   const uint32_t row0 = first_block / bx, row1 = (first_block + num_blocks + bx - 1) / bx;
@@ -742,14 +824,14 @@ int compress_impl(int format, const uint8_t *rgba_host, uint32_t width, uint32_t
   if (format == FASTC_GPU_BPTC) chain.before = host_prefix_solid(rgba_host, width, height, first_block);
   if (num_gpus == 1) {
     cudaGetDevice(&shards[0].dev);  // one GPU: the caller's current device
-    shards[0].rc = run_shard_locked(shards[0], format, rgba_host, width, height, out_host, prm, chain);
+    shards[0].rc = run_shard_locked(shards[0], format, rgba_host, width, height, out_host, prm, chain, stats);
     if (shards[0].rc) snprintf(shards[0].err, sizeof(shards[0].err), "%s", tl_error);
   } else {
     std::vector<std::thread> th;
     for (int g = 0; g < num_gpus; g++)
       th.emplace_back([&, g] {
         if (shards[g].num_blocks == 0) return;
-        shards[g].rc = run_shard_locked(shards[g], format, rgba_host, width, height, out_host, prm, chain);
+        shards[g].rc = run_shard_locked(shards[g], format, rgba_host, width, height, out_host, prm, chain, stats);
         if (shards[g].rc) snprintf(shards[g].err, sizeof(shards[g].err), "%s", tl_error);
       });
     for (auto &t : th) t.join();

@@ -41,6 +41,7 @@ struct Bc7Workspace {
   cudaEvent_t ev[kMaxTimedChunks][5] = {};
   cudaEvent_t ev_mid[kMaxTimedChunks] = {};  // between setup(+sort) and anneal
   cudaEvent_t *cur_ev = nullptr;             // the timed chunk bc7_back closes
+  bool nu = false;                           // the submission in flight uses the non-uniform metric
 };
 void bc7_free_workspace(Bc7Workspace &ws);
 
@@ -67,9 +68,12 @@ uint32_t bc7_max_submission();
 cudaError_t bc7_front(Bc7Workspace &ws, const void *rgba_dev, uint32_t width, uint32_t first_block,
                       uint32_t num_blocks, const EncodeParams &prm, uint32_t block_index_base, cudaStream_t stream,
                       cudaEvent_t count_ready, uint32_t *launches);
+// stats_dev: optional device array of bc7_stat_doubles() doubles per block of the submission
+// (mode, path, error of every mode tried: the records of the reference's CompressWithStats)
 cudaError_t bc7_back(Bc7Workspace &ws, const void *rgba_dev, uint32_t width, uint32_t first_block,
                      uint32_t num_blocks, void *out_dev, uint32_t wm_base, bool base_on_device, cudaStream_t stream,
-                     uint32_t *launches);
+                     uint32_t *launches, double *stats_dev = nullptr);
+uint32_t bc7_stat_doubles();
 
 cudaError_t bc7_count_solid(Bc7Workspace &ws, const void *rgba_dev, uint32_t width, uint32_t first_block,
                             uint32_t num_blocks, cudaStream_t stream, uint32_t *count_out);

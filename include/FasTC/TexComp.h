@@ -24,7 +24,7 @@ struct SCompressionSettings {
   bool bUseAtomics;       // accepted (the GPU path has no separate "atomics" scheduler)
   bool bUsePVRTexLib;     // PVRTC is not supported on the GPU path
   bool bUseNVTT;          // no NVTT back end
-  std::ostream *logStream;  // per-block statistics are not produced; must be NULL or is ignored
+  std::ostream *logStream;  // BPTC: per-block statistics lines (path, mode, error of every mode tried) are written here
 
   // ---- extensions (appended, so reference call sites compile unchanged) ----
   int iNumGPUs;                  // devices to shard block rows over (0 = all visible, default 1)

@@ -83,13 +83,27 @@ typedef struct fastc_gpu_timing {
  * (ETCEncoder/src/rg_etc1.h:24-29; FasTC itself always passes cLowQuality,
  * ETCEncoder/src/Compressor.cpp:36-37).  Taken by the *_opt variants of the compress entry
  * points; a NULL pointer means the defaults below, which is what the plain entry points use. */
+/* Per-block record of the BPTC statistics (the lines BPTCC::CompressWithStats logs per block,
+ * BPTCEncoder/src/Compressor.cpp:1577-1624, :1954-2183): the mode packed, the path taken
+ * (0 solid colour, 1 transparent, 2 a partition shape estimated to ~zero error, 3 full search) and
+ * the best error of every mode tried (-1: not tried).  The reference's stats variant also logs
+ * per-mode shape ESTIMATES; the GPU selection kernel does not keep them. */
+typedef struct fastc_gpu_bptc_block_stat {
+  double mode;
+  double path;
+  double mode_error[8];
+} fastc_gpu_bptc_block_stat;
+
 typedef struct fastc_gpu_options {
   uint32_t struct_size;       /* = sizeof(fastc_gpu_options) */
   uint32_t bptc_block_modes;  /* m_BlockModes: bit m set = BC7 mode m may be used (default 0xFF)     */
   int32_t bptc_error_metric;  /* m_ErrorMetric: 0 = eErrorMetric_Uniform (default), 1 = _Nonuniform  */
   int32_t etc1_quality;       /* 0 = cLowQuality (default), 1 = cMediumQuality, 2 = cHighQuality     */
+  /* host-pointer BPTC submissions only (fastc_gpu_compress_opt): NULL, or one record per block of the
+   * IMAGE (index = raster block index); the records of the encoded block range are filled */
+  fastc_gpu_bptc_block_stat *bptc_block_stats;
 } fastc_gpu_options;
-#define FASTC_GPU_OPTIONS_INIT { (uint32_t)sizeof(fastc_gpu_options), 0xFFu, 0, 0 }
+#define FASTC_GPU_OPTIONS_INIT { (uint32_t)sizeof(fastc_gpu_options), 0xFFu, 0, 0, 0 }
 
 /* Number of visible CUDA devices (<0 on error). Creates nothing. */
 int fastc_gpu_device_count(void);

@@ -244,3 +244,27 @@ def test_ktx_file_is_byte_identical_to_the_reference_writer(tmp_path, fmt):
     ours, ref = (tmp_path / "ours.ktx").read_bytes(), (tmp_path / "ref.ktx").read_bytes()
     assert len(ours) == 96 + payload.size
     assert ours == ref
+
+
+@pytest.mark.gpu
+def test_tc_l_writes_the_per_block_log(gpu, oracle, tmp_path):
+    """`tc -l`: "<basename>.log" with the reference's per-block statistics lines
+    ("<block>: BlockStat_Mode -- m", ... reference BPTCEncoder/src/Compressor.cpp:106-131, :1947-1992);
+    the compressed output is the same as without -l."""
+    img = synth_rgba(64, 48, 1, full_height=256, y0=40)
+    write_tga(tmp_path / "img.tga", img)
+    r = _run([TC, "-f", "BPTC", "-q", "0", "-l", "-d", "out.ktx", "img.tga"], cwd=tmp_path)
+    assert r.returncode == 0, r.stdout + r.stderr
+    want, _ = oracle.compress("BPTC", img, quality=0)
+    assert (tmp_path / "out.ktx").read_bytes()[96:96 + want.size] == want.tobytes()
+    log = (tmp_path / "img.log").read_text().splitlines()
+    nblk = 16 * 12
+    assert len(log) == nblk * 18
+    b0 = want.reshape(-1, 16)[:, 0].astype(np.int64)
+    modes = np.log2(b0 & -b0).astype(int)
+    for i in (0, 17, nblk - 1):
+        blk = [ln for ln in log if ln.startswith(f"{i}: ")]
+        assert len(blk) == 18
+        assert blk[1] == f"{i}: BlockStat_Mode -- {modes[i]}"
+        assert blk[0].startswith(f"{i}: BlockStat_Path -- ")
+        assert blk[2] == f"{i}: BlockStat_ModeZeroEstimate -- -1"

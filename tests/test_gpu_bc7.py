@@ -300,3 +300,80 @@ def test_all_visible_gpus_host_path_equals_single_gpu(gpu, oracle):
     out = np.zeros_like(one)
     gpu.compress(F.BPTC, img, out, quality=2, seed=9, num_gpus=0, first_block=1000, num_blocks=50000)
     assert (out[1000 * 16:51000 * 16] == one[1000 * 16:51000 * 16]).all() and not out[:16000].any()
+
+
+@pytest.mark.parametrize("mask,q", [(0xFF, 0), (0x4A, 0), (0xF0, 0), (0xFF, 2), (0xF0, 5), (0xCF, 8)])
+def test_bc7_nonuniform_metric_matches_oracle(gpu, oracle, mask, q):
+    """m_ErrorMetric = eErrorMetric_Nonuniform (Compressor.cpp:205-208): float-weighted channel errors in
+    shape selection, the fits, the annealing and the mode choice.  Bit-exact against the oracle (pinned to
+    the reference's BPTCC::Compress(job, settings) in tests/test_oracle_vs_ref.py), at -q 0 and with
+    annealing on the keyed RNG streams, with and without a mode mask."""
+    img = synth_rgba(128, 128, 6, noise_mask=63)
+    got, _ = gpu.compress(F.BPTC, img, quality=q, seed=11, block_modes=mask, error_metric=1)
+    want, _ = oracle.compress("BPTC", img, quality=q, rng_mode=1, seed=11, block_modes=mask, error_metric=1)
+    bad = _bad(got, want)
+    assert len(bad) == 0, f"mask {mask:#x} q {q}: {len(bad)} blocks differ, first {bad[:8]}"
+    # and it is a different encoding from the uniform metric's
+    uni, _ = gpu.compress(F.BPTC, img, quality=q, seed=11, block_modes=mask)
+    assert len(_bad(got, uni)) > 0
+
+
+def test_bc7_nonuniform_metric_special_blocks_and_device_path(gpu, oracle):
+    import torch
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, (64, 128, 4), dtype=np.uint8)
+    img[:, 64:, 3] = 255
+    img[0:4, 8:12, :3] = (50, 60, 70); img[0:4, 8:12, 3] = 255
+    img[0:2, 8:12, :3] = (200, 10, 30)                     # two colours
+    img[4:8, 0:4] = (1, 2, 3, 255); img[4, 0] = (1, 2, 4, 255)
+    img[8:12, 64:68, :] = np.arange(16, dtype=np.uint8).reshape(4, 4, 1) * 16
+    img[8:12, 64:68, 3] = 255
+    img[12:16, 0:4, :3] = (9, 9, 9); img[12:16, 0:4, 3] = np.arange(16, dtype=np.uint8).reshape(4, 4) * 15  # alpha ramp
+    want, _ = oracle.compress("BPTC", img, quality=3, rng_mode=1, seed=2, error_metric=1)
+    d_in = torch.from_numpy(img).cuda()
+    d_out = torch.zeros(want.size, dtype=torch.uint8, device="cuda")
+    gpu.compress_device(F.BPTC, d_in, d_out, width=128, height=64, quality=3, seed=2, error_metric=1)
+    torch.cuda.synchronize()
+    bad = _bad(d_out.cpu().numpy(), want)
+    assert len(bad) == 0, f"{len(bad)} blocks differ, first {bad[:8]}"
+
+
+def test_bc7_block_statistics(gpu, oracle):
+    """The per-block records behind `tc -l` (BPTCC::CompressWithStats' log): mode packed, path taken,
+    error of every mode tried.  Checked for consistency with the compressed blocks, for both metrics,
+    and through a chunked submission."""
+    img = synth_rgba(256, 256, 1)
+    nblk = 64 * 64
+    blocks = img.reshape(64, 4, 64, 4, 4).transpose(0, 2, 1, 3, 4).reshape(-1, 16, 4)
+    solid = (blocks == blocks[:, :1]).all((1, 2))
+    transparent = (blocks[..., 3] == 0).all(1) & ~solid
+    for metric in (0, 1):
+        stats = np.full((nblk, 10), -7.0)
+        got, _ = gpu.compress(F.BPTC, img, quality=2, seed=3, error_metric=metric, block_stats=stats, chunk_blocks=64 * 9)
+        plain, _ = gpu.compress(F.BPTC, img, quality=2, seed=3, error_metric=metric)
+        assert (got == plain).all()                      # asking for statistics does not change the encoding
+        b0 = got.reshape(-1, 16)[:, 0].astype(np.int64)
+        mode_in_block = np.log2(b0 & -b0).astype(int)
+        assert (stats[:, 0].astype(int) == mode_in_block).all()
+        assert (stats[solid, 1] == 0).all() and (stats[transparent, 1] == 1).all()
+        normal = ~solid & ~transparent
+        assert set(np.unique(stats[normal, 1])) <= {2.0, 3.0} and (stats[normal, 1] == 3).any()
+        errs = stats[normal, 2:]
+        tried = errs >= 0
+        assert tried.any(1).all() and (errs[~tried] == -1).all()
+        # the packed mode is the first minimum in the reference's mode order {0, 2, 1, 3, 7, 4, 5, 6}
+        order = [0, 2, 1, 3, 7, 4, 5, 6]
+        e = np.where(tried, errs, np.inf)[:, order]
+        assert (np.array(order)[e.argmin(1)] == stats[normal, 0].astype(int)).all()
+    # uniform metric: a mode's error is the decoded block's squared error when that mode won
+    dec = oracle.decode("BPTC", got, 256, 256).reshape(64, 4, 64, 4, 4).transpose(0, 2, 1, 3, 4).reshape(-1, 16, 4)
+    stats = np.zeros((nblk, 10))
+    got, _ = gpu.compress(F.BPTC, img, quality=0, block_stats=stats)
+    dec = oracle.decode("BPTC", got, 256, 256).reshape(64, 4, 64, 4, 4).transpose(0, 2, 1, 3, 4).reshape(-1, 16, 4)
+    sq = ((dec.astype(np.int64) - blocks.astype(np.int64)) ** 2)
+    opaque_modes = np.isin(stats[:, 0].astype(int), [0, 1, 2, 3]) & normal
+    win = stats[np.arange(nblk), 2 + stats[:, 0].astype(int)]
+    # opaque modes decode alpha as 255 but count the alpha difference of "opaque" (>= 250) pixels (T18)
+    assert (win[opaque_modes] >= sq[opaque_modes][..., :3].sum((1, 2))).all()
+    alpha_modes = np.isin(stats[:, 0].astype(int), [6, 7]) & normal
+    assert (win[alpha_modes] == sq[alpha_modes].sum((1, 2))).all()
