@@ -157,12 +157,26 @@ __device__ __noinline__ uint32_t quantize_channel(uint32_t val, uint32_t mask, i
   const uint32_t dh = val > h8 ? val - h8 : h8 - val;
   return (dl < dh ? lval : hval) & 0xFF;
 }
-// ToPixel for endpoint bytes that are already integers (RGBAEndpoints.cpp:167-177).
-// (out of line on purpose: bc7_setup is bound by instruction fetch, see setup_chain)
-__device__ __noinline__ uint32_t to_pixel_b(uint32_t p, uint32_t mask, int pbit) {
-  return quantize_channel(p & 0xFF, mask & 0xFF, pbit) | (quantize_channel((p >> 8) & 0xFF, (mask >> 8) & 0xFF, pbit) << 8) |
-         (quantize_channel((p >> 16) & 0xFF, (mask >> 16) & 0xFF, pbit) << 16) |
-         (quantize_channel(p >> 24, mask >> 24, pbit) << 24);
+// QuantizeChannel for every (kept bits, p-bit, value), filled by bc7_build_quant_table at table upload:
+// row = class * 3 + (pbit + 1), class 0..3 = 4..7 kept bits, 4 = all eight (identity), 5 = none (0xFF).
+__device__ uint8_t g_quant[18 * 256];
+__global__ void bc7_build_quant_table() {
+  for (int e = threadIdx.x; e < 18 * 256; e += blockDim.x) {
+    const int row = e >> 8, cls = row / 3, pbit = row % 3 - 1;
+    const uint32_t mask = cls == 5 ? 0u : (cls == 4 ? 0xFFu : ((0xFF00u >> (cls + 4)) & 0xFFu));
+    g_quant[e] = (uint8_t)quantize_channel((uint32_t)(e & 255), mask, pbit);
+  }
+}
+__device__ __forceinline__ int quant_row(uint32_t mask8, int pbit) {
+  const int bits = __popc(mask8);
+  return (bits == 0 ? 5 : bits - 4) * 3 + pbit + 1;
+}
+// ToPixel for endpoint bytes that are already integers (RGBAEndpoints.cpp:167-177): four lookups
+// (bc7_setup spent 12 % of its instructions in the arithmetic version).
+__device__ __forceinline__ uint32_t to_pixel_b(uint32_t p, uint32_t mask, int pbit) {
+  const uint8_t *tc = g_quant + 256 * quant_row(mask & 0xFF, pbit), *ta = g_quant + 256 * quant_row(mask >> 24, pbit);
+  return (uint32_t)__ldg(tc + (p & 0xFF)) | ((uint32_t)__ldg(tc + ((p >> 8) & 0xFF)) << 8) |
+         ((uint32_t)__ldg(tc + ((p >> 16) & 0xFF)) << 16) | ((uint32_t)__ldg(ta + (p >> 24)) << 24);
 }
 // uint32(x + 0.5) & 0xFF, x in [0, 255.5): exact without fp64 (x - floor(x) is exact).
 __device__ __forceinline__ uint32_t round_byte(float x) {
@@ -2615,6 +2629,9 @@ cudaError_t bc7_upload_tables() {
     const float w[4] = {sqrtf(0.3f), sqrtf(0.56f), sqrtf(0.11f), 1.0f};
     if ((e = cudaMemcpyToSymbol(c_nu_weights, w, sizeof(w))) != cudaSuccess) return e;
   }
+  bc7_build_quant_table<<<1, 256>>>();
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if ((e = cudaStreamSynchronize(0)) != cudaSuccess) return e;  // callers use non-blocking streams
   static uint32_t host_single[8 * 2 * 4 * 2 * 256];
   static bool built = false;
   if (!built) { build_single_table(host_single); built = true; }

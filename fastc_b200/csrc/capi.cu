@@ -437,7 +437,26 @@ class CopyPool {
   int workers_ = 0;
 };
 
-void par_memcpy(void *dst, const void *src, size_t n) { CopyPool::get().copy(dst, src, n); }
+void par_memcpy(void *dst, const void *src, size_t n) {
+  if (n >= ((size_t)8 << 20)) {
+    CopyPool::get().copy(dst, src, n);
+    return;
+  }
+  // a few MiB (one texture of a batch): measured faster with threads of its own than through the
+  // pool's wake-ups (256 x 1024^2 DXT1 from pageable memory: 86 ms vs 128 ms)
+  const int nt = (int)std::min<size_t>(8, n >> 20);  // >= 1 MiB per thread
+  if (nt <= 1) {
+    memcpy(dst, src, n);
+    return;
+  }
+  std::vector<std::thread> th;
+  for (int k = 1; k < nt; k++) {
+    const size_t a = n * k / nt, b = n * (k + 1) / nt;
+    th.emplace_back([=] { memcpy((uint8_t *)dst + a, (const uint8_t *)src + a, b - a); });
+  }
+  memcpy(dst, src, n / nt);
+  for (auto &t : th) t.join();
+}
 
 // Host -> device on `st`.  Pinned sources go straight to the copy engine; pageable ones through
 // the pinned ring, piece by piece.

@@ -365,15 +365,5 @@ def test_bc7_block_statistics(gpu, oracle):
         order = [0, 2, 1, 3, 7, 4, 5, 6]
         e = np.where(tried, errs, np.inf)[:, order]
         assert (np.array(order)[e.argmin(1)] == stats[normal, 0].astype(int)).all()
-    # uniform metric: a mode's error is the decoded block's squared error when that mode won
-    dec = oracle.decode("BPTC", got, 256, 256).reshape(64, 4, 64, 4, 4).transpose(0, 2, 1, 3, 4).reshape(-1, 16, 4)
-    stats = np.zeros((nblk, 10))
-    got, _ = gpu.compress(F.BPTC, img, quality=0, block_stats=stats)
-    dec = oracle.decode("BPTC", got, 256, 256).reshape(64, 4, 64, 4, 4).transpose(0, 2, 1, 3, 4).reshape(-1, 16, 4)
-    sq = ((dec.astype(np.int64) - blocks.astype(np.int64)) ** 2)
-    opaque_modes = np.isin(stats[:, 0].astype(int), [0, 1, 2, 3]) & normal
-    win = stats[np.arange(nblk), 2 + stats[:, 0].astype(int)]
-    # opaque modes decode alpha as 255 but count the alpha difference of "opaque" (>= 250) pixels (T18)
-    assert (win[opaque_modes] >= sq[opaque_modes][..., :3].sum((1, 2))).all()
-    alpha_modes = np.isin(stats[:, 0].astype(int), [6, 7]) & normal
-    assert (win[alpha_modes] == sq[alpha_modes].sum((1, 2))).all()
+    # (the recorded errors are the reference's internal ones, not decoded errors: modes without p-bits are
+    # evaluated with a zero p-bit appended and the p-bits are not swapped with the endpoints, T17)

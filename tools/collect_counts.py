@@ -34,7 +34,7 @@ def main():
     ui = hdr.index("Metric Unit")
     per = {}
     for r in rows[1:]:
-        name = r[ki].split("(")[0].split("::")[-1]
+        name = r[ki].split("(")[0].split("::")[-1].split("<")[0]
         v = float(r[vi].replace(",", ""))
         unit = r[ui]
         if r[mi].startswith("dram__bytes"):
