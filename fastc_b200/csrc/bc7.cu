@@ -1915,6 +1915,12 @@ __device__ __forceinline__ uint32_t sa_eval(uint32_t (*s_pix)[kPixStride], uint2
   // >= nbm1 for k >= nbm1 (tests/test_tables.py::test_projection_exact_buckets), so floor == ceil
   // and only bucket clamp(k) is tested.  The rest replay the reference's float sequence
   // (RGBAEndpoints.cpp:262-289); coinciding endpoints test bucket 0 (:226-251).
+  // The main loop has already added a provisional key for them (both candidates of the floor
+  // bucket's row, lower bucket on ties).  It is wrong only when the reference tests ONE bucket and
+  // the row's other colour happened to be closer, or when the replayed floor differs: so an
+  // exactly-on-boundary pixel whose provisional pick already is the boundary's bucket needs nothing,
+  // and with coinciding endpoints (every colour equal, every pixel flagged) nothing ever changes.
+  if (den == 0) slow = 0;
   while (slow) {
     const int bit = __ffs(slow) - 1;
     slow &= slow - 1u;
@@ -1922,7 +1928,21 @@ __device__ __forceinline__ uint32_t sa_eval(uint32_t (*s_pix)[kPixStride], uint2
     const uint32_t px = s_pix[i][tid];
     const int num = (int)(__dp4a(px, q2p, 0u) - __dp4a(px, q1p, cq));
     const int vp = __float2int_rd(__fmaf_rn((float)num, inv16, 1.0f));
-    {  // take the main loop's provisional key of this pixel back
+    const int sh = 4 * (i & 7);
+    const uint32_t prov = ((i < 8 ? word[0] : word[1]) >> sh) & 15u;
+    const int k = (vp - 1 + 0x8000) >> 16;
+    int ja;
+    bool two = false;
+    if (num * nbm1 == k * den) {
+      ja = __vimin_s32_relu(k, nbm1);
+      if (prov == (uint32_t)ja) continue;
+    } else {
+      const float t = __fmul_rn(__fdiv_rn((float)num, fden), fnb);
+      const int x1 = min(max(0, (int)floorf(t)), nbm1), x2 = min((int)ceilf(t), nbm1);
+      ja = x1;
+      two = x1 + 1 <= x2;
+    }
+    {  // take the provisional key back
       const int jp = __vimin_s32_relu(vp >> 16, nbm1);
       const uint2 c = pal[jp * kSaThreads];
       const uint32_t da = __vabsdiffu4(c.x, px), db = __vabsdiffu4(c.y, px);
@@ -1931,26 +1951,12 @@ __device__ __forceinline__ uint32_t sa_eval(uint32_t (*s_pix)[kPixStride], uint2
       if (vp >= 1) ka = __viaddmin_u32(kb, 1u, ka);
       total -= ka;
     }
-    int ja = 0;
-    bool two = false;
-    if (den != 0) {
-      const int k = (vp - 1 + 0x8000) >> 16;
-      if (num * nbm1 == k * den) {
-        ja = __vimin_s32_relu(k, nbm1);
-      } else {
-        const float t = __fmul_rn(__fdiv_rn((float)num, fden), fnb);
-        const int x1 = min(max(0, (int)floorf(t)), nbm1), x2 = min((int)ceilf(t), nbm1);
-        ja = x1;
-        two = x1 + 1 <= x2;
-      }
-    }
     const uint2 c = pal[ja * kSaThreads];
     const uint32_t da = __vabsdiffu4(c.x, px), db = __vabsdiffu4(c.y, px);
     const uint32_t ea = __dp4a(da, da, 0u), eb = __dp4a(db, db, 0u);
     const bool up = two && eb < ea;
     const uint32_t pick = (uint32_t)ja + (up ? 1u : 0u);
     total += ((up ? eb : ea) << 8) | pick;
-    const int sh = 4 * (i & 7);
     const uint32_t clr = ~(0xFu << sh), ins = pick << sh;
     if (i < 8) word[0] = (word[0] & clr) | ins;
     else word[1] = (word[1] & clr) | ins;
