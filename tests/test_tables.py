@@ -177,3 +177,27 @@ def test_fast_projection_guard_band():
         assert okp.mean() > 0.5
         assert (jp[okp] == j1[okp]).all(), nbm1
         assert (two_p[okp] == ref_two[okp]).all(), nbm1
+
+
+def test_dxt_quantisation_identities():
+    """dxt_block.cuh replaces stb_dxt's Mul8Bit / Expand tables by multiply-shifts and spreads a row's four
+    2-bit indices to the byte weights of stb__RefineBlock's w1Tab: every input checked here."""
+    def mul8bit(a, b):
+        t = a * b + 128
+        return (t + (t >> 8)) >> 8
+    for x in range(256):
+        assert mul8bit(x, 31) == (x * 7967 + 32896) >> 16
+        assert mul8bit(x, 63) == (x * 16191 + 32896) >> 16
+    for q in range(32):
+        assert ((q << 3) | (q >> 2)) == (q * 33) >> 2
+    for q in range(64):
+        assert ((q << 2) | (q >> 4)) == (q * 65) >> 4
+    w1tab = [3, 0, 2, 1]
+    for m in range(256):
+        s = m
+        s = (s | (s << 12)) & 0x000F000F
+        s = (s | (s << 6)) & 0x03030303
+        s0, s1 = s & 0x01010101, (s >> 1) & 0x01010101
+        w1 = ((s0 ^ 0x01010101) << 1) | (s0 ^ s1 ^ 0x01010101)
+        for k in range(4):
+            assert (w1 >> (8 * k)) & 0xFF == w1tab[(m >> (2 * k)) & 3]
