@@ -95,6 +95,7 @@ struct Ws {
   uint4 *sorted;        // [nblocks*kSlots][2] the live chains' start states, sorted by descending
                         // (index precision, cluster size); word 7 = the chain's id (block * kSlots + slot)
   uint32_t *bins;       // histogram / offsets / cursors (see bc7_bin_offsets)
+  uint32_t *tail_list;  // [kTailCap] chains handed from bc7_anneal to bc7_anneal_tail
   double *stats;        // [nblocks][kStatDoubles] per-block statistics (mode, path, error of every mode tried), or NULL
   double *err64;        // [nblocks][kSlots] non-uniform metric only: the chains' errors as doubles (else NULL)
   const uint32_t *wm_running;    // watermark base of this chunk (device side, chunks chain without a host sync)
@@ -1170,7 +1171,11 @@ constexpr int kBinTotal = 1536;
 constexpr int kBinFetch = 1537;   // [3] fetch cursor of precision class c (= index bits - 2)
 constexpr int kBinEnd = 1540;     // [3] end of class c's region
 constexpr int kBinHome = 1544;    // [3] first CTA whose home class is c or lower
+constexpr int kBinTailCount = 1600;  // chains handed to bc7_anneal_tail
+constexpr int kBinTailFetch = 1601;  // its fetch cursor
 constexpr int kBinWords = 2048;
+constexpr int kTailChains = 16;      // a warp of bc7_anneal hands its chains over once it is down to this many
+constexpr uint32_t kTailCap = 1u << 18;  // capacity of the hand-over list
 
 // (under the non-uniform metric R.err is a float's bit pattern: the length predictor takes its value)
 __device__ __forceinline__ uint32_t sort_error(const Ws &ws, uint32_t err) {
@@ -1815,9 +1820,11 @@ __device__ __forceinline__ void sa_palette_uniform(uint2 (*s_pal)[kSaThreads], i
 // The palette is stored as PAIRS: row j of the lane's column holds (colour j, colour j + 1), the
 // last row (colour nbm1, colour nbm1) -- the weight table is padded with 64 -- so the two
 // candidate buckets of a pixel (floor and ceil of its projection) come from one 64-bit load.
+// tid: the lane's own palette column; ptid: the s_pix column holding the cluster (the lane's own,
+// except in the tail mode of bc7_anneal where a group of lanes evaluates one chain).
 template <bool NU>
 __device__ __forceinline__ uint32_t sa_eval(uint32_t (*s_pix)[kPixStride], uint2 (*s_pal)[kSaThreads],
-                                            const uint8_t *__restrict__ s_w, int tid, const SaConst &K, int nmax,
+                                            const uint8_t *__restrict__ s_w, int tid, int ptid, const SaConst &K, int nmax,
                                             int nbmax, int uflags, uint32_t q1, uint32_t q2, uint32_t k256, int rot,
                                             uint32_t &idx_lo, uint32_t &idx_hi) {
   const uint32_t d11 = __dp4a(q1, q1, 0u), d12 = __dp4a(q1, q2, 0u), d22 = __dp4a(q2, q2, 0u);
@@ -1868,7 +1875,7 @@ __device__ __forceinline__ uint32_t sa_eval(uint32_t (*s_pix)[kPixStride], uint2
     uint32_t word[2] = {0u, 0u};
 #pragma unroll 1
     for (int i = 0; i < n; i++) {
-      const uint32_t px = s_pix[i][tid];
+      const uint32_t px = s_pix[i][ptid];
       const int num = (int)(__dp4a(px, q2p, 0u) - __dp4a(px, q1p, cq));
       const int vp = __float2int_rd(__fmaf_rn((float)num, inv16, 1.0f));
       int ja = __vimin_s32_relu(vp >> 16, nbm1);
@@ -1904,9 +1911,9 @@ __device__ __forceinline__ uint32_t sa_eval(uint32_t (*s_pix)[kPixStride], uint2
   }
   uint32_t total = 0, slow = 0, word[2];
   // `total` sums the pixels' keys (error << 8 | bucket, see SA_PIXEL)
-  if ((uflags & 1) && nmax == 16) sa_pixels16(s_pix, pal, tid, nbm1, q1p, q2p, cq, inv16, k256, total, slow, word);
-  else if (uflags & 1) sa_pixels<true>(s_pix, pal, tid, n, nbm1, nmax, q1p, q2p, cq, inv16, k256, total, slow, word);
-  else sa_pixels<false>(s_pix, pal, tid, n, nbm1, nmax, q1p, q2p, cq, inv16, k256, total, slow, word);
+  if ((uflags & 1) && nmax == 16) sa_pixels16(s_pix, pal, ptid, nbm1, q1p, q2p, cq, inv16, k256, total, slow, word);
+  else if (uflags & 1) sa_pixels<true>(s_pix, pal, ptid, n, nbm1, nmax, q1p, q2p, cq, inv16, k256, total, slow, word);
+  else sa_pixels<false>(s_pix, pal, ptid, n, nbm1, nmax, q1p, q2p, cq, inv16, k256, total, slow, word);
   // pixel i sits at bit nmax - 1 - i of `slow`; drop the flags of pixels past the lane's cluster
   slow &= 0xFFFFFFFFu << (nmax - n);
   // Flagged pixels: too close to a bucket boundary for the fast product.  Nearly all of them sit
@@ -1925,7 +1932,7 @@ __device__ __forceinline__ uint32_t sa_eval(uint32_t (*s_pix)[kPixStride], uint2
     const int bit = __ffs(slow) - 1;
     slow &= slow - 1u;
     const int i = nmax - 1 - bit;
-    const uint32_t px = s_pix[i][tid];
+    const uint32_t px = s_pix[i][ptid];
     const int num = (int)(__dp4a(px, q2p, 0u) - __dp4a(px, q1p, cq));
     const int vp = __float2int_rd(__fmaf_rn((float)num, inv16, 1.0f));
     const int sh = 4 * (i & 7);
@@ -1964,6 +1971,169 @@ __device__ __forceinline__ uint32_t sa_eval(uint32_t (*s_pix)[kPixStride], uint2
   idx_lo = word[0];
   idx_hi = word[1];
   return total >> 8;
+}
+
+// The CTA's shared tables (kSaThreads threads; the caller synchronises): quantisation rows, padded
+// weight rows, and per (mode, index mode) the annealing constants of the mode
+//   x: per-channel step bytes (opaque modes never move alpha, T3)
+//   y: nbm1 [0:3] | weight row offset [4:11] | p-bit flip mask [12:13] | p-bit shift [14] |
+//      colour / alpha quantisation rows [15:18] [19:22] | rotation [23]
+__device__ __forceinline__ void sa_init_tables(uint8_t (*s_q)[256], uint8_t *s_w, uint2 *s_mode) {
+  if (threadIdx.x < 80) {
+    const int row = threadIdx.x >> 4, k = threadIdx.x & 15;  // row = index bits - 1
+    s_w[threadIdx.x] = (row < 4 && k < (2 << row)) ? c_weight[threadIdx.x] : (uint8_t)64;
+  }
+  for (int e = threadIdx.x; e < kQuantRows * 256; e += kSaThreads) {
+    const int row = e >> 8, cls = row >> 1, pbit = row & 1;
+    const uint32_t mask = cls == 5 ? 0u : ((0xFF00u >> (cls + 4)) & 0xFFu);
+    s_q[row][e & 255] = (uint8_t)quantize_channel((uint32_t)(e & 255), mask, pbit);
+  }
+  if (threadIdx.x < 16) {
+    const int mode = threadIdx.x >> 1, idx_mode = threadIdx.x & 1;
+    const ModeAttr A = c_modes[mode];
+    const int ibits = max(1, idx_mode == 0 ? A.index_bits : A.alpha_index_bits);
+    const uint32_t sc = 1u << (8 - A.color_bits), sa = (A.alpha_bits && mode >= 4) ? (1u << (8 - A.alpha_bits)) : 0u;
+    const uint32_t xm = A.pbit == kPbitShared ? 1u : (A.pbit == kPbitPerEndpoint ? 3u : 0u);
+    const uint32_t tab_c = (uint32_t)(A.color_bits - 4) * 2u, tab_a = (uint32_t)(A.alpha_bits ? A.alpha_bits - 4 : 5) * 2u;
+    s_mode[threadIdx.x] = make_uint2(sc | (sc << 8) | (sc << 16) | (sa << 24),
+                                     (uint32_t)((1 << ibits) - 1) | ((uint32_t)(16 * (ibits - 1)) << 4) | (xm << 12) |
+                                         ((A.pbit == kPbitPerEndpoint ? 1u : 0u) << 14) | (tab_c << 15) | (tab_a << 19) |
+                                         ((uint32_t)A.rotation << 23));
+  }
+}
+
+// The constants of a chain from word 0 of its start state (see kStateWords) and its mode's table row.
+__device__ __forceinline__ void sa_decode(uint32_t w0, const uint2 *s_mode, SaConst &K, int &rotation) {
+  const int mode = (w0 >> 16) & 7, rot = (w0 >> 19) & 3, idx_mode = (w0 >> 21) & 1;
+  const uint2 mt = s_mode[mode * 2 + idx_mode];
+  K.n = (w0 >> 24) & 31;
+  K.stepb = mt.x;
+  K.nbm1 = mt.y & 15;
+  K.woff = (mt.y >> 4) & 0xFF;
+  K.xm = (mt.y >> 12) & 3;
+  K.sh0 = (mt.y >> 14) & 1;
+  K.tab_c = (mt.y >> 15) & 15;
+  K.tab_a = (mt.y >> 19) & 15;
+  rotation = (mt.y >> 23) & 1;
+  K.qkeep = 0xFFFFFFFFu; K.qins = 0; K.qsh = 0; K.calpha = 0;
+  if (rotation) {
+    K.calpha = 255;
+    K.qkeep = 0x00FFFFFFu;
+    if (rot) { K.qsh = 8 * (rot - 1); K.qins = 0xFF000000u; K.qkeep &= ~(0xFFu << K.qsh); }
+  }
+}
+
+// The state of one annealing chain: registers of the lane that runs it.
+struct SaChain {
+  uint32_t gid, cur1, cur2, best1, best2, cur_err, best_err, rng, best_lo, best_hi;
+  int cur_combo, best_combo, energy, rotation;
+  bool improved;
+#ifdef FASTC_GPU_COUNTERS
+  uint32_t ncalls, npbe;
+#endif
+};
+// What a step needs besides the chain: the CTA's shared tables and the launch constants.
+struct SaShared {
+  uint32_t (*pix)[kPixStride];
+  uint2 (*pal)[kSaThreads];
+  const uint8_t (*q)[256];
+  const uint8_t *w;
+  uint32_t k256;
+  float f_tm1, c_x;
+  int sa_steps;
+};
+
+// One annealing step of a chain, in place.  tid: the lane's palette column, pcol: the s_pix column
+// holding the cluster.  Returns true when the step was anything but a CLEAN REJECTION -- state
+// unchanged, energy + 1, exactly three LCG draws (two moves, one Metropolis draw) -- which is what
+// sa_tail speculates on.
+template <bool NU>
+__device__ __forceinline__ bool sa_step(SaChain &c, const SaConst &K, const SaShared &S, int tid, int pcol, int nmax,
+                                        int nbmax, int uflags) {
+    // PickBestNeighboringEndpoints (:426-498)
+    const int has_pbit = K.xm != 0;
+    const int ncombo = c.cur_combo ^ K.xm;  // the p-bit always flips (shared: 0 <-> 1, per endpoint: c <-> 3 - c)
+    const int opb0 = (c.cur_combo >> K.sh0) & 1, opb1 = c.cur_combo & 1;
+    uint32_t n1, n2;
+    int guard = -1;
+    bool visited;
+    do {
+      // pt = 0 moves endpoint 2 first and (as the reference does) tests p-bit [0] for it
+      n2 = move_endpoint(c.cur2, lcg_next(c.rng), opb0, has_pbit, K.stepb);
+      n1 = move_endpoint(c.cur1, lcg_next(c.rng), opb1, has_pbit, K.stepb);
+      visited = (c.best1 == n1) && (c.best2 == n2) && (c.best_combo == ncombo);
+    } while (visited && ++guard < 15);
+    // modes without p-bits evaluate with a zero p-bit (reference quirk, see fit_cluster): their combo is 0
+    const uint32_t q1 = sa_quantize(S.q, K, n1, (ncombo >> K.sh0) & 1), q2 = sa_quantize(S.q, K, n2, ncombo & 1);
+    uint32_t ilo, ihi;
+    const uint32_t err = sa_eval<NU>(S.pix, S.pal, S.w, tid, pcol, K, nmax, nbmax, uflags, q1, q2, S.k256,
+                                     c.rotation ? (K.qins ? (K.qsh >> 3) + 1 : 0) : 0, ilo, ihi);
+#ifdef FASTC_GPU_COUNTERS
+    c.ncalls++; c.npbe += K.n;
+#endif
+    // AcceptNewEndpointError (:524-536)
+    bool accept;
+    if (err < c.cur_err) {
+      accept = true;
+    } else {
+      const uint32_t r = lcg_next(c.rng) & 0xFFFF;
+      const uint32_t m = ((r << 8) | (r >> 7)) & 0x7FFFFF;
+      const float fr = __fsub_rn(__uint_as_float((127u << 23) | m), 1.0f);
+      if (c.energy == 0) {
+        accept = false;  // temp == 0: exp(-inf) = 0, exp(NaN) = NaN -> never accepted
+      } else if (NU) {  // the errors are floats (bit patterns): the reference's double expression
+        const float temp = __fdiv_rn((float)c.energy, S.f_tm1);
+        const double x = ((double)0.1f * ((double)__uint_as_float(c.cur_err) - (double)__uint_as_float(err))) / (double)temp;
+        accept = (double)fr < exp(x);
+      } else {
+        const float diff = (float)((int)c.cur_err - (int)err);  // exact (|.| < 2^24)
+        // exp(0.1 * diff / temp), temp = c.energy / (steps - 1), through fast reciprocal / exponential
+        const float pf = __expf(__fdividef(__fmul_rn(diff, S.c_x), (float)c.energy));
+        if (fr < pf * (1.0f - 3e-5f)) accept = true;
+        else if (fr > pf * (1.0f + 3e-5f)) accept = false;
+        else {  // within the fast path's error band: the reference's double expression
+          const float temp = __fdiv_rn((float)c.energy, S.f_tm1);
+          const double x = ((double)0.1f * ((double)c.cur_err - (double)err)) / (double)temp;
+          accept = (double)fr < exp(x);
+        }
+      }
+    }
+    if (accept) { c.cur_err = err; c.cur1 = n1; c.cur2 = n2; c.cur_combo = ncombo; }
+    if (err < c.best_err) {
+      c.best_err = err; c.best1 = n1; c.best2 = n2; c.best_combo = ncombo;
+      c.best_lo = ilo; c.best_hi = ihi; c.improved = true;
+      c.energy = 0;  // restart; the increment below makes it 1
+    }
+    c.energy++;
+    return accept || guard >= 0;
+}
+
+// The chain has ended: its result record.
+template <bool NU>
+__device__ __forceinline__ void sa_finish(const SaChain &c, const SaConst &K, const Ws &ws) {
+    // the indices belong to the evaluation that produced c.best_err: the start state's were
+    // stored by bc7_setup, an c.improved state's were kept when it was found
+    uint32_t *res = ws.results + (size_t)c.gid * kResWords;
+    uint32_t o1 = c.best1, o2 = c.best2, alpha_err = 0;
+    if (c.rotation) {
+      const uint32_t *st = ws.states + (size_t)c.gid * kStateWords;
+      const uint32_t abytes = st[6];
+      alpha_err = st[5];
+      o1 = (o1 & 0x00FFFFFFu) | ((abytes & 0xFF) << 24);
+      o2 = (o2 & 0x00FFFFFFu) | (((abytes >> 8) & 0xFF) << 24);
+    }
+    *reinterpret_cast<uint4 *>(res) = make_uint4(c.best_err + alpha_err, o1, o2, (uint32_t)c.best_combo);
+    if constexpr (NU) {  // the chain's error as the reference's double: colour fit (+ the alpha fit's, parked by bc7_setup)
+      const double e = (double)__uint_as_float(c.best_err);
+      ws.err64[c.gid] = c.rotation ? __dadd_rn(e, ws.err64[c.gid]) : e;
+    }
+    if (c.improved) {
+      // nibbles past the cluster size come from the warp's longer loops: clear them
+      const int n = K.n;
+      const uint32_t mlo = n >= 8 ? 0xFFFFFFFFu : ((1u << (4 * n)) - 1u);
+      const uint32_t mhi = n >= 16 ? 0xFFFFFFFFu : (n > 8 ? ((1u << (4 * (n - 8))) - 1u) : 0u);
+      *reinterpret_cast<uint2 *>(res + 4) = make_uint2(c.best_lo & mlo, c.best_hi & mhi);
+    }
 }
 
 #ifdef FASTC_GPU_TAILSTATS
@@ -2015,6 +2185,26 @@ __global__ void bc7_chainstats_report() {
   }
 }
 #endif
+
+// A chain of bc7_anneal parked for bc7_anneal_tail: its state goes into its own, now unused,
+// start-state / result records, its id into the list.  Returns false when the list is full (the
+// chain then stays with its lane).  Out of line: the caller's loop sits at the register limit.
+__device__ __noinline__ bool sa_hand_over(Ws ws, uint32_t gid, uint32_t cur1, uint32_t cur2, uint32_t best1, uint32_t best2,
+                                          uint32_t cur_err, uint32_t best_err, uint32_t rng, uint32_t packed, bool improved,
+                                          int n, uint32_t best_lo, uint32_t best_hi) {
+  const uint32_t slot = atomicAdd(&ws.bins[kBinTailCount], 1u);
+  if (slot >= kTailCap) return false;
+  ws.tail_list[slot] = gid;
+  uint32_t *st = ws.states + (size_t)gid * kStateWords, *res = ws.results + (size_t)gid * kResWords;
+  st[1] = cur1; st[2] = cur2; st[3] = best1; st[4] = best2;
+  *reinterpret_cast<uint4 *>(res) = make_uint4(cur_err, best_err, rng, packed);
+  if (improved) {  // as at the end of a chain: the start state's indices stand otherwise
+    const uint32_t mlo = n >= 8 ? 0xFFFFFFFFu : ((1u << (4 * n)) - 1u);
+    const uint32_t mhi = n >= 16 ? 0xFFFFFFFFu : (n > 8 ? ((1u << (4 * (n - 8))) - 1u) : 0u);
+    *reinterpret_cast<uint2 *>(res + 4) = make_uint2(best_lo & mlo, best_hi & mhi);
+  }
+  return true;
+}
 
 template <bool NU>
 __global__ void __launch_bounds__(kSaThreads, kSaCtasPerSm)
@@ -2169,11 +2359,23 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
       nbmax = __reduce_max_sync(full, have ? K.nbm1 : 0);
       // bit 0: every lane's cluster has nmax pixels, bit 1: every lane has nbmax + 1 buckets
       uflags = (__all_sync(full, !have || K.n == nmax) ? 1 : 0) | (__all_sync(full, !have || K.nbm1 == nbmax) ? 2 : 0);
+      // ---- hand-over to bc7_anneal_tail (see there).  Every lane passes here when it goes idle with
+      // the queues dry (that is when it sees the last class run dry), so the warp notices the moment
+      // it is down to kTailChains chains: they are parked in their own, now unused, start-state /
+      // result records and listed; the warp is done.
+      if (__any_sync(full, drymask == 7u) && __popc(__ballot_sync(full, have)) <= kTailChains) {
+        if (have)
+          have = !sa_hand_over(ws, gid, cur1, cur2, best1, best2, cur_err, best_err, rng,
+                               (uint32_t)cur_combo | ((uint32_t)best_combo << 2) | ((uint32_t)energy << 8), improved, K.n,
+                               best_lo, best_hi);
+      }
     }
     if (!__any_sync(full, have)) break;
     if (!have) continue;
 
-    // ---- one annealing step
+    // ---- one annealing step.  (The step and the chain's end are spelled out here although sa_step /
+    // sa_finish hold the same code for bc7_anneal_tail: calling them from this loop, which sits at
+    // the register limit of 8 CTAs / SM, measured 3 % slower.)
     bool done = !(best_err > 0 && energy < sa_steps);
     if (!done) {
       // PickBestNeighboringEndpoints (:426-498)
@@ -2192,7 +2394,7 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
       // modes without p-bits evaluate with a zero p-bit (reference quirk, see fit_cluster): their combo is 0
       const uint32_t q1 = sa_quantize(s_q, K, n1, (ncombo >> K.sh0) & 1), q2 = sa_quantize(s_q, K, n2, ncombo & 1);
       uint32_t ilo, ihi;
-      const uint32_t err = sa_eval<NU>(s_pix, s_pal, s_w, tid, K, nmax, nbmax, uflags, q1, q2, k256,
+      const uint32_t err = sa_eval<NU>(s_pix, s_pal, s_w, tid, tid, K, nmax, nbmax, uflags, q1, q2, k256,
                                        rotation ? (K.qins ? (K.qsh >> 3) + 1 : 0) : 0, ilo, ihi);
 #ifdef FASTC_GPU_COUNTERS
       ncalls++; npbe += K.n;
@@ -2301,6 +2503,89 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
     atomicAdd(&g_tail[5], 1ull);
   }
 #endif
+}
+
+// The tail of the annealing.  bc7_anneal ends when its longest remaining chain does -- a fixed cost per
+// launch that weighs on small submissions (a 1/8 shard, a 2048^2 texture): chain lengths are very
+// uneven and a chain is serial.  But nearly all of its steps are clean rejections (see sa_step), so
+// the last chains of every warp (handed over when the queues are dry and the warp is down to
+// kTailChains) are finished here by a WARP each: lane d evaluates step t + d of the chain on the
+// assumption that steps t .. t + d - 1 are clean rejections (energy + d, LCG jumped 3 d draws
+// ahead).  The warp then commits up to its first step that is NOT a clean rejection: every lane
+// takes the state that lane left behind -- exactly the state the serial chain has after those
+// steps -- and the later lanes' work is discarded.  Results are bit-identical to the
+// one-lane-per-chain schedule; the tail gets several times shorter.
+template <bool NU>
+__global__ void __launch_bounds__(kSaThreads, 4)
+bc7_anneal_tail(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, uint32_t first_block, Ws ws,
+                int sa_steps) {
+  __shared__ uint2 s_pal[16][kSaThreads];
+  __shared__ uint32_t s_pix[16][kPixStride];  // (one column per warp is used: column `wbase`)
+  __shared__ uint8_t s_q[kQuantRows][256];
+  __shared__ uint8_t s_w[80];
+  __shared__ uint2 s_mode[16];
+  sa_init_tables(s_q, s_w, s_mode);
+  __syncthreads();
+  const int tid = threadIdx.x, lane = tid & 31, wbase = tid & ~31;
+  const unsigned full = 0xffffffffu;
+  const uint32_t k256 = ws.bins[kBinWords - 1] + 256u;
+  const float f_tm1 = (float)(sa_steps - 1);
+  const SaShared S = {s_pix, s_pal, s_q, s_w, k256, f_tm1, __fmul_rn(0.1f, f_tm1), sa_steps};
+  const uint32_t count = min(ws.bins[kBinTailCount], kTailCap);
+  // LCG jump over 3 * lane draws: x -> jmp_a * x + jmp_c
+  uint32_t jmp_a = 1u, jmp_c = 0u;
+  for (int i = 0; i < 3 * lane; i++) { jmp_c = 214013u * jmp_c + 2531011u; jmp_a *= 214013u; }
+  for (;;) {
+    uint32_t slot = 0;
+    if (lane == 0) slot = atomicAdd(&ws.bins[kBinTailFetch], 1u);
+    slot = __shfl_sync(full, slot, 0);
+    if (slot >= count) break;
+    SaChain c = {};
+    SaConst K;
+    c.gid = ws.tail_list[slot];
+    const uint32_t *st = ws.states + (size_t)c.gid * kStateWords, *res = ws.results + (size_t)c.gid * kResWords;
+    const uint32_t w0 = st[0];
+    sa_decode(w0, s_mode, K, c.rotation);
+    c.cur1 = st[1]; c.cur2 = st[2]; c.best1 = st[3]; c.best2 = st[4];
+    const uint4 r0 = *reinterpret_cast<const uint4 *>(res);
+    const uint2 r1 = *reinterpret_cast<const uint2 *>(res + 4);
+    c.cur_err = r0.x; c.best_err = r0.y; c.rng = r0.z;
+    c.cur_combo = r0.w & 3; c.best_combo = (r0.w >> 2) & 3; c.energy = (int)(r0.w >> 8);
+    c.best_lo = r1.x; c.best_hi = r1.y;
+    c.improved = true;  // the record's indices are the best state's (they are rewritten as they are)
+    __syncwarp();       // (the previous chain's pixels are no longer read)
+    if (lane < 16 && ((w0 >> lane) & 1)) {
+      const uint32_t bi = first_block + c.gid / kSlots;
+      const uint32_t *base = img + (size_t)(bi / blocks_x) * 4 * width + (size_t)(bi % blocks_x) * 4;
+      s_pix[__popc(w0 & ((1u << lane) - 1u))][wbase] = __ldg(base + (size_t)(lane >> 2) * width + (lane & 3));
+    }
+    __syncwarp();
+    const int nbmax = K.nbm1;
+    for (;;) {
+      // every lane holds the chain's state: move to this lane's speculative position
+      c.energy += lane;
+      c.rng = jmp_a * c.rng + jmp_c;
+      bool stepped = false, changed = false;
+      if (c.best_err > 0 && c.energy < sa_steps) {
+        stepped = true;
+        changed = sa_step<NU>(c, K, S, tid, wbase, K.n, nbmax, 3);
+      }
+      // commit: the first step that is not a clean rejection, else the last step taken (the steps
+      // taken are a prefix of the lanes: lane d steps iff energy + d < sa_steps)
+      const unsigned chg = __ballot_sync(full, stepped && changed), stp = __ballot_sync(full, stepped);
+      const int cl = chg ? __ffs(chg) - 1 : 31 - __clz(stp);
+#define SA_TAKE(v) v = __shfl_sync(full, v, cl)
+      SA_TAKE(c.cur1); SA_TAKE(c.cur2); SA_TAKE(c.best1); SA_TAKE(c.best2); SA_TAKE(c.cur_err); SA_TAKE(c.best_err); SA_TAKE(c.rng);
+      SA_TAKE(c.best_lo); SA_TAKE(c.best_hi); SA_TAKE(c.cur_combo); SA_TAKE(c.best_combo); SA_TAKE(c.energy);
+#undef SA_TAKE
+      if (!(c.best_err > 0 && c.energy < sa_steps)) break;
+    }
+    if (lane == 0) sa_finish<NU>(c, K, ws);
+#ifdef FASTC_GPU_COUNTERS  // evaluations executed, the discarded speculative ones included
+    atomicAdd(&ws.counters[0], (unsigned long long)c.ncalls);
+    atomicAdd(&ws.counters[1], (unsigned long long)c.npbe);
+#endif
+  }
 }
 
 // ------------------------------------------------------------------ pack
@@ -2566,6 +2851,7 @@ size_t ws_bytes(uint32_t nblocks, bool nu) {
   b += (size_t)nblocks * kSlots * 8 * 4;                         // states
   b += (size_t)nblocks * kSlots * kStateWords * 4;               // sorted states
   b += kBinWords * 4;                                            // bins
+  b += (size_t)kTailCap * 4;                                     // hand-over list of the annealing tail
   if (nu) b += (size_t)nblocks * kSlots * 8;                     // chain errors as doubles (non-uniform metric)
   return b;
 }
@@ -2583,6 +2869,7 @@ Ws carve(void *base, uint32_t nblocks, bool nu) {
   w.states = reinterpret_cast<uint32_t *>(p); p += (size_t)nblocks * kSlots * 8 * 4;
   w.sorted = reinterpret_cast<uint4 *>(p); p += (size_t)nblocks * kSlots * kStateWords * 4;
   w.bins = reinterpret_cast<uint32_t *>(p); p += kBinWords * 4;
+  w.tail_list = reinterpret_cast<uint32_t *>(p); p += (size_t)kTailCap * 4;
   w.err64 = nu ? reinterpret_cast<double *>(p) : nullptr;
   w.stats = nullptr;
   return w;
@@ -2736,13 +3023,15 @@ cudaError_t bc7_front(Bc7Workspace &wsp, const void *rgba_dev, uint32_t width, u
 #endif
     if (nu) bc7_anneal<true><<<sa_grid, kSaThreads, 0, stream>>>(img, width, bx, fb, ws, prm.quality);
     else bc7_anneal<false><<<sa_grid, kSaThreads, 0, stream>>>(img, width, bx, fb, ws, prm.quality);
+    if (nu) bc7_anneal_tail<true><<<(uint32_t)sms * 4, kSaThreads, 0, stream>>>(img, width, bx, fb, ws, prm.quality);
+    else bc7_anneal_tail<false><<<(uint32_t)sms * 4, kSaThreads, 0, stream>>>(img, width, bx, fb, ws, prm.quality);
 #ifdef FASTC_GPU_CHAINSTATS
     bc7_chainstats_report<<<1, 1, 0, stream>>>();
 #endif
 #ifdef FASTC_GPU_TAILSTATS
     bc7_tail_report<<<1, 1, 0, stream>>>();
 #endif
-    n += 3;
+    n += 4;
   } else if (ev) {
     cudaEventRecord(wsp.ev_mid[wsp.timed_chunks - 1], stream);
   }

@@ -40,7 +40,8 @@ def main():
         gbs = nblk * (64 + bpb) / (t / 1e3) / 1e9
         print(json.dumps({"format": fmt, "size": size, "ms": t, "mpix_s": size * size / 1e6 / (t / 1e3),
                           "algo_gbs": gbs, "hbm_peak_gbs": hbm, "hbm_frac": gbs / hbm}))
-    batch_config4(g, hbm)
+    if "--quick" not in sys.argv:
+        batch_config4(g, hbm)
 
 
 def batch_config4(g, hbm):
