@@ -1176,6 +1176,7 @@ constexpr int kBinTailFetch = 1601;  // its fetch cursor
 constexpr int kBinWords = 2048;
 constexpr int kTailChains = 16;      // a warp of bc7_anneal hands its chains over once it is down to this many
 constexpr uint32_t kTailCap = 1u << 18;  // capacity of the hand-over list
+constexpr uint32_t kTailMaxBlocks = 1000000u;  // submissions below this size use the hand-over (see launch_bc7)
 
 // (under the non-uniform metric R.err is a float's bit pattern: the length predictor takes its value)
 __device__ __forceinline__ uint32_t sort_error(const Ws &ws, uint32_t err) {
@@ -2206,7 +2207,8 @@ __device__ __noinline__ bool sa_hand_over(Ws ws, uint32_t gid, uint32_t cur1, ui
   return true;
 }
 
-template <bool NU>
+// HAND: the warp's last chains go to bc7_anneal_tail (small submissions, where the kernel's tail counts).
+template <bool NU, bool HAND>
 __global__ void __launch_bounds__(kSaThreads, kSaCtasPerSm)
 bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, uint32_t first_block, Ws ws,
            int sa_steps) {
@@ -2363,7 +2365,7 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
       // the queues dry (that is when it sees the last class run dry), so the warp notices the moment
       // it is down to kTailChains chains: they are parked in their own, now unused, start-state /
       // result records and listed; the warp is done.
-      if (__any_sync(full, drymask == 7u) && __popc(__ballot_sync(full, have)) <= kTailChains) {
+      if (HAND && __any_sync(full, drymask == 7u) && __popc(__ballot_sync(full, have)) <= kTailChains) {
         if (have)
           have = !sa_hand_over(ws, gid, cur1, cur2, best1, best2, cur_err, best_err, rng,
                                (uint32_t)cur_combo | ((uint32_t)best_combo << 2) | ((uint32_t)energy << 8), improved, K.n,
@@ -3021,17 +3023,26 @@ cudaError_t bc7_front(Bc7Workspace &wsp, const void *rgba_dev, uint32_t width, u
 #ifdef FASTC_GPU_CHAINSTATS
     bc7_chainstats_reset<<<1, 32, 0, stream>>>();
 #endif
-    if (nu) bc7_anneal<true><<<sa_grid, kSaThreads, 0, stream>>>(img, width, bx, fb, ws, prm.quality);
-    else bc7_anneal<false><<<sa_grid, kSaThreads, 0, stream>>>(img, width, bx, fb, ws, prm.quality);
-    if (nu) bc7_anneal_tail<true><<<(uint32_t)sms * 4, kSaThreads, 0, stream>>>(img, width, bx, fb, ws, prm.quality);
-    else bc7_anneal_tail<false><<<(uint32_t)sms * 4, kSaThreads, 0, stream>>>(img, width, bx, fb, ws, prm.quality);
+    // The hand-over to bc7_anneal_tail saves most of the persistent kernel's tail (0.5 - 1 ms per launch)
+    // but any edit of that kernel's loop costs ~1 % of its time (profiles/r02_tail_notes.md): it pays
+    // below ~1 M blocks per submission (measured: -7 % at 2048^2, -1 % on a 1/8 shard of 8192^2, +0.7 % on a half).
+    const bool hand = nb < kTailMaxBlocks;
+    if (nu) {
+      if (hand) bc7_anneal<true, true><<<sa_grid, kSaThreads, 0, stream>>>(img, width, bx, fb, ws, prm.quality);
+      else bc7_anneal<true, false><<<sa_grid, kSaThreads, 0, stream>>>(img, width, bx, fb, ws, prm.quality);
+      if (hand) bc7_anneal_tail<true><<<(uint32_t)sms * 4, kSaThreads, 0, stream>>>(img, width, bx, fb, ws, prm.quality);
+    } else {
+      if (hand) bc7_anneal<false, true><<<sa_grid, kSaThreads, 0, stream>>>(img, width, bx, fb, ws, prm.quality);
+      else bc7_anneal<false, false><<<sa_grid, kSaThreads, 0, stream>>>(img, width, bx, fb, ws, prm.quality);
+      if (hand) bc7_anneal_tail<false><<<(uint32_t)sms * 4, kSaThreads, 0, stream>>>(img, width, bx, fb, ws, prm.quality);
+    }
 #ifdef FASTC_GPU_CHAINSTATS
     bc7_chainstats_report<<<1, 1, 0, stream>>>();
 #endif
 #ifdef FASTC_GPU_TAILSTATS
     bc7_tail_report<<<1, 1, 0, stream>>>();
 #endif
-    n += 4;
+    n += hand ? 4 : 3;
   } else if (ev) {
     cudaEventRecord(wsp.ev_mid[wsp.timed_chunks - 1], stream);
   }
