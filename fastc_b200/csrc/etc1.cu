@@ -23,8 +23,8 @@
 //     (2*luma_p >= mid0) + (2*luma_p >= mid1) + (2*luma_p >= mid2) because the
 //     midpoints are non-decreasing -- no sort is needed, only min / max luma for
 //     the two "skip this table" tests;
-//   * squared RGB distances are evaluated as |p|^2 + |c|^2 - 2 dp4a(p, c) on
-//     packed bytes (exact integers).
+//   * squared RGB distances are VABSDIFF4 + DP4A on packed bytes (exact integers), and the four
+//     colours of an intensity table come from 16x2 SIMD clamped adds (table_colors).
 // A CTA of 128 threads stages its 32 blocks (2 KiB) through shared memory with
 // 16 B coalesced row loads; stores are 8 B per block, contiguous per warp.
 #include <initializer_list>
@@ -61,27 +61,38 @@ __device__ __forceinline__ uint32_t scale_color(uint32_t c, bool color4) {
   return color4 ? (c | (c << 4)) : (((c >> 2) & 0x07070707u) | (c << 3));
 }
 
+// The four colours of intensity table `it` around the scaled base colour, packed r | g << 8 | b << 16,
+// and their luma sums.  base_rb = r | b << 16, base_g = g: the clamped adds are 16x2 SIMD
+// instructions (add + min 255 / add + max 0 in one), one byte permute packs a colour.
+__device__ __forceinline__ void table_colors(uint32_t base_rb, int base_g, int it, uint32_t (&bc)[4], uint32_t (&bi)[4]) {
+#pragma unroll
+  for (int s = 0; s < 4; s++) {
+    const int yd = c_inten[it][s];  // {-L, -S, +S, +L}
+    const uint32_t yd2 = ((uint32_t)yd & 0xFFFFu) * 0x10001u;
+    const uint32_t rb = s < 2 ? __viaddmax_s16x2_relu(base_rb, yd2, 0u) : __viaddmin_s16x2(base_rb, yd2, 0x00FF00FFu);
+    const uint32_t g = (uint32_t)clamp255(base_g + yd);
+    bc[s] = __byte_perm(rb, g, 0x5240);
+    bi[s] = __dp4a(bc[s], 0x00010101u, 0u);
+  }
+}
+
 // evaluate_solution_fast (rg_etc1.cpp:1767-1885) for base colour `color` (unscaled).
-// px: 8 packed pixels (alpha cleared), p2: their squared norms, luma2: 2 * (r+g+b).
-__device__ __forceinline__ void evaluate(const uint32_t (&px)[8], const uint32_t (&p2)[8], const uint32_t (&luma2)[8],
+// px: 8 packed pixels (alpha cleared), luma2: 2 * (r+g+b).  Squared distances are VABSDIFF4 + DP4A on
+// packed bytes (exact integers).  The table loop only totals the error; the selectors are derived
+// once, for the winning table (they are a pure function of the table and the lumas).
+__device__ __forceinline__ void evaluate(const uint32_t (&px)[8], const uint32_t (&luma2)[8],
                                          uint32_t lmin, uint32_t lmax, uint32_t color, bool color4, Sol &trial) {
   const uint32_t base = scale_color(color, color4);
-  const int b0 = base & 0xFF, b1 = (base >> 8) & 0xFF, b2 = (base >> 16) & 0xFF;
+  const uint32_t base_rb = (base & 0xFFu) | ((base & 0xFF0000u));
+  const int base_g = (base >> 8) & 0xFF;
   trial.err = 0xFFFFFFFFu;
   trial.color = color;
   trial.inten = 0;
   trial.sel = 0;
 #pragma unroll 1
   for (int it = 7; it >= 0; --it) {
-    uint32_t bc[4], bc2[4], bi[4];
-#pragma unroll
-    for (int s = 0; s < 4; s++) {
-      const int yd = c_inten[it][s];
-      const uint32_t r = clamp255(b0 + yd), g = clamp255(b1 + yd), b = clamp255(b2 + yd);
-      bc[s] = r | (g << 8) | (b << 16);
-      bi[s] = r + g + b;
-      bc2[s] = __dp4a(bc[s], bc[s], 0u);
-    }
+    uint32_t bc[4], bi[4];
+    table_colors(base_rb, base_g, it, bc, bi);
     const uint32_t mid0 = bi[0] + bi[1], mid1 = bi[1] + bi[2], mid2 = bi[2] + bi[3];
     // the two "all pixels beyond one end" cases may skip the table (rg_etc1.cpp:1809-1836)
     if (lmax * 2 < mid0) {
@@ -89,21 +100,31 @@ __device__ __forceinline__ void evaluate(const uint32_t (&px)[8], const uint32_t
     } else if (lmin * 2 >= mid2) {
       if (lmin > bi[3] && lmin - bi[3] >= trial.err) continue;
     }
-    uint32_t total = 0, sel = 0;
+    uint32_t total = 0;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
       const bool g0 = luma2[i] >= mid0, g1 = luma2[i] >= mid1, g2 = luma2[i] >= mid2;
       const uint32_t c = g2 ? bc[3] : (g1 ? bc[2] : (g0 ? bc[1] : bc[0]));
-      const uint32_t c2 = g2 ? bc2[3] : (g1 ? bc2[2] : (g0 ? bc2[1] : bc2[0]));
-      total += p2[i] + c2 - 2u * __dp4a(px[i], c, 0u);
-      sel |= ((uint32_t)g0 + (uint32_t)g1 + (uint32_t)g2) << (2 * i);
+      const uint32_t d = __vabsdiffu4(px[i], c);
+      total = __dp4a(d, d, total);
     }
     if (total < trial.err) {
       trial.err = total;
       trial.inten = it;
-      trial.sel = sel;
       if (!total) break;
     }
+  }
+  if (trial.err != 0xFFFFFFFFu) {
+    uint32_t bc[4], bi[4];
+    table_colors(base_rb, base_g, trial.inten, bc, bi);
+    const uint32_t mid0 = bi[0] + bi[1], mid1 = bi[1] + bi[2], mid2 = bi[2] + bi[3];
+    uint32_t sel = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const bool g0 = luma2[i] >= mid0, g1 = luma2[i] >= mid1, g2 = luma2[i] >= mid2;
+      sel |= ((uint32_t)g0 + (uint32_t)g1 + (uint32_t)g2) << (2 * i);
+    }
+    trial.sel = sel;
   }
 }
 
@@ -112,7 +133,7 @@ __device__ __forceinline__ void evaluate(const uint32_t (&px)[8], const uint32_t
 // constrain: differential mode's second sub-block, base5 = first sub-block's colour.
 __device__ __forceinline__ bool optimize(const uint32_t (&px)[8], bool color4, bool constrain, uint32_t base5, Sol &best) {
   const int limit = color4 ? 15 : 31;
-  uint32_t p2[8], luma2[8];
+  uint32_t luma2[8];
   uint32_t sr = 0, sg = 0, sb = 0, lmin = 0xFFFFFFFFu, lmax = 0;
 #pragma unroll
   for (int i = 0; i < 8; i++) {
@@ -122,7 +143,6 @@ __device__ __forceinline__ bool optimize(const uint32_t (&px)[8], bool color4, b
     lmin = min(lmin, l);
     lmax = max(lmax, l);
     luma2[i] = 2 * l;
-    p2[i] = __dp4a(px[i], px[i], 0u);
   }
   const float flimit = (float)limit;
   const float avg[3] = {__fmul_rn((float)sr, 0.125f), __fmul_rn((float)sg, 0.125f), __fmul_rn((float)sb, 0.125f)};
@@ -139,7 +159,7 @@ __device__ __forceinline__ bool optimize(const uint32_t (&px)[8], bool color4, b
 
   best.err = 0xFFFFFFFFu;
   if (!allowed(m[0], m[1], m[2])) return false;
-  evaluate(px, p2, luma2, lmin, lmax, (uint32_t)m[0] | ((uint32_t)m[1] << 8) | ((uint32_t)m[2] << 16), color4, best);
+  evaluate(px, luma2, lmin, lmax, (uint32_t)m[0] | ((uint32_t)m[1] << 8) | ((uint32_t)m[2] << 16), color4, best);
 
 #pragma unroll 1
   for (int trial = 0; trial < 2; trial++) {
@@ -175,7 +195,7 @@ __device__ __forceinline__ bool optimize(const uint32_t (&px)[8], bool color4, b
     if (ncol == best.color) break;
     if (!allowed(n1[0], n1[1], n1[2])) break;
     Sol t;
-    evaluate(px, p2, luma2, lmin, lmax, ncol, color4, t);
+    evaluate(px, luma2, lmin, lmax, ncol, color4, t);
     if (t.err < best.err) best = t;
     else break;
   }
@@ -273,7 +293,7 @@ struct Optimizer {
     const uint32_t col = (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16);
     Sol t;
     if (Q == 2) evaluate_full(px, p2, col, color4, t);
-    else evaluate(px, p2, luma2, lmin, lmax, col, color4, t);
+    else evaluate(px, luma2, lmin, lmax, col, color4, t);
     if (t.err < best.err) { best = t; valid = true; return true; }
     return false;
   }
