@@ -466,6 +466,36 @@ __device__ uint2 pack_solid(uint32_t pixel) {
   return o;
 }
 
+// The 8 bytes of a block from its winning candidate (rg_etc1.cpp:2369-2448).
+__device__ __forceinline__ uint2 pack_block(bool flip, bool color4, const Sol &r0, const Sol &r1) {
+  const uint32_t c0 = r0.color, c1 = r1.color;
+  uint32_t bytes[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const int a = (c0 >> (8 * k)) & 0xFF, b = (c1 >> (8 * k)) & 0xFF;
+    if (color4) bytes[k] = (uint32_t)(b | (a << 4));
+    else bytes[k] = (uint32_t)((a << 3) | ((b - a) & 7));
+  }
+  const uint32_t b3 = ((uint32_t)r1.inten << 2) | ((uint32_t)r0.inten << 5) | ((color4 ? 0u : 1u) << 1) | (flip ? 1u : 0u);
+  uint32_t lsb = 0, msb = 0;
+#pragma unroll
+  for (int y = 0; y < 4; y++)
+#pragma unroll
+    for (int x = 0; x < 4; x++) {
+      const int sbf = y >> 1, kf = (y & 1) * 4 + x;  // flipped
+      const int sbn = x >> 1, kn = (x & 1) * 4 + y;  // not flipped
+      const uint32_t sf = ((sbf ? r1.sel : r0.sel) >> (2 * kf)) & 3, sn = ((sbn ? r1.sel : r0.sel) >> (2 * kn)) & 3;
+      const uint32_t s = flip ? sf : sn;
+      const uint32_t e = (0x4B >> (2 * s)) & 3;  // selector index -> ETC1 code {3,2,0,1}
+      lsb |= (e & 1) << (x * 4 + y);
+      msb |= (e >> 1) << (x * 4 + y);
+    }
+  uint2 o;
+  o.x = bytes[0] | (bytes[1] << 8) | (bytes[2] << 16) | (b3 << 24);
+  o.y = (msb >> 8) | ((msb & 0xFF) << 8) | ((lsb >> 8) << 16) | ((lsb & 0xFF) << 24);
+  return o;
+}
+
 constexpr int kEtcThreads = 128;
 constexpr int kEtcBlocksPerCta = kEtcThreads / 4;
 
@@ -550,33 +580,203 @@ etc1_encode_kernel(const uint32_t *__restrict__ img, uint32_t width, uint32_t bl
   best = min(best, __shfl_xor_sync(qmask, best, 2));
   if (best != key) return;
 
-  // ---- pack (rg_etc1.cpp:2369-2448)
-  const uint32_t c0 = res[0].color, c1 = res[1].color;
-  uint32_t bytes[3];
-#pragma unroll
-  for (int k = 0; k < 3; k++) {
-    const int a = (c0 >> (8 * k)) & 0xFF, b = (c1 >> (8 * k)) & 0xFF;
-    if (color4) bytes[k] = (uint32_t)(b | (a << 4));
-    else bytes[k] = (uint32_t)((a << 3) | ((b - a) & 7));
+  out[bi] = pack_block(flip, color4, res[0], res[1]);
+}
+
+// ---- cLowQuality, dynamically scheduled.  In the quad kernel above a lane's candidate takes 2 to 6
+// evaluations (one per sub-block plus up to two refinement trials each) and the warp waits for its
+// slowest lane at every call: 19 of 32 lanes are busy on average.  Here a CTA owns a tile of 256
+// blocks whose pixels it stages in shared memory, the (block, candidate) pairs are TASKS handed out
+// through a shared cursor, and every lane runs the optimizer as a state machine -- fetch a task, set
+// up a sub-block, evaluate, decide what comes next -- so that the one expensive step, evaluate(), is
+// executed by the whole warp on every trip, each lane for whatever task / sub-block / trial it has
+// reached.  Candidate results are parked in shared memory; a last pass picks each block's winner in
+// the reference's order (strict <, lowest candidate index first) and packs it.
+constexpr int kDynTile = 256;
+
+__device__ __forceinline__ bool etc1_allowed(bool constrain, uint32_t base5, int r, int g, int b) {
+  if (!constrain) return true;
+  const int dr = r - (int)(base5 & 0xFF), dg = g - (int)((base5 >> 8) & 0xFF), db = b - (int)(base5 >> 16);
+  return min(dr, min(dg, db)) >= -4 && max(dr, max(dg, db)) <= 3;
+}
+
+__global__ void __launch_bounds__(kEtcThreads, 6)
+etc1_encode_dyn_kernel(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, uint32_t first_block,
+                       uint32_t num_blocks, uint2 *__restrict__ out) {
+  __shared__ uint32_t s_blk[kDynTile][17];  // +1 word: lanes on different blocks hit different banks
+  __shared__ uint4 s_res[4][kDynTile];      // per candidate: error, colour 0 | inten 0 << 24, colour 1 | inten 1 << 24, sel 0 | sel 1 << 16
+  __shared__ uint32_t s_solid[kDynTile / 32];
+  __shared__ uint32_t s_next;
+  const int tid = threadIdx.x;
+  const uint32_t tile0 = blockIdx.x * kDynTile;
+  const int nbt = (int)min((uint32_t)kDynTile, num_blocks - tile0);
+  if (tid < kDynTile / 32) s_solid[tid] = 0;
+  if (tid == 0) s_next = 0;
+  // stage the tile: consecutive threads take the same row of consecutive blocks (16 B each, contiguous
+  // while the blocks share a block row)
+  for (int item = tid; item < 4 * nbt; item += kEtcThreads) {
+    const int row = item / nbt, b = item - row * nbt;
+    const uint32_t bi = first_block + tile0 + b;
+    const uint32_t bx = bi % blocks_x, by = bi / blocks_x;
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(img + (size_t)(by * 4 + row) * width + (size_t)bx * 4));
+    s_blk[b][4 * row + 0] = v.x; s_blk[b][4 * row + 1] = v.y; s_blk[b][4 * row + 2] = v.z; s_blk[b][4 * row + 3] = v.w;
   }
-  const uint32_t b3 = ((uint32_t)res[1].inten << 2) | ((uint32_t)res[0].inten << 5) | ((color4 ? 0u : 1u) << 1) | (flip ? 1u : 0u);
-  uint32_t lsb = 0, msb = 0;
+  __syncthreads();
+  for (int b = tid; b < nbt; b += kEtcThreads) {
+    bool solid = true;
 #pragma unroll
-  for (int y = 0; y < 4; y++)
+    for (int i = 1; i < 16; i++) solid = solid && (s_blk[b][i] == s_blk[b][0]);  // includes the alpha byte
+    if (solid) atomicOr(&s_solid[b >> 5], 1u << (b & 31));
+  }
+  __syncthreads();
+
+  // ---- the optimizer as a per-lane state machine (rg_etc1.cpp:2251-2367 with optimize() unrolled in time)
+  enum { kNeedTask, kNeedSub, kReady, kDone };
+  const int ntasks = 4 * nbt;
+  int stage = kNeedTask, task = 0, blk = 0, sub = 0, ktrial = 0;
+  bool flip = false, color4 = false, constrain = false;
+  uint32_t px[8], luma2[8], lmin = 0, lmax = 0, mcol = 0, cur_color = 0;
+  float avg[3] = {0.0f, 0.0f, 0.0f};
+  Sol best = {0xFFFFFFFFu, 0, 0, 0}, res0 = {0xFFFFFFFFu, 0, 0, 0};
+  for (;;) {
+    // [setup] lanes between tasks / sub-blocks; a constrained second sub-block whose mean colour is
+    // out of the differential range ends the candidate at once (rg_etc1.cpp:1511-1518), so try again
+#pragma unroll 1
+    for (int tries = 0; tries < 3 && (stage == kNeedTask || stage == kNeedSub); tries++) {
+      if (stage == kNeedTask) {
+        for (;;) {
+          task = (int)atomicAdd(&s_next, 1u);
+          if (task >= ntasks) { stage = kDone; break; }
+          const int cand = task & 3;  // (block-major: measured 3 % faster than candidate-major)
+          blk = task >> 2;
+          if ((s_solid[blk >> 5] >> (blk & 31)) & 1u) continue;
+          flip = cand >> 1; color4 = cand & 1;  // reference loop order, rg_etc1.cpp:2251-2254
+          sub = 0;
+          stage = kNeedSub;
+          break;
+        }
+      }
+      if (stage == kNeedSub) {
+        uint32_t sr = 0, sg = 0, sb = 0;
+        lmin = 0xFFFFFFFFu; lmax = 0;
 #pragma unroll
-    for (int x = 0; x < 4; x++) {
-      const int sbf = y >> 1, kf = (y & 1) * 4 + x;  // flipped
-      const int sbn = x >> 1, kn = (x & 1) * 4 + y;  // not flipped
-      const uint32_t sf = (res[sbf].sel >> (2 * kf)) & 3, sn = (res[sbn].sel >> (2 * kn)) & 3;
-      const uint32_t s = flip ? sf : sn;
-      const uint32_t e = (0x4B >> (2 * s)) & 3;  // selector index -> ETC1 code {3,2,0,1}
-      lsb |= (e & 1) << (x * 4 + y);
-      msb |= (e >> 1) << (x * 4 + y);
+        for (int i = 0; i < 8; i++) {
+          // flipped: rows 2*sub, 2*sub+1 in raster order; else columns 2*sub, 2*sub+1, column-major
+          const int pos = flip ? sub * 8 + i : sub * 2 + (i >> 2) + 4 * (i & 3);
+          px[i] = s_blk[blk][pos] & 0x00FFFFFFu;
+          const uint32_t r = px[i] & 0xFF, g = (px[i] >> 8) & 0xFF, b = px[i] >> 16;
+          sr += r; sg += g; sb += b;
+          const uint32_t l = r + g + b;
+          lmin = min(lmin, l);
+          lmax = max(lmax, l);
+          luma2[i] = 2 * l;
+        }
+        const int limit = color4 ? 15 : 31;
+        const float flimit = (float)limit;
+        avg[0] = __fmul_rn((float)sr, 0.125f); avg[1] = __fmul_rn((float)sg, 0.125f); avg[2] = __fmul_rn((float)sb, 0.125f);
+        int m[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+          m[k] = min(max(__float2int_rz(__fadd_rn(__fdiv_rn(__fmul_rn(avg[k], flimit), 255.0f), 0.5f)), 0), limit);
+        mcol = (uint32_t)m[0] | ((uint32_t)m[1] << 8) | ((uint32_t)m[2] << 16);
+        constrain = !color4 && sub == 1;
+        if (!etc1_allowed(constrain, res0.color, m[0], m[1], m[2])) {
+          s_res[task & 3][blk] = make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);  // the candidate fails
+          stage = kNeedTask;
+        } else {
+          cur_color = mcol;
+          ktrial = 0;
+          stage = kReady;
+        }
+      }
     }
-  uint2 o;
-  o.x = bytes[0] | (bytes[1] << 8) | (bytes[2] << 16) | (b3 << 24);
-  o.y = (msb >> 8) | ((msb & 0xFF) << 8) | ((lsb >> 8) << 16) | ((lsb & 0xFF) << 24);
-  out[bi] = o;
+    if (__all_sync(0xffffffffu, stage == kDone)) break;
+
+    // [evaluate] the one expensive step, by every lane that has something to evaluate
+    Sol t = {0xFFFFFFFFu, 0, 0, 0};
+    if (stage == kReady) evaluate(px, luma2, lmin, lmax, cur_color, color4, t);
+
+    // [decide] etc1_optimizer::compute's refinement loop (rg_etc1.cpp:1531-1612), one trip per evaluation
+    if (stage == kReady) {
+      bool finish = false;
+      if (ktrial == 0) best = t;
+      else if (t.err < best.err) best = t;
+      else finish = true;
+      if (!finish && ktrial == 2) finish = true;  // both refinement trials are used up
+      if (!finish) {
+        const int limit = color4 ? 15 : 31;
+        const float flimit = (float)limit;
+        const uint32_t base = scale_color(best.color, color4);
+        // sum of the clamped intensity deltas actually applied under the best selectors
+        int cnt[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const uint32_t s = (best.sel >> (2 * i)) & 3;
+#pragma unroll
+          for (int q = 0; q < 4; q++) cnt[q] += (s == (uint32_t)q);
+        }
+        int ds[3] = {0, 0, 0};
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+          const int yd = c_inten[best.inten][s];
+#pragma unroll
+          for (int k = 0; k < 3; k++) {
+            const int bk = (base >> (8 * k)) & 0xFF;
+            ds[k] += cnt[s] * (clamp255(bk + yd) - bk);
+          }
+        }
+        if (!ds[0] && !ds[1] && !ds[2]) {
+          finish = true;
+        } else {
+          int n1[3];
+#pragma unroll
+          for (int k = 0; k < 3; k++) {
+            const float ad = __fdiv_rn((float)ds[k], 8.0f);
+            const float f = __fadd_rn(__fdiv_rn(__fmul_rn(__fsub_rn(avg[k], ad), flimit), 255.0f), 0.5f);
+            n1[k] = min(max(__float2int_rz(f), 0), limit);  // x86 cvttss2si, then clamp<int>
+          }
+          const uint32_t ncol = (uint32_t)n1[0] | ((uint32_t)n1[1] << 8) | ((uint32_t)n1[2] << 16);
+          if (ncol == mcol || ncol == best.color || !etc1_allowed(constrain, res0.color, n1[0], n1[1], n1[2])) {
+            finish = true;
+          } else {
+            cur_color = ncol;
+            ktrial++;
+          }
+        }
+      }
+      if (finish) {
+        if (sub == 0) {
+          res0 = best;
+          sub = 1;
+          stage = kNeedSub;
+        } else {
+          s_res[task & 3][blk] = make_uint4(res0.err + best.err, res0.color | ((uint32_t)res0.inten << 24),
+                                             best.color | ((uint32_t)best.inten << 24), res0.sel | (best.sel << 16));
+          stage = kNeedTask;
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- winners: strict-< scan over the candidates in index order, then pack
+  for (int b = tid; b < nbt; b += kEtcThreads) {
+    const uint32_t bi = first_block + tile0 + b;
+    if ((s_solid[b >> 5] >> (b & 31)) & 1u) {
+      out[bi] = pack_solid(s_blk[b][0]);
+      continue;
+    }
+    uint4 w = s_res[0][b];
+    int wc = 0;
+#pragma unroll
+    for (int cand = 1; cand < 4; cand++) {
+      const uint4 r = s_res[cand][b];
+      if (r.x < w.x) { w = r; wc = cand; }
+    }
+    const Sol r0 = {w.x, w.y & 0x00FFFFFFu, w.w & 0xFFFFu, (int)(w.y >> 24)};
+    const Sol r1 = {w.x, w.z & 0x00FFFFFFu, w.w >> 16, (int)(w.z >> 24)};
+    out[bi] = pack_block(wc >> 1, wc & 1, r0, r1);
+  }
 }
 
 // rg_etc1.cpp:1887-1901
@@ -646,7 +846,9 @@ cudaError_t launch_etc1(const void *rgba_dev, uint32_t width, uint32_t first_blo
   const uint32_t grid = (num_blocks + kEtcBlocksPerCta - 1) / kEtcBlocksPerCta;
   const uint32_t *img = static_cast<const uint32_t *>(rgba_dev);
   uint2 *out = static_cast<uint2 *>(out_dev);
-  if (quality == 0) etc1_encode_kernel<0><<<grid, kEtcThreads, 0, stream>>>(img, width, width / 4, first_block, num_blocks, out);
+  if (quality == 0)
+    etc1_encode_dyn_kernel<<<(num_blocks + kDynTile - 1) / kDynTile, kEtcThreads, 0, stream>>>(img, width, width / 4, first_block,
+                                                                                              num_blocks, out);
   else if (quality == 1) etc1_encode_kernel<1><<<grid, kEtcThreads, 0, stream>>>(img, width, width / 4, first_block, num_blocks, out);
   else if (quality == 2) etc1_encode_kernel<2><<<grid, kEtcThreads, 0, stream>>>(img, width, width / 4, first_block, num_blocks, out);
   else return cudaErrorInvalidValue;
