@@ -8,7 +8,7 @@ ARCH      := -gencode arch=compute_100a,code=sm_100a
 # which never fuses a multiply with an add (SURVEY.md trap T4).
 NVCCFLAGS := $(ARCH) -O3 -lineinfo -fmad=false -std=c++17 -Xcompiler -fPIC $(EXTRA_NVCCFLAGS)
 CSRC      := fastc_b200/csrc
-GPU_SRCS  := $(CSRC)/capi.cu $(CSRC)/dxt.cu $(CSRC)/etc1.cu $(CSRC)/bc7.cu $(CSRC)/decode.cu
+GPU_SRCS  := $(CSRC)/capi.cu $(CSRC)/dxt.cu $(CSRC)/etc1.cu $(CSRC)/bc7.cu $(CSRC)/decode.cu $(CSRC)/pvrtc.cu
 GPU_OBJS  := $(GPU_SRCS:.cu=.o)
 GPU_SO    := fastc_b200/libfastc_gpu.so
 

@@ -33,10 +33,11 @@ class ECompressionFormat(enum.IntEnum):
     DXT5 = 1
     ETC1 = 2
     BPTC = 3
+    PVRTC4 = 4  # image-level: square power-of-two textures, whole texture per call, Morton block order
 
 
 BLOCK_BYTES = {ECompressionFormat.DXT1: 8, ECompressionFormat.DXT5: 16,
-               ECompressionFormat.ETC1: 8, ECompressionFormat.BPTC: 16}
+               ECompressionFormat.ETC1: 8, ECompressionFormat.BPTC: 16, ECompressionFormat.PVRTC4: 8}
 
 
 @dataclass

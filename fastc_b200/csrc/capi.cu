@@ -97,6 +97,10 @@ struct DeviceCtx {
   // each use waits for the previous one (api_done) before it touches the scratch
   cudaEvent_t api_done = nullptr;
   bool api_used = false;
+  // PVRTC scratch (one per device, uses ordered by pvr_done like the BC7 device-API scratch)
+  PvrtcWorkspace pvrws;
+  cudaEvent_t pvr_done = nullptr;
+  bool pvr_used = false;
   std::mutex mu;
 };
 
@@ -149,13 +153,16 @@ int grow(void **buf, size_t *cap, size_t need) {
   return 0;
 }
 
-bool valid_format(int f) { return f >= FASTC_GPU_DXT1 && f <= FASTC_GPU_BPTC; }
+bool valid_format(int f) { return f >= FASTC_GPU_DXT1 && f <= FASTC_GPU_PVRTC4; }
 
 int check_dims(int format, uint32_t width, uint32_t height) {
   if (!valid_format(format)) return fail("unknown compression format %d", format);
   // reference: "Image dimensions must be multiples of the block size" (TexComp.cpp:472-476)
   if (width == 0 || height == 0 || (width & 3) || (height & 3))
     return fail("image dimensions %ux%u are not non-zero multiples of the 4x4 block", width, height);
+  // reference: "PVRTC4 images must be square and power-of-two" (TexComp.cpp:477-482)
+  if (format == FASTC_GPU_PVRTC4 && (width != height || (width & (width - 1)) || width < 8 || width > 16384))
+    return fail("PVRTC4 images must be square with a power-of-two side in [8, 16384] (got %ux%u)", width, height);
   return 0;
 }
 
@@ -175,6 +182,19 @@ int enqueue(int dev, int format, const void *rgba_dev, uint32_t width, uint32_t 
       CU_TRY(launch_etc1(rgba_dev, width, first_block, num_blocks, out_dev, prm.etc1_quality, stream));
       n = num_blocks ? 1 : 0;
       break;
+    case FASTC_GPU_PVRTC4: {
+      if (first_block != 0 || num_blocks != (width / 4) * (height / 4))
+        return fail("PVRTC4 encodes whole textures: block ranges are not supported");
+      DeviceCtx &c = g_ctx[dev];
+      std::lock_guard<std::mutex> lk(c.mu);
+      // one scratch per device: order this use after the previous one, whatever its stream
+      if (!c.pvr_done) CU_TRY(cudaEventCreateWithFlags(&c.pvr_done, cudaEventDisableTiming));
+      if (c.pvr_used) CU_TRY(cudaStreamWaitEvent(stream, c.pvr_done, 0));
+      CU_TRY(launch_pvrtc(c.pvrws, rgba_dev, width, height, out_dev, stream, &n));
+      CU_TRY(cudaEventRecord(c.pvr_done, stream));
+      c.pvr_used = true;
+      break;
+    }
     case FASTC_GPU_BPTC: {
       DeviceCtx &c = g_ctx[dev];
       std::lock_guard<std::mutex> lk(c.mu);
@@ -323,7 +343,9 @@ void plan_chunks(Shard &s, int format, uint32_t width, uint32_t chunk_blocks) {
   const uint32_t row1 = (s.first_block + s.num_blocks + bx - 1) / bx;
   const uint32_t total_rows = row1 - row0;
   uint32_t rows_per_chunk;
-  if (chunk_blocks == 0 && format == FASTC_GPU_BPTC) {
+  if (format == FASTC_GPU_PVRTC4) {
+    rows_per_chunk = total_rows;  // image-level encoder: the whole texture is one submission
+  } else if (chunk_blocks == 0 && format == FASTC_GPU_BPTC) {
     // BC7 is compute-bound (copies are ~1% of the time): no chunking unless asked for
     rows_per_chunk = total_rows;
   } else if (chunk_blocks == 0) {
@@ -727,6 +749,9 @@ void fastc_gpu_shutdown(void) {
       c.in_buf[i] = c.out_buf[i] = nullptr; c.in_cap[i] = c.out_cap[i] = 0;
     }
     for (int i = 0; i <= kPipeDepth; i++) bc7_free_workspace(c.bc7ws[i]);
+    pvrtc_free_workspace(c.pvrws);
+    if (c.pvr_done) cudaEventDestroy(c.pvr_done);
+    c.pvr_done = nullptr; c.pvr_used = false;
     for (int i = 0; i < kStagePieces; i++) {
       if (c.pin_in[i]) cudaFreeHost(c.pin_in[i]);
       if (c.pin_in_ev[i]) cudaEventDestroy(c.pin_in_ev[i]);
@@ -747,7 +772,7 @@ void fastc_gpu_shutdown(void) {
 }
 
 uint32_t fastc_gpu_block_bytes(int format) {
-  return (format == FASTC_GPU_DXT1 || format == FASTC_GPU_ETC1) ? 8u : 16u;
+  return (format == FASTC_GPU_DXT1 || format == FASTC_GPU_ETC1 || format == FASTC_GPU_PVRTC4) ? 8u : 16u;
 }
 
 uint64_t fastc_gpu_compressed_size(int format, uint32_t width, uint32_t height) {
@@ -821,6 +846,10 @@ int compress_impl(int format, const uint8_t *rgba_host, uint32_t width, uint32_t
   const uint32_t row0 = first_block / bx, row1 = (first_block + num_blocks + bx - 1) / bx;
   const uint32_t rows = row1 - row0;
   num_gpus = std::max(1, std::min<int>(num_gpus, rows));
+  if (format == FASTC_GPU_PVRTC4) {  // neighbour-coupled over the whole texture: one GPU, all of it
+    if (first_block != 0 || num_blocks != bx * (height / 4)) return fail("PVRTC4 encodes whole textures: block ranges are not supported");
+    num_gpus = 1;
+  }
   std::vector<Shard> shards(num_gpus);
   WmChain chain;
   int npieces = 0;

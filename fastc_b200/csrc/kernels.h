@@ -18,6 +18,18 @@ cudaError_t launch_dxt(bool dxt5, const void *rgba_dev, uint32_t width, uint32_t
 cudaError_t launch_etc1(const void *rgba_dev, uint32_t width, uint32_t first_block, uint32_t num_blocks,
                         void *out_dev, int quality, cudaStream_t stream);
 
+// PVRTC 4bpp (pvrtc.cu): image-level encoder, the whole (square, power-of-two) texture per call.
+// Scratch (intensities, extremum classes, per-pixel label lists: 168 B per pixel) is owned by the
+// per-device context and grown on demand.
+struct PvrtcWorkspace {
+  void *base = nullptr;
+  size_t bytes = 0;
+  uint32_t *host_flag = nullptr;
+};
+void pvrtc_free_workspace(PvrtcWorkspace &ws);
+cudaError_t launch_pvrtc(PvrtcWorkspace &ws, const void *rgba_dev, uint32_t width, uint32_t height, void *out_dev,
+                         cudaStream_t stream, uint32_t *launches);
+
 // Decoders + PSNR (decode.cu).  format: include/fastc_gpu.h numbering.
 cudaError_t launch_decode(int format, const void *cmp_dev, uint32_t width, uint32_t first_block, uint32_t num_blocks,
                           void *rgba_dev, cudaStream_t stream);

@@ -59,7 +59,14 @@ enum fastc_gpu_format {
   FASTC_GPU_DXT1 = 0, /* FasTC::eCompressionFormat_DXT1, 8 B/block  */
   FASTC_GPU_DXT5 = 1, /* FasTC::eCompressionFormat_DXT5, 16 B/block */
   FASTC_GPU_ETC1 = 2, /* FasTC::eCompressionFormat_ETC1, 8 B/block (rg_etc1 cLowQuality) */
-  FASTC_GPU_BPTC = 3  /* FasTC::eCompressionFormat_BPTC, 16 B/block (BC7) */
+  FASTC_GPU_BPTC = 3, /* FasTC::eCompressionFormat_BPTC, 16 B/block (BC7) */
+  /* FasTC::eCompressionFormat_PVRTC4, 8 B/block, PVRTCC::Compress(job, eWrapMode_Wrap)
+   * (PVRTCEncoder/src/Compressor.cpp:861-944).  Image-level: the texture must be square with a
+   * power-of-two side >= 8 (Core/src/TexComp.cpp:477-482), a call encodes all of it on one GPU
+   * (first_block 0, every block), and blocks are stored in the reference's interleaved (Morton)
+   * order.  Its labelling scan is one serial chain per texture, so it scales over the textures of
+   * a batch, not inside one. */
+  FASTC_GPU_PVRTC4 = 4
 };
 
 /* One texture of a batch submission (CompressionJob: Base/include/FasTC/CompressionJob.h:40-140). */

@@ -47,6 +47,7 @@ FasTC::ECompressionFormat to_format(int f) {
     case 0: return FasTC::eCompressionFormat_DXT1;
     case 1: return FasTC::eCompressionFormat_DXT5;
     case 2: return FasTC::eCompressionFormat_ETC1;
+    case 4: return FasTC::eCompressionFormat_PVRTC4;
     default: return FasTC::eCompressionFormat_BPTC;
   }
 }
@@ -54,7 +55,7 @@ FasTC::ECompressionFormat to_format(int f) {
 
 extern "C" {
 
-// format: 0=DXT1 1=DXT5 2=ETC1 3=BPTC (same numbering as include/fastc_gpu.h)
+// format: 0=DXT1 1=DXT5 2=ETC1 3=BPTC 4=PVRTC4 (same numbering as include/fastc_gpu.h)
 // Returns 0 on success. *ms receives the wall time of the CompressImageData call.
 int fastc_ref_compress(int format, const uint8_t *rgba, uint32_t width,
                        uint32_t height, uint8_t *out, uint32_t out_size,

@@ -15,8 +15,8 @@ ROOT = Path(__file__).resolve().parent.parent
 ORACLE_SO = ROOT / "oracle" / "libfastc_oracle.so"
 REF_SO = ROOT / "oracle" / "_ref" / "libfastc_ref.so"
 
-FMT = {"DXT1": 0, "DXT5": 1, "ETC1": 2, "BPTC": 3}
-BLOCK_BYTES = {"DXT1": 8, "DXT5": 16, "ETC1": 8, "BPTC": 16}
+FMT = {"DXT1": 0, "DXT5": 1, "ETC1": 2, "BPTC": 3, "PVRTC4": 4}
+BLOCK_BYTES = {"DXT1": 8, "DXT5": 16, "ETC1": 8, "BPTC": 16, "PVRTC4": 8}
 
 _u8p = C.POINTER(C.c_uint8)
 
