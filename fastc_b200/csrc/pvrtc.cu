@@ -16,9 +16,10 @@
 //     visit exactly the neighbour states the raster scan gives, wrap-around reads of unvisited
 //     pixels included);
 //   * the backward scan reads the right neighbour AND, at the start of a row, the last pixel of the
-//     row processed before (through the wrap-around): it is one serial chain over all pixels in the
-//     reference, and it is one here -- one thread per label kind (the high and the low labels never
-//     mix).  It bounds the encoder: PVRTC scales over textures (batches), not inside one.
+//     row processed before (through the wrap-around): one serial chain over all pixels in the
+//     reference.  Rows stay sequential here (one CTA per label kind walks them), but inside a row
+//     the distances are a scan over maps on {0..4} and the lists follow in three rounds (see
+//     pvr_backward_rows).
 #include "kernels.h"
 #include "pvrtc_block.cuh"
 
@@ -51,23 +52,134 @@ __global__ void pvr_forward_diag(PixelLabels *labels, const uint8_t *__restrict_
   if (!forward_pixel(labels, w, h, x, yy, cls[wrap((int32_t)yy, h) * w + x])) atomicOr(overflow, 1u);
 }
 
-// LabelImageBackward: the serial chain, block 0 = high labels, block 1 = low labels.
-__global__ void pvr_backward(PixelLabels *labels, uint32_t w, uint32_t h, uint32_t *overflow) {
-  if (threadIdx.x != 0) return;
+// ---- LabelImageBackward.  In the reference this is one serial chain over all pixels: a pixel reads its
+// RIGHT neighbour's new label, and the first pixel of a row reads the last pixel of the row before
+// (wrap-around).  Rows therefore stay sequential here, but a row is parallel:
+//   * the new DISTANCE of a pixel is a function of its right neighbour's new distance alone once the
+//     other four neighbours (row below: final, row above: untouched) are known -- a map on {0..4}.
+//     The row's distances are the running composition of these maps from the row's start: a scan;
+//   * a label LIST taken over from the right neighbour means distance = the neighbour's + 1, and
+//     distances stop at 4, so list dependencies are chains of at most three pixels: the lists are
+//     written in three rounds, new distance 2, then 3, then 4; what a pixel reads from its right
+//     neighbour in its round is final.
+// One CTA per label kind (the high and the low labels never mix), one thread per pixel (per group of
+// pixels for rows wider than the CTA).
+constexpr int kBackThreads = 1024;
+constexpr int kBackMaxPer = 16;  // pixels per thread: rows up to 16384 wide
+
+// a map on {0..4} as five 3-bit fields
+__device__ __forceinline__ uint32_t fn_apply(uint32_t f, uint32_t x) { return (f >> (3 * x)) & 7u; }
+__device__ __forceinline__ uint32_t fn_after(uint32_t g, uint32_t f) {  // x -> g(f(x))
+  uint32_t r = 0;
+#pragma unroll
+  for (int x = 0; x < 5; x++) r |= fn_apply(g, fn_apply(f, x)) << (3 * x);
+  return r;
+}
+constexpr uint32_t kFnIdentity = 0u | (1u << 3) | (2u << 6) | (3u << 9) | (4u << 12);
+
+// DilateLabelBackward's distance rule (:358-388) for own distance c, the smallest positive distance m
+// among the other four neighbours (5: none) and the right neighbour's distance x.  upd: the label is
+// rewritten (distance and list).
+__device__ __forceinline__ uint32_t back_distance(uint32_t c, uint32_t m, uint32_t x, bool &upd) {
+  upd = false;
+  if (c == 1) return 1;
+  const uint32_t md = (x > 0 && x < m) ? x : m;
+  const uint32_t nd = md + 1;
+  if ((c != 0 && c < nd) || nd > 4) return c;
+  upd = true;
+  return nd;
+}
+
+__global__ void __launch_bounds__(kBackThreads)
+pvr_backward_rows(PixelLabels *labels, uint32_t w, uint32_t h, uint32_t *overflow) {
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_prev[kBackThreads];  // composition of everything before thread t's pixels
+  __shared__ Label s_first_right;            // column 0's label as the row's first pixel sees it
   const bool high = blockIdx.x == 0;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nthreads = blockDim.x;
+  // pixels per thread (rows narrower than a warp leave the upper lanes without pixels: identity maps)
+  const uint32_t per = (uint32_t)tid < w ? (w >= (uint32_t)nthreads ? w / (uint32_t)nthreads : 1u) : 0u;
+  const uint32_t k0 = (uint32_t)tid * (w >= (uint32_t)nthreads ? w / (uint32_t)nthreads : 1u);
+  auto lab = [&](uint32_t idx) -> Label & { return high ? labels[idx].high : labels[idx].low; };
   bool ok = true;
   for (int32_t j = (int32_t)h + 2; j >= 0; j--) {
     const uint32_t r = wrap(j, h) * w, ra = wrap(j - 1, h) * w, rb = wrap(j + 1, h) * w;
-    for (int32_t i = (int32_t)w - 1; i >= 0; i--) {
-      const uint32_t xr = wrap(i + 1, w), xl = wrap(i - 1, w);
-      PixelLabels &l = labels[r + (uint32_t)i];
-      Label &me = high ? l.high : l.low;
-      if (me.distance == 1) continue;
-      const PixelLabels *nb[5] = {&labels[ra + xr], &labels[r + xr], &labels[rb + xr], &labels[rb + (uint32_t)i], &labels[rb + xl]};
-      const Label *n5[5];
-      for (int q = 0; q < 5; q++) n5[q] = high ? &nb[q]->high : &nb[q]->low;
-      ok = dilate_backward(me, n5) && ok;
+    // ---- the maps of this thread's pixels (processing position k = tid * per + q, column w - 1 - k)
+    uint8_t own[kBackMaxPer], others[kBackMaxPer];
+    uint32_t f_chunk = kFnIdentity;
+    for (uint32_t q = 0; q < per; q++) {
+      const uint32_t i = w - 1 - (k0 + q), xr = wrap((int32_t)i + 1, w), xl = wrap((int32_t)i - 1, w);
+      const uint32_t c = lab(r + i).distance;
+      const uint32_t d0 = lab(ra + xr).distance, d2 = lab(rb + xr).distance, d3 = lab(rb + i).distance, d4 = lab(rb + xl).distance;
+      uint32_t m = 5;
+      if (d0 > 0 && d0 < m) m = d0;
+      if (d2 > 0 && d2 < m) m = d2;
+      if (d3 > 0 && d3 < m) m = d3;
+      if (d4 > 0 && d4 < m) m = d4;
+      own[q] = (uint8_t)c; others[q] = (uint8_t)m;
+      uint32_t f = 0;
+      bool upd;
+#pragma unroll
+      for (uint32_t x = 0; x < 5; x++) f |= back_distance(c, m, x, upd) << (3 * x);
+      f_chunk = fn_after(f, f_chunk);
     }
+    if (tid == 0) s_first_right = lab(r + 0);  // pre-state: column 0 is the row's LAST pixel
+    // ---- exclusive scan of the maps over the threads
+    uint32_t f_incl = f_chunk;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t up = __shfl_up_sync(0xffffffffu, f_incl, d);
+      if (lane >= d) f_incl = fn_after(f_incl, up);
+    }
+    if (lane == 31) s_warp[wid] = f_incl;
+    __syncthreads();
+    if (wid == 0) {
+      uint32_t v = lane < (nthreads >> 5) ? s_warp[lane] : kFnIdentity;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v = fn_after(v, up);
+      }
+      s_warp[lane] = v;  // inclusive over warps
+    }
+    __syncthreads();
+    {
+      uint32_t f_excl = __shfl_up_sync(0xffffffffu, f_incl, 1);
+      if (lane == 0) f_excl = kFnIdentity;
+      if (wid > 0) f_excl = fn_after(f_excl, s_warp[wid - 1]);
+      s_prev[tid] = f_excl;
+    }
+    // the right neighbour of the row's first pixel is column 0 in its pre-state
+    uint32_t x = fn_apply(s_prev[tid], s_first_right.distance);
+    // ---- new distances of this thread's pixels, and which are rewritten (with what round)
+    uint8_t right[kBackMaxPer], round[kBackMaxPer];
+    for (uint32_t q = 0; q < per; q++) {
+      bool upd;
+      const uint32_t nd = back_distance(own[q], others[q], x, upd);
+      right[q] = (uint8_t)x;
+      round[q] = upd ? (uint8_t)nd : 0;
+      x = nd;
+    }
+    // ---- the lists, in rounds of the new distance
+    for (uint32_t rnd = 2; rnd <= 4; rnd++) {
+      __syncthreads();
+      for (uint32_t q = 0; q < per; q++) {
+        if (round[q] != rnd) continue;
+        const uint32_t k = k0 + q, i = w - 1 - k, xr = wrap((int32_t)i + 1, w), xl = wrap((int32_t)i - 1, w);
+        Label &me = lab(r + i);
+        const uint32_t md = rnd - 1;
+        if (me.distance != rnd) me.nLabels = 0;
+        const Label *nb[5] = {&lab(ra + xr), k == 0 ? &s_first_right : &lab(r + xr), &lab(rb + xr), &lab(rb + i), &lab(rb + xl)};
+        for (int n = 0; n < 5; n++) {
+          const uint32_t dn = n == 1 ? right[q] : nb[n]->distance;
+          if (dn != md) continue;
+          const uint32_t cnt = nb[n]->nLabels;
+          for (uint32_t e = 0; e < cnt; e++) ok = add_idx(me, nb[n]->idxs[e]) && ok;  // Combine
+        }
+        me.distance = (uint8_t)rnd;
+      }
+    }
+    __syncthreads();
   }
   if (!ok) atomicOr(overflow, 1u);
 }
@@ -134,7 +246,7 @@ cudaError_t launch_pvrtc(PvrtcWorkspace &ws, const void *rgba_dev, uint32_t widt
     pvr_forward_diag<<<(count + 127) / 128, 128, 0, stream>>>(labels, cls, w, h, t, yy0, count, flag);
     nl++;
   }
-  pvr_backward<<<2, 32, 0, stream>>>(labels, w, h, flag);
+  pvr_backward_rows<<<2, std::max<uint32_t>(32u, std::min<uint32_t>(w, kBackThreads)), 0, stream>>>(labels, w, h, flag);
   pvr_low_high<<<(nb + 127) / 128, 128, 0, stream>>>(labels, intensity, img, w, h, fields);
   pvr_modulate<<<(nb + 127) / 128, 128, 0, stream>>>(fields, img, w, h, static_cast<uint2 *>(out_dev));
   nl += 3;
