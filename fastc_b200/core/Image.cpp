@@ -95,6 +95,7 @@ int GpuFormatOf(FasTC::ECompressionFormat f) {
     case FasTC::eCompressionFormat_DXT5: return FASTC_GPU_DXT5;
     case FasTC::eCompressionFormat_ETC1: return FASTC_GPU_ETC1;
     case FasTC::eCompressionFormat_BPTC: return FASTC_GPU_BPTC;
+    case FasTC::eCompressionFormat_PVRTC4: return FASTC_GPU_PVRTC4;
     default: return -1;
   }
 }

@@ -37,6 +37,7 @@ int GpuFormat(ECompressionFormat f) {
     case FasTC::eCompressionFormat_DXT5: return FASTC_GPU_DXT5;
     case FasTC::eCompressionFormat_ETC1: return FASTC_GPU_ETC1;
     case FasTC::eCompressionFormat_BPTC: return FASTC_GPU_BPTC;
+    case FasTC::eCompressionFormat_PVRTC4: return FASTC_GPU_PVRTC4;
     default: return -1;
   }
 }
@@ -132,8 +133,13 @@ bool ValidateRequest(const SCompressionSettings &settings, uint32 width, uint32 
     return false;
   }
   if (GpuFormat(settings.format) < 0 || settings.bUsePVRTexLib || settings.bUseNVTT) {
-    // PVRTC couples neighbouring blocks and ASTC has no encoder in FasTC either
+    // PVRTC2 and ASTC have no encoder in FasTC either; the external libraries are not linked
     ReportError("Could not find adequate compression function for specified settings");
+    return false;
+  }
+  if (settings.format == FasTC::eCompressionFormat_PVRTC4 &&
+      (width != height || (width & (width - 1)) != 0 || width < 8)) {  // reference TexComp.cpp:477-482
+    ReportError("ERROR - CompressImageData: PVRTC4 images must be square and power-of-two.");
     return false;
   }
   if (settings.iQuality < 0) {

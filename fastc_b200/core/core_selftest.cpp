@@ -93,8 +93,13 @@ static int TestApi() {
   CHECK(!CompressImageData(img.data(), 6, 8, cmp.data(), 64, st));
   CHECK(!CompressImageData(img.data(), 8, 8, cmp.data(), 8, st));
   CHECK(!CompressImageData(img.data(), 0, 8, cmp.data(), 64, st));
-  st.format = eCompressionFormat_PVRTC4;
+  st.format = eCompressionFormat_PVRTC2;  // no encoder in FasTC
   CHECK(!CompressImageData(img.data(), 8, 8, cmp.data(), 64, st));
+  {  // PVRTC4: square power-of-two images only (reference TexComp.cpp:477-482)
+    st.format = eCompressionFormat_PVRTC4;
+    std::vector<uint8> wide(16 * 8 * 4, 0), wcmp(64, 0);
+    CHECK(!CompressImageData(wide.data(), 16, 8, wcmp.data(), 64, st));
+  }
   st.format = eCompressionFormat_ASTC4x4;
   CHECK(!CompressImageData(img.data(), 8, 8, cmp.data(), 64, st));
   CHECK(CompressImage<FasTC::Pixel>(NULL, st) == NULL);

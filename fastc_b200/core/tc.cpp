@@ -1,8 +1,8 @@
 // `tc`: the command-line front end.  Flag surface, defaults, stdout lines and exit codes of
 // reference CLTool/src/tc.cpp:40-346 (`-f -q -n -d -nd -t -j -a -l -v -simd -h`), driving
 // the GPU library through CompressImage.  Additions: `-g N` shards over N GPUs (0 = all),
-// `-s SEED` pins the annealing RNG key.  Differences: PVRTC / *Lib formats are rejected
-// (no GPU encoder), `-l` and `-v` statistics are accepted and ignored, input is PNG (8-bit, non-interlaced) / TGA / KTX.
+// `-s SEED` pins the annealing RNG key.  Differences: the *Lib formats (PVRTexLib, NVTT) are rejected
+// (external libraries), `-l` and `-v` statistics are accepted and ignored, input is PNG (8-bit, non-interlaced) / TGA / KTX.
 #include <algorithm>
 #include <cstdio>
 #include <fstream>
@@ -18,7 +18,7 @@ static void PrintUsage() {
   fprintf(stderr, "Usage: tc [OPTIONS] imagefile\n");
   fprintf(stderr, "\n");
   fprintf(stderr, "\t-v\t\tVerbose mode (accepted; image statistics are not computed)\n");
-  fprintf(stderr, "\t-f <fmt>\tFormat to use. Either \"BPTC\", \"ETC1\", \"DXT1\" or \"DXT5\".\n");
+  fprintf(stderr, "\t-f <fmt>\tFormat to use. Either \"BPTC\", \"ETC1\", \"DXT1\", \"DXT5\" or \"PVRTC\".\n");
   fprintf(stderr, "\t\t\tDefault: BPTC\n");
   fprintf(stderr, "\t-l\t\tSave an output log (<basename>.log: BPTC per-block path / mode / errors).\n");
   fprintf(stderr, "\t-d <file>\tSpecify decompressed output (default: basename-<fmt>.png); .ktx stores the compressed payload\n");
@@ -88,7 +88,8 @@ int main(int argc, char **argv) {
       else if (!strcmp(f, "DXT1")) format = FasTC::eCompressionFormat_DXT1;
       else if (!strcmp(f, "DXT5")) format = FasTC::eCompressionFormat_DXT5;
       else if (!strcmp(f, "BPTC")) format = FasTC::eCompressionFormat_BPTC;
-      else if (!strcmp(f, "PVRTC") || !strcmp(f, "PVRTCLib") || !strcmp(f, "BPTCLib")) bFormatOk = false;
+      else if (!strcmp(f, "PVRTC")) format = FasTC::eCompressionFormat_PVRTC4;
+      else if (!strcmp(f, "PVRTCLib") || !strcmp(f, "BPTCLib")) bFormatOk = false;
       // any other string silently keeps the current format, like the reference (tc.cpp:121-148)
     } else if (!strcmp(a, "-h") || !strcmp(a, "--help")) {
       PrintUsage();
@@ -109,7 +110,7 @@ int main(int argc, char **argv) {
     exit(1);
   }
   if (!bFormatOk) {
-    fprintf(stderr, "TexComp -- PVRTC and the external-library encoders are not supported on the GPU path\n");
+    fprintf(stderr, "TexComp -- the external-library encoders (PVRTCLib, BPTCLib) are not supported on the GPU path\n");
     return 1;
   }
 
@@ -160,6 +161,7 @@ int main(int argc, char **argv) {
       const char *suffix = format == FasTC::eCompressionFormat_BPTC   ? "-bptc.png"
                            : format == FasTC::eCompressionFormat_DXT1 ? "-dxt1.png"
                            : format == FasTC::eCompressionFormat_DXT5 ? "-dxt5.png"
+                           : format == FasTC::eCompressionFormat_PVRTC4 ? "-pvrtc-4bpp.png"
                                                                       : "-etc1.png";
       snprintf(outname, sizeof(outname), "%s%s", basename, suffix);
     }

@@ -1050,8 +1050,12 @@ int fastc_gpu_decompress_device(int format, const void *cmp_dev, uint32_t width,
   int dev = 0;
   if (current_device(&dev)) return 1;
   if (ensure_tables(dev)) return 1;
-  CU_TRY(launch_decode(format, cmp_dev, width, 0, (width / 4) * (height / 4), rgba_out_dev,
-                       static_cast<cudaStream_t>(cuda_stream)));
+  if (format == FASTC_GPU_PVRTC4)
+    CU_TRY(launch_pvrtc_decode(cmp_dev, width, height, 0, (width / 4) * (height / 4), rgba_out_dev,
+                               static_cast<cudaStream_t>(cuda_stream)));
+  else
+    CU_TRY(launch_decode(format, cmp_dev, width, 0, (width / 4) * (height / 4), rgba_out_dev,
+                         static_cast<cudaStream_t>(cuda_stream)));
   return 0;
 }
 
@@ -1074,7 +1078,10 @@ int fastc_gpu_decompress(int format, const uint8_t *cmp_host, uint32_t width, ui
   if (grow(&c.out_buf[0], &c.out_cap[0], cmp_bytes)) return 1;
   CU_TRY(cudaMemcpyAsync(c.out_buf[0], cmp_host, cmp_bytes, cudaMemcpyHostToDevice, st));
   CU_TRY(cudaEventRecord(c.ev_start[0], st));
-  CU_TRY(launch_decode(format, c.out_buf[0], width, 0, (width / 4) * (height / 4), c.in_buf[0], st));
+  if (format == FASTC_GPU_PVRTC4)
+    CU_TRY(launch_pvrtc_decode(c.out_buf[0], width, height, 0, (width / 4) * (height / 4), c.in_buf[0], st));
+  else
+    CU_TRY(launch_decode(format, c.out_buf[0], width, 0, (width / 4) * (height / 4), c.in_buf[0], st));
   CU_TRY(cudaEventRecord(c.ev_stop[0], st));
   CU_TRY(cudaMemcpyAsync(rgba_out_host, c.in_buf[0], out_bytes, cudaMemcpyDeviceToHost, st));
   CU_TRY(cudaStreamSynchronize(st));

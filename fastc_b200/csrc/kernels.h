@@ -29,6 +29,8 @@ struct PvrtcWorkspace {
 void pvrtc_free_workspace(PvrtcWorkspace &ws);
 cudaError_t launch_pvrtc(PvrtcWorkspace &ws, const void *rgba_dev, uint32_t width, uint32_t height, void *out_dev,
                          cudaStream_t stream, uint32_t *launches);
+cudaError_t launch_pvrtc_decode(const void *cmp_dev, uint32_t width, uint32_t height, uint32_t first_block,
+                                uint32_t num_blocks, void *rgba_dev, cudaStream_t stream);
 
 // Decoders + PSNR (decode.cu).  format: include/fastc_gpu.h numbering.
 cudaError_t launch_decode(int format, const void *cmp_dev, uint32_t width, uint32_t first_block, uint32_t num_blocks,

@@ -203,9 +203,27 @@ __global__ void pvr_modulate(const uint32_t *__restrict__ fields, const uint32_t
   out[block_index(bx, by)] = make_uint2(modulation_block(fields, img, w, h, bx, by), fields[b]);
 }
 
+// decoder: one thread per pixel of the block range
+__global__ void pvr_decode(const uint2 *__restrict__ blocks, uint32_t w, uint32_t h, uint32_t first_block, uint32_t num_blocks,
+                           uint32_t *__restrict__ out) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= num_blocks * 16) return;
+  const uint32_t b = first_block + (t >> 4), bw = w >> 2;
+  const uint32_t i = (b % bw) * 4 + (t & 3), j = (b / bw) * 4 + ((t >> 2) & 3);
+  out[(size_t)j * w + i] = decode_pixel(blocks, w, h, i, j);
+}
+
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 }  // namespace
+
+cudaError_t launch_pvrtc_decode(const void *cmp_dev, uint32_t width, uint32_t height, uint32_t first_block,
+                                uint32_t num_blocks, void *rgba_dev, cudaStream_t stream) {
+  if (num_blocks == 0) return cudaSuccess;
+  pvr_decode<<<(num_blocks * 16 + 255) / 256, 256, 0, stream>>>(static_cast<const uint2 *>(cmp_dev), width, height, first_block,
+                                                                num_blocks, static_cast<uint32_t *>(rgba_dev));
+  return cudaGetLastError();
+}
 
 void pvrtc_free_workspace(PvrtcWorkspace &ws) {
   if (ws.base) cudaFree(ws.base);

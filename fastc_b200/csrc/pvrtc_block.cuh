@@ -22,6 +22,7 @@
 #else
 #include <math.h>
 #define PVR_HD inline
+struct uint2 { uint32_t x, y; };
 #endif
 
 namespace fastc {
@@ -428,5 +429,42 @@ PVR_HD uint32_t modulation_block(const uint32_t *fields, const uint32_t *pixels,
   return bits;
 }
 
+
+// ---- decoder: PVRTCC::Decompress (Decompressor.cpp:245-352) for 4bpp, one pixel.
+// blocks: the compressed texture (Morton order).  BilinearUpscale(2, 2) + ExpandTo8888
+// (PVRTCImage.cpp:94-160, :437-462) are the encoder's BilerpPixels with x = (i + 2) % 4 between the
+// blocks (i + 2) / 4 - 1 and (i + 2) / 4; then Decompress4BPP (:52-118) incl. the punch-through mode.
+PVR_HD uint32_t decode_pixel(const uint2 *blocks, uint32_t w, uint32_t h, uint32_t i, uint32_t j) {
+  const uint32_t bw = w >> 2, bh = h >> 2;
+  const uint32_t hx = wrap((int32_t)((i + 2) >> 2), bw), lx = wrap((int32_t)((i + 2) >> 2) - 1, bw);
+  const uint32_t hy = wrap((int32_t)((j + 2) >> 2), bh), ly = wrap((int32_t)((j + 2) >> 2) - 1, bh);
+  const uint32_t x = (i + 2) & 3, y = (j + 2) & 3;
+  const uint32_t ftl = blocks[block_index(lx, ly)].y, ftr = blocks[block_index(hx, ly)].y;
+  const uint32_t fbl = blocks[block_index(lx, hy)].y, fbr = blocks[block_index(hx, hy)].y;
+  int tl[4], tr[4], bl[4], br[4], ca[4], cb[4];
+  decode_4555(ftl >> 16, 0, tl); decode_4555(ftr >> 16, 0, tr); decode_4555(fbl >> 16, 0, bl); decode_4555(fbr >> 16, 0, br);
+  bilerp(x, y, tl, tr, bl, br, ca);
+  decode_4555(ftl & 0xFFFF, 1, tl); decode_4555(ftr & 0xFFFF, 1, tr); decode_4555(fbl & 0xFFFF, 1, bl); decode_4555(fbr & 0xFFFF, 1, br);
+  bilerp(x, y, tl, tr, bl, br, cb);
+  const uint2 b = blocks[block_index(i >> 2, j >> 2)];
+  uint32_t mod = (b.x >> (2 * ((j & 3) * 4 + (i & 3)))) & 3u;
+  bool punch = false;
+  int lerp;
+  if (b.y & 1u) {  // mode bit: {8, 4, punch-through 4, 0}
+    if (mod >= 2) { punch = mod == 2; mod -= 1; }
+    lerp = mod == 0 ? 8 : (mod == 1 ? 4 : 0);
+  } else {
+    lerp = mod == 0 ? 8 : (mod == 1 ? 5 : (mod == 2 ? 3 : 0));
+  }
+  int res[4];
+  for (int c = 0; c < 4; c++) res[c] = (int)(int16_t)((int16_t)(ca[c] * (8 - lerp)) + (int16_t)(cb[c] * lerp)) / 8;
+  if (punch) res[0] = 0;
+  // Pixel::Pack: a << 24 | b << 16 | g << 8 | r (the shifts carry any bits above 8 upwards)
+  uint32_t r = (uint32_t)(uint16_t)res[0];
+  r = (r << 8) | (uint32_t)(uint16_t)res[3];
+  r = (r << 8) | (uint32_t)(uint16_t)res[2];
+  r = (r << 8) | (uint32_t)(uint16_t)res[1];
+  return r;
+}
 }  // namespace pvr
 }  // namespace fastc

@@ -12,6 +12,7 @@
 
 #include "pvrtc_block.cuh"
 
+extern "C" int fastc_ref_decompress(int format, const uint8_t *cmp, uint32_t width, uint32_t height, uint8_t *rgba_out);
 extern "C" int fastc_ref_compress(int format, const uint8_t *rgba, uint32_t width, uint32_t height, uint8_t *out,
                                   uint32_t out_size, int quality, int threads, int job_size, double *ms);
 
@@ -55,7 +56,18 @@ int main(int argc, char **argv) {
     bad += got[b] != want[b];
     bad_col += (got[b] >> 32) != (want[b] >> 32);
   }
-  printf("blocks %u mismatches %u (colour fields %u) label lists %s\n", nb, bad, bad_col, ok ? "ok" : "OVERFLOWED");
+  // the decoder, on the reference's blocks, against the reference's decoder
+  std::vector<uint32_t> dec_want((size_t)w * h), dec_got((size_t)w * h);
+  if (fastc_ref_decompress(4, reinterpret_cast<const uint8_t *>(want.data()), w, h, reinterpret_cast<uint8_t *>(dec_want.data()))) return 5;
+  uint32_t bad_px = 0;
+  for (uint32_t j = 0; j < h; j++)
+    for (uint32_t i = 0; i < w; i++) {
+      dec_got[j * w + i] = decode_pixel(reinterpret_cast<const uint2 *>(want.data()), w, h, i, j);
+      bad_px += dec_got[j * w + i] != dec_want[j * w + i];
+    }
+  bad += bad_px;
+  printf("blocks %u mismatches %u (colour fields %u) label lists %s decoded pixels differing %u\n", nb, bad - bad_px, bad_col,
+         ok ? "ok" : "OVERFLOWED", bad_px);
   if (bad && argc > 3)
     for (uint32_t b = 0, shown = 0; b < nb && shown < 8; b++)
       if (got[b] != want[b]) { printf("  block %u: got %016llx want %016llx\n", b, (unsigned long long)got[b], (unsigned long long)want[b]); shown++; }

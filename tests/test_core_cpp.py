@@ -57,8 +57,10 @@ def test_tc_cli_argument_handling(tmp_path):
     assert _run([TC, tmp_path / "missing.tga"]).returncode == 1
     img = synth_rgba(16, 8, 1)
     write_tga(tmp_path / "a.tga", img)
-    r = _run([TC, "-f", "PVRTC", tmp_path / "a.tga"])
+    r = _run([TC, "-f", "PVRTCLib", tmp_path / "a.tga"])
     assert r.returncode == 1 and "not supported on the GPU path" in r.stderr
+    r = _run([TC, "-f", "PVRTC", "-nd", tmp_path / "a.tga"])  # 16 x 8: the reference's own size check
+    assert r.returncode == 1 and "PVRTC4 images must be square and power-of-two" in r.stderr
     r = _run([TC, "-simd", "-nd", tmp_path / "a.tga"])  # rejected before any GPU work
     assert r.returncode == 1 and "Platform does not support SIMD!" in r.stderr
 
@@ -268,3 +270,17 @@ def test_tc_l_writes_the_per_block_log(gpu, oracle, tmp_path):
         assert blk[1] == f"{i}: BlockStat_Mode -- {modes[i]}"
         assert blk[0].startswith(f"{i}: BlockStat_Path -- ")
         assert blk[2] == f"{i}: BlockStat_ModeZeroEstimate -- -1"
+
+
+@pytest.mark.gpu
+def test_tc_cli_pvrtc_end_to_end(gpu, tmp_path):
+    """tc -f PVRTC: compress, decode, PSNR line, decoded PNG written (the decode equals the reference's decoder
+    on the reference's blocks, tests/test_gpu_pvrtc.py)."""
+    img = synth_rgba(128, 128, 2)
+    write_tga(tmp_path / "p.tga", img)
+    out = tmp_path / "p-dec.png"
+    r = _run([TC, "-f", "PVRTC", "-d", out, tmp_path / "p.tga"])
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Compression time: " in r.stdout and "PSNR: " in r.stdout and out.exists()
+    psnr = float(r.stdout.split("PSNR: ")[1].split()[0])
+    assert 15.0 < psnr < 60.0

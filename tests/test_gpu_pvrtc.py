@@ -75,3 +75,15 @@ def test_pvrtc_rejects_what_the_reference_rejects(gpu):
             gpu.compress(F.PVRTC4, np.zeros(shape, np.uint8), out)
     with pytest.raises(FastcGpuError):  # block ranges make no sense for an image-level encoder
         gpu.compress(F.PVRTC4, np.zeros((64, 64, 4), np.uint8), out, first_block=4, num_blocks=8)
+
+
+def test_pvrtc_decoder_matches_reference_decoder(gpu, ref):
+    for size, seed in ((64, 2), (256, 1)):
+        img = synth_rgba(size, size, seed)
+        cmp_ref, _ = ref.compress("PVRTC4", img, seed=None)
+        want = np.zeros((size, size, 4), np.uint8)
+        assert ref.lib.fastc_ref_decompress(4, cmp_ref.ctypes.data_as(__import__("ctypes").POINTER(__import__("ctypes").c_uint8)),
+                                            size, size, want.ctypes.data_as(__import__("ctypes").POINTER(__import__("ctypes").c_uint8))) == 0
+        got = gpu.decompress(F.PVRTC4, cmp_ref, size, size)
+        got = got[0] if isinstance(got, tuple) else got
+        assert np.array_equal(np.asarray(got).reshape(size, size, 4), want)
