@@ -325,7 +325,7 @@ def other_configs(g, dev, flush, hbm_peak, reps=3):
     nblk = (size // 4) ** 2
     h_pin = _pin(d_in).numpy()
     h_page = np.array(h_pin)
-    for q, qname in ((0, "low"), (2, "high")):
+    for q, qname in ((0, "low"), (2, "high")):  # (low: the dynamically scheduled kernel; high: the quad kernel)
         d_out = torch.zeros(nblk * 8, dtype=torch.uint8, device=dev)
         run = lambda: g.compress_device(F.ETC1, d_in, d_out, width=size, height=size, etc1_quality=q)
         try:
@@ -354,6 +354,36 @@ def other_configs(g, dev, flush, hbm_peak, reps=3):
             "e2e_pageable_gpix_s": size * size / e_page / 1e6, "bit_exact_vs_oracle_sample": exact,
             "sample": f"blocks [{first}, {first + n_s}) vs the oracle; pageable == pinned bytes"}
         del d_out
+    del d_in
+
+    # ---- PVRTC 4bpp, 1024^2 (image-level encoder; the whole texture is compared with the
+    # compiled reference, which is also the CPU time next to it: PVRTCC::Compress is single-threaded)
+    try:
+        from _checkers import Reference
+        size = 1024
+        d_in = synth_rgba_torch(size, size, SEED, device=dev)
+        nblk = (size // 4) ** 2
+        d_out = torch.zeros(nblk * 8, dtype=torch.uint8, device=dev)
+        run = lambda: g.compress_device(F.PVRTC4, d_in, d_out, width=size, height=size)
+        run(); torch.cuda.synchronize()
+        k_min, _ = _time_device(run, reps, flush)
+        h_pin = _pin(d_in).numpy()
+        h_out = _pin(d_out).numpy()
+        g.compress(F.PVRTC4, h_pin, h_out)
+        e_pin, _ = _time_host(lambda: g.compress(F.PVRTC4, h_pin, h_out), reps)
+        entry = {"workload": "PVRTC 4bpp, synthetic 1024x1024 RGBA, 1 GPU", "kernel_ms": k_min,
+                 "kernel_mpix_s": size * size / k_min / 1e3, "e2e_pinned_ms": e_pin,
+                 "e2e_pinned_mpix_s": size * size / e_pin / 1e3,
+                 "note": "the reference's backward labelling scan is one serial chain per texture; here rows stay "
+                         "sequential and a row is a scan (pvrtc.cu): the encoder scales over the textures of a batch"}
+        if Reference.available():
+            want, ref_ms = Reference().compress("PVRTC4", h_pin, seed=None)
+            entry.update({"bit_exact_vs_reference": bool((want == h_out).all()), "reference_cpu_ms": ref_ms,
+                          "reference_cpu_mpix_s": size * size / ref_ms / 1e3, "reference_threads": 1})
+        out["n4_pvrtc4_1024"] = entry
+        del d_in, d_out
+    except Exception as e:  # noqa: BLE001
+        out["n4_pvrtc4_1024"] = {"unavailable": str(e)[:200]}
     return out
 
 
