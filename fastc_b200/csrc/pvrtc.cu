@@ -11,10 +11,10 @@
 //   * intensities, extremum classes, block colours and modulation bits are per-pixel / per-block
 //     work: plain data-parallel kernels;
 //   * the forward scan reads the up and left neighbours: pixels of one anti-diagonal are
-//     independent, so it runs as one launch per anti-diagonal over the (h + 3) x w visits (stream
-//     order is the barrier; for the square images the reference accepts this order gives every
-//     visit exactly the neighbour states the raster scan gives, wrap-around reads of unvisited
-//     pixels included);
+//     independent.  One CTA per label kind walks the anti-diagonals of a band of rows with a barrier
+//     per step (pvr_forward_rows); for the square images the reference accepts this order gives
+//     every visit exactly the neighbour states the raster scan gives, wrap-around reads of
+//     unvisited pixels included;
 //   * the backward scan reads the right neighbour AND, at the start of a row, the last pixel of the
 //     row processed before (through the wrap-around): one serial chain over all pixels in the
 //     reference.  Rows stay sequential here (one CTA per label kind walks them), but inside a row
@@ -43,13 +43,25 @@ __global__ void pvr_classify(const uint8_t *__restrict__ ibyte, uint32_t w, uint
     cls[i] = (uint8_t)classify_extremum(ibyte, w, h, i % w, i / w);
 }
 
-// One anti-diagonal t = x + yy of LabelImageForward's (h + 3) x w visits.
-__global__ void pvr_forward_diag(PixelLabels *labels, const uint8_t *__restrict__ cls, uint32_t w, uint32_t h, uint32_t t,
-                                 uint32_t yy0, uint32_t count, uint32_t *overflow) {
-  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= count) return;
-  const uint32_t yy = yy0 + k, x = t - yy;
-  if (!forward_pixel(labels, w, h, x, yy, cls[wrap((int32_t)yy, h) * w + x])) atomicOr(overflow, 1u);
+// LabelImageForward in one launch: one CTA per label kind, one thread per visited row of a band of up
+// to 1,024 rows; at step s thread t handles column s - t of its row, so its up neighbour (thread
+// t - 1, step s - 1) and left neighbour (itself, step s - 1) are done: the anti-diagonal order of
+// anti-diagonal order of the scan with a CTA barrier per diagonal.  Bands follow each other.
+__global__ void __launch_bounds__(1024)
+pvr_forward_rows(PixelLabels *labels, const uint8_t *__restrict__ cls, uint32_t w, uint32_t h, uint32_t *overflow) {
+  const bool high = blockIdx.x == 0;
+  const uint32_t rows = h + 3, tid = threadIdx.x, nt = blockDim.x;
+  bool ok = true;
+  for (uint32_t band = 0; band < rows; band += nt) {
+    const uint32_t nrows = min(nt, rows - band), yy = band + tid;
+    const uint32_t crow = wrap((int32_t)yy, h) * w;
+    for (uint32_t s = 0; s < w + nrows - 1; s++) {
+      const uint32_t x = s - tid;  // (wraps for s < tid: then x >= w)
+      if (tid < nrows && x < w) ok = forward_pixel_kind(labels, w, h, x, yy, cls[crow + x], high) && ok;
+      __syncthreads();
+    }
+  }
+  if (!ok) atomicOr(overflow, 1u);
 }
 
 // ---- LabelImageBackward.  In the reference this is one serial chain over all pixels: a pixel reads its
@@ -258,12 +270,8 @@ cudaError_t launch_pvrtc(PvrtcWorkspace &ws, const void *rgba_dev, uint32_t widt
   pvr_intensity<<<grid, 256, 0, stream>>>(img, n, intensity, ibyte);
   pvr_classify<<<grid, 256, 0, stream>>>(ibyte, w, h, cls);
   uint32_t nl = 2;
-  for (uint32_t t = 0; t <= (w - 1) + (h + 2); t++) {
-    const uint32_t yy0 = t > w - 1 ? t - (w - 1) : 0, yy1 = std::min(h + 2, t);
-    const uint32_t count = yy1 - yy0 + 1;
-    pvr_forward_diag<<<(count + 127) / 128, 128, 0, stream>>>(labels, cls, w, h, t, yy0, count, flag);
-    nl++;
-  }
+  pvr_forward_rows<<<2, std::min<uint32_t>(1024u, (h + 3 + 31) & ~31u), 0, stream>>>(labels, cls, w, h, flag);
+  nl++;
   pvr_backward_rows<<<2, std::max<uint32_t>(32u, std::min<uint32_t>(w, kBackThreads)), 0, stream>>>(labels, w, h, flag);
   pvr_low_high<<<(nb + 127) / 128, 128, 0, stream>>>(labels, intensity, img, w, h, fields);
   pvr_modulate<<<(nb + 127) / 128, 128, 0, stream>>>(fields, img, w, h, static_cast<uint2 *>(out_dev));

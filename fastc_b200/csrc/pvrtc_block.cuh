@@ -164,6 +164,21 @@ PVR_HD bool forward_pixel(PixelLabels *labels, uint32_t w, uint32_t h, uint32_t 
   return ok;
 }
 
+// The same for one label kind (the high and the low labels never mix)
+PVR_HD bool forward_pixel_kind(PixelLabels *labels, uint32_t w, uint32_t h, uint32_t x, uint32_t yy, int cls, bool high) {
+  const uint32_t y = wrap((int32_t)yy, h);
+  const uint32_t idx0 = y * w + x;
+  Label &l = high ? labels[idx0].high : labels[idx0].low;
+  const bool extremum = cls == (high ? 2 : 1);
+  if (extremum) {
+    l.distance = 1;
+    return add_idx(l, idx0);
+  }
+  const PixelLabels &up = labels[wrap((int32_t)yy - 1, h) * w + x];
+  const PixelLabels &left = labels[y * w + wrap((int32_t)x - 1, w)];
+  return dilate_forward(l, high ? up.high : up.low, high ? left.high : left.low);
+}
+
 // DilateLabelBackward (:358-404)
 PVR_HD bool dilate_backward(Label &l, const Label *const nbs[5]) {
   if (l.distance == 1) return true;
