@@ -203,37 +203,32 @@ __device__ __forceinline__ bool optimize(const uint32_t (&px)[8], bool color4, b
 }
 
 // evaluate_solution (rg_etc1.cpp:1674-1765): every selector of every intensity table for every
-// pixel, first strict minimum in ascending selector / table order.
-__device__ __forceinline__ void evaluate_full(const uint32_t (&px)[8], const uint32_t (&p2)[8], uint32_t color,
-                                              bool color4, Sol &trial) {
+// pixel, first strict minimum in ascending selector / table order.  Per pixel the four squared
+// distances (VABSDIFF4 + DP4A, < 2^18) become keys distance * 4 + selector, so one min over the
+// keys picks the distance and the selector together, the lower selector on ties.
+__device__ __forceinline__ void evaluate_full(const uint32_t (&px)[8], uint32_t color, bool color4, Sol &trial) {
   const uint32_t base = scale_color(color, color4);
-  const int b0 = base & 0xFF, b1 = (base >> 8) & 0xFF, b2 = (base >> 16) & 0xFF;
+  const uint32_t base_rb = (base & 0xFFu) | ((base & 0xFF0000u));
+  const int base_g = (base >> 8) & 0xFF;
   trial.err = 0xFFFFFFFFu;
   trial.color = color;
   trial.inten = 0;
   trial.sel = 0;
 #pragma unroll 1
   for (int it = 0; it < 8; it++) {
-    uint32_t bc[4], bc2[4];
-#pragma unroll
-    for (int s = 0; s < 4; s++) {
-      const int yd = c_inten[it][s];
-      const uint32_t r = clamp255(b0 + yd), g = clamp255(b1 + yd), b = clamp255(b2 + yd);
-      bc[s] = r | (g << 8) | (b << 16);
-      bc2[s] = __dp4a(bc[s], bc[s], 0u);
-    }
+    uint32_t bc[4], bi[4];
+    table_colors(base_rb, base_g, it, bc, bi);
     uint32_t total = 0, sel = 0;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-      // distances relative to |p|^2 (added once below): the comparison order is unchanged
-      uint32_t be = bc2[0] - 2u * __dp4a(px[i], bc[0], 0u) + p2[i], bs = 0;
+      uint32_t key = 0xFFFFFFFFu;
 #pragma unroll
-      for (uint32_t s2 = 1; s2 < 4; s2++) {
-        const uint32_t e = bc2[s2] - 2u * __dp4a(px[i], bc[s2], 0u) + p2[i];
-        if (e < be) { be = e; bs = s2; }
+      for (uint32_t s2 = 0; s2 < 4; s2++) {
+        const uint32_t d = __vabsdiffu4(px[i], bc[s2]);
+        key = min(key, __dp4a(d, d, 0u) * 4u + s2);
       }
-      total += be;
-      sel |= bs << (2 * i);
+      total += key >> 2;
+      sel |= (key & 3u) << (2 * i);
     }
     // (the reference's running "total >= trial error" break only skips work: a table that triggers
     // it is never accepted)
@@ -249,7 +244,7 @@ __device__ __forceinline__ void evaluate_full(const uint32_t (&px)[8], const uin
 // of scan deltas (rg_etc1.cpp:1483-1625, :2283-2340); the running best survives between the calls.
 template <int Q>
 struct Optimizer {
-  uint32_t px[8], p2[8], luma2[8];
+  uint32_t px[8], luma2[8];
   uint32_t lmin, lmax, base5;
   float avg[3];
   int m[3], limit;
@@ -270,7 +265,6 @@ struct Optimizer {
       lmin = min(lmin, l);
       lmax = max(lmax, l);
       luma2[i] = 2 * l;
-      p2[i] = __dp4a(px[i], px[i], 0u);
     }
     const float flimit = (float)limit;
     avg[0] = __fmul_rn((float)sr, 0.125f); avg[1] = __fmul_rn((float)sg, 0.125f); avg[2] = __fmul_rn((float)sb, 0.125f);
@@ -292,7 +286,7 @@ struct Optimizer {
     if (!allowed(r, g, b)) return false;
     const uint32_t col = (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16);
     Sol t;
-    if (Q == 2) evaluate_full(px, p2, col, color4, t);
+    if (Q == 2) evaluate_full(px, col, color4, t);
     else evaluate(px, luma2, lmin, lmax, col, color4, t);
     if (t.err < best.err) { best = t; valid = true; return true; }
     return false;
