@@ -2343,6 +2343,7 @@ bc7_anneal(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
       }
       // ... and the warp loads the new chains' pixels together: lane i < 16 fetches pixel i of the
       // block and stores it at its rank within the subset mask, into the owner lane's column
+      __syncwarp();  // (the columns written below were read by their owners' last steps)
       unsigned gm = __ballot_sync(full, got);
       while (gm) {
         const int owner = __ffs(gm) - 1;
