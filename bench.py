@@ -381,6 +381,18 @@ def other_configs(g, dev, flush, hbm_peak, reps=3):
             want, ref_ms = Reference().compress("PVRTC4", h_pin, seed=None)
             entry.update({"bit_exact_vs_reference": bool((want == h_out).all()), "reference_cpu_ms": ref_ms,
                           "reference_cpu_mpix_s": size * size / ref_ms / 1e3, "reference_threads": 1})
+        # a batch: the textures are encoded side by side (grid.y = texture of a run of equal sizes)
+        nb_, bs_ = 64, 512
+        bimgs = [_pin(synth_rgba_torch(bs_, bs_, k + 1, device=dev)).numpy() for k in range(nb_)]
+        g.compress_batch(F.PVRTC4, bimgs[:2])
+        b_ms, _ = _time_host(lambda: g.compress_batch(F.PVRTC4, bimgs), reps)
+        entry["batch_64x512"] = {"e2e_pinned_ms": b_ms, "e2e_mpix_s": nb_ * bs_ * bs_ / b_ms / 1e3}
+        if Reference.available():
+            outs, _ = g.compress_batch(F.PVRTC4, bimgs)
+            wantb, refb_ms = Reference().compress("PVRTC4", bimgs[-1], seed=None)
+            entry["batch_64x512"].update({"bit_exact_vs_reference_last": bool((outs[-1] == wantb).all()),
+                                          "reference_cpu_ms_per_texture": refb_ms,
+                                          "reference_cpu_mpix_s_one_core": bs_ * bs_ / refb_ms / 1e3})
         out["n4_pvrtc4_1024"] = entry
         del d_in, d_out
     except Exception as e:  # noqa: BLE001

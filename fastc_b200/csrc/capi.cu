@@ -190,7 +190,7 @@ int enqueue(int dev, int format, const void *rgba_dev, uint32_t width, uint32_t 
       // one scratch per device: order this use after the previous one, whatever its stream
       if (!c.pvr_done) CU_TRY(cudaEventCreateWithFlags(&c.pvr_done, cudaEventDisableTiming));
       if (c.pvr_used) CU_TRY(cudaStreamWaitEvent(stream, c.pvr_done, 0));
-      CU_TRY(launch_pvrtc(c.pvrws, rgba_dev, width, height, out_dev, stream, &n));
+      CU_TRY(launch_pvrtc(c.pvrws, rgba_dev, width, height, 1, out_dev, stream, &n));
       CU_TRY(cudaEventRecord(c.pvr_done, stream));
       c.pvr_used = true;
       break;
@@ -925,6 +925,52 @@ int compress_batch_impl(int format, const fastc_gpu_job *jobs, uint32_t num_jobs
     if (num_gpus == 1) cudaGetDevice(&dev);
     if (dev < 0 || dev >= kMaxDevices) { rcs[g] = 1; errs[g] = "bad device"; return; }
     std::lock_guard<std::mutex> lk(g_ctx[dev].host_mu);
+    if (format == FASTC_GPU_PVRTC4) {
+      // PVRTC: a texture is (nearly) a serial job for two CTAs, so the textures of a batch are encoded
+      // SIDE BY SIDE: runs of equally sized jobs go through the kernels together (grid.y = texture),
+      // as many at a time as fit ~8 GiB of scratch.
+      if (ensure_ctx(dev)) { rcs[g] = 1; errs[g] = tl_error; return; }
+      DeviceCtx &c = g_ctx[dev];
+      cudaStream_t st = c.streams[0];
+      std::vector<uint32_t> mine;
+      for (uint32_t j = g; j < num_jobs; j += num_gpus) mine.push_back(j);
+      auto failed = [&]() { rcs[g] = 1; errs[g] = tl_error; abort_slots(c); };
+      for (size_t a = 0; a < mine.size();) {
+        const uint32_t w = jobs[mine[a]].width, h = jobs[mine[a]].height;
+        const size_t in_b = (size_t)w * h * 4, out_b = (size_t)(w / 4) * (h / 4) * 8;
+        const size_t cap = std::max<size_t>(1, std::min<size_t>(((size_t)8 << 30) / pvrtc_scratch_bytes(w, h), 0xFFFFFFFFull / ((size_t)w * h)));
+        size_t b = a;
+        while (b < mine.size() && b - a < cap && jobs[mine[b]].width == w && jobs[mine[b]].height == h) b++;
+        const uint32_t n = (uint32_t)(b - a);
+        if (cudaStreamSynchronize(st) != cudaSuccess || grow(&c.in_buf[0], &c.in_cap[0], in_b * n) ||
+            grow(&c.out_buf[0], &c.out_cap[0], out_b * n)) { failed(); return; }
+        for (uint32_t k = 0; k < n; k++)
+          if (upload(c, (uint8_t *)c.in_buf[0] + in_b * k, jobs[mine[a + k]].rgba_host, in_b, st)) { failed(); return; }
+        uint32_t nl = 0;
+        bool ok = cudaEventRecord(c.ev_start[0], st) == cudaSuccess;
+        {
+          std::lock_guard<std::mutex> dl(c.mu);
+          if (!c.pvr_done) ok = ok && cudaEventCreateWithFlags(&c.pvr_done, cudaEventDisableTiming) == cudaSuccess;
+          if (ok && c.pvr_used) ok = cudaStreamWaitEvent(st, c.pvr_done, 0) == cudaSuccess;
+          ok = ok && launch_pvrtc(c.pvrws, c.in_buf[0], w, h, n, c.out_buf[0], st, &nl) == cudaSuccess;
+          ok = ok && cudaEventRecord(c.pvr_done, st) == cudaSuccess;
+          c.pvr_used = true;
+        }
+        ok = ok && cudaEventRecord(c.ev_stop[0], st) == cudaSuccess;
+        for (uint32_t k = 0; ok && k < n; k++)
+          ok = cudaMemcpyAsync(jobs[mine[a + k]].out_host, (uint8_t *)c.out_buf[0] + out_b * k, out_b, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+        ok = ok && cudaStreamSynchronize(st) == cudaSuccess;
+        float ms = 0;
+        ok = ok && cudaEventElapsedTime(&ms, c.ev_start[0], c.ev_stop[0]) == cudaSuccess;
+        if (!ok) { fail("PVRTC batch: %s", cudaGetErrorString(cudaGetLastError())); failed(); return; }
+        per[g].kernel_ms += ms;
+        per[g].kernel_launches += nl;
+        per[g].h2d_bytes += in_b * n;
+        per[g].d2h_bytes += out_b * n;
+        a = b;
+      }
+      return;
+    }
     bool any = false;
     for (uint32_t j = g; j < num_jobs; j += num_gpus) {
       Shard s;

@@ -27,8 +27,10 @@ struct PvrtcWorkspace {
   uint32_t *host_flag = nullptr;
 };
 void pvrtc_free_workspace(PvrtcWorkspace &ws);
-cudaError_t launch_pvrtc(PvrtcWorkspace &ws, const void *rgba_dev, uint32_t width, uint32_t height, void *out_dev,
-                         cudaStream_t stream, uint32_t *launches);
+// ntex textures of width x height back to back in rgba_dev, their compressed blocks back to back in out_dev
+cudaError_t launch_pvrtc(PvrtcWorkspace &ws, const void *rgba_dev, uint32_t width, uint32_t height, uint32_t ntex,
+                         void *out_dev, cudaStream_t stream, uint32_t *launches);
+size_t pvrtc_scratch_bytes(uint32_t width, uint32_t height);  // per texture
 cudaError_t launch_pvrtc_decode(const void *cmp_dev, uint32_t width, uint32_t height, uint32_t first_block,
                                 uint32_t num_blocks, void *rgba_dev, cudaStream_t stream);
 

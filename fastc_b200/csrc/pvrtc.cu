@@ -37,10 +37,13 @@ __global__ void pvr_intensity(const uint32_t *__restrict__ img, uint32_t n, floa
   }
 }
 
-__global__ void pvr_classify(const uint8_t *__restrict__ ibyte, uint32_t w, uint32_t h, uint8_t *__restrict__ cls) {
-  const uint32_t n = w * h;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    cls[i] = (uint8_t)classify_extremum(ibyte, w, h, i % w, i / w);
+// (ntex textures of w x h, one after the other)
+__global__ void pvr_classify(const uint8_t *__restrict__ ibyte, uint32_t w, uint32_t h, uint32_t ntex, uint8_t *__restrict__ cls) {
+  const uint32_t per = w * h, n = per * ntex;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t t = i / per, k = i - t * per;
+    cls[i] = (uint8_t)classify_extremum(ibyte + (size_t)t * per, w, h, k % w, k / w);
+  }
 }
 
 // LabelImageForward in one launch: one CTA per label kind, one thread per visited row of a band of up
@@ -50,6 +53,8 @@ __global__ void pvr_classify(const uint8_t *__restrict__ ibyte, uint32_t w, uint
 __global__ void __launch_bounds__(1024)
 pvr_forward_rows(PixelLabels *labels, const uint8_t *__restrict__ cls, uint32_t w, uint32_t h, uint32_t *overflow) {
   const bool high = blockIdx.x == 0;
+  labels += (size_t)blockIdx.y * w * h;  // blockIdx.y: the texture of a batch
+  cls += (size_t)blockIdx.y * w * h;
   const uint32_t rows = h + 3, tid = threadIdx.x, nt = blockDim.x;
   bool ok = true;
   for (uint32_t band = 0; band < rows; band += nt) {
@@ -108,6 +113,7 @@ pvr_backward_rows(PixelLabels *labels, uint32_t w, uint32_t h, uint32_t *overflo
   __shared__ uint32_t s_prev[kBackThreads];  // composition of everything before thread t's pixels
   __shared__ Label s_first_right;            // column 0's label as the row's first pixel sees it
   const bool high = blockIdx.x == 0;
+  labels += (size_t)blockIdx.y * w * h;  // blockIdx.y: the texture of a batch
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nthreads = blockDim.x;
   // pixels per thread (rows narrower than a warp leave the upper lanes without pixels: identity maps)
   const uint32_t per = (uint32_t)tid < w ? (w >= (uint32_t)nthreads ? w / (uint32_t)nthreads : 1u) : 0u;
@@ -201,7 +207,8 @@ __global__ void pvr_low_high(const PixelLabels *__restrict__ labels, const float
   const uint32_t bw = w >> 2, nb = bw * (h >> 2);
   const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
-  fields[b] = low_high_block(labels, intensity, img, w, h, b % bw, b / bw);
+  const size_t po = (size_t)blockIdx.y * w * h;
+  fields[(size_t)blockIdx.y * nb + b] = low_high_block(labels + po, intensity + po, img + po, w, h, b % bw, b / bw);
 }
 
 __global__ void pvr_modulate(const uint32_t *__restrict__ fields, const uint32_t *__restrict__ img, uint32_t w, uint32_t h,
@@ -210,9 +217,11 @@ __global__ void pvr_modulate(const uint32_t *__restrict__ fields, const uint32_t
   const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
   const uint32_t bx = b % bw, by = b / bw;
+  fields += (size_t)blockIdx.y * nb;
+  img += (size_t)blockIdx.y * w * h;
   // the block's 64 bits: modulation in the low word, colour fields in the high word; blocks are
   // stored in the reference's interleaved (Morton) order
-  out[block_index(bx, by)] = make_uint2(modulation_block(fields, img, w, h, bx, by), fields[b]);
+  out[(size_t)blockIdx.y * nb + block_index(bx, by)] = make_uint2(modulation_block(fields, img, w, h, bx, by), fields[b]);
 }
 
 // decoder: one thread per pixel of the block range
@@ -243,12 +252,23 @@ void pvrtc_free_workspace(PvrtcWorkspace &ws) {
   ws.base = nullptr; ws.bytes = 0; ws.host_flag = nullptr;
 }
 
-cudaError_t launch_pvrtc(PvrtcWorkspace &ws, const void *rgba_dev, uint32_t width, uint32_t height, void *out_dev,
-                         cudaStream_t stream, uint32_t *launches) {
-  const uint32_t w = width, h = height, n = w * h, nb = (w >> 2) * (h >> 2);
-  const size_t o_int = 0, o_ib = o_int + align256((size_t)n * 4), o_cls = o_ib + align256(n), o_fields = o_cls + align256(n),
-               o_flag = o_fields + align256((size_t)nb * 4), o_labels = o_flag + 256,
-               total = o_labels + (size_t)n * sizeof(pvr::PixelLabels);
+size_t pvrtc_scratch_bytes(uint32_t width, uint32_t height) {
+  const size_t n = (size_t)width * height, nb = n / 16;
+  return n * (4 + 1 + 1 + sizeof(pvr::PixelLabels)) + nb * 4 + 4096;
+}
+
+// ntex textures of width x height, one after the other in rgba_dev; their blocks one after the other in
+// out_dev.  The textures of a batch are independent: every kernel takes the texture index from its
+// grid (the two labelling kernels: 2 x ntex CTAs), which is what lets PVRTC use the GPU at all.
+cudaError_t launch_pvrtc(PvrtcWorkspace &ws, const void *rgba_dev, uint32_t width, uint32_t height, uint32_t ntex,
+                         void *out_dev, cudaStream_t stream, uint32_t *launches) {
+  if (ntex == 0) return cudaSuccess;
+  const uint32_t w = width, h = height, nb = (w >> 2) * (h >> 2);
+  const size_t n = (size_t)w * h * ntex;
+  if (n > 0xFFFFFFFFull) return cudaErrorInvalidValue;
+  const size_t o_int = 0, o_ib = o_int + align256(n * 4), o_cls = o_ib + align256(n), o_fields = o_cls + align256(n),
+               o_flag = o_fields + align256((size_t)nb * ntex * 4), o_labels = o_flag + 256,
+               total = o_labels + n * sizeof(pvr::PixelLabels);
   if (ws.bytes < total) {
     cudaError_t e = cudaStreamSynchronize(stream);
     if (e != cudaSuccess) return e;
@@ -264,19 +284,16 @@ cudaError_t launch_pvrtc(PvrtcWorkspace &ws, const void *rgba_dev, uint32_t widt
   uint32_t *fields = reinterpret_cast<uint32_t *>(base + o_fields), *flag = reinterpret_cast<uint32_t *>(base + o_flag);
   pvr::PixelLabels *labels = reinterpret_cast<pvr::PixelLabels *>(base + o_labels);
   const uint32_t *img = static_cast<const uint32_t *>(rgba_dev);
-  cudaError_t e = cudaMemsetAsync(base + o_flag, 0, 256 + (size_t)n * sizeof(pvr::PixelLabels), stream);  // calloc'ed labels
+  cudaError_t e = cudaMemsetAsync(base + o_flag, 0, 256 + n * sizeof(pvr::PixelLabels), stream);  // calloc'ed labels
   if (e != cudaSuccess) return e;
-  const uint32_t grid = std::min<uint32_t>((n + 255) / 256, 148 * 16);
-  pvr_intensity<<<grid, 256, 0, stream>>>(img, n, intensity, ibyte);
-  pvr_classify<<<grid, 256, 0, stream>>>(ibyte, w, h, cls);
-  uint32_t nl = 2;
-  pvr_forward_rows<<<2, std::min<uint32_t>(1024u, (h + 3 + 31) & ~31u), 0, stream>>>(labels, cls, w, h, flag);
-  nl++;
-  pvr_backward_rows<<<2, std::max<uint32_t>(32u, std::min<uint32_t>(w, kBackThreads)), 0, stream>>>(labels, w, h, flag);
-  pvr_low_high<<<(nb + 127) / 128, 128, 0, stream>>>(labels, intensity, img, w, h, fields);
-  pvr_modulate<<<(nb + 127) / 128, 128, 0, stream>>>(fields, img, w, h, static_cast<uint2 *>(out_dev));
-  nl += 3;
-  if (launches) *launches += nl;
+  const uint32_t grid = (uint32_t)std::min<size_t>((n + 255) / 256, 148 * 16);
+  pvr_intensity<<<grid, 256, 0, stream>>>(img, (uint32_t)n, intensity, ibyte);
+  pvr_classify<<<grid, 256, 0, stream>>>(ibyte, w, h, ntex, cls);
+  pvr_forward_rows<<<dim3(2, ntex), std::min<uint32_t>(1024u, (h + 3 + 31) & ~31u), 0, stream>>>(labels, cls, w, h, flag);
+  pvr_backward_rows<<<dim3(2, ntex), std::max<uint32_t>(32u, std::min<uint32_t>(w, kBackThreads)), 0, stream>>>(labels, w, h, flag);
+  pvr_low_high<<<dim3((nb + 127) / 128, ntex), 128, 0, stream>>>(labels, intensity, img, w, h, fields);
+  pvr_modulate<<<dim3((nb + 127) / 128, ntex), 128, 0, stream>>>(fields, img, w, h, static_cast<uint2 *>(out_dev));
+  if (launches) *launches += 6;
   return cudaGetLastError();
 }
 

@@ -54,7 +54,9 @@ def test_pvrtc_matches_reference_at_size(gpu, ref, size, seed):
 
 
 def test_pvrtc_device_api_and_batch(gpu, ref):
-    imgs = [synth_rgba(128, 128, s) for s in range(1, 6)]
+    # runs of equal sizes go through the kernels side by side (grid.y = texture); sizes may change in a batch
+    imgs = [synth_rgba(128, 128, s) for s in range(1, 6)] + [synth_rgba(64, 64, 9), synth_rgba(256, 256, 4),
+                                                             synth_rgba(256, 256, 5), synth_rgba(32, 32, 2)]
     outs, tm = gpu.compress_batch(F.PVRTC4, imgs)
     for im, o in zip(imgs, outs):
         want, _ = ref.compress("PVRTC4", im, seed=None)

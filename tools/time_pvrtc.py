@@ -15,3 +15,13 @@ for size in (256, 1024, 2048):
     ms = a.elapsed_time(b)
     t0 = time.perf_counter(); want, rms = r.compress("PVRTC4", img, seed=None); 
     print(json.dumps({"size": size, "gpu_ms": ms, "ref_ms": rms, "equal": bool(np.array_equal(d_out.cpu().numpy(), want))}))
+
+# a batch: the textures are encoded side by side (grid.y = texture)
+for size, n in ((512, 64), (1024, 32)):
+    imgs = [synth_rgba(size, size, k + 1) for k in range(n)]
+    g.compress_batch(F.PVRTC4, imgs[:2])
+    t0 = time.perf_counter(); outs, tm = g.compress_batch(F.PVRTC4, imgs); dt = (time.perf_counter() - t0) * 1e3
+    want, rms = r.compress("PVRTC4", imgs[-1], seed=None)
+    print(json.dumps({"batch": n, "size": size, "gpu_total_ms": dt, "gpu_kernel_ms": tm["kernel_ms"],
+                      "gpu_mpix_s": n * size * size / dt / 1e3, "ref_ms_per_texture": rms,
+                      "ref_mpix_s_one_core": size * size / rms / 1e3, "last_equal": bool(np.array_equal(outs[-1], want))}))
