@@ -51,7 +51,8 @@ uint32 Get32(const uint8 *p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint
 // OpenGL enums (reference IO/src/GLDefines.h)
 enum {
   kGL_BYTE = 0x1400, kGL_UNSIGNED_BYTE = 0x1401, kGL_RGB = 0x1907, kGL_RGBA = 0x1908, kGL_RGBA8 = 0x8058,
-  kGL_DXT1 = 0x83F0, kGL_DXT5 = 0x83F3, kGL_BPTC = 0x8E8C, kGL_ETC1 = 0x8D64
+  kGL_DXT1 = 0x83F0, kGL_DXT5 = 0x83F3, kGL_BPTC = 0x8E8C, kGL_ETC1 = 0x8D64,
+  kGL_PVRTC4 = 0x8C02  // GL_COMPRESSED_RGBA_PVRTC_4BPPV1_IMG (IO/src/GLDefines.h:70-72)
 };
 const uint8 kKtxId[12] = {0xAB, 0x4B, 0x54, 0x58, 0x20, 0x31, 0x31, 0xBB, 0x0D, 0x0A, 0x1A, 0x0A};
 
@@ -130,6 +131,7 @@ bool WriteKTX(const char *path, FasTC::Image<> &img) {
       case FasTC::eCompressionFormat_BPTC: internal = kGL_BPTC; base = kGL_RGBA; break;
       case FasTC::eCompressionFormat_DXT1: internal = kGL_DXT1; base = kGL_RGB; break;
       case FasTC::eCompressionFormat_DXT5: internal = kGL_DXT5; base = kGL_RGBA; break;
+      case FasTC::eCompressionFormat_PVRTC4: internal = kGL_PVRTC4; base = kGL_RGBA; break;
       case FasTC::eCompressionFormat_ETC1: internal = kGL_ETC1; base = kGL_RGB; break;  // not writable by the reference
       default:
         fprintf(stderr, "Unsupported KTX compressed format: %d\n", ci->GetFormat());
@@ -177,6 +179,7 @@ FasTC::Image<> *LoadKTX(const std::vector<uint8> &d) {
     case kGL_DXT1: fmt = FasTC::eCompressionFormat_DXT1; break;
     case kGL_DXT5: fmt = FasTC::eCompressionFormat_DXT5; break;
     case kGL_ETC1: fmt = FasTC::eCompressionFormat_ETC1; break;
+    case kGL_PVRTC4: fmt = FasTC::eCompressionFormat_PVRTC4; break;  // (ImageLoaderKTX.cpp:247)
     default:
       if ((glType == kGL_BYTE || glType == kGL_UNSIGNED_BYTE) && imageSize >= (uint64)w * h * 4)
         return new FasTC::Image<>(w, h, reinterpret_cast<const uint32 *>(payload));

@@ -28,6 +28,7 @@ static FasTC::ECompressionFormat ParseFormat(const char *s) {
   if (!strcmp(s, "DXT1")) return FasTC::eCompressionFormat_DXT1;
   if (!strcmp(s, "DXT5")) return FasTC::eCompressionFormat_DXT5;
   if (!strcmp(s, "ETC1")) return FasTC::eCompressionFormat_ETC1;
+  if (!strcmp(s, "PVRTC4")) return FasTC::eCompressionFormat_PVRTC4;
   return FasTC::eCompressionFormat_BPTC;
 }
 

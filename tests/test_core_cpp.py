@@ -3,6 +3,7 @@ CLI over the C ABI.  CPU tests cover job arithmetic, the job list, error behavio
 CLI's argument handling; GPU tests drive CompressImageData / the per-format CompressionFunc
 entry points / CompressImageList / CompressedImage / `tc` and compare with the oracle."""
 import os
+import sys
 import struct
 import subprocess
 from pathlib import Path
@@ -227,7 +228,7 @@ def test_png_write_then_load_roundtrip(tmp_path):
     assert (np.asarray(PILImage.open(tmp_path / "b.png").convert("RGBA")) == img).all()
 
 
-@pytest.mark.parametrize("fmt", ["BPTC", "DXT1", "DXT5"])
+@pytest.mark.parametrize("fmt", ["BPTC", "DXT1", "DXT5", "PVRTC4"])
 def test_ktx_file_is_byte_identical_to_the_reference_writer(tmp_path, fmt):
     """a whole .ktx written by our ImageFile (what `tc -d out.ktx` calls) equals, byte
     for byte, the file the reference's ImageWriterKTX (IO/src/ImageWriterKTX.cpp:69-160) writes for
@@ -236,13 +237,17 @@ def test_ktx_file_is_byte_identical_to_the_reference_writer(tmp_path, fmt):
     from _checkers import Reference, BLOCK_BYTES
     if not Reference.available():
         pytest.skip("oracle/_ref/libfastc_ref.so not built")
-    w, h = 64, 32  # one size per process: the reference writer caches imageSize in a static
+    w, h = (64, 64) if fmt == "PVRTC4" else (64, 32)
     payload = np.random.default_rng(3).integers(0, 256, (w // 4) * (h // 4) * BLOCK_BYTES[fmt], dtype=np.uint8)
     (tmp_path / "p.bin").write_bytes(payload.tobytes())
     r = subprocess.run([str(SELFTEST), "writektx", fmt, str(w), str(h), str(tmp_path / "p.bin"), str(tmp_path / "ours.ktx")],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
-    Reference().write_ktx(fmt, payload, w, h, tmp_path / "ref.ktx")
+    # (a fresh process per file: the reference writer caches imageSize in function-local statics)
+    code = ("import sys, numpy as np; sys.path.insert(0, sys.argv[1]); from _checkers import Reference; "
+            "Reference().write_ktx(sys.argv[2], np.fromfile(sys.argv[3], dtype=np.uint8), int(sys.argv[4]), int(sys.argv[5]), sys.argv[6])")
+    subprocess.run([sys.executable, "-c", code, str(ROOT / "tests"), fmt, str(tmp_path / "p.bin"), str(w), str(h),
+                    str(tmp_path / "ref.ktx")], check=True)
     ours, ref = (tmp_path / "ours.ktx").read_bytes(), (tmp_path / "ref.ktx").read_bytes()
     assert len(ours) == 96 + payload.size
     assert ours == ref
