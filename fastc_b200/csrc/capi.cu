@@ -47,8 +47,9 @@ int fail(const char *fmt, ...) {
 
 constexpr int kMaxDevices = 16;
 constexpr int kPipeDepth = 3;  // staging slots per device for the host path
-constexpr int kStagePieces = 4;               // pinned upload ring (pageable inputs)
-constexpr size_t kStagePieceBytes = 16u << 20;
+constexpr int kStagePieces = 16;              // pinned upload ring (pageable inputs)
+constexpr size_t kStagePieceBytes = 4u << 20;
+constexpr int kStageWindow = 8;               // pieces being filled at once, one host thread each
 
 struct DeviceCtx {
   bool tables_ready = false;
@@ -81,6 +82,12 @@ struct DeviceCtx {
   size_t pin_out_cap[kPipeDepth] = {};
   uint8_t *pend_dst[kPipeDepth] = {};  // copy-out the slot still owes the caller
   size_t pend_bytes[kPipeDepth] = {};
+  std::atomic<int> out_left[kPipeDepth] = {};  // parts of a slot's copy-out still running on the pool
+  // batch submissions from pageable memory: whole textures are staged by threads running ahead of the
+  // submitting thread (compress_batch_impl)
+  static constexpr int kBatchRing = 16;
+  void *batch_pin[kBatchRing] = {};
+  size_t batch_pin_cap[kBatchRing] = {};
   unsigned long long *psnr_sum = nullptr, *psnr_host = nullptr;  // device / pinned accumulators of fastc_gpu_psnr*
   void *stats_buf[kPipeDepth] = {};  // BPTC per-block statistics of the chunk in the slot (only when asked for)
   size_t stats_cap[kPipeDepth] = {};
@@ -383,39 +390,28 @@ bool is_pageable(const void *p) {
   return a.type == cudaMemoryTypeUnregistered;
 }
 
-// memcpy split over a few host threads (one thread moves ~10 GB/s; PCIe 5 x16 wants ~50).  The
-// threads are a process-wide pool created on first use (spawning threads per 16 MiB piece cost as
-// much as the copy itself); the caller works too, so the pool can be shared by the per-GPU host
-// threads of one submission without deadlock.
+// Host copies on a few threads (one thread moves ~8 GB/s; PCIe 5 x16 wants ~50).  The threads are a
+// process-wide pool created on first use (spawning threads per piece costs as much as the copy
+// itself), shared by the per-GPU host threads of a submission.
 class CopyPool {
  public:
   static CopyPool &get() {
     static CopyPool *pool = new CopyPool();  // leaked on purpose: its threads may outlive static destructors
     return *pool;
   }
-  void copy(void *dst, const void *src, size_t n) {
-    const size_t kPart = (size_t)1 << 20;
-    if (n < 2 * kPart || workers_ == 0) {
-      memcpy(dst, src, n);
+  // One whole copy as one task for one worker (`left` drops by one when it is done).  Copying whole
+  // pieces on several threads at once moves ~50 GB/s on the GPU box's host, splitting each piece over
+  // threads spawned for it ~23 GB/s (tools/host_copy_bw.cu).
+  void submit(void *dst, const void *src, size_t n, std::atomic<int> *left) {
+    if (workers_ == 0) {
+      run(Task{(uint8_t *)dst, (const uint8_t *)src, n, left});
       return;
     }
-    const int parts = (int)std::min<size_t>((size_t)workers_ + 1, n / kPart);
-    std::atomic<int> left(parts);
     {
       std::lock_guard<std::mutex> lk(mu_);
-      for (int k = 1; k < parts; k++) {
-        const size_t a = n * k / parts, b = n * (k + 1) / parts;
-        tasks_.push_back(Task{(uint8_t *)dst + a, (const uint8_t *)src + a, b - a, &left});
-      }
+      tasks_.push_back(Task{(uint8_t *)dst, (const uint8_t *)src, n, left});
     }
-    cv_.notify_all();
-    memcpy(dst, src, n / parts);
-    left.fetch_sub(1, std::memory_order_acq_rel);
-    Task t;
-    while (left.load(std::memory_order_acquire) > 0) {
-      if (pop(t)) run(t);  // help: the tasks queued may be this call's own
-      else std::this_thread::yield();
-    }
+    cv_.notify_one();
   }
 
  private:
@@ -433,13 +429,6 @@ class CopyPool {
   static void run(const Task &t) {
     memcpy(t.dst, t.src, t.n);
     t.left->fetch_sub(1, std::memory_order_acq_rel);
-  }
-  bool pop(Task &t) {
-    std::lock_guard<std::mutex> lk(mu_);
-    if (tasks_.empty()) return false;
-    t = tasks_.front();
-    tasks_.pop_front();
-    return true;
   }
   void loop() {
     for (;;) {
@@ -459,27 +448,6 @@ class CopyPool {
   int workers_ = 0;
 };
 
-void par_memcpy(void *dst, const void *src, size_t n) {
-  if (n >= ((size_t)8 << 20)) {
-    CopyPool::get().copy(dst, src, n);
-    return;
-  }
-  // a few MiB (one texture of a batch): measured faster with threads of its own than through the
-  // pool's wake-ups (256 x 1024^2 DXT1 from pageable memory: 86 ms vs 128 ms)
-  const int nt = (int)std::min<size_t>(8, n >> 20);  // >= 1 MiB per thread
-  if (nt <= 1) {
-    memcpy(dst, src, n);
-    return;
-  }
-  std::vector<std::thread> th;
-  for (int k = 1; k < nt; k++) {
-    const size_t a = n * k / nt, b = n * (k + 1) / nt;
-    th.emplace_back([=] { memcpy((uint8_t *)dst + a, (const uint8_t *)src + a, b - a); });
-  }
-  memcpy(dst, src, n / nt);
-  for (auto &t : th) t.join();
-}
-
 // Host -> device on `st`.  Pinned sources go straight to the copy engine; pageable ones through
 // the pinned ring, piece by piece.
 int upload(DeviceCtx &c, void *dst_dev, const uint8_t *src, size_t bytes, cudaStream_t st) {
@@ -487,20 +455,55 @@ int upload(DeviceCtx &c, void *dst_dev, const uint8_t *src, size_t bytes, cudaSt
     CU_TRY(cudaMemcpyAsync(dst_dev, src, bytes, cudaMemcpyHostToDevice, st));
     return 0;
   }
-  for (size_t off = 0; off < bytes; off += kStagePieceBytes) {
+  // Pieces of <= 4 MiB go through a ring of pinned buffers: up to kStageWindow pieces are being filled at
+  // once, each by one pool thread, and every piece is sent as soon as it and the pieces before it are
+  // full -- the host copies run alongside the wire instead of in front of it.  Small uploads (one
+  // texture of a batch) are cut finer, so that they too are filled by a window of threads.
+  const size_t piece = std::min(kStagePieceBytes, std::max<size_t>((size_t)256 << 10, ((bytes / kStageWindow + 65535) >> 16) << 16));
+  const size_t np = (bytes + piece - 1) / piece;
+  std::vector<std::atomic<int>> done(np);
+  std::vector<int> slot_of(np);
+  CopyPool &pool = CopyPool::get();
+  auto start_piece = [&](size_t k) -> int {
     const int i = (int)(c.pin_in_next++ % kStagePieces);
-    const size_t n = std::min(kStagePieceBytes, bytes - off);
+    slot_of[k] = i;
     if (!c.pin_in[i]) {
       CU_TRY(cudaHostAlloc(&c.pin_in[i], kStagePieceBytes, cudaHostAllocDefault));
       CU_TRY(cudaEventCreateWithFlags(&c.pin_in_ev[i], cudaEventDisableTiming));
     }
     if (c.pin_in_used[i]) CU_TRY(cudaEventSynchronize(c.pin_in_ev[i]));  // its previous upload has left the buffer
-    par_memcpy(c.pin_in[i], src + off, n);
-    CU_TRY(cudaMemcpyAsync((uint8_t *)dst_dev + off, c.pin_in[i], n, cudaMemcpyHostToDevice, st));
-    CU_TRY(cudaEventRecord(c.pin_in_ev[i], st));
-    c.pin_in_used[i] = true;
+    const size_t off = k * piece;
+    done[k].store(1, std::memory_order_relaxed);
+    pool.submit(c.pin_in[i], src + off, std::min(piece, bytes - off), &done[k]);
+    return 0;
+  };
+  int rc = 0;
+  size_t started = 0;
+  while (started < np && started < (size_t)kStageWindow && !rc) {
+    rc = start_piece(started);
+    if (!rc) started++;
   }
-  return 0;
+  for (size_t k = 0; k < started; k++) {  // (on an error: only wait for what was started)
+    // (without helping: this thread's job is to send every piece the moment it is full)
+    while (done[k].load(std::memory_order_acquire) > 0) std::this_thread::yield();
+    if (rc) continue;
+    const size_t off = k * piece, n = std::min(piece, bytes - off);
+    const int i = slot_of[k];
+    if (cudaMemcpyAsync((uint8_t *)dst_dev + off, c.pin_in[i], n, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaEventRecord(c.pin_in_ev[i], st) != cudaSuccess) {
+      rc = fail("CUDA: %s", cudaGetErrorString(cudaGetLastError()));
+      continue;
+    }
+    c.pin_in_used[i] = true;
+    if (started < np) { rc = start_piece(started); started += rc ? 0 : 1; }
+  }
+  return rc;
+}
+
+// The copy-out of a staged download runs on the pool while the submission goes on; it has to be
+// over before its pinned source is reused and before the call returns.
+void wait_copy_out(DeviceCtx &c, int slot) {
+  while (c.out_left[slot].load(std::memory_order_acquire) > 0) std::this_thread::yield();
 }
 
 // Device -> host on `st` for the chunk in `slot`.  Pageable destinations receive their bytes
@@ -510,6 +513,7 @@ int download(DeviceCtx &c, int slot, uint8_t *dst, const void *src_dev, size_t b
     CU_TRY(cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, st));
     return 0;
   }
+  wait_copy_out(c, slot);  // the pinned buffer may still be the source of the previous copy-out
   if (c.pin_out_cap[slot] < bytes) {
     if (c.pin_out[slot]) CU_TRY(cudaFreeHost(c.pin_out[slot]));
     c.pin_out[slot] = nullptr;
@@ -561,9 +565,17 @@ int finish_slot(DeviceCtx &c, int slot, double *kernel_ms) {
   CU_TRY(cudaEventElapsedTime(&ms, c.ev_start[slot], c.ev_stop[slot]));
   if (kernel_ms) *kernel_ms += ms;
   if (c.pend_dst[slot]) {
-    par_memcpy(c.pend_dst[slot], c.pin_out[slot], c.pend_bytes[slot]);
+    // pinned -> caller memory on the pool, ~1 MiB per task; waited for in download() / drain_slots()
+    const size_t n = c.pend_bytes[slot], parts = std::max<size_t>(1, std::min<size_t>(8, n >> 20));
+    c.out_left[slot].store((int)parts, std::memory_order_release);
+    for (size_t k = 0; k < parts; k++) {
+      const size_t a = n * k / parts, b = n * (k + 1) / parts;
+      CopyPool::get().submit(c.pend_dst[slot] + a, (const uint8_t *)c.pin_out[slot] + a, b - a, &c.out_left[slot]);
+    }
     c.pend_dst[slot] = nullptr;
     c.pend_bytes[slot] = 0;
+    static const bool sync_out = getenv("FASTC_GPU_SYNC_COPYOUT") != nullptr;  // (measurement switch)
+    if (sync_out) wait_copy_out(c, slot);
   }
   c.slot_busy[slot] = false;
   return 0;
@@ -571,9 +583,11 @@ int finish_slot(DeviceCtx &c, int slot, double *kernel_ms) {
 
 // Waits for every chunk still in flight on the device's staging slots.
 int drain_slots(DeviceCtx &c, double *kernel_ms) {
+  int rc = 0;
   for (int slot = 0; slot < kPipeDepth; slot++)
-    if (finish_slot(c, slot, kernel_ms)) return 1;
-  return 0;
+    if (finish_slot(c, slot, kernel_ms)) { rc = 1; break; }
+  for (int slot = 0; slot < kPipeDepth; slot++) wait_copy_out(c, slot);  // the caller's buffers are complete on return
+  return rc;
 }
 
 // Error path: nothing of a failed submission may linger in the slots (a later submission would
@@ -581,6 +595,7 @@ int drain_slots(DeviceCtx &c, double *kernel_ms) {
 void abort_slots(DeviceCtx &c) {
   for (int slot = 0; slot < kPipeDepth; slot++) {
     if (c.streams[slot]) cudaStreamSynchronize(c.streams[slot]);
+    while (c.out_left[slot].load(std::memory_order_acquire) > 0) std::this_thread::yield();  // copy-outs under way finish
     c.slot_busy[slot] = false;
     c.pending[slot].active = false;
     c.pend_dst[slot] = nullptr;
@@ -750,6 +765,10 @@ void fastc_gpu_shutdown(void) {
     }
     for (int i = 0; i <= kPipeDepth; i++) bc7_free_workspace(c.bc7ws[i]);
     pvrtc_free_workspace(c.pvrws);
+    for (int i = 0; i < DeviceCtx::kBatchRing; i++) {
+      if (c.batch_pin[i]) cudaFreeHost(c.batch_pin[i]);
+      c.batch_pin[i] = nullptr; c.batch_pin_cap[i] = 0;
+    }
     if (c.pvr_done) cudaEventDestroy(c.pvr_done);
     c.pvr_done = nullptr; c.pvr_used = false;
     for (int i = 0; i < kStagePieces; i++) {
@@ -971,8 +990,71 @@ int compress_batch_impl(int format, const fastc_gpu_job *jobs, uint32_t num_jobs
       }
       return;
     }
+    // Pageable inputs of small textures: staging texture by texture inside upload() leaves the host copy
+    // (one thread moves ~8 GB/s) in front of every transfer.  Instead a few threads stage WHOLE textures
+    // into a ring of pinned buffers, running ahead of this thread, which then submits from pinned
+    // memory: the copies proceed at the rate of several threads (~50 GB/s on the GPU box's host).
+    constexpr int kStagers = 8;
+    constexpr size_t kStageMaxJob = (size_t)16 << 20;
+    std::vector<uint32_t> mine;
+    for (uint32_t j = g; j < num_jobs; j += num_gpus) mine.push_back(j);
+    std::vector<const uint8_t *> src_of(mine.size());
+    std::vector<std::atomic<int>> staged(mine.size());
+    std::atomic<long> submitted(-1);
+    std::atomic<bool> stop(false);
+    std::vector<std::thread> stagers;
+    {
+      bool want = false;
+      if (ensure_ctx(dev)) { rcs[g] = 1; errs[g] = tl_error; return; }
+      DeviceCtx &c = g_ctx[dev];
+      for (size_t k = 0; k < mine.size(); k++) {
+        const fastc_gpu_job &jb = jobs[mine[k]];
+        const size_t bytes = (size_t)jb.width * jb.height * 4;
+        src_of[k] = jb.rgba_host;
+        const bool stage = mine.size() >= 4 && bytes <= kStageMaxJob && is_pageable(jb.rgba_host);
+        staged[k].store(stage ? 0 : 1, std::memory_order_relaxed);
+        if (!stage) continue;
+        want = true;
+        void *&buf = c.batch_pin[k % DeviceCtx::kBatchRing];
+        size_t &cap = c.batch_pin_cap[k % DeviceCtx::kBatchRing];
+        if (cap < bytes) {
+          if (buf) cudaFreeHost(buf);
+          buf = nullptr; cap = 0;
+          if (cudaHostAlloc(&buf, kStageMaxJob, cudaHostAllocDefault) != cudaSuccess) {
+            fail("cudaHostAlloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+            rcs[g] = 1; errs[g] = tl_error;
+            return;
+          }
+          cap = kStageMaxJob;
+        }
+        src_of[k] = static_cast<const uint8_t *>(buf);
+      }
+      if (want)
+        for (int t = 0; t < kStagers; t++)
+          stagers.emplace_back([&, t] {
+            for (size_t k = (size_t)t; k < mine.size() && !stop.load(std::memory_order_acquire); k += kStagers) {
+              if (staged[k].load(std::memory_order_acquire)) continue;
+              // the ring buffer's previous texture (k - ring) has left it once kPipeDepth more textures were
+              // submitted: their chunks have cycled through every staging slot (finish_slot synchronises)
+              while (submitted.load(std::memory_order_acquire) < (long)k - DeviceCtx::kBatchRing + kPipeDepth &&
+                     !stop.load(std::memory_order_acquire))
+                std::this_thread::yield();
+              if (stop.load(std::memory_order_acquire)) break;
+              const fastc_gpu_job &jb = jobs[mine[k]];
+              memcpy(const_cast<uint8_t *>(src_of[k]), jb.rgba_host, (size_t)jb.width * jb.height * 4);
+              staged[k].store(1, std::memory_order_release);
+            }
+          });
+    }
+    auto join_stagers = [&] {
+      stop.store(true, std::memory_order_release);
+      for (auto &t : stagers) t.join();
+      stagers.clear();
+    };
     bool any = false;
-    for (uint32_t j = g; j < num_jobs; j += num_gpus) {
+    for (size_t k = 0; k < mine.size(); k++) {
+      const uint32_t j = mine[k];
+      while (!staged[k].load(std::memory_order_acquire)) std::this_thread::yield();
       Shard s;
       s.dev = dev;
       s.first_block = 0;
@@ -982,18 +1064,21 @@ int compress_batch_impl(int format, const fastc_gpu_job *jobs, uint32_t num_jobs
       chain.resize(s.bounds.size() - 1);
       EncodeParams prm = make_params(quality, seed + ((uint64_t)j << 40), opt);
       // no drain between textures: the staging slots keep rotating across jobs
-      if (run_shard(s, format, jobs[j].rgba_host, jobs[j].width, jobs[j].height, jobs[j].out_host, prm, chain,
+      if (run_shard(s, format, src_of[k], jobs[j].width, jobs[j].height, jobs[j].out_host, prm, chain,
                     /*drain=*/false)) {
         rcs[g] = 1;
         errs[g] = tl_error;
+        join_stagers();
         return;
       }
+      submitted.store((long)k, std::memory_order_release);
       per[g].kernel_ms += s.kernel_ms;
       per[g].kernel_launches += s.launches;
       per[g].h2d_bytes += s.h2d;
       per[g].d2h_bytes += s.d2h;
       any = true;
     }
+    join_stagers();
     if (any) {
       double ms = 0;
       if (drain_slots(g_ctx[dev], &ms)) {
