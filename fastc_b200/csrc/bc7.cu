@@ -640,6 +640,15 @@ __device__ __forceinline__ float div_small(float a, float c, float rc) {
 // instructions per site, and that kernel is bound by instruction fetch (see setup_chain)
 __device__ __noinline__ float div_cold(float a, float b) { return __fdiv_rn(a, b); }
 
+// Packed f32x2 arithmetic (sm_100 FFMA2 / FMUL2: one instruction, two independent IEEE RN results).
+// ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into a fused FFMA2 even with --fmad=false (it never does
+// that to the scalar forms), which would break the reference's separately rounded products and sums
+// (T4).  So a packed sum is written as RN(a * one + b) with `one` = 1.0f LOADED AT RUN TIME: the
+// multiplication by one is exact, the result is the correctly rounded sum, and there is nothing left to
+// contract (a product can feed an FFMA2 only as an operand).  A difference p - c is RN(c * -1 + p).
+__device__ __forceinline__ float2 sub2(float2 p, float c) { return __ffma2_rn(make_float2(c, c), make_float2(-1.0f, -1.0f), p); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b, float one) { return __ffma2_rn(a, make_float2(one, one), b); }
+
 struct F4 { float v[4]; };
 __device__ __forceinline__ float dot4(const float a[4], const float b[4]) {
   float s = __fmul_rn(a[0], b[0]);  // 0 + x == x
@@ -696,8 +705,19 @@ __device__ __forceinline__ uint32_t single_color_nu(int mode, int idx_mode, int 
 #define COUNT_QE(ws, ncalls, npbe) do { } while (0)
 #endif
 
+// A thread's column of a [16][kChainThreads] shared-memory plane: element i of the thread's private
+// 16-entry array.  bc7_setup keeps its per-chain arrays (the block, the cluster's points, the unique
+// points, the k-means accumulators) in such columns: rolled loops index them dynamically, which in
+// per-thread arrays means local memory -- and that kernel's L1 could not hold 640 threads' arrays.
+constexpr int kChainThreads = 128;
+struct Col {
+  uint32_t *p;
+  __device__ __forceinline__ uint32_t operator[](int i) const { return p[i * kChainThreads]; }
+  __device__ __forceinline__ void set(int i, uint32_t v) const { p[i * kChainThreads] = v; }
+};
+
 // Full QuantizedError over a cluster (returns the integer total; optionally the indices).
-__device__ __forceinline__ uint32_t qe_cluster(const uint32_t *pts, const uint32_t *pix, int n, uint32_t q1, uint32_t q2,
+__device__ __forceinline__ uint32_t qe_cluster(const Col pts, const Col pix, int n, uint32_t q1, uint32_t q2,
                                                int nbm1, const uint8_t *__restrict__ wtab, unsigned long long *indices) {
   QeEndpoints q;
   qe_prepare(q, q1, q2);
@@ -726,7 +746,7 @@ __device__ __forceinline__ float qe_bucket_error_nu(const QeEndpoints &q, const 
   }
   return err;
 }
-__device__ __forceinline__ uint32_t qe_cluster_nu(const uint32_t *pts, const uint32_t *pix, int n, uint32_t q1, uint32_t q2,
+__device__ __forceinline__ uint32_t qe_cluster_nu(const Col pts, const Col pix, int n, uint32_t q1, uint32_t q2,
                                                   int nbm1, const uint8_t *__restrict__ wtab, const float w[4],
                                                   unsigned long long *indices) {
   QeEndpoints q;
@@ -787,26 +807,20 @@ struct FitCore {
   float p1[4], p2[4];
 };
 
-__device__ __noinline__ void fit_core(int ibits, const uint32_t *pts, int n, const float avg[4], bool all_same,
-                                      uint32_t (*s_acc)[16][128], const float *__restrict__ s_rcp, int tid, FitCore &C) {
-  const int nb = 1 << ibits, nbm1 = nb - 1;
-  if (all_same) {  // AllSamePoint -> CompressSingleColor on point 0 (fit_finish)
-    C.kind = 0;
-    C.single = pts[0];
-    return;
-  }
-
+// GetPrincipalAxis and the two extreme projections along it: the float endpoints the k-means starts from.
+// `upts` is a scratch column for the unique points.
+__device__ __forceinline__ void fit_pca(const Col pts, const Col upts, int n, const float avg[4], float p1[4], float p2[4]) {
   // ---- GetPrincipalAxis (RGBAEndpoints.cpp:327-428)
   float axis[4];
   {
     // unique points; entries past the unique count stay (-1,-1,-1,-1) (T7)
-    uint32_t upts[16];
     int nu = 0;
 #pragma unroll 1
     for (int i = 0; i < n; i++) {
+      const uint32_t p = pts[i];
       bool has = false;
-      for (int j = 0; j < nu; j++) has = has || (upts[j] == pts[i]);
-      if (!has) upts[nu++] = pts[i];
+      for (int j = 0; j < nu; j++) has = has || (upts[j] == p);
+      if (!has) upts.set(nu++, p);
     }
     if (nu == 1) {
       axis[0] = axis[1] = axis[2] = axis[3] = 0.0f;
@@ -897,7 +911,6 @@ __device__ __noinline__ void fit_core(int ibits, const uint32_t *pts, int n, con
   }
 
   // ---- endpoints along the axis (Compressor.cpp:946-959)
-  float p1[4], p2[4];
   {
     float mindp = FLT_MAX, maxdp = -FLT_MAX;
 #pragma unroll 1
@@ -918,61 +931,85 @@ __device__ __noinline__ void fit_core(int ibits, const uint32_t *pts, int n, con
     }
   }
 
-  // ---- k-means over the nb interpolation points until a fixed point (:961-1026, T15)
-  float cen[16][4];
-#pragma unroll 1
-  for (int i = 0; i < nb; i++) {
-    const float s = div_cold((float)i, (float)nbm1);
-    const float oms = __fsub_rn(1.0f, s);
+}
+
+// fit_core: one instantiation per bucket count NB = 2^(index bits).  The centroids live in registers
+// (every loop over the buckets is unrolled, so their indices are static), the interpolation fractions
+// i / (NB - 1) are compile-time constants, the bucket of each point is a nibble of a register pair, the
+// points and the per-bucket sums are columns of shared memory: the k-means, the part of the fit that
+// dominates, runs without a single local-memory access.
+__host__ __device__ constexpr float ratio_c(int a, int b) { return (float)a / (float)b; }  // IEEE RN division, folded
+
+template <int NB>
+__device__ __noinline__ void fit_core(const Col pts, int n, const float avg[4], bool all_same,
+                                      uint32_t (*s_acc)[16][kChainThreads], const float *__restrict__ s_rcp, int tid, FitCore &C) {
+  constexpr int nbm1 = NB - 1;
+  if (all_same) {  // AllSamePoint -> CompressSingleColor on point 0 (fit_finish)
+    C.kind = 0;
+    C.single = pts[0];
+    return;
+  }
+  float p1[4], p2[4];
+  fit_pca(pts, Col{&s_acc[1][0][tid]}, n, avg, p1, p2);  // (the accumulator planes are free until the k-means starts)
+
+  // ---- k-means over the NB interpolation points until a fixed point (:961-1026, T15)
+  const float one = s_rcp[1];  // 1.0f the compiler cannot see (add2)
+  float cen[NB][4];
+#pragma unroll
+  for (int i = 0; i < NB; i++) {
+    const float s = ratio_c(i, nbm1);
+    const float oms = 1.0f - s;  // one rounding, like the reference's runtime subtraction; folded
 #pragma unroll
     for (int k = 0; k < 4; k++) cen[i][k] = __fadd_rn(__fmul_rn(p1[k], oms), __fmul_rn(p2[k], s));
   }
   {
-    uint8_t bucket[16];
     bool fixed = false;
     int guard = 0;
     while (!fixed && guard++ < 4096) {
-      // two points per pass over the centroids: half the centroid loads and two independent
-      // dependency chains (an odd cluster's last point is paired with itself)
+      // two points per pass over the centroids: two independent dependency chains (an odd
+      // cluster's last point is paired with itself); buckets: nibble i & 7 of blo (i < 8) / bhi
+      uint32_t blo = 0, bhi = 0;
 #pragma unroll 1
       for (int i = 0; i < n; i += 2) {
-        const int i1 = min(i + 1, n - 1);
-        float pa[4], pb[4];
+        const uint32_t qa = pts[i], qb = pts[min(i + 1, n - 1)];
+        float2 pab[4];  // (point a, point b) per channel: the two points go through the packed pipe together
 #pragma unroll
-        for (int k = 0; k < 4; k++) { pa[k] = (float)chan(pts[i], k); pb[k] = (float)chan(pts[i1], k); }
+        for (int k = 0; k < 4; k++) pab[k] = make_float2((float)chan(qa, k), (float)chan(qb, k));
         int mba = 0, mbb = 0;
         float mda = FLT_MAX, mdb = FLT_MAX;
-#pragma unroll 1
-        for (int j = 0; j < nb; j++) {
-          float va[4], vb[4];
+#pragma unroll
+        for (int j = 0; j < NB; j++) {
+          float2 m[4];
 #pragma unroll
           for (int k = 0; k < 4; k++) {
-            const float c = cen[j][k];
-            va[k] = __fsub_rn(pa[k], c);
-            vb[k] = __fsub_rn(pb[k], c);
+            const float2 v = sub2(pab[k], cen[j][k]);
+            m[k] = __fmul2_rn(v, v);
           }
-          const float da = dot4(va, va), db = dot4(vb, vb);
-          if (da < mda) { mda = da; mba = j; }
-          if (db < mdb) { mdb = db; mbb = j; }
+          const float2 d = add2(m[3], add2(m[2], add2(m[1], m[0], one), one), one);  // dot4's order
+          if (d.x < mda) { mda = d.x; mba = j; }
+          if (d.y < mdb) { mdb = d.y; mbb = j; }
         }
-        bucket[i] = (uint8_t)mba;
-        bucket[i1] = (uint8_t)mbb;
+        // (i is even: the pair shares a word; a self-paired last point ORs the same nibble value into
+        // the next, unused, nibble position -- never read, since reads stop at n)
+        const uint32_t pair = ((uint32_t)mba | ((uint32_t)mbb << 4)) << (4 * (i & 7));
+        if (i < 8) blo |= pair; else bhi |= pair;
       }
       // centroids: bucket sums are exact small integers (<= 16 * 255), so they are accumulated as
       // packed 16-bit pairs per bucket in shared memory -- O(n) instead of the reference's
       // O(n * buckets) scan -- and only the division is done in float, as the reference does
-#pragma unroll 1
-      for (int j = 0; j < nb; j++) { s_acc[0][j][tid] = 0; s_acc[1][j][tid] = 0; s_acc[2][j][tid] = 0; }
+#pragma unroll
+      for (int j = 0; j < NB; j++) { s_acc[0][j][tid] = 0; s_acc[1][j][tid] = 0; s_acc[2][j][tid] = 0; }
 #pragma unroll 1
       for (int i = 0; i < n; i++) {
-        const int b = bucket[i];
-        s_acc[0][b][tid] += pts[i] & 0x00FF00FFu;
-        s_acc[1][b][tid] += (pts[i] >> 8) & 0x00FF00FFu;
+        const int b = (int)(((i < 8 ? blo : bhi) >> (4 * (i & 7))) & 15u);
+        const uint32_t q = pts[i];
+        s_acc[0][b][tid] += q & 0x00FF00FFu;
+        s_acc[1][b][tid] += (q >> 8) & 0x00FF00FFu;
         s_acc[2][b][tid] += 1u;
       }
       fixed = true;
-#pragma unroll 1
-      for (int j = 0; j < nb; j++) {
+#pragma unroll
+      for (int j = 0; j < NB; j++) {
         const uint32_t rb = s_acc[0][j][tid], ga = s_acc[1][j][tid];
         const int c = (int)s_acc[2][j][tid];
         float sum[4] = {(float)(rb & 0xFFFFu), (float)(ga & 0xFFFFu), (float)(rb >> 16), (float)(ga >> 16)};
@@ -989,13 +1026,18 @@ __device__ __noinline__ void fit_core(int ibits, const uint32_t *pts, int n, con
       }
     }
   }
-  int filled = 0, last = -1;
-#pragma unroll 1
-  for (int j = 0; j < nb; j++)
-    if (s_acc[2][j][tid] > 0) { filled++; last = j; }  // the last pass's counts
+  int filled = 0;
+  float lastc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+  for (int j = 0; j < NB; j++)
+    if (s_acc[2][j][tid] > 0) {  // the last pass's counts
+      filled++;
+#pragma unroll
+      for (int k = 0; k < 4; k++) lastc[k] = cen[j][k];
+    }
   if (filled == 1) {  // one bucket -> CompressSingleColor on its centroid (:1038-1047, fit_finish)
     C.kind = 1;
-    C.single = pack_round(cen[last]);
+    C.single = pack_round(lastc);
     return;
   }
 
@@ -1003,11 +1045,10 @@ __device__ __noinline__ void fit_core(int ibits, const uint32_t *pts, int n, con
   {
     float asq = 0.0f, bsq = 0.0f, ab = 0.0f;
     float ax[4] = {0, 0, 0, 0}, bx[4] = {0, 0, 0, 0};
-    const float fb = (float)nbm1;
-#pragma unroll 1
-    for (int i = 0; i < nb; i++) {
+#pragma unroll
+    for (int i = 0; i < NB; i++) {
       const float fn = (float)s_acc[2][i][tid];
-      const float a = div_cold((float)(nbm1 - i), fb), b = div_cold((float)i, fb);
+      const float a = ratio_c(nbm1 - i, nbm1), b = ratio_c(i, nbm1);
       asq = __fadd_rn(asq, __fmul_rn(__fmul_rn(fn, a), a));
       bsq = __fadd_rn(bsq, __fmul_rn(__fmul_rn(fn, b), b));
       ab = __fadd_rn(ab, __fmul_rn(__fmul_rn(fn, a), b));
@@ -1029,7 +1070,7 @@ __device__ __noinline__ void fit_core(int ibits, const uint32_t *pts, int n, con
 
 template <bool NU>
 __device__ __noinline__ void fit_finish(const Ws &ws, const ModeAttr &A, int mode, int idx_mode, int rot, const FitCore &C,
-                                        const uint32_t *pts, const uint32_t *pix, int n, int sa_steps,
+                                        const Col pts, const Col pix, int n, int sa_steps,
                                         const uint8_t *__restrict__ s_w, FitResult &R) {
   R.need_sa = false;
   R.err64 = 0.0;
@@ -1122,9 +1163,6 @@ __device__ __noinline__ void fit_finish(const Ws &ws, const ModeAttr &A, int mod
   R.p1 = cur1; R.p2 = cur2; R.combo = combo;
   R.indices = indices;
 }
-
-constexpr int kChainThreads = 128;
-
 
 // Sort key of an annealing chain: ((index bits - 2) * 17 + cluster size) * 4 + expected-length level.
 // A chain runs until 50 (-q) consecutive steps bring no new best, so its length is unknown in
@@ -1222,10 +1260,10 @@ __device__ __forceinline__ int primary_slot(int layout_b, int slot) {  // invers
 // of modes 4/5, and the result / annealing start state.
 template <bool NU>
 __device__ __forceinline__ void setup_variant(const Ws &ws, const Chain &c, const ModeAttr &A, const FitCore &core,
-                                              const uint32_t *pts, const uint32_t *pix, int n, uint32_t mask,
+                                              const Col pts, const Col pix, int n, uint32_t mask,
                                               int sa_steps, const uint8_t *__restrict__ s_w, const float *__restrict__ s_rcp,
-                                              uint32_t (*s_acc)[16][128], int tid, uint32_t gid, uint32_t rng,
-                                              uint32_t *res, const float *alpha_vals, float amin, float amax) {
+                                              uint32_t (*s_acc)[16][kChainThreads], int tid, uint32_t gid, uint32_t rng,
+                                              uint32_t *res, float amin, float amax) {
   FitResult R;
   fit_finish<NU>(ws, A, c.mode, c.idx_mode, c.rot, core, pts, pix, n, sa_steps, s_w, R);  // the one call site
   res[4] = (uint32_t)R.indices; res[5] = (uint32_t)(R.indices >> 32);
@@ -1281,28 +1319,30 @@ __device__ __forceinline__ void setup_variant(const Ws &ws, const Chain &c, cons
       }
     }
   } else {
-    // scalar k-means over the alpha interpolation points (:770-842)
-    float vals[8];
-    uint8_t bucket[16];
+    // scalar k-means over the alpha interpolation points (:770-842).  The alpha values are re-read
+    // from the block (`pix`), the interpolation points live in the lane's column of accumulator
+    // plane 1 (float bits), the buckets in the nibbles of a register pair.
+    const int ash = c.rot == 0 ? 24 : 8 * (c.rot - 1);  // the channel the rotation put into alpha
+    const Col vals{&s_acc[1][0][tid]};
+    uint32_t blo = 0, bhi = 0;
 #pragma unroll 1
     for (int i = 0; i < nba; i++)
-      vals[i] = __fadd_rn(amin, __fmul_rn(div_cold((float)i, (float)(nba - 1)), __fsub_rn(amax, amin)));
+      vals.set(i, __float_as_uint(__fadd_rn(amin, __fmul_rn(div_cold((float)i, (float)(nba - 1)), __fsub_rn(amax, amin)))));
 #pragma unroll 1
     for (int i = 0; i < 16; i++) {
+      const float av = (float)((pix[i] >> ash) & 0xFFu);
       float md = 255.0f;
-      int b = 0;
+      uint32_t b = 0;
 #pragma unroll 1
       for (int j = 0; j < nba; j++) {
-        const float d = fabsf(__fsub_rn(alpha_vals[i], vals[j]));
-        if (d < md) { md = d; b = j; }
+        const float d = fabsf(__fsub_rn(av, __uint_as_float(vals[j])));
+        if (d < md) { md = d; b = (uint32_t)j; }
       }
-      bucket[i] = (uint8_t)b;
+      if (i < 8) blo |= b << (4 * i); else bhi |= b << (4 * (i - 8));
     }
-    float npts[8];
     bool fixed = false;
     int guard = 0;
     while (!fixed && guard++ < 4096) {
-      float av[8];
       fixed = true;
       // bucket sums / counts are small integers (exact in any order): one pass over the pixels into
       // the lane's shared accumulators instead of the reference's bucket x pixel scan (:790-806)
@@ -1310,38 +1350,38 @@ __device__ __forceinline__ void setup_variant(const Ws &ws, const Chain &c, cons
       for (int i = 0; i < nba; i++) { s_acc[0][i][tid] = 0; s_acc[2][i][tid] = 0; }
 #pragma unroll 1
       for (int j = 0; j < 16; j++) {
-        const int b = bucket[j];
-        s_acc[0][b][tid] += (uint32_t)alpha_vals[j];
+        const int b = (int)(((j < 8 ? blo : bhi) >> (4 * (j & 7))) & 15u);
+        s_acc[0][b][tid] += (pix[j] >> ash) & 0xFFu;
         s_acc[2][b][tid] += 1u;
       }
 #pragma unroll 1
       for (int i = 0; i < nba; i++) {
         const int cnt = (int)s_acc[2][i][tid];
         float s = (float)s_acc[0][i][tid];
-        const float c2 = (float)cnt;
-        if (cnt > 0) s = div_small(s, c2, s_rcp[cnt]);
-        av[i] = s; npts[i] = c2;
-        fixed = fixed && (av[i] == vals[i]);
+        if (cnt > 0) s = div_small(s, (float)cnt, s_rcp[cnt]);
+        fixed = fixed && (s == __uint_as_float(vals[i]));
+        vals.set(i, __float_as_uint(s));
       }
-#pragma unroll 1
-      for (int i = 0; i < nba; i++) vals[i] = av[i];
+      uint32_t nlo = 0, nhi = 0;
 #pragma unroll 1
       for (int i = 0; i < 16; i++) {
+        const float av = (float)((pix[i] >> ash) & 0xFFu);
         float md = 255.0f;
-        int b = bucket[i];  // reference keeps the previous bucket when nothing is closer than 255
+        uint32_t b = ((i < 8 ? blo : bhi) >> (4 * (i & 7))) & 15u;  // reference keeps the previous bucket when nothing is closer than 255
         for (int j = 0; j < nba; j++) {
-          const float d = fabsf(__fsub_rn(alpha_vals[i], vals[j]));
-          if (d < md) { md = d; b = j; }
+          const float d = fabsf(__fsub_rn(av, __uint_as_float(vals[j])));
+          if (d < md) { md = d; b = (uint32_t)j; }
         }
-        bucket[i] = (uint8_t)b;
+        if (i < 8) nlo |= b << (4 * i); else nhi |= b << (4 * (i - 8));
       }
+      blo = nlo; bhi = nhi;
     }
     float asq = 0.0f, bsq = 0.0f, ab = 0.0f, ax = 0.0f, bx = 0.0f;
     const float fb = (float)(nba - 1);
 #pragma unroll 1
     for (int i = 0; i < nba; i++) {
       const float a = div_cold((float)(nba - 1 - i), fb), b = div_cold((float)i, fb);
-      const float nn = npts[i], x = vals[i];
+      const float nn = (float)s_acc[2][i][tid], x = __uint_as_float(vals[i]);  // the last pass's counts
       asq = __fadd_rn(asq, __fmul_rn(__fmul_rn(nn, a), a));
       bsq = __fadd_rn(bsq, __fmul_rn(__fmul_rn(nn, b), b));
       ab = __fadd_rn(ab, __fmul_rn(__fmul_rn(nn, a), b));
@@ -1359,7 +1399,7 @@ __device__ __forceinline__ void setup_variant(const Ws &ws, const Chain &c, cons
     const int a2b = (int)quantize_channel((uint32_t)(int)a2, qmask8, -1);
 #pragma unroll 1
     for (int i = 0; i < 16; i++) {
-      const int val = (int)alpha_vals[i];
+      const int val = (int)((pix[i] >> ash) & 0xFFu);
       int me = 0x7fffffff, bb = 0;
 #pragma unroll 1
       for (int j = 0; j < nba; j++) {
@@ -1394,31 +1434,32 @@ __device__ __forceinline__ void setup_variant(const Ws &ws, const Chain &c, cons
 // One endpoint-fit chain: cluster statistics, CompressCluster's start (fit_cluster), and for
 // modes 4/5 the scalar alpha fit.  Writes either the finished result or the start state of the
 // annealing chain.
-template <bool NU>
+template <bool NU, int IB>
 __device__ __forceinline__ void setup_chain(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x,
                                             uint32_t first_block, const Ws &ws, int sa_steps, uint64_t seed,
                                             uint32_t block_index_base, uint32_t t, int slot,
                                             const uint8_t *__restrict__ s_w, const float *__restrict__ s_rcp,
-                                            uint32_t (*s_acc)[16][128], int tid) {
+                                            uint32_t (*s_acc)[16][kChainThreads], uint32_t (*s_blk)[kChainThreads],
+                                            uint32_t (*s_pts)[kChainThreads], int tid) {
   const uint32_t selw = ws.sel[t];
-  const Chain c = decode_chain(selw, slot), &c0 = c;
+  const Chain c = decode_chain(selw, slot);
   if (!c.active) return;  // (the caller's list only holds live chains)
   const ModeAttr A0 = c_modes[c.mode];
   int twin = twin_slot((selw >> 22) & 1, slot);
   if (twin >= 0 && !decode_chain(selw, twin).active) twin = -1;
 
-  // The kernel is bound by instruction fetch (5-6 k SASS instructions, the resident warps are in
-  // different phases: "no instruction" is its top stall), so the loops below stay rolled.  Rolled
-  // loops index the block dynamically; to keep it out of local memory it is parked in the lane's
-  // accumulator column, which is free until the k-means starts (fit_core).  Per-thread arrays live
-  // in local memory and their footprint decides the L1 hit rate, so nothing is stored twice: the
-  // error pixels (`pix`) are the points themselves, except for modes 4/5 (n == 16).
+  // The kernel's code is large (the resident warps are in different phases: "no instruction" is one of
+  // its top stalls), so the loops over the points stay rolled.  Rolled loops index their arrays
+  // dynamically; so that this does not mean local memory, the block and the cluster's points are
+  // columns of shared memory (Col).  The error pixels (`pix`) are the points themselves, except for
+  // modes 4/5 (n == 16), where they are the block.
   {
     uint32_t blk[16];
     load_block(img, width, blocks_x, first_block + t, blk);
 #pragma unroll
-    for (int i = 0; i < 16; i++) s_acc[0][i][tid] = blk[i];
+    for (int i = 0; i < 16; i++) s_blk[i][tid] = blk[i];
   }
+  const Col blk{&s_blk[0][tid]}, pts{&s_pts[0][tid]};
 
   // Cluster of this chain: points in raster order of the subset (m_PointMap).
   uint32_t smask;  // pixels of the subset
@@ -1433,7 +1474,6 @@ __device__ __forceinline__ void setup_chain(const uint32_t *__restrict__ img, ui
 #pragma unroll 1
     for (int i = 0; i < 16; i++) smask |= ((sel >> (2 * i)) & 1u) << i;
   }
-  uint32_t pts[16];
   int n = 0;
   const uint32_t mask = smask;
   float sum[4] = {0, 0, 0, 0};
@@ -1441,8 +1481,8 @@ __device__ __forceinline__ void setup_chain(const uint32_t *__restrict__ img, ui
 #pragma unroll 1
   for (int i = 0; i < 16; i++) {
     if ((smask >> i) & 1u) {
-      const uint32_t p = s_acc[0][i][tid];
-      pts[n++] = p;
+      const uint32_t p = blk[i];
+      pts.set(n++, p);
 #pragma unroll
       for (int k = 0; k < 4; k++) sum[k] = __fadd_rn(sum[k], (float)chan(p, k));  // exact integers
       mn = __vminu4(mn, p);
@@ -1458,27 +1498,23 @@ __device__ __forceinline__ void setup_chain(const uint32_t *__restrict__ img, ui
   // ---- modes 4/5: CompressCluster alpha variant (Compressor.cpp:632-919), n == 16.
   // Points are rotated and their alpha forced to 255, but avg / bounds / error
   // pixels stay those of the original block (T16).
-  uint32_t pixl[16];
-  float alpha_vals[16];
   float amin = FLT_MAX, amax = -FLT_MAX;
   if (A0.rotation) {
 #pragma unroll 1
     for (int i = 0; i < 16; i++) {
-      const uint32_t p = s_acc[0][i][tid];
+      const uint32_t p = blk[i];
       const uint32_t a = c.rot == 0 ? (p >> 24) : chan(p, c.rot - 1);
       uint32_t q = p;
       if (c.rot) q = (p & ~(0xFFu << (8 * (c.rot - 1)))) | ((p >> 24) << (8 * (c.rot - 1)));  // channel <- old alpha
-      pts[i] = q | 0xFF000000u;
-      pixl[i] = p;
-      alpha_vals[i] = (float)a;
+      pts.set(i, q | 0xFF000000u);
       amin = fminf(amin, (float)a);
       amax = fmaxf(amax, (float)a);
     }
   }
-  const uint32_t *pix = A0.rotation ? pixl : pts;
+  const Col pix = A0.rotation ? blk : pts;
   // the expensive, mode-independent part runs once for the chain and its twin
   FitCore core;
-  fit_core(c0.idx_mode == 0 ? A0.index_bits : A0.alpha_index_bits, pts, n, avg, all_same, s_acc, s_rcp, tid, core);
+  fit_core<(1 << IB)>(pts, n, avg, all_same, s_acc, s_rcp, tid, core);
   const int nvariants = twin >= 0 ? 2 : 1;
 #pragma unroll 1
   for (int variant = 0; variant < nvariants; variant++) {
@@ -1488,7 +1524,7 @@ __device__ __forceinline__ void setup_chain(const uint32_t *__restrict__ img, ui
     const uint32_t gid = t * kSlots + vslot;
     const uint32_t rng = chain_seed(seed, gblock, (uint32_t)c.chain_id);
     uint32_t *res = ws.results + (size_t)gid * kResWords;
-    setup_variant<NU>(ws, c, A, core, pts, pix, n, mask, sa_steps, s_w, s_rcp, s_acc, tid, gid, rng, res, alpha_vals, amin, amax);
+    setup_variant<NU>(ws, c, A, core, pts, pix, n, mask, sa_steps, s_w, s_rcp, s_acc, tid, gid, rng, res, amin, amax);
   }
 }
 
@@ -1503,47 +1539,59 @@ __device__ __forceinline__ int chain_pixels(const Chain &c) {
   return c.subset == 0 ? 16 - __popc(lo | hi) : (c.subset == 1 ? __popc(lo & ~hi) : __popc(hi & ~lo));
 }
 
-// A CTA owns one GROUP of chain slots (the two or three subsets of one candidate mode) of 128
-// consecutive blocks.  It first compacts the live chains of those blocks into a shared list
-// sorted by cluster size, then its lanes walk the list: no lane idles on a dead slot (mode 0 is
-// only tried for a quarter of the shapes, solid / transparent blocks have no chains), and the
-// lanes of a warp fit clusters of (nearly) the same size with the same bucket count, so the
-// k-means / least-squares loops run with uniform trip counts.  Consecutive CTAs walk the groups
-// of the same 128 blocks, which keeps their pixels in L1/L2.
-constexpr int kSlotGroups = 5;
-__constant__ uint8_t c_group_first[kSlotGroups] = {0, 3, 6, 8, 12};
-__constant__ uint8_t c_group_count[kSlotGroups] = {3, 3, 2, 4, 4};  // the last group also owns the dead slot 15
-
-template <bool NU>
-__global__ void __launch_bounds__(kChainThreads, 5)
+// One kernel per index precision IB (2, 3, 4 bits = 4, 8, 16 buckets), so that the bucket count is a
+// compile-time constant of the fit (fit_core<NB>: centroids in registers) while each kernel still holds
+// a single copy of the code.  A CTA owns 128 consecutive blocks.  It first compacts the live chains OF
+// ITS PRECISION (from all 16 slots of those blocks) into a shared list sorted by cluster size, then its
+// lanes walk the list: no lane idles on a dead slot (mode 0 is only tried for a quarter of the shapes,
+// solid / transparent blocks have no chains), and the lanes of a warp fit clusters of (nearly) the same
+// size, so the loops over the points run with uniform trip counts.
+// Index precision of the chain in a slot, per layout: 2 bits per slot, value = IB - 2, 3 = none
+//   opaque: 0-2 mode 0 (3), 3-5 mode 2 (2), 6-7 mode 1 (3), 8-9 mode 3 (2), 10-11 mode 7 (2), 12-13 mode 6 (4)
+//   alpha : 0-7 mode 4 rotation r, index mode 0 / 1 (2 / 3), 8-11 mode 5 (2), 12 mode 6 (4), 13-14 mode 7 (2)
+__device__ __forceinline__ int slot_class(int layout_b, int slot) {
+  const uint32_t opaque = 0xFA005015u;  // slots 15..0, two bits each
+  const uint32_t alpha = 0xC2004444u;
+  return (int)(((layout_b ? alpha : opaque) >> (2 * slot)) & 3u);
+}
+constexpr int kClassList = 6 * kChainThreads;  // at most six primary chains of one precision per block
+#ifndef FASTC_SETUP_CTAS
+#define FASTC_SETUP_CTAS 4
+#endif
+#ifndef FASTC_SETUP_CTAS16
+#define FASTC_SETUP_CTAS16 4
+#endif
+template <bool NU, int IB>
+__global__ void __launch_bounds__(kChainThreads, IB == 4 ? FASTC_SETUP_CTAS16 : FASTC_SETUP_CTAS)
 bc7_setup(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, uint32_t first_block,
           uint32_t num_blocks, Ws ws, int sa_steps, uint64_t seed, uint32_t block_index_base) {
   __shared__ uint8_t s_w[64];
-  __shared__ uint32_t s_acc[3][16][kChainThreads];
-  __shared__ uint16_t s_list[4 * kChainThreads];
+  __shared__ uint32_t s_acc[3][16][kChainThreads];  // k-means accumulators (before that: the unique points)
+  __shared__ uint32_t s_blk[16][kChainThreads];     // the chain's block
+  __shared__ uint32_t s_pts[16][kChainThreads];     // the chain's cluster
+  __shared__ uint16_t s_list[kClassList];
   __shared__ uint32_t s_hist[17], s_cur[17];
   __shared__ float s_rcp[17];  // RN(1 / c) for the bucket counts 1..16 (div_small)
   const int tid = threadIdx.x;
   if (tid < 64) s_w[tid] = c_weight[tid];
   if (tid < 17) { s_hist[tid] = 0; s_cur[tid] = 0; s_rcp[tid] = tid ? __frcp_rn((float)tid) : 0.0f; }
   __syncthreads();
-  const int group = blockIdx.x % kSlotGroups;
-  const uint32_t tile = blockIdx.x / kSlotGroups;
-  const int first = c_group_first[group], count = c_group_count[group];
+  const uint32_t tile = blockIdx.x;
   const uint32_t t = tile * kChainThreads + tid;
   const uint32_t selw = t < num_blocks ? ws.sel[t] : (uint32_t)kTypeSolid << 24;
-  // pass 1: histogram of the live chains by cluster size (bc7_select has reset the state words)
-  int sizes[4];
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    sizes[k] = 0;
-    if (k < count && t < num_blocks) {
-      const Chain c = decode_chain(selw, first + k);
+  const int layout_b = (selw >> 22) & 1;
+  // pass 1: histogram of the live chains of this precision by cluster size; `live` = their slots
+  uint32_t live = 0;
+  if ((selw >> 24) == kTypeNormal) {
+#pragma unroll 1
+    for (int k = 0; k < 15; k++) {
+      if (slot_class(layout_b, k) != IB - 2) continue;
+      const Chain c = decode_chain(selw, k);
       // a twin is fitted by its primary chain's lane (see twin_slot)
-      const int prim = primary_slot((selw >> 22) & 1, first + k);
+      const int prim = primary_slot(layout_b, k);
       if (c.active && !(prim >= 0 && decode_chain(selw, prim).active)) {
-        sizes[k] = chain_pixels(c);
-        atomicAdd(&s_hist[sizes[k]], 1u);
+        live |= 1u << k;
+        atomicAdd(&s_hist[chain_pixels(c)], 1u);
       }
     }
   }
@@ -1554,16 +1602,19 @@ bc7_setup(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, u
     s_cur[0] = off;  // total
   }
   __syncthreads();
-#pragma unroll
-  for (int k = 0; k < 4; k++)
-    if (sizes[k]) s_list[s_hist[sizes[k]] + atomicAdd(&s_cur[sizes[k]], 1u)] = (uint16_t)((tid << 4) | (first + k));
+  while (live) {
+    const int k = __ffs(live) - 1;
+    live &= live - 1;
+    const int sz = chain_pixels(decode_chain(selw, k));
+    s_list[s_hist[sz] + atomicAdd(&s_cur[sz], 1u)] = (uint16_t)((tid << 4) | k);
+  }
   __syncthreads();
-  const uint32_t total = s_cur[0] - 0u;  // s_cur[0] is only touched by size-0 chains, which do not exist
+  const uint32_t total = s_cur[0];  // s_cur[0] is only touched by size-0 chains, which do not exist
   // pass 2: one chain per lane and trip
   for (uint32_t e = tid; e < total; e += kChainThreads) {
     const uint32_t entry = s_list[e];
-    setup_chain<NU>(img, width, blocks_x, first_block, ws, sa_steps, seed, block_index_base,
-                    tile * kChainThreads + (entry >> 4), (int)(entry & 15), s_w, s_rcp, s_acc, tid);
+    setup_chain<NU, IB>(img, width, blocks_x, first_block, ws, sa_steps, seed, block_index_base,
+                        tile * kChainThreads + (entry >> 4), (int)(entry & 15), s_w, s_rcp, s_acc, s_blk, s_pts, tid);
   }
 }
 
@@ -3007,13 +3058,20 @@ cudaError_t bc7_front(Bc7Workspace &wsp, const void *rgba_dev, uint32_t width, u
   if (ev) cudaEventRecord(ev[2], stream);
   const uint64_t nthreads = (uint64_t)nb * kSlots;
   cudaMemsetAsync(ws.bins, 0, kBinWords * 4, stream);
-  if (nu)
-    bc7_setup<true><<<((nb + kChainThreads - 1) / kChainThreads) * kSlotGroups, kChainThreads, 0, stream>>>(
-        img, width, bx, fb, nb, ws, prm.quality, prm.seed, block_index_base);
-  else
-    bc7_setup<false><<<((nb + kChainThreads - 1) / kChainThreads) * kSlotGroups, kChainThreads, 0, stream>>>(
-        img, width, bx, fb, nb, ws, prm.quality, prm.seed, block_index_base);
-  n += 2;
+  {
+    const uint32_t tiles = (nb + kChainThreads - 1) / kChainThreads;
+    // the 16-bucket fits (mode 6, whole blocks) are the longest chains: first
+    if (nu) {
+      bc7_setup<true, 4><<<tiles, kChainThreads, 0, stream>>>(img, width, bx, fb, nb, ws, prm.quality, prm.seed, block_index_base);
+      bc7_setup<true, 3><<<tiles, kChainThreads, 0, stream>>>(img, width, bx, fb, nb, ws, prm.quality, prm.seed, block_index_base);
+      bc7_setup<true, 2><<<tiles, kChainThreads, 0, stream>>>(img, width, bx, fb, nb, ws, prm.quality, prm.seed, block_index_base);
+    } else {
+      bc7_setup<false, 4><<<tiles, kChainThreads, 0, stream>>>(img, width, bx, fb, nb, ws, prm.quality, prm.seed, block_index_base);
+      bc7_setup<false, 3><<<tiles, kChainThreads, 0, stream>>>(img, width, bx, fb, nb, ws, prm.quality, prm.seed, block_index_base);
+      bc7_setup<false, 2><<<tiles, kChainThreads, 0, stream>>>(img, width, bx, fb, nb, ws, prm.quality, prm.seed, block_index_base);
+    }
+  }
+  n += 4;
   if (prm.quality > 0) {
     bc7_bin_offsets<<<1, 1, 0, stream>>>(ws.bins, sa_grid);
     bc7_scatter<<<(uint32_t)((nthreads + 255) / 256), 256, 0, stream>>>(ws, nb);
