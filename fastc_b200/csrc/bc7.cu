@@ -647,7 +647,9 @@ __device__ __noinline__ float div_cold(float a, float b) { return __fdiv_rn(a, b
 // multiplication by one is exact, the result is the correctly rounded sum, and there is nothing left to
 // contract (a product can feed an FFMA2 only as an operand).  A difference p - c is RN(c * -1 + p).
 __device__ __forceinline__ float2 sub2(float2 p, float c) { return __ffma2_rn(make_float2(c, c), make_float2(-1.0f, -1.0f), p); }
+__device__ __forceinline__ float2 sub2(float2 p, float2 c) { return __ffma2_rn(c, make_float2(-1.0f, -1.0f), p); }
 __device__ __forceinline__ float2 add2(float2 a, float2 b, float one) { return __ffma2_rn(a, make_float2(one, one), b); }
+__device__ __forceinline__ float2 mul2(float2 a, float b) { return __fmul2_rn(a, make_float2(b, b)); }
 
 struct F4 { float v[4]; };
 __device__ __forceinline__ float dot4(const float a[4], const float b[4]) {
@@ -809,7 +811,8 @@ struct FitCore {
 
 // GetPrincipalAxis and the two extreme projections along it: the float endpoints the k-means starts from.
 // `upts` is a scratch column for the unique points.
-__device__ __forceinline__ void fit_pca(const Col pts, const Col upts, int n, const float avg[4], float p1[4], float p2[4]) {
+// `one`: see add2.
+__device__ __forceinline__ void fit_pca(const Col pts, const Col upts, int n, const float avg[4], float one, float p1[4], float p2[4]) {
   // ---- GetPrincipalAxis (RGBAEndpoints.cpp:327-428)
   float axis[4];
   {
@@ -850,17 +853,26 @@ __device__ __forceinline__ void fit_pca(const Col pts, const Col upts, int n, co
       } else {
         // covariance of (pt - avg), divided by 3 (T8): ten running sums (lower triangle), each
         // accumulated over the points in order exactly like the reference's per-entry loops
-        float cs[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        // (packed: the products of one row of the triangle share a factor, so a row is one or two FMUL2
+        // with that factor broadcast; two of the twelve lanes hold products nobody reads)
+        float cs[10];
+        {
+          const float2 avg01 = make_float2(avg[0], avg[1]), avg23 = make_float2(avg[2], avg[3]);
+          float2 c0 = make_float2(0.0f, 0.0f), c1 = c0, c2 = c0, c3 = c0, c4 = c0, c5 = c0;
 #pragma unroll 1
-        for (int k = 0; k < n; k++) {
-          float a[4];
-#pragma unroll
-          for (int c2 = 0; c2 < 4; c2++) a[c2] = __fsub_rn((float)chan(pts[k], c2), avg[c2]);
-          int e = 0;
-#pragma unroll
-          for (int i = 0; i < 4; i++)
-#pragma unroll
-            for (int j = 0; j <= i; j++, e++) cs[e] = __fadd_rn(cs[e], __fmul_rn(a[i], a[j]));
+          for (int k = 0; k < n; k++) {
+            const uint32_t q = pts[k];
+            const float2 a01 = sub2(make_float2((float)chan(q, 0), (float)chan(q, 1)), avg01);
+            const float2 a23 = sub2(make_float2((float)chan(q, 2), (float)chan(q, 3)), avg23);
+            c0 = add2(mul2(a01, a01.x), c0, one);  // (0,0) (1,0)
+            c1 = add2(mul2(a01, a01.y), c1, one);  //   -   (1,1)
+            c2 = add2(mul2(a23, a01.x), c2, one);  // (2,0) (3,0)
+            c3 = add2(mul2(a23, a01.y), c3, one);  // (2,1) (3,1)
+            c4 = add2(mul2(a23, a23.x), c4, one);  // (2,2) (3,2)
+            c5 = add2(mul2(a23, a23.y), c5, one);  //   -   (3,3)
+          }
+          cs[0] = c0.x; cs[1] = c0.y; cs[2] = c1.y; cs[3] = c2.x; cs[4] = c3.x; cs[5] = c4.x;
+          cs[6] = c2.y; cs[7] = c3.y; cs[8] = c4.y; cs[9] = c5.y;
         }
         float cov[4][4];
         {
@@ -914,13 +926,16 @@ __device__ __forceinline__ void fit_pca(const Col pts, const Col upts, int n, co
   {
     float mindp = FLT_MAX, maxdp = -FLT_MAX;
 #pragma unroll 1
-    for (int i = 0; i < n; i++) {
-      float v[4];
+    for (int i = 0; i < n; i += 2) {  // two points per trip (an odd cluster's last point twice: min / max do not mind)
+      const uint32_t qa = pts[i], qb = pts[min(i + 1, n - 1)];
+      float2 m[4];
 #pragma unroll
-      for (int k = 0; k < 4; k++) v[k] = __fsub_rn((float)chan(pts[i], k), avg[k]);
-      const float dp = dot4(v, axis);
-      if (dp < mindp) mindp = dp;
-      if (dp > maxdp) maxdp = dp;
+      for (int k = 0; k < 4; k++) m[k] = mul2(sub2(make_float2((float)chan(qa, k), (float)chan(qb, k)), avg[k]), axis[k]);
+      const float2 dp = add2(m[3], add2(m[2], add2(m[1], m[0], one), one), one);  // dot4's order
+      if (dp.x < mindp) mindp = dp.x;
+      if (dp.x > maxdp) maxdp = dp.x;
+      if (dp.y < mindp) mindp = dp.y;
+      if (dp.y > maxdp) maxdp = dp.y;
     }
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -950,17 +965,20 @@ __device__ __noinline__ void fit_core(const Col pts, int n, const float avg[4], 
     return;
   }
   float p1[4], p2[4];
-  fit_pca(pts, Col{&s_acc[1][0][tid]}, n, avg, p1, p2);  // (the accumulator planes are free until the k-means starts)
+  const float one = s_rcp[1];  // 1.0f the compiler cannot see (add2)
+  fit_pca(pts, Col{&s_acc[1][0][tid]}, n, avg, one, p1, p2);  // (the accumulator planes are free until the k-means starts)
 
   // ---- k-means over the NB interpolation points until a fixed point (:961-1026, T15)
-  const float one = s_rcp[1];  // 1.0f the compiler cannot see (add2)
   float cen[NB][4];
 #pragma unroll
   for (int i = 0; i < NB; i++) {
     const float s = ratio_c(i, nbm1);
     const float oms = 1.0f - s;  // one rounding, like the reference's runtime subtraction; folded
 #pragma unroll
-    for (int k = 0; k < 4; k++) cen[i][k] = __fadd_rn(__fmul_rn(p1[k], oms), __fmul_rn(p2[k], s));
+    for (int k = 0; k < 4; k += 2) {
+      const float2 c = add2(mul2(make_float2(p1[k], p1[k + 1]), oms), mul2(make_float2(p2[k], p2[k + 1]), s), one);
+      cen[i][k] = c.x; cen[i][k + 1] = c.y;
+    }
   }
   {
     bool fixed = false;
@@ -1012,12 +1030,15 @@ __device__ __noinline__ void fit_core(const Col pts, int n, const float avg[4], 
       for (int j = 0; j < NB; j++) {
         const uint32_t rb = s_acc[0][j][tid], ga = s_acc[1][j][tid];
         const int c = (int)s_acc[2][j][tid];
-        float sum[4] = {(float)(rb & 0xFFFFu), (float)(ga & 0xFFFFu), (float)(rb >> 16), (float)(ga >> 16)};
-        if (c != 0) {
-          const float fc = (float)c, rc = s_rcp[c];
-#pragma unroll
-          for (int k = 0; k < 4; k++) sum[k] = div_small(sum[k], fc, rc);
+        float2 s01 = make_float2((float)(rb & 0xFFFFu), (float)(ga & 0xFFFFu)), s23 = make_float2((float)(rb >> 16), (float)(ga >> 16));
+        if (c != 0) {  // div_small on two channels at a time
+          const float nfc = -(float)c, rc = s_rcp[c];
+          const float2 q01 = mul2(s01, rc), q23 = mul2(s23, rc);
+          const float2 r01 = __ffma2_rn(q01, make_float2(nfc, nfc), s01), r23 = __ffma2_rn(q23, make_float2(nfc, nfc), s23);
+          s01 = __ffma2_rn(r01, make_float2(rc, rc), q01);
+          s23 = __ffma2_rn(r23, make_float2(rc, rc), q23);
         }
+        const float sum[4] = {s01.x, s01.y, s23.x, s23.y};
 #pragma unroll
         for (int k = 0; k < 4; k++) {
           if (!(cen[j][k] == sum[k])) fixed = false;
@@ -1043,21 +1064,22 @@ __device__ __noinline__ void fit_core(const Col pts, int n, const float avg[4], 
 
   // ---- least squares endpoints (:1053-1077)
   {
-    float asq = 0.0f, bsq = 0.0f, ab = 0.0f;
-    float ax[4] = {0, 0, 0, 0}, bx[4] = {0, 0, 0, 0};
+    float ab = 0.0f;
+    float2 sq = make_float2(0.0f, 0.0f), abx[4] = {sq, sq, sq, sq};
 #pragma unroll
     for (int i = 0; i < NB; i++) {
       const float fn = (float)s_acc[2][i][tid];
-      const float a = ratio_c(nbm1 - i, nbm1), b = ratio_c(i, nbm1);
-      asq = __fadd_rn(asq, __fmul_rn(__fmul_rn(fn, a), a));
-      bsq = __fadd_rn(bsq, __fmul_rn(__fmul_rn(fn, b), b));
-      ab = __fadd_rn(ab, __fmul_rn(__fmul_rn(fn, a), b));
+      const float2 wab = make_float2(ratio_c(nbm1 - i, nbm1), ratio_c(i, nbm1));  // (a, b)
+      const float2 fab = __fmul2_rn(make_float2(fn, fn), wab);                      // (fn * a, fn * b)
+      sq = add2(__fmul2_rn(fab, wab), sq, one);                                     // (asq, bsq)
+      ab = __fadd_rn(ab, __fmul_rn(fab.x, wab.y));
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        ax[k] = __fadd_rn(ax[k], __fmul_rn(__fmul_rn(cen[i][k], a), fn));
-        bx[k] = __fadd_rn(bx[k], __fmul_rn(__fmul_rn(cen[i][k], b), fn));
-      }
+      for (int k = 0; k < 4; k++) abx[k] = add2(mul2(mul2(wab, cen[i][k]), fn), abx[k], one);  // (ax[k], bx[k])
     }
+    const float asq = sq.x, bsq = sq.y;
+    float ax[4], bx[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) { ax[k] = abx[k].x; bx[k] = abx[k].y; }
     const float f = div_cold(1.0f, __fsub_rn(__fmul_rn(asq, bsq), __fmul_rn(ab, ab)));
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -1329,16 +1351,18 @@ __device__ __forceinline__ void setup_variant(const Ws &ws, const Chain &c, cons
     for (int i = 0; i < nba; i++)
       vals.set(i, __float_as_uint(__fadd_rn(amin, __fmul_rn(div_cold((float)i, (float)(nba - 1)), __fsub_rn(amax, amin)))));
 #pragma unroll 1
-    for (int i = 0; i < 16; i++) {
-      const float av = (float)((pix[i] >> ash) & 0xFFu);
-      float md = 255.0f;
-      uint32_t b = 0;
+    for (int i = 0; i < 16; i += 2) {  // two pixels per trip through the packed pipe
+      const float2 av = make_float2((float)((pix[i] >> ash) & 0xFFu), (float)((pix[i + 1] >> ash) & 0xFFu));
+      float mda = 255.0f, mdb = 255.0f;
+      uint32_t ba = 0, bb = 0;
 #pragma unroll 1
       for (int j = 0; j < nba; j++) {
-        const float d = fabsf(__fsub_rn(av, __uint_as_float(vals[j])));
-        if (d < md) { md = d; b = (uint32_t)j; }
+        const float2 d = sub2(av, __uint_as_float(vals[j]));
+        if (fabsf(d.x) < mda) { mda = fabsf(d.x); ba = (uint32_t)j; }
+        if (fabsf(d.y) < mdb) { mdb = fabsf(d.y); bb = (uint32_t)j; }
       }
-      if (i < 8) blo |= b << (4 * i); else bhi |= b << (4 * (i - 8));
+      const uint32_t pair = (ba | (bb << 4)) << (4 * (i & 7));
+      if (i < 8) blo |= pair; else bhi |= pair;
     }
     bool fixed = false;
     int guard = 0;
@@ -1364,15 +1388,19 @@ __device__ __forceinline__ void setup_variant(const Ws &ws, const Chain &c, cons
       }
       uint32_t nlo = 0, nhi = 0;
 #pragma unroll 1
-      for (int i = 0; i < 16; i++) {
-        const float av = (float)((pix[i] >> ash) & 0xFFu);
-        float md = 255.0f;
-        uint32_t b = ((i < 8 ? blo : bhi) >> (4 * (i & 7))) & 15u;  // reference keeps the previous bucket when nothing is closer than 255
+      for (int i = 0; i < 16; i += 2) {
+        const float2 av = make_float2((float)((pix[i] >> ash) & 0xFFu), (float)((pix[i + 1] >> ash) & 0xFFu));
+        float mda = 255.0f, mdb = 255.0f;
+        const uint32_t old = (i < 8 ? blo : bhi) >> (4 * (i & 7));
+        uint32_t ba = old & 15u, bb = (old >> 4) & 15u;  // reference keeps the previous bucket when nothing is closer than 255
+#pragma unroll 1
         for (int j = 0; j < nba; j++) {
-          const float d = fabsf(__fsub_rn(av, __uint_as_float(vals[j])));
-          if (d < md) { md = d; b = (uint32_t)j; }
+          const float2 d = sub2(av, __uint_as_float(vals[j]));
+          if (fabsf(d.x) < mda) { mda = fabsf(d.x); ba = (uint32_t)j; }
+          if (fabsf(d.y) < mdb) { mdb = fabsf(d.y); bb = (uint32_t)j; }
         }
-        if (i < 8) nlo |= b << (4 * i); else nhi |= b << (4 * (i - 8));
+        const uint32_t pair = (ba | (bb << 4)) << (4 * (i & 7));
+        if (i < 8) nlo |= pair; else nhi |= pair;
       }
       blo = nlo; bhi = nhi;
     }
