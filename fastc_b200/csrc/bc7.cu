@@ -712,6 +712,10 @@ __device__ __forceinline__ uint32_t single_color_nu(int mode, int idx_mode, int 
 // points, the k-means accumulators) in such columns: rolled loops index them dynamically, which in
 // per-thread arrays means local memory -- and that kernel's L1 could not hold 640 threads' arrays.
 constexpr int kChainThreads = 128;
+#ifndef FASTC_ALPHA_UNROLL
+#define FASTC_ALPHA_UNROLL 1
+#endif
+constexpr int kAlphaUnroll = FASTC_ALPHA_UNROLL;
 struct Col {
   uint32_t *p;
   __device__ __forceinline__ uint32_t operator[](int i) const { return p[i * kChainThreads]; }
@@ -1273,9 +1277,13 @@ __device__ __forceinline__ int twin_slot(int layout_b, int slot) {
   if (!layout_b) return (slot == 8 || slot == 9) ? slot + 2 : (slot == 12 ? 13 : -1);
   return (slot < 8 && !(slot & 1)) ? 8 + (slot >> 1) : -1;
 }
-__device__ __forceinline__ int primary_slot(int layout_b, int slot) {  // inverse of twin_slot, -1: not a twin
-  if (!layout_b) return (slot == 10 || slot == 11) ? slot - 2 : (slot == 13 ? 12 : -1);
-  return (slot >= 8 && slot < 12) ? (slot - 8) * 2 : -1;
+// Is the chain in `slot` a twin whose primary chain is live (and therefore fits it)?  A primary is live
+// exactly when its mode is enabled: modes 3, 6 and 4 have no other condition in decode_chain (their
+// shape slot always exists).
+__device__ __forceinline__ bool fitted_by_primary(uint32_t selw, int slot) {
+  const uint32_t modes = (selw >> 12) & 0xFF;
+  if (!((selw >> 22) & 1)) return ((slot == 10 || slot == 11) && ((modes >> 3) & 1)) || (slot == 13 && ((modes >> 6) & 1));
+  return slot >= 8 && slot < 12 && ((modes >> 4) & 1);
 }
 
 // Per-mode tail of one chain: ClampEndpointsToGrid + first evaluation (fit_finish), the scalar alpha fit
@@ -1355,8 +1363,8 @@ __device__ __forceinline__ void setup_variant(const Ws &ws, const Chain &c, cons
       const float2 av = make_float2((float)((pix[i] >> ash) & 0xFFu), (float)((pix[i + 1] >> ash) & 0xFFu));
       float mda = 255.0f, mdb = 255.0f;
       uint32_t ba = 0, bb = 0;
-#pragma unroll 1
-      for (int j = 0; j < nba; j++) {
+#pragma unroll kAlphaUnroll
+      for (int j = 0; j < nba; j++) {  // (nba is 4 or 8)
         const float2 d = sub2(av, __uint_as_float(vals[j]));
         if (fabsf(d.x) < mda) { mda = fabsf(d.x); ba = (uint32_t)j; }
         if (fabsf(d.y) < mdb) { mdb = fabsf(d.y); bb = (uint32_t)j; }
@@ -1393,8 +1401,8 @@ __device__ __forceinline__ void setup_variant(const Ws &ws, const Chain &c, cons
         float mda = 255.0f, mdb = 255.0f;
         const uint32_t old = (i < 8 ? blo : bhi) >> (4 * (i & 7));
         uint32_t ba = old & 15u, bb = (old >> 4) & 15u;  // reference keeps the previous bucket when nothing is closer than 255
-#pragma unroll 1
-        for (int j = 0; j < nba; j++) {
+#pragma unroll kAlphaUnroll
+        for (int j = 0; j < nba; j++) {  // (nba is 4 or 8)
           const float2 d = sub2(av, __uint_as_float(vals[j]));
           if (fabsf(d.x) < mda) { mda = fabsf(d.x); ba = (uint32_t)j; }
           if (fabsf(d.y) < mdb) { mdb = fabsf(d.y); bb = (uint32_t)j; }
@@ -1470,11 +1478,15 @@ __device__ __forceinline__ void setup_chain(const uint32_t *__restrict__ img, ui
                                             uint32_t (*s_acc)[16][kChainThreads], uint32_t (*s_blk)[kChainThreads],
                                             uint32_t (*s_pts)[kChainThreads], int tid) {
   const uint32_t selw = ws.sel[t];
-  const Chain c = decode_chain(selw, slot);
+  const Chain c = decode_chain(selw, slot), &c0 = c;
   if (!c.active) return;  // (the caller's list only holds live chains)
   const ModeAttr A0 = c_modes[c.mode];
   int twin = twin_slot((selw >> 22) & 1, slot);
-  if (twin >= 0 && !decode_chain(selw, twin).active) twin = -1;
+  Chain ctwin = c;
+  if (twin >= 0) {
+    ctwin = decode_chain(selw, twin);
+    if (!ctwin.active) twin = -1;
+  }
 
   // The kernel's code is large (the resident warps are in different phases: "no instruction" is one of
   // its top stalls), so the loops over the points stay rolled.  Rolled loops index their arrays
@@ -1547,7 +1559,7 @@ __device__ __forceinline__ void setup_chain(const uint32_t *__restrict__ img, ui
 #pragma unroll 1
   for (int variant = 0; variant < nvariants; variant++) {
     const int vslot = variant == 0 ? slot : twin;
-    const Chain c = decode_chain(selw, vslot);
+    const Chain &c = variant == 0 ? c0 : ctwin;
     const ModeAttr A = c_modes[c.mode];
     const uint32_t gid = t * kSlots + vslot;
     const uint32_t rng = chain_seed(seed, gblock, (uint32_t)c.chain_id);
@@ -1609,17 +1621,20 @@ bc7_setup(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, u
   const uint32_t selw = t < num_blocks ? ws.sel[t] : (uint32_t)kTypeSolid << 24;
   const int layout_b = (selw >> 22) & 1;
   // pass 1: histogram of the live chains of this precision by cluster size; `live` = their slots
-  uint32_t live = 0;
+  uint32_t live = 0, sizes = 0;
+  int nlive = 0;
   if ((selw >> 24) == kTypeNormal) {
 #pragma unroll 1
     for (int k = 0; k < 15; k++) {
-      if (slot_class(layout_b, k) != IB - 2) continue;
-      const Chain c = decode_chain(selw, k);
       // a twin is fitted by its primary chain's lane (see twin_slot)
-      const int prim = primary_slot(layout_b, k);
-      if (c.active && !(prim >= 0 && decode_chain(selw, prim).active)) {
+      if (slot_class(layout_b, k) != IB - 2 || fitted_by_primary(selw, k)) continue;
+      const Chain c = decode_chain(selw, k);
+      if (c.active) {
+        const int sz = chain_pixels(c);
         live |= 1u << k;
-        atomicAdd(&s_hist[chain_pixels(c)], 1u);
+        sizes = (sizes << 5) | (uint32_t)sz;  // at most six live chains: 30 bits, first chain in the top field
+        nlive++;
+        atomicAdd(&s_hist[sz], 1u);
       }
     }
   }
@@ -1633,7 +1648,7 @@ bc7_setup(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, u
   while (live) {
     const int k = __ffs(live) - 1;
     live &= live - 1;
-    const int sz = chain_pixels(decode_chain(selw, k));
+    const int sz = (int)((sizes >> (5 * --nlive)) & 31u);
     s_list[s_hist[sz] + atomicAdd(&s_cur[sz], 1u)] = (uint16_t)((tid << 4) | k);
   }
   __syncthreads();
