@@ -826,6 +826,7 @@ __device__ __forceinline__ void fit_pca(const Col pts, const Col upts, int n, co
     for (int i = 0; i < n; i++) {
       const uint32_t p = pts[i];
       bool has = false;
+#pragma unroll 1
       for (int j = 0; j < nu; j++) has = has || (upts[j] == p);
       if (!has) upts.set(nu++, p);
     }
@@ -960,7 +961,7 @@ __device__ __forceinline__ void fit_pca(const Col pts, const Col upts, int n, co
 __host__ __device__ constexpr float ratio_c(int a, int b) { return (float)a / (float)b; }  // IEEE RN division, folded
 
 template <int NB>
-__device__ __noinline__ void fit_core(const Col pts, int n, const float avg[4], bool all_same,
+__device__ __forceinline__ void fit_core(const Col pts, int n, const float avg[4], bool all_same,
                                       uint32_t (*s_acc)[16][kChainThreads], const float *__restrict__ s_rcp, int tid, FitCore &C) {
   constexpr int nbm1 = NB - 1;
   if (all_same) {  // AllSamePoint -> CompressSingleColor on point 0 (fit_finish)
@@ -1095,7 +1096,7 @@ __device__ __noinline__ void fit_core(const Col pts, int n, const float avg[4], 
 }
 
 template <bool NU>
-__device__ __noinline__ void fit_finish(const Ws &ws, const ModeAttr &A, int mode, int idx_mode, int rot, const FitCore &C,
+__device__ __forceinline__ void fit_finish(const Ws &ws, const ModeAttr &A, int mode, int idx_mode, int rot, const FitCore &C,
                                         const Col pts, const Col pix, int n, int sa_steps,
                                         const uint8_t *__restrict__ s_w, FitResult &R) {
   R.need_sa = false;
@@ -1159,10 +1160,10 @@ __device__ __noinline__ void fit_finish(const Ws &ws, const ModeAttr &A, int mod
   // WITHOUT p-bits GetPBitCombo() returns {0,0} (CompressionMode.h:244-251), so inside the error
   // evaluation (and only there) their endpoints are quantised as if a p-bit of 0 followed the
   // colour bits.  The endpoint state itself and Pack quantise without a p-bit.
-  int pb0, pb1;
-  pbit_combo(A.pbit, combo, pb0, pb1);
   const bool has_pbit = A.pbit != kPbitNone;
-  uint32_t cur1 = to_pixel_b(c1, qm, pb0), cur2 = to_pixel_b(c2, qm, pb1);  // idempotent: c1/c2 are on the grid
+  const uint32_t cur1 = c1, cur2 = c2;  // on the mode's grid already (quantisation is idempotent)
+  // what QuantizedError sees: the same, except that modes without p-bits are quantised with a p-bit of 0
+  const uint32_t qe1 = has_pbit ? c1 : to_pixel_b(c1, qm, 0), qe2 = has_pbit ? c2 : to_pixel_b(c2, qm, 0);
   // one evaluation serves both outcomes: its error starts the annealing chain, its indices are
   // the result when there is no annealing (same quirky quantisation either way)
   unsigned long long indices;
@@ -1170,12 +1171,10 @@ __device__ __noinline__ void fit_finish(const Ws &ws, const ModeAttr &A, int mod
   if constexpr (NU) {
     float w[4];
     nu_metric(A.rotation ? rot : 0, w);
-    cur_err = qe_cluster_nu(pts, pix, n, to_pixel_b(c1, qm, has_pbit ? pb0 : 0), to_pixel_b(c2, qm, has_pbit ? pb1 : 0),
-                            nbm1, wtab, w, &indices);
+    cur_err = qe_cluster_nu(pts, pix, n, qe1, qe2, nbm1, wtab, w, &indices);
     R.err64 = (double)__uint_as_float(cur_err);
   } else {
-    cur_err = qe_cluster(pts, pix, n, to_pixel_b(c1, qm, has_pbit ? pb0 : 0), to_pixel_b(c2, qm, has_pbit ? pb1 : 0), nbm1,
-                         wtab, &indices);
+    cur_err = qe_cluster(pts, pix, n, qe1, qe2, nbm1, wtab, &indices);
   }
   COUNT_QE(ws, 1, 0);
   if (sa_steps > 0 && cur_err > 0) {  // hand over to bc7_anneal
@@ -1203,9 +1202,10 @@ constexpr int kLenLevels = 8;
 constexpr int kSortKeys = 51 * kLenLevels;
 __device__ __forceinline__ int sort_key(int ibits, int n, uint32_t err) {
   // start error per pixel: < 128 | < 4096 | < 8192 | < 16384 | < 32768 | < 49152 | < 65536 | above
-  const uint32_t e = err / (uint32_t)max(n, 1);
-  const int lvl = e < 4096u ? (e < 128u ? 0 : 1)
-                            : (e < 16384u ? (e < 8192u ? 2 : 3) : (e < 32768u ? 4 : (e < 49152u ? 5 : (e < 65536u ? 6 : 7))));
+  // (an ordering heuristic, not a result: the quotient may be off by one at a level's edge, but bc7_setup's
+  // histogram and bc7_scatter evaluate this same function, which is all that has to agree)
+  const uint32_t e = __float2uint_rz(__fmul_rn((float)err, __frcp_rn((float)max(n, 1))));
+  const int lvl = (e >= 128u) + (e >= 4096u) + (e >= 8192u) + (e >= 16384u) + (e >= 32768u) + (e >= 49152u) + (e >= 65536u);
 #ifdef FASTC_SORT_SIZE_MAJOR
   return ((ibits - 2) * 17 + n) * kLenLevels + lvl;
 #else
