@@ -1288,7 +1288,7 @@ __device__ __forceinline__ bool fitted_by_primary(uint32_t selw, int slot) {
 
 // Per-mode tail of one chain: ClampEndpointsToGrid + first evaluation (fit_finish), the scalar alpha fit
 // of modes 4/5, and the result / annealing start state.
-template <bool NU>
+template <bool NU, bool ROT>
 __device__ __forceinline__ void setup_variant(const Ws &ws, const Chain &c, const ModeAttr &A, const FitCore &core,
                                               const Col pts, const Col pix, int n, uint32_t mask,
                                               int sa_steps, const uint8_t *__restrict__ s_w, const float *__restrict__ s_rcp,
@@ -1297,7 +1297,7 @@ __device__ __forceinline__ void setup_variant(const Ws &ws, const Chain &c, cons
   FitResult R;
   fit_finish<NU>(ws, A, c.mode, c.idx_mode, c.rot, core, pts, pix, n, sa_steps, s_w, R);  // the one call site
   res[4] = (uint32_t)R.indices; res[5] = (uint32_t)(R.indices >> 32);
-  if (!A.rotation) {
+  if constexpr (!ROT) {
     if (R.need_sa) {
       write_state(ws, gid, mask, c, n, R, rng, 0, 0);
       return;
@@ -1306,7 +1306,7 @@ __device__ __forceinline__ void setup_variant(const Ws &ws, const Chain &c, cons
     res[4] = (uint32_t)R.indices; res[5] = (uint32_t)(R.indices >> 32);
     if constexpr (NU) ws.err64[gid] = R.err64;
     return;
-  }
+  } else {
 
   const int abits = c.idx_mode == 0 ? A.alpha_index_bits : A.index_bits;
   const int nba = 1 << abits;
@@ -1465,12 +1465,13 @@ __device__ __forceinline__ void setup_variant(const Ws &ws, const Chain &c, cons
   res[0] = R.err + alpha_err; res[1] = e1; res[2] = e2; res[3] = 0;
   res[4] = (uint32_t)R.indices; res[5] = (uint32_t)(R.indices >> 32);
   if constexpr (NU) ws.err64[gid] = __dadd_rn(R.err64, alpha_err64);
+  }
 }
 
 // One endpoint-fit chain: cluster statistics, CompressCluster's start (fit_cluster), and for
 // modes 4/5 the scalar alpha fit.  Writes either the finished result or the start state of the
 // annealing chain.
-template <bool NU, int IB>
+template <bool NU, int IB, bool ROT>
 __device__ __forceinline__ void setup_chain(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x,
                                             uint32_t first_block, const Ws &ws, int sa_steps, uint64_t seed,
                                             uint32_t block_index_base, uint32_t t, int slot,
@@ -1501,48 +1502,45 @@ __device__ __forceinline__ void setup_chain(const uint32_t *__restrict__ img, ui
   }
   const Col blk{&s_blk[0][tid]}, pts{&s_pts[0][tid]};
 
-  // Cluster of this chain: points in raster order of the subset (m_PointMap).
-  uint32_t smask;  // pixels of the subset
-  if (c.nsub == 1) {
-    smask = 0xFFFFu;
-  } else if (c.nsub == 2) {
-    smask = c.subset ? (uint32_t)c_shape2[c.shape] : (~(uint32_t)c_shape2[c.shape] & 0xFFFFu);
-  } else {
-    const uint32_t m3 = c_shape3[c.shape], lo = m3 & 0x55555555u, hi = (m3 >> 1) & 0x55555555u;
-    const uint32_t sel = c.subset == 0 ? ~(lo | hi) & 0x55555555u : (c.subset == 1 ? lo & ~hi : hi & ~lo);
-    smask = 0;  // one bit per 2-bit field
-#pragma unroll 1
-    for (int i = 0; i < 16; i++) smask |= ((sel >> (2 * i)) & 1u) << i;
-  }
   int n = 0;
-  const uint32_t mask = smask;
+  uint32_t mask = 0xFFFFu;  // pixels of the subset
   float sum[4] = {0, 0, 0, 0};
   uint32_t mn = 0xFFFFFFFFu, mx = 0;
+  float amin = FLT_MAX, amax = -FLT_MAX;
+  if constexpr (!ROT) {
+    // Cluster of this chain: points in raster order of the subset (m_PointMap).
+    if (c.nsub == 2) {
+      mask = c.subset ? (uint32_t)c_shape2[c.shape] : (~(uint32_t)c_shape2[c.shape] & 0xFFFFu);
+    } else if (c.nsub == 3) {
+      const uint32_t m3 = c_shape3[c.shape], lo = m3 & 0x55555555u, hi = (m3 >> 1) & 0x55555555u;
+      const uint32_t sel = c.subset == 0 ? ~(lo | hi) & 0x55555555u : (c.subset == 1 ? lo & ~hi : hi & ~lo);
+      mask = 0;  // one bit per 2-bit field
 #pragma unroll 1
-  for (int i = 0; i < 16; i++) {
-    if ((smask >> i) & 1u) {
+      for (int i = 0; i < 16; i++) mask |= ((sel >> (2 * i)) & 1u) << i;
+    }
+#pragma unroll 1
+    for (int i = 0; i < 16; i++) {
+      if ((mask >> i) & 1u) {
+        const uint32_t p = blk[i];
+        pts.set(n++, p);
+#pragma unroll
+        for (int k = 0; k < 4; k++) sum[k] = __fadd_rn(sum[k], (float)chan(p, k));  // exact integers
+        mn = __vminu4(mn, p);
+        mx = __vmaxu4(mx, p);
+      }
+    }
+  } else {
+    // ---- modes 4/5: CompressCluster alpha variant (Compressor.cpp:632-919), the whole block.
+    // Points are rotated and their alpha forced to 255, but avg / bounds / error
+    // pixels stay those of the original block (T16).
+    n = 16;
+#pragma unroll 1
+    for (int i = 0; i < 16; i++) {
       const uint32_t p = blk[i];
-      pts.set(n++, p);
 #pragma unroll
       for (int k = 0; k < 4; k++) sum[k] = __fadd_rn(sum[k], (float)chan(p, k));  // exact integers
       mn = __vminu4(mn, p);
       mx = __vmaxu4(mx, p);
-    }
-  }
-  float avg[4];
-#pragma unroll
-  for (int k = 0; k < 4; k++) avg[k] = div_cold(sum[k], (float)n);
-  const bool all_same = mn == mx;
-  const uint32_t gblock = block_index_base + first_block + t;
-
-  // ---- modes 4/5: CompressCluster alpha variant (Compressor.cpp:632-919), n == 16.
-  // Points are rotated and their alpha forced to 255, but avg / bounds / error
-  // pixels stay those of the original block (T16).
-  float amin = FLT_MAX, amax = -FLT_MAX;
-  if (A0.rotation) {
-#pragma unroll 1
-    for (int i = 0; i < 16; i++) {
-      const uint32_t p = blk[i];
       const uint32_t a = c.rot == 0 ? (p >> 24) : chan(p, c.rot - 1);
       uint32_t q = p;
       if (c.rot) q = (p & ~(0xFFu << (8 * (c.rot - 1)))) | ((p >> 24) << (8 * (c.rot - 1)));  // channel <- old alpha
@@ -1551,7 +1549,12 @@ __device__ __forceinline__ void setup_chain(const uint32_t *__restrict__ img, ui
       amax = fmaxf(amax, (float)a);
     }
   }
-  const Col pix = A0.rotation ? blk : pts;
+  float avg[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) avg[k] = div_cold(sum[k], (float)n);
+  const bool all_same = mn == mx;
+  const uint32_t gblock = block_index_base + first_block + t;
+  const Col pix = ROT ? blk : pts;
   // the expensive, mode-independent part runs once for the chain and its twin
   FitCore core;
   fit_core<(1 << IB)>(pts, n, avg, all_same, s_acc, s_rcp, tid, core);
@@ -1564,7 +1567,7 @@ __device__ __forceinline__ void setup_chain(const uint32_t *__restrict__ img, ui
     const uint32_t gid = t * kSlots + vslot;
     const uint32_t rng = chain_seed(seed, gblock, (uint32_t)c.chain_id);
     uint32_t *res = ws.results + (size_t)gid * kResWords;
-    setup_variant<NU>(ws, c, A, core, pts, pix, n, mask, sa_steps, s_w, s_rcp, s_acc, tid, gid, rng, res, amin, amax);
+    setup_variant<NU, ROT>(ws, c, A, core, pts, pix, n, mask, sa_steps, s_w, s_rcp, s_acc, tid, gid, rng, res, amin, amax);
   }
 }
 
@@ -1601,7 +1604,7 @@ constexpr int kClassList = 6 * kChainThreads;  // at most six primary chains of 
 #ifndef FASTC_SETUP_CTAS16
 #define FASTC_SETUP_CTAS16 4
 #endif
-template <bool NU, int IB>
+template <bool NU, int IB, bool ROT>
 __global__ void __launch_bounds__(kChainThreads, IB == 4 ? FASTC_SETUP_CTAS16 : FASTC_SETUP_CTAS)
 bc7_setup(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, uint32_t first_block,
           uint32_t num_blocks, Ws ws, int sa_steps, uint64_t seed, uint32_t block_index_base) {
@@ -1628,6 +1631,7 @@ bc7_setup(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, u
     for (int k = 0; k < 15; k++) {
       // a twin is fitted by its primary chain's lane (see twin_slot)
       if (slot_class(layout_b, k) != IB - 2 || fitted_by_primary(selw, k)) continue;
+      if (ROT != (layout_b && k < 12)) continue;  // the rotation fits (modes 4/5) have kernels of their own
       const Chain c = decode_chain(selw, k);
       if (c.active) {
         const int sz = chain_pixels(c);
@@ -1641,6 +1645,7 @@ bc7_setup(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, u
   __syncthreads();
   if (tid == 0) {  // start offsets, largest clusters first
     uint32_t off = 0;
+#pragma unroll 1
     for (int n = 16; n >= 0; n--) { const uint32_t c = s_hist[n]; s_hist[n] = off; off += c; }
     s_cur[0] = off;  // total
   }
@@ -1656,7 +1661,7 @@ bc7_setup(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, u
   // pass 2: one chain per lane and trip
   for (uint32_t e = tid; e < total; e += kChainThreads) {
     const uint32_t entry = s_list[e];
-    setup_chain<NU, IB>(img, width, blocks_x, first_block, ws, sa_steps, seed, block_index_base,
+    setup_chain<NU, IB, ROT>(img, width, blocks_x, first_block, ws, sa_steps, seed, block_index_base,
                         tile * kChainThreads + (entry >> 4), (int)(entry & 15), s_w, s_rcp, s_acc, s_blk, s_pts, tid);
   }
 }
@@ -3104,17 +3109,24 @@ cudaError_t bc7_front(Bc7Workspace &wsp, const void *rgba_dev, uint32_t width, u
   {
     const uint32_t tiles = (nb + kChainThreads - 1) / kChainThreads;
     // the 16-bucket fits (mode 6, whole blocks) are the longest chains: first
+#define FASTC_SETUP_LAUNCH(NU_, IB_, ROT_) \
+  bc7_setup<NU_, IB_, ROT_><<<tiles, kChainThreads, 0, stream>>>(img, width, bx, fb, nb, ws, prm.quality, prm.seed, block_index_base)
     if (nu) {
-      bc7_setup<true, 4><<<tiles, kChainThreads, 0, stream>>>(img, width, bx, fb, nb, ws, prm.quality, prm.seed, block_index_base);
-      bc7_setup<true, 3><<<tiles, kChainThreads, 0, stream>>>(img, width, bx, fb, nb, ws, prm.quality, prm.seed, block_index_base);
-      bc7_setup<true, 2><<<tiles, kChainThreads, 0, stream>>>(img, width, bx, fb, nb, ws, prm.quality, prm.seed, block_index_base);
+      FASTC_SETUP_LAUNCH(true, 4, false);
+      FASTC_SETUP_LAUNCH(true, 3, true);
+      FASTC_SETUP_LAUNCH(true, 2, true);
+      FASTC_SETUP_LAUNCH(true, 3, false);
+      FASTC_SETUP_LAUNCH(true, 2, false);
     } else {
-      bc7_setup<false, 4><<<tiles, kChainThreads, 0, stream>>>(img, width, bx, fb, nb, ws, prm.quality, prm.seed, block_index_base);
-      bc7_setup<false, 3><<<tiles, kChainThreads, 0, stream>>>(img, width, bx, fb, nb, ws, prm.quality, prm.seed, block_index_base);
-      bc7_setup<false, 2><<<tiles, kChainThreads, 0, stream>>>(img, width, bx, fb, nb, ws, prm.quality, prm.seed, block_index_base);
+      FASTC_SETUP_LAUNCH(false, 4, false);
+      FASTC_SETUP_LAUNCH(false, 3, true);
+      FASTC_SETUP_LAUNCH(false, 2, true);
+      FASTC_SETUP_LAUNCH(false, 3, false);
+      FASTC_SETUP_LAUNCH(false, 2, false);
     }
+#undef FASTC_SETUP_LAUNCH
   }
-  n += 4;
+  n += 6;
   if (prm.quality > 0) {
     bc7_bin_offsets<<<1, 1, 0, stream>>>(ws.bins, sa_grid);
     bc7_scatter<<<(uint32_t)((nthreads + 255) / 256), 256, 0, stream>>>(ws, nb);
