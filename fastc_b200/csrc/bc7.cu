@@ -174,18 +174,16 @@ __device__ __forceinline__ int quant_row(uint32_t mask8, int pbit) {
 }
 // ToPixel for endpoint bytes that are already integers (RGBAEndpoints.cpp:167-177): four lookups
 // (bc7_setup spent 12 % of its instructions in the arithmetic version).
-__device__ __forceinline__ uint32_t to_pixel_b(uint32_t p, uint32_t mask, int pbit) {
+__device__ __noinline__ uint32_t to_pixel_b(uint32_t p, uint32_t mask, int pbit) {
   const uint8_t *tc = g_quant + 256 * quant_row(mask & 0xFF, pbit), *ta = g_quant + 256 * quant_row(mask >> 24, pbit);
   return (uint32_t)__ldg(tc + (p & 0xFF)) | ((uint32_t)__ldg(tc + ((p >> 8) & 0xFF)) << 8) |
          ((uint32_t)__ldg(tc + ((p >> 16) & 0xFF)) << 16) | ((uint32_t)__ldg(ta + (p >> 24)) << 24);
 }
 // uint32(x + 0.5) & 0xFF, x in [0, 255.5): exact without fp64 (x - floor(x) is exact).
+// floor(x + 0.5) = (floor(2 x) + 1) >> 1, and 2 x is exact; the conversion maps NaN to 0 like x86's
+// cvttsd2si does in the low byte.
 __device__ __forceinline__ uint32_t round_byte(float x) {
-  if (!(x == x)) return 0;  // x86 cvttsd2si of NaN -> low byte 0
-  const float f = floorf(x);
-  uint32_t r = (uint32_t)(int)f;
-  if (__fsub_rn(x, f) >= 0.5f) r++;
-  return r & 0xFF;
+  return (uint32_t)((__float2int_rd(__fadd_rn(x, x)) + 1) >> 1) & 0xFF;
 }
 __device__ __forceinline__ uint32_t pack_round(const float p[4]) {
   return round_byte(p[0]) | (round_byte(p[1]) << 8) | (round_byte(p[2]) << 16) | (round_byte(p[3]) << 24);
@@ -636,6 +634,14 @@ __device__ __forceinline__ float div_small(float a, float c, float rc) {
   return __fmaf_rn(r, rc, q);
 }
 
+// x / 3, correctly rounded, in three instructions (Markstein's sequence with RN(1/3)): equal to the IEEE
+// quotient for EVERY normal float -- checked exhaustively by tests/native/div3_check.c.
+__device__ __forceinline__ float div3(float x) {
+  const float y = 0.3333333432674407958984375f;  // RN(1 / 3)
+  const float q = __fmul_rn(x, y);
+  return __fmaf_rn(__fmaf_rn(-q, 3.0f, x), y, q);
+}
+
 // IEEE division for the once-per-chain code of bc7_setup, out of line: the inline expansion is ~10
 // instructions per site, and that kernel is bound by instruction fetch (see setup_chain)
 __device__ __noinline__ float div_cold(float a, float b) { return __fdiv_rn(a, b); }
@@ -886,7 +892,7 @@ __device__ __forceinline__ void fit_pca(const Col pts, const Col upts, int n, co
           for (int i = 0; i < 4; i++)
 #pragma unroll
             for (int j = 0; j <= i; j++, e++) {
-              cov[i][j] = div_cold(cs[e], 3.0f);
+              cov[i][j] = div3(cs[e]);
               cov[j][i] = cov[i][j];
             }
         }
@@ -1481,7 +1487,6 @@ __device__ __forceinline__ void setup_chain(const uint32_t *__restrict__ img, ui
   const uint32_t selw = ws.sel[t];
   const Chain c = decode_chain(selw, slot), &c0 = c;
   if (!c.active) return;  // (the caller's list only holds live chains)
-  const ModeAttr A0 = c_modes[c.mode];
   int twin = twin_slot((selw >> 22) & 1, slot);
   Chain ctwin = c;
   if (twin >= 0) {
@@ -1549,9 +1554,9 @@ __device__ __forceinline__ void setup_chain(const uint32_t *__restrict__ img, ui
       amax = fmaxf(amax, (float)a);
     }
   }
-  float avg[4];
+  float avg[4];  // channel sums <= 16 * 255 over a count <= 16: div_small's domain
 #pragma unroll
-  for (int k = 0; k < 4; k++) avg[k] = div_cold(sum[k], (float)n);
+  for (int k = 0; k < 4; k++) avg[k] = div_small(sum[k], (float)n, s_rcp[n]);
   const bool all_same = mn == mx;
   const uint32_t gblock = block_index_base + first_block + t;
   const Col pix = ROT ? blk : pts;
@@ -1599,7 +1604,7 @@ __device__ __forceinline__ int slot_class(int layout_b, int slot) {
 }
 constexpr int kClassList = 6 * kChainThreads;  // at most six primary chains of one precision per block
 #ifndef FASTC_SETUP_CTAS
-#define FASTC_SETUP_CTAS 4
+#define FASTC_SETUP_CTAS 5
 #endif
 #ifndef FASTC_SETUP_CTAS16
 #define FASTC_SETUP_CTAS16 4
