@@ -92,6 +92,7 @@ struct Ws {
   uint32_t *total_solid;
   uint32_t *results;    // [nblocks][kSlots][kResWords]
   uint32_t *states;     // [nblocks][kSlots][kStateWords] annealing start states
+  uint32_t *sa_mask;    // [nblocks] bit s: slot s holds a start state (zeroed per submission, set by bc7_setup)
   uint4 *sorted;        // [nblocks*kSlots][2] the live chains' start states, sorted by descending
                         // (index precision, cluster size); word 7 = the chain's id (block * kSlots + slot)
   uint32_t *bins;       // histogram / offsets / cursors (see bc7_bin_offsets)
@@ -498,7 +499,7 @@ __device__ __forceinline__ void warp_argmin(double &err, int &idx) {
 template <bool NU>
 __global__ void __launch_bounds__(kSelWarps * 32)
 bc7_select(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, uint32_t first_block,
-           uint32_t num_blocks, uint32_t *__restrict__ sel, uint32_t *__restrict__ states, uint32_t block_modes) {
+           uint32_t num_blocks, uint32_t *__restrict__ sel, uint32_t block_modes) {
   // block_modes: BPTCC::CompressionSettings::m_BlockModes, ANDed into the selection's mode set
   // (Compressor.cpp:1857); solid / transparent blocks never reach it (:1822-1846)
   const uint32_t mode_keep = ~(0xFFu << 12) | ((block_modes & 0xFFu) << 12);
@@ -510,10 +511,6 @@ bc7_select(const uint32_t *__restrict__ img, uint32_t width, uint32_t blocks_x, 
   const bool valid = t < num_blocks;
   uint32_t type = kTypeNormal;
   if (valid) {
-    // every annealing start state of the block begins as "no chain".  This must happen before
-    // bc7_setup runs at all: there a chain also writes the state of its twin (twin_slot), whose
-    // slot is owned by another CTA.
-    if (lane < kSlots) states[((size_t)t * kSlots + lane) * kStateWords] = 0;
     type = sel[t] >> 24;
     if (lane < 16) {
       const uint32_t bi = first_block + t, bx = bi % blocks_x, by = bi / blocks_x;
@@ -1256,6 +1253,7 @@ __device__ __forceinline__ void write_state(const Ws &ws, uint32_t gid, uint32_t
                                             const FitResult &R, uint32_t rng, uint32_t alpha_err, uint32_t abytes) {
   uint32_t *st = ws.states + (size_t)gid * kStateWords;
   st[1] = R.p1; st[2] = R.p2; st[3] = R.err; st[4] = rng; st[5] = alpha_err; st[6] = abytes;
+  atomicOr(&ws.sa_mask[gid / kSlots], 1u << (gid % kSlots));
   st[0] = mask | ((uint32_t)c.mode << 16) | ((uint32_t)c.rot << 19) | ((uint32_t)c.idx_mode << 21) |
           ((uint32_t)R.combo << 22) | ((uint32_t)n << 24) | (1u << 31);
   // histogram by (index precision, cluster size): bc7_anneal runs chains sorted by that key so the
@@ -1724,10 +1722,10 @@ __global__ void __launch_bounds__(256) bc7_scatter(Ws ws, uint32_t num_blocks) {
   int key = -1;
   uint32_t rank = 0;
   uint4 st0 = make_uint4(0, 0, 0, 0);
-  if (gid < num_blocks * kSlots) {
+  if (gid < num_blocks * kSlots && ((ws.sa_mask[gid / kSlots] >> (gid % kSlots)) & 1u)) {
     st0 = *reinterpret_cast<const uint4 *>(ws.states + (size_t)gid * kStateWords);
     const uint32_t w0 = st0.x;
-    if (w0 >> 31) {
+    {
       const int mode = (w0 >> 16) & 7, idx_mode = (w0 >> 21) & 1;
       const int ibits = idx_mode == 0 ? c_modes[mode].index_bits : c_modes[mode].alpha_index_bits;
       key = sort_key(ibits, (w0 >> 24) & 31, sort_error(ws, st0.w));
@@ -2956,6 +2954,7 @@ size_t ws_bytes(uint32_t nblocks, bool nu) {
   b += 256;                                                      // total
   b += (size_t)nblocks * kSlots * kResWords * 4;                 // results
   b += (size_t)nblocks * kSlots * 8 * 4;                         // states
+  b += ((size_t)nblocks * 4 + 255) & ~(size_t)255;               // start-state masks
   b += (size_t)nblocks * kSlots * kStateWords * 4;               // sorted states
   b += kBinWords * 4;                                            // bins
   b += (size_t)kTailCap * 4;                                     // hand-over list of the annealing tail
@@ -2974,6 +2973,7 @@ Ws carve(void *base, uint32_t nblocks, bool nu) {
   w.wm_running = nullptr;
   w.results = reinterpret_cast<uint32_t *>(p); p += (size_t)nblocks * kSlots * kResWords * 4;
   w.states = reinterpret_cast<uint32_t *>(p); p += (size_t)nblocks * kSlots * 8 * 4;
+  w.sa_mask = reinterpret_cast<uint32_t *>(p); p += ((size_t)nblocks * 4 + 255) & ~(size_t)255;
   w.sorted = reinterpret_cast<uint4 *>(p); p += (size_t)nblocks * kSlots * kStateWords * 4;
   w.bins = reinterpret_cast<uint32_t *>(p); p += kBinWords * 4;
   w.tail_list = reinterpret_cast<uint32_t *>(p); p += (size_t)kTailCap * 4;
@@ -3103,14 +3103,15 @@ cudaError_t bc7_front(Bc7Workspace &wsp, const void *rgba_dev, uint32_t width, u
   }
   if (ev) cudaEventRecord(ev[1], stream);
   if (nu)
-    bc7_select<true><<<(nb + kSelWarps - 1) / kSelWarps, kSelWarps * 32, 0, stream>>>(img, width, bx, fb, nb, ws.sel, ws.states,
+    bc7_select<true><<<(nb + kSelWarps - 1) / kSelWarps, kSelWarps * 32, 0, stream>>>(img, width, bx, fb, nb, ws.sel,
                                                                                     prm.block_modes);
   else
-    bc7_select<false><<<(nb + kSelWarps - 1) / kSelWarps, kSelWarps * 32, 0, stream>>>(img, width, bx, fb, nb, ws.sel, ws.states,
+    bc7_select<false><<<(nb + kSelWarps - 1) / kSelWarps, kSelWarps * 32, 0, stream>>>(img, width, bx, fb, nb, ws.sel,
                                                                                      prm.block_modes);
   if (ev) cudaEventRecord(ev[2], stream);
   const uint64_t nthreads = (uint64_t)nb * kSlots;
   cudaMemsetAsync(ws.bins, 0, kBinWords * 4, stream);
+  cudaMemsetAsync(ws.sa_mask, 0, (size_t)nb * 4, stream);  // no start states yet
   {
     const uint32_t tiles = (nb + kChainThreads - 1) / kChainThreads;
     // the 16-bucket fits (mode 6, whole blocks) are the longest chains: first
