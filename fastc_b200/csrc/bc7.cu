@@ -716,7 +716,7 @@ __device__ __forceinline__ uint32_t single_color_nu(int mode, int idx_mode, int 
 // per-thread arrays means local memory -- and that kernel's L1 could not hold 640 threads' arrays.
 constexpr int kChainThreads = 128;
 #ifndef FASTC_ALPHA_UNROLL
-#define FASTC_ALPHA_UNROLL 1
+#define FASTC_ALPHA_UNROLL 4
 #endif
 constexpr int kAlphaUnroll = FASTC_ALPHA_UNROLL;
 struct Col {
@@ -1362,23 +1362,29 @@ __device__ __forceinline__ void setup_variant(const Ws &ws, const Chain &c, cons
 #pragma unroll 1
     for (int i = 0; i < nba; i++)
       vals.set(i, __float_as_uint(__fadd_rn(amin, __fmul_rn(div_cold((float)i, (float)(nba - 1)), __fsub_rn(amax, amin)))));
-#pragma unroll 1
-    for (int i = 0; i < 16; i += 2) {  // two pixels per trip through the packed pipe
-      const float2 av = make_float2((float)((pix[i] >> ash) & 0xFFu), (float)((pix[i + 1] >> ash) & 0xFFu));
-      float mda = 255.0f, mdb = 255.0f;
-      uint32_t ba = 0, bb = 0;
-#pragma unroll kAlphaUnroll
-      for (int j = 0; j < nba; j++) {  // (nba is 4 or 8)
-        const float2 d = sub2(av, __uint_as_float(vals[j]));
-        if (fabsf(d.x) < mda) { mda = fabsf(d.x); ba = (uint32_t)j; }
-        if (fabsf(d.y) < mdb) { mdb = fabsf(d.y); bb = (uint32_t)j; }
-      }
-      const uint32_t pair = (ba | (bb << 4)) << (4 * (i & 7));
-      if (i < 8) blo |= pair; else bhi |= pair;
-    }
+    // (one copy of the assignment pass: the reference's initial assignment is the loop's with every
+    // previous bucket 0; the pass after the update that found the fixed point still runs, as there)
     bool fixed = false;
     int guard = 0;
-    while (!fixed && guard++ < 4096) {
+    for (;;) {
+      uint32_t nlo = 0, nhi = 0;
+#pragma unroll 1
+      for (int i = 0; i < 16; i += 2) {  // two pixels per trip through the packed pipe
+        const float2 av = make_float2((float)((pix[i] >> ash) & 0xFFu), (float)((pix[i + 1] >> ash) & 0xFFu));
+        float mda = 255.0f, mdb = 255.0f;
+        const uint32_t old = (i < 8 ? blo : bhi) >> (4 * (i & 7));
+        uint32_t ba = old & 15u, bb = (old >> 4) & 15u;  // reference keeps the previous bucket when nothing is closer than 255
+#pragma unroll kAlphaUnroll
+        for (int j = 0; j < nba; j++) {  // (nba is 4 or 8)
+          const float2 d = sub2(av, __uint_as_float(vals[j]));
+          if (fabsf(d.x) < mda) { mda = fabsf(d.x); ba = (uint32_t)j; }
+          if (fabsf(d.y) < mdb) { mdb = fabsf(d.y); bb = (uint32_t)j; }
+        }
+        const uint32_t pair = (ba | (bb << 4)) << (4 * (i & 7));
+        if (i < 8) nlo |= pair; else nhi |= pair;
+      }
+      blo = nlo; bhi = nhi;
+      if (fixed || guard++ >= 4096) break;
       fixed = true;
       // bucket sums / counts are small integers (exact in any order): one pass over the pixels into
       // the lane's shared accumulators instead of the reference's bucket x pixel scan (:790-806)
@@ -1398,23 +1404,6 @@ __device__ __forceinline__ void setup_variant(const Ws &ws, const Chain &c, cons
         fixed = fixed && (s == __uint_as_float(vals[i]));
         vals.set(i, __float_as_uint(s));
       }
-      uint32_t nlo = 0, nhi = 0;
-#pragma unroll 1
-      for (int i = 0; i < 16; i += 2) {
-        const float2 av = make_float2((float)((pix[i] >> ash) & 0xFFu), (float)((pix[i + 1] >> ash) & 0xFFu));
-        float mda = 255.0f, mdb = 255.0f;
-        const uint32_t old = (i < 8 ? blo : bhi) >> (4 * (i & 7));
-        uint32_t ba = old & 15u, bb = (old >> 4) & 15u;  // reference keeps the previous bucket when nothing is closer than 255
-#pragma unroll kAlphaUnroll
-        for (int j = 0; j < nba; j++) {  // (nba is 4 or 8)
-          const float2 d = sub2(av, __uint_as_float(vals[j]));
-          if (fabsf(d.x) < mda) { mda = fabsf(d.x); ba = (uint32_t)j; }
-          if (fabsf(d.y) < mdb) { mdb = fabsf(d.y); bb = (uint32_t)j; }
-        }
-        const uint32_t pair = (ba | (bb << 4)) << (4 * (i & 7));
-        if (i < 8) nlo |= pair; else nhi |= pair;
-      }
-      blo = nlo; bhi = nhi;
     }
     float asq = 0.0f, bsq = 0.0f, ab = 0.0f, ax = 0.0f, bx = 0.0f;
     const float fb = (float)(nba - 1);
