@@ -60,9 +60,12 @@ def gather_slabs(local, rank: int, world: int, sizes: list[int], gather_list=Non
         if gather_list is None:
             gather_list = [torch.empty(s, dtype=torch.uint8, device=local.device) for s in sizes]
         gather_list[0].copy_(local)
-        reqs = [dist.irecv(gather_list[r], src=r, group=group) for r in range(1, world)]
-        for q in reqs:
+        # one batch: the receives are independent transfers (NCCL runs them as one group; issued one by
+        # one they are serialised on the process group: 7 x 8 MB took 0.44 ms of a 24 ms step at N = 8)
+        ops = [dist.P2POp(dist.irecv, gather_list[r], r, group) for r in range(1, world)]
+        for q in dist.batch_isend_irecv(ops):
             q.wait()
         return gather_list
-    dist.send(local, dst=0, group=group)
+    for q in dist.batch_isend_irecv([dist.P2POp(dist.isend, local, 0, group)]):
+        q.wait()
     return None
