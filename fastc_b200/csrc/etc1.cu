@@ -206,7 +206,10 @@ __device__ __forceinline__ bool optimize(const uint32_t (&px)[8], bool color4, b
 // pixel, first strict minimum in ascending selector / table order.  Per pixel the four squared
 // distances (VABSDIFF4 + DP4A, < 2^18) become keys distance * 4 + selector, so one min over the
 // keys picks the distance and the selector together, the lower selector on ties.
-__device__ __forceinline__ void evaluate_full(const uint32_t (&px)[8], uint32_t color, bool color4, Sol &trial) {
+#ifndef FASTC_ETC1_PRUNE_MASK
+#define FASTC_ETC1_PRUNE_MASK 0x7F  // the pixels after which the bound is tested (measured: every one, r02_ap_etc1.log)
+#endif
+__device__ __forceinline__ void evaluate_full(const uint32_t (&px)[8], uint32_t color, bool color4, uint32_t bound, Sol &trial) {
   const uint32_t base = scale_color(color, color4);
   const uint32_t base_rb = (base & 0xFFu) | ((base & 0xFF0000u));
   const int base_g = (base >> 8) & 0xFF;
@@ -219,6 +222,7 @@ __device__ __forceinline__ void evaluate_full(const uint32_t (&px)[8], uint32_t 
     uint32_t bc[4], bi[4];
     table_colors(base_rb, base_g, it, bc, bi);
     uint32_t total = 0, sel = 0;
+    bool pruned = false;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
       uint32_t key = 0xFFFFFFFFu;
@@ -229,10 +233,17 @@ __device__ __forceinline__ void evaluate_full(const uint32_t (&px)[8], uint32_t 
       }
       total += key >> 2;
       sel |= (key & 3u) << (2 * i);
+#ifndef FASTC_ETC1_NO_PRUNE
+      // A table whose partial sum has reached the error of the best table of this point, or of the
+      // best point so far (`bound`), cannot become either (the sums only grow; the caller accepts a
+      // point on strict <): the reference's own "total >= trial error" break (rg_etc1.cpp:1739),
+      // taken earlier.  The lanes of a warp scan the same lattice offset at the same time, so for an
+      // offset that is far from the optimum every lane is past its bound after a few pixels and
+      // the whole warp leaves the table; a lane whose neighbours go on just goes on with them.
+      if (((FASTC_ETC1_PRUNE_MASK >> i) & 1) && __all_sync(__activemask(), total >= min(trial.err, bound))) { pruned = true; break; }
+#endif
     }
-    // (the reference's running "total >= trial error" break only skips work: a table that triggers
-    // it is never accepted)
-    if (total < trial.err) {
+    if (!pruned && total < trial.err) {
       trial.err = total;
       trial.inten = it;
       trial.sel = sel;
@@ -286,7 +297,7 @@ struct Optimizer {
     if (!allowed(r, g, b)) return false;
     const uint32_t col = (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16);
     Sol t;
-    if (Q == 2) evaluate_full(px, col, color4, t);
+    if (Q == 2) evaluate_full(px, col, color4, best.err, t);
     else evaluate(px, luma2, lmin, lmax, col, color4, t);
     if (t.err < best.err) { best = t; valid = true; return true; }
     return false;
