@@ -19,7 +19,10 @@
 //   bc7_setup      1 thread / endpoint-fit "chain": PCA + k-means + least squares + grid clamp +
 //                                     first evaluation; chains that share a cluster and an index
 //                                     precision share the fit (twin_slot); writes either a final
-//                                     result or the start state of the chain's annealing
+//                                     result or the start state of the chain's annealing.  Five
+//                                     instantiations <index precision, rotation fit or not>, each
+//                                     with only the code its chains run (the kernel is bound by
+//                                     instruction fetch); float work in packed f32x2 pairs
 //   bc7_bin_offsets / bc7_scatter   : counting sort of the start states by (precision, cluster size)
 //   bc7_anneal     persistent lanes : 1 chain / lane, refilled from the sorted list; all-integer
 //                                     evaluation (paired palette rows, VABSDIFF4 + DP4A)
